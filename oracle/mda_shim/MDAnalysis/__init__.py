@@ -1,0 +1,538 @@
+"""TEST INFRASTRUCTURE ONLY -- a minimal stand-in for the MDAnalysis package.
+
+MDAnalysis cannot be installed in the build container (no wheel, no network),
+so the unmodified reference (`/root/reference/waterEntropy`) is executed on
+top of this shim to (a) validate the oracle restatement and (b) generate the
+golden vectors under `tests/golden/` (see `oracle/make_golden.py`).  Nothing in
+the product package imports this module.
+
+Only the API surface the reference's hot path touches is provided (SURVEY.md
+section 8(c) lists it).  Arithmetic that the real MDAnalysis performs in C or
+NumPy is restated here from its published behaviour:
+
+* `lib.distances.capped_distance`  -> brute force, float32 coordinate
+  difference widened to float64, round-based orthorhombic minimum image,
+  fp64 sqrt (`calc_distances.h::_calc_distance_array_ortho`);  triclinic boxes
+  use wrap-into-cell + 27-image search (parity UNPINNED: no reference test
+  covers a triclinic box).
+* `AtomGroup.center_of_mass / moment_of_inertia / principal_axes`
+  (`numpy.linalg.eig`, descending eigenvalue order, right-handed flip).
+
+It is pinned by the reference's own golden values: with this shim the
+reference's non-SLURM tests pass (`oracle/run_reference_tests.sh`).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from . import lib  # noqa: F401
+from .lib import distances  # noqa: F401
+
+__version__ = "2.10.0-shim"
+
+_WATER_RESNAMES = frozenset(
+    "H2O HOH OH2 HHO OHH TIP T3P T4P T5P SOL WAT TIP2 TIP3 TIP4".split()
+)
+
+
+class _Topology:
+    def __init__(self, names, types, charges, masses, resids, resnames, bonds):
+        self.n = len(names)
+        self.names = np.asarray(names, dtype=object)
+        self.types = np.asarray(types, dtype=object)
+        self.charges = np.asarray(charges, dtype=np.float64)
+        self.masses = np.asarray(masses, dtype=np.float64)
+        self.resids = np.asarray(resids, dtype=np.int64)
+        self.resnames = np.asarray(resnames, dtype=object)
+        self.bonds = np.asarray(bonds, dtype=np.int64).reshape(-1, 2)
+        self.is_water = np.array([r in _WATER_RESNAMES for r in self.resnames])
+        adj = [[] for _ in range(self.n)]
+        atom_bonds = [[] for _ in range(self.n)]
+        for a, b in self.bonds:
+            adj[a].append(int(b))
+            adj[b].append(int(a))
+            atom_bonds[a].append((int(a), int(b)))
+            atom_bonds[b].append((int(a), int(b)))
+        self.adj = adj
+        self.atom_bonds = atom_bonds
+        # connected components -> fragments
+        frag = -np.ones(self.n, dtype=np.int64)
+        nfrag = 0
+        for s in range(self.n):
+            if frag[s] >= 0:
+                continue
+            stack = [s]
+            frag[s] = nfrag
+            while stack:
+                v = stack.pop()
+                for w in adj[v]:
+                    if frag[w] < 0:
+                        frag[w] = nfrag
+                        stack.append(w)
+            nfrag += 1
+        self.fragment_id = frag
+        self.fragment_members = [[] for _ in range(nfrag)]
+        for i in range(self.n):
+            self.fragment_members[frag[i]].append(i)
+
+
+class Timestep:
+    def __init__(self, frame):
+        self.frame = frame
+
+
+class _Trajectory:
+    def __init__(self, universe, positions, forces, dimensions):
+        self._u = universe
+        self._pos = positions
+        self._frc = forces
+        self._dim = dimensions
+        self.n_frames = positions.shape[0]
+        self.ts = Timestep(0)
+        self._load(0)
+
+    def _load(self, i):
+        if i < 0:
+            i += self.n_frames
+        if not 0 <= i < self.n_frames:
+            raise IndexError(f"frame {i} out of range")
+        self.ts = Timestep(i)
+        self._u._positions = self._pos[i]
+        self._u._forces = None if self._frc is None else self._frc[i]
+        self._u._dimensions = self._dim[i]
+        return self.ts
+
+    def __len__(self):
+        return self.n_frames
+
+    def __getitem__(self, item):
+        if isinstance(item, slice):
+            return _TrajectorySlice(self, range(*item.indices(self.n_frames)))
+        return self._load(int(item))
+
+    def __iter__(self):
+        for i in range(self.n_frames):
+            yield self._load(i)
+
+
+class _TrajectorySlice:
+    def __init__(self, traj, frames):
+        self._traj = traj
+        self._frames = frames
+
+    def __len__(self):
+        return len(self._frames)
+
+    def __iter__(self):
+        for i in self._frames:
+            yield self._traj._load(i)
+
+
+class Bond:
+    def __init__(self, a, b):
+        self.indices = np.array([a, b])
+
+
+class _BondGroup:
+    def __init__(self, pairs):
+        self._pairs = pairs
+
+    @property
+    def indices(self):
+        return np.array(self._pairs, dtype=np.int64).reshape(-1, 2)
+
+    def __iter__(self):
+        for a, b in self._pairs:
+            yield Bond(a, b)
+
+    def __len__(self):
+        return len(self._pairs)
+
+
+class Residue:
+    def __init__(self, resid, resname):
+        self.resid = resid
+        self.resname = resname
+
+
+class Atom:
+    def __init__(self, universe, index):
+        self._u = universe
+        self.index = int(index)
+
+    @property
+    def ix(self):
+        return self.index
+
+    @property
+    def position(self):
+        return self._u._positions[self.index].copy()
+
+    @property
+    def force(self):
+        return self._u._forces[self.index].copy()
+
+    @property
+    def mass(self):
+        return self._u._top.masses[self.index]
+
+    @property
+    def charge(self):
+        return self._u._top.charges[self.index]
+
+    @property
+    def resname(self):
+        return self._u._top.resnames[self.index]
+
+    @property
+    def resid(self):
+        return int(self._u._top.resids[self.index])
+
+    @property
+    def type(self):
+        return self._u._top.types[self.index]
+
+    @property
+    def name(self):
+        return self._u._top.names[self.index]
+
+    @property
+    def bonds(self):
+        return _BondGroup(self._u._top.atom_bonds[self.index])
+
+    @property
+    def fragment(self):
+        top = self._u._top
+        return AtomGroup(
+            self._u, np.array(top.fragment_members[top.fragment_id[self.index]])
+        )
+
+    def __repr__(self):
+        return f"<Atom {self.index}: {self.name} of {self.resname} {self.resid}>"
+
+
+class AtomGroup:
+    def __init__(self, universe, indices):
+        self._u = universe
+        self._ix = np.asarray(indices, dtype=np.int64).reshape(-1)
+
+    # ---- container protocol -------------------------------------------
+    def __len__(self):
+        return len(self._ix)
+
+    def __iter__(self):
+        for i in self._ix:
+            yield Atom(self._u, i)
+
+    def __getitem__(self, item):
+        if isinstance(item, (int, np.integer)):
+            return Atom(self._u, self._ix[item])
+        return AtomGroup(self._u, self._ix[item])
+
+    def __add__(self, other):
+        if isinstance(other, Atom):
+            return AtomGroup(self._u, np.append(self._ix, other.index))
+        return AtomGroup(self._u, np.concatenate([self._ix, other._ix]))
+
+    def __repr__(self):
+        return f"<AtomGroup with {len(self)} atoms>"
+
+    # ---- attributes ------------------------------------------------------
+    @property
+    def atoms(self):
+        return self
+
+    @property
+    def universe(self):
+        return self._u
+
+    @property
+    def indices(self):
+        return self._ix.copy()
+
+    ix = indices
+
+    @property
+    def positions(self):
+        if self._ix is self._u._all_ix:
+            return self._u._positions  # whole system: no copy (read-only use)
+        return self._u._positions[self._ix]  # fancy index -> copy, float32
+
+    @property
+    def forces(self):
+        return self._u._forces[self._ix]
+
+    @property
+    def masses(self):
+        return self._u._top.masses[self._ix]
+
+    @property
+    def charges(self):
+        return self._u._top.charges[self._ix]
+
+    @property
+    def names(self):
+        return self._u._top.names[self._ix]
+
+    @property
+    def types(self):
+        return self._u._top.types[self._ix]
+
+    @property
+    def resnames(self):
+        return self._u._top.resnames[self._ix]
+
+    @property
+    def resids(self):
+        return self._u._top.resids[self._ix]
+
+    @property
+    def residues(self):
+        top = self._u._top
+        seen = {}
+        for i in self._ix:
+            rid = int(top.resids[i])
+            if rid not in seen:
+                seen[rid] = Residue(rid, top.resnames[i])
+        return [seen[k] for k in sorted(seen)]
+
+    @property
+    def fragments(self):
+        top = self._u._top
+        fids = []
+        seen = set()
+        for i in self._ix:
+            f = int(top.fragment_id[i])
+            if f not in seen:
+                seen.add(f)
+                fids.append(f)
+        fids.sort(key=lambda f: top.fragment_members[f][0])
+        return tuple(AtomGroup(self._u, np.array(top.fragment_members[f])) for f in fids)
+
+    @property
+    def bonds(self):
+        inside = set(int(i) for i in self._ix)
+        pairs = sorted(
+            {
+                p
+                for i in self._ix
+                for p in self._u._top.atom_bonds[i]
+                if p[0] in inside or p[1] in inside
+            }
+        )
+        return _BondGroup(pairs)
+
+    # ---- geometry (restated MDAnalysis arithmetic) -----------------------
+    def center_of_mass(self):
+        coords = self.positions.astype(np.float64)
+        weights = self.masses.astype(np.float64)
+        return (coords * weights[:, None]).sum(axis=0) / weights.sum()
+
+    def moment_of_inertia(self):
+        com = self.center_of_mass()
+        pos = self.positions - com
+        masses = self.masses
+        tens = np.zeros((3, 3), dtype=np.float64)
+        tens[0][0] = (masses * (pos[:, 1] ** 2 + pos[:, 2] ** 2)).sum()
+        tens[0][1] = tens[1][0] = -(masses * pos[:, 0] * pos[:, 1]).sum()
+        tens[0][2] = tens[2][0] = -(masses * pos[:, 0] * pos[:, 2]).sum()
+        tens[1][1] = (masses * (pos[:, 0] ** 2 + pos[:, 2] ** 2)).sum()
+        tens[1][2] = tens[2][1] = -(masses * pos[:, 1] * pos[:, 2]).sum()
+        tens[2][2] = (masses * (pos[:, 0] ** 2 + pos[:, 1] ** 2)).sum()
+        return tens
+
+    def principal_axes(self):
+        e_val, e_vec = np.linalg.eig(self.moment_of_inertia())
+        order = np.argsort(e_val)[::-1]
+        e_vec = e_vec[:, order].T
+        if np.dot(np.cross(e_vec[0], e_vec[1]), e_vec[2]) < 0:
+            e_vec = e_vec * -1
+        return e_vec
+
+    # ---- selections ------------------------------------------------------
+    def select_atoms(self, sel: str):
+        mask = _Selection(self._u, sel).evaluate()
+        return AtomGroup(self._u, np.unique(self._ix[mask[self._ix]]))
+
+
+class _Selection:
+    """Recursive-descent parser for the closed set of selection strings the
+    reference issues: and / not / or, parentheses, `all`, `water`,
+    `index i j ...`, `resid r ...`, `mass a to b`, `bonded <selection>`."""
+
+    KEYWORDS = {"and", "or", "not", "(", ")"}
+
+    def __init__(self, universe, text):
+        self.u = universe
+        self.top = universe._top
+        self.tokens = text.replace("(", " ( ").replace(")", " ) ").split()
+        self.pos = 0
+
+    def peek(self):
+        return self.tokens[self.pos] if self.pos < len(self.tokens) else None
+
+    def next(self):
+        tok = self.peek()
+        self.pos += 1
+        return tok
+
+    def evaluate(self):
+        if not self.tokens:
+            raise ValueError("empty selection")
+        mask = self.parse_or()
+        if self.pos != len(self.tokens):
+            raise ValueError(f"unparsed selection tail: {self.tokens[self.pos:]}")
+        return mask
+
+    def parse_or(self):
+        mask = self.parse_and()
+        while self.peek() == "or":
+            self.next()
+            mask = mask | self.parse_and()
+        return mask
+
+    def parse_and(self):
+        mask = self.parse_not()
+        while self.peek() == "and":
+            self.next()
+            mask = mask & self.parse_not()
+        return mask
+
+    def parse_not(self):
+        if self.peek() == "not":
+            self.next()
+            return ~self.parse_not()
+        return self.parse_primary()
+
+    def _numbers(self):
+        vals = []
+        while self.peek() is not None and self.peek() not in self.KEYWORDS:
+            tok = self.peek()
+            try:
+                vals.append(int(tok))
+            except ValueError:
+                break
+            self.next()
+        return vals
+
+    def parse_primary(self):
+        tok = self.next()
+        n = self.top.n
+        if tok == "(":
+            mask = self.parse_or()
+            if self.next() != ")":
+                raise ValueError("missing )")
+            return mask
+        if tok == "all":
+            return np.ones(n, dtype=bool)
+        if tok == "water":
+            return self.top.is_water.copy()
+        if tok == "index":
+            vals = self._numbers()
+            if not vals:
+                raise ValueError("index selection needs values")
+            mask = np.zeros(n, dtype=bool)
+            mask[np.array(vals, dtype=np.int64)] = True
+            return mask
+        if tok == "resid":
+            vals = self._numbers()
+            if not vals:
+                raise ValueError("resid selection needs values")
+            return np.isin(self.top.resids, np.array(vals))
+        if tok == "mass":
+            lo = float(self.next())
+            if self.peek() == "to":
+                self.next()
+                hi = float(self.next())
+                return (self.top.masses >= lo) & (self.top.masses <= hi)
+            return self.top.masses == lo
+        if tok == "bonded":
+            inner = self.parse_not()
+            mask = np.zeros(n, dtype=bool)
+            for i in np.nonzero(inner)[0]:
+                for j in self.top.adj[i]:
+                    mask[j] = True
+            return mask
+        raise ValueError(f"unsupported selection token {tok!r}")
+
+
+class Universe:
+    """`Universe(topology, coordinates)` for PRMTOP+NetCDF and GRO+TRR, or
+    `Universe.from_arrays(...)` for synthetic systems."""
+
+    def __init__(self, topology=None, coordinates=None, **kwargs):
+        if topology is None:
+            return
+        ext_t = os.path.splitext(str(topology))[1].lower()
+        ext_c = os.path.splitext(str(coordinates))[1].lower()
+        if ext_t in (".prmtop", ".top", ".parm7") and ext_c in (".nc", ".ncdf"):
+            from waterentropy_b200.io.amber import AmberTopology, NetCDFTrajectory
+
+            top = AmberTopology(topology)
+            trj = NetCDFTrajectory(coordinates)
+            self._init(
+                _Topology(
+                    top.names,
+                    top.types,
+                    top.charges,
+                    top.masses,
+                    top.resids,
+                    top.resnames,
+                    top.bonds,
+                ),
+                trj.positions,
+                trj.forces,
+                trj.dimensions,
+            )
+        else:
+            raise NotImplementedError(
+                f"shim has no reader for {ext_t!r} + {ext_c!r}"
+            )
+
+    @classmethod
+    def from_arrays(
+        cls,
+        names,
+        types,
+        charges,
+        masses,
+        resids,
+        resnames,
+        bonds,
+        positions,
+        forces,
+        dimensions,
+    ):
+        u = cls()
+        u._init(
+            _Topology(names, types, charges, masses, resids, resnames, bonds),
+            np.asarray(positions, dtype=np.float32),
+            None if forces is None else np.asarray(forces, dtype=np.float32),
+            np.asarray(dimensions, dtype=np.float32),
+        )
+        return u
+
+    def _init(self, top, positions, forces, dimensions):
+        self._top = top
+        self._positions = None
+        self._forces = None
+        self._dimensions = None
+        self.trajectory = _Trajectory(self, positions, forces, dimensions)
+        self._all_ix = np.arange(top.n)
+        self.atoms = AtomGroup(self, self._all_ix)
+        self.atoms._ix = self._all_ix
+
+    @property
+    def dimensions(self):
+        return self._dimensions.copy()
+
+    def select_atoms(self, sel):
+        return self.atoms.select_atoms(sel)
+
+    def __getstate__(self):
+        return self.__dict__
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
