@@ -1,0 +1,198 @@
+/*
+ * waterentropy_b200 -- C ABI of the B200-native per-frame interfacial-solvent
+ * analysis (drop-in for the hot path of jkalayan/waterEntropy 2.2.0).
+ *
+ * The reference is pure Python and has no FFI; its natural seam is the
+ * per-frame worker that dask ships between processes plus the two recipe
+ * entry points.  Each entry point below names the reference interface it
+ * replaces (paths relative to /root/reference/waterEntropy/).  The Python
+ * package `waterentropy_b200` binds these with ctypes (INTEGRATION.md shows the
+ * stub a reference maintainer would add).
+ *
+ * Conventions: plain pointers and sizes, no torch / numpy types.  Every call
+ * returns 0 on success or a negative WE_ERR_* code; `we_last_error()` gives the
+ * text.  One context per GPU; a context is not thread-safe.  All host arrays
+ * are owned by the caller; the library copies what it needs during the call
+ * (frame buffers passed to `we_submit` must stay valid until the next
+ * `we_sync` / `we_finalize`).
+ */
+#ifndef WATERENTROPY_B200_H
+#define WATERENTROPY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WE_VERSION 100
+
+/* recipes */
+#define WE_RECIPE_INTERFACIAL 0 /* recipes/interfacial_solvent.py:273-345 (_entropy_per_step) */
+#define WE_RECIPE_BULK 1        /* recipes/bulk_water.py:37-72 */
+
+/* error codes (negative return values) */
+#define WE_OK 0
+#define WE_ERR_DUPLICATE_COORD -1 /* ValueError of maths/trig.py:40-42 */
+#define WE_ERR_NO_NEIGHBOURS -2   /* implicit ValueError of maths/trig.py:36-38 */
+#define WE_ERR_CAND_OVERFLOW -3   /* > 128 candidates inside the adaptive search radius */
+#define WE_ERR_TABLE_FULL -4      /* label count table full: raise we_options.table_log2 */
+#define WE_ERR_HASH_COLLISION -5  /* two label keys share a 128-bit hash (never observed) */
+#define WE_ERR_INVALID -10        /* bad argument / topology */
+#define WE_ERR_CUDA -11           /* CUDA runtime failure (no CPU fallback exists) */
+
+#define WE_MAX_SHELL 25 /* analysis/RAD.py:39 */
+
+/*
+ * Frame-invariant system description.  Replaces what the reference
+ * re-derives every frame through MDAnalysis selection strings
+ * (utils/selections.py:8-105, recipes/interfacial_solvent.py:298-299); the
+ * Python host builds it once (`waterentropy_b200.system.SystemTopology`).
+ */
+typedef struct we_topology {
+    int32_t n_atoms;
+    const double *masses;       /* [n_atoms] */
+    const double *charges;      /* [n_atoms] */
+    const int32_t *resid;       /* [n_atoms] */
+    const int32_t *resname_id;  /* [n_atoms] index into the host's resname table (< 8192) */
+    const int32_t *type_id;     /* [n_atoms] index into the host's atom-type table */
+    const uint8_t *is_water;    /* [n_atoms] MDAnalysis "water" selection */
+    int32_t n_bonds;
+    const int32_t *bonds;       /* [n_bonds][2] */
+    int32_t n_solute_ua;        /* utils/selections.py:34-56 + interfacial_solvent.py:39-43 */
+    const int32_t *solute_ua;   /* [n_solute_ua] atom indices of solute united atoms */
+    int32_t n_centres;          /* water heavy atoms that can be analysed */
+    const int32_t *centres;     /* [n_centres] atom indices, ascending */
+    const int32_t *frag_ptr;    /* [n_centres+1] CSR: atoms of each centre's molecule */
+    const int32_t *frag_atoms;
+    const int32_t *bin_of_atom; /* [n_atoms] covariance pair-bin of (resname, resid), -1 = none */
+    const int32_t *centre_class;/* [n_atoms] class of a centre's resname, -1 = not a centre */
+    int32_t n_pair_bins;
+    int32_t n_classes;
+    int32_t recipe;             /* WE_RECIPE_* */
+} we_topology;
+
+typedef struct we_options {
+    int32_t device;          /* CUDA device ordinal */
+    int32_t chunk_frames;    /* frames per kernel batch (0 = auto) */
+    int32_t table_log2;      /* log2 capacity of the label count table (0 = 16) */
+    int32_t keep_records;    /* 1: keep per-frame recorded-water lists (frame_solvent_indices) */
+    int32_t keep_debug;      /* 1: keep all-centre shells / neighbours / acceptors / F,T of every frame */
+    float search_radius;     /* first-pass candidate radius in A (0 = 7.0) */
+    float max_box;           /* largest box edge expected in A (0 = take from first frame x 1.25) */
+} we_options;
+
+typedef struct we_ctx we_ctx;
+
+typedef struct we_diag {
+    uint64_t ambiguous_rad;   /* RAD comparisons within 4 ulp (libm pow vs x*x could differ) */
+    uint64_t ambiguous_hb;
+    uint64_t wide_searches;   /* centres that needed the 10 A wide search */
+    uint64_t shrink_retries;
+    uint64_t table_entries;
+    uint64_t kernel_launches; /* kernels launched so far by this context */
+    uint64_t frames_done;
+    uint64_t recorded;        /* recorded (water, frame) pairs so far */
+} we_diag;
+
+const char *we_last_error(void);
+int we_version(void);
+
+/* Build a context: uploads the topology, allocates per-GPU accumulators
+ * (CovarianceCollection / HBLabelCollection state, entropy/convariances.py:10-19,
+ * analysis/HB_labels.py:33-35) and the frame workspace. */
+int we_create(const we_topology *topo, const we_options *opt, we_ctx **out);
+void we_destroy(we_ctx *ctx);
+
+/* Analyse `n_frames` frames held in HOST memory (pinned or pageable):
+ *   pos, frc  float32 [n_frames][n_atoms][3]   (ts.positions / ts.forces)
+ *   dims      float32 [n_frames][6]            (ts.dimensions)
+ *   frame_ids int64   [n_frames]               (ts.frame)
+ * Replaces a `client.map(_entropy_per_step, ...)` over those frames
+ * (recipes/interfacial_solvent.py:229-243) or the frame loop of
+ * recipes/bulk_water.py:37.  Copies are asynchronous and double buffered;
+ * accumulation happens on the device. */
+int we_submit(we_ctx *ctx, const float *pos, const float *frc, const float *dims,
+              const int64_t *frame_ids, int32_t n_frames);
+
+/* Same, with pos / frc already resident in DEVICE memory (dims and frame_ids
+ * stay on the host; they are 32 bytes per frame). */
+int we_submit_device(we_ctx *ctx, const float *d_pos, const float *d_frc, const float *dims,
+                     const int64_t *frame_ids, int32_t n_frames);
+
+/* Wait for all submitted work; surfaces the reference's per-frame exceptions
+ * as WE_ERR_DUPLICATE_COORD / WE_ERR_NO_NEIGHBOURS. */
+int we_sync(we_ctx *ctx);
+int we_get_diag(we_ctx *ctx, we_diag *out);
+int we_error_location(we_ctx *ctx, int64_t *frame_id, int32_t *atom);
+
+/* ---- results (after we_sync) ------------------------------------------------ */
+
+/* Dense covariance table: sums over recorded waters of the two 3x3 outer
+ * products (force, torque; recipes/forces_torques.py:50-53) and the counts
+ * (entropy/convariances.py:21-84 keeps running means; mean = sum / count).
+ *   cov_sum [n_bins][2][3][3] float64, cov_cnt [n_bins] uint64,
+ *   n_bins = n_pair_bins * n_classes (interfacial) or n_classes (bulk). */
+int we_n_bins(we_ctx *ctx);
+int we_copy_cov(we_ctx *ctx, double *cov_sum, uint64_t *cov_cnt);
+/* device pointers of the same tables, for an NCCL all-reduce across ranks
+ * (replaces CovarianceCollection.merge, entropy/convariances.py:86-108) */
+int we_device_tables(we_ctx *ctx, void **d_cov_sum, void **d_cov_cnt);
+
+/* Label count table (HBLabelCollection, analysis/HB_labels.py:15-156).
+ * Each entry is 512 bytes, layout `we_label_entry`. */
+typedef struct we_label_entry {
+    uint64_t hash, hash2;
+    uint64_t first_seen_inv;  /* ~min(frame_id * n_atoms + atom): N_w is frozen by the first insert */
+    uint64_t shell_count;
+    int32_t nearest_resid;      /* -1 for the bulk recipe */
+    int32_t nearest_resname_id; /* bulk: the water resname */
+    int32_t n_labels;
+    int32_t n_w;
+    uint16_t labels[32];        /* sorted codes: (prefix << 13) | resname_id; prefix 0:"0_" 1:"" 2:"1_" 3:"2_" 4:"X_" */
+    uint32_t donates[25];       /* per label position (first occurrence) */
+    uint32_t accepts[25];
+    uint32_t pad[50];
+} we_label_entry;
+int we_n_label_entries(we_ctx *ctx);
+int we_copy_label_entries(we_ctx *ctx, we_label_entry *out, int32_t capacity);
+
+/* Per-frame recorded waters (frame_solvent_indices, recipes/interfacial_solvent.py:69-88);
+ * needs we_options.keep_records.  `k` counts submitted frames from 0.
+ * out = int32 [count][2] = (water atom index, nearest non-like atom index or -1), ascending. */
+int we_frame_record_count(we_ctx *ctx, int64_t k);
+int we_copy_frame_records(we_ctx *ctx, int64_t k, int32_t *out, int32_t capacity);
+
+/* All-centre per-frame state (needs we_options.keep_debug); used by
+ * get_interfacial_shells (recipes/interfacial_solvent.py:104-146) and by the
+ * parity tests.  field: */
+#define WE_DBG_SHELL_N 0   /* int32 [n_heavy] */
+#define WE_DBG_SHELL_IDX 1 /* int32 [n_heavy][25] atom indices, distance order */
+#define WE_DBG_NEAREST 2   /* int32 [n_heavy] nearest non-like atom or -1 */
+#define WE_DBG_FLAGS 3     /* int32 [n_heavy] bit0 gate, bits 8.. status */
+#define WE_DBG_ACCEPTOR 4  /* int32 [n_donors] acceptor atom or -(1+status) */
+#define WE_DBG_NBR_IDX 5   /* int32 [n_heavy][25] sorted candidates */
+#define WE_DBG_NBR_DIST 6  /* float64 [n_heavy][25] */
+#define WE_DBG_FT 7        /* float64 [n_records][6] F(3), torque(3) in record order */
+#define WE_DBG_REC 8       /* int32 [n_records][4] atom, nearest, bin, 0 (unsorted) */
+int we_n_heavy(we_ctx *ctx);
+int we_n_donors(we_ctx *ctx);
+int we_copy_heavy_idx(we_ctx *ctx, int32_t *out);
+int we_copy_donors(we_ctx *ctx, int32_t *don_x_atom, int32_t *don_h_atom);
+int64_t we_debug_size(we_ctx *ctx, int64_t k, int32_t field);
+int we_debug_copy(we_ctx *ctx, int64_t k, int32_t field, void *out, int64_t bytes);
+
+/* Clear the accumulators (start a new analysis with the same topology). */
+int we_reset(we_ctx *ctx);
+
+/* Scalar arithmetic hooks (device-executed) so the float32 angle / powf
+ * replay and the distance formula can be pinned directly in tests:
+ *   maths/trig.py:103-122 (get_angle), MDAnalysis capped_distance formula. */
+int we_test_angle_cos(int32_t device, const float *abc /*[n][9]*/, const float *dim3, int32_t n, float *out);
+int we_test_powf2(int32_t device, const float *x, int32_t n, float *out);
+int we_test_distance(int32_t device, const float *pairs /*[n][6]*/, const float *dims6, int32_t n, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

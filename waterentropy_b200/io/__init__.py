@@ -1,0 +1,1 @@
+from .universe import Universe  # noqa: F401

@@ -1,0 +1,134 @@
+"""Interfacial-water recipes on the B200 path.
+
+Drop-in for `waterEntropy/recipes/interfacial_solvent.py` (same function names,
+positional order and return objects; reference lines cited per function).  The
+per-frame work -- neighbour search, RAD shells, HB labelling, shell labels,
+force/torque covariances, count tables -- runs in the CUDA kernels behind
+`WaterEntropyEngine`; this module only stages frames and rebuilds the
+reference's Python objects from the device tables.
+"""
+from __future__ import annotations
+
+from waterentropy_b200 import distributed as wdist
+from waterentropy_b200.engine import WaterEntropyEngine
+from waterentropy_b200.entropy.orientations import Orientations
+from waterentropy_b200.entropy.vibrations import Vibrations
+from waterentropy_b200.frames import iter_batches
+from waterentropy_b200.system import SystemTopology
+from waterentropy_b200.utils.helpers import nested_dict
+
+
+def _device():
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            return torch.cuda.current_device()
+    except Exception:  # pragma: no cover
+        pass
+    return 0
+
+
+def _run(system, indices, recipe, keep_debug=False, keep_records=True):
+    eng = WaterEntropyEngine(system, recipe, device=_device(), keep_records=keep_records,
+                             keep_debug=keep_debug)
+    batch = max(1, min(64, 400_000 // max(1, len(eng.top.heavy_idx))))
+    for P, F, D, ids in iter_batches(system, indices, batch):
+        eng.submit(P, F, D, ids)
+    eng.sync()
+    return eng
+
+
+def get_interfacial_water_orient_entropy(system, start: int, end: int, step: int, temperature=298,
+                                         parallel=False, client=None):
+    """Reference: `recipes/interfacial_solvent.py:181-270`.
+
+    Returns `(Sorient_dict, covariances, vibrations, frame_solvent_indices, n_frames)`.
+    `parallel=True` shards the frames over the ranks of an initialised
+    `torch.distributed` job (one process per GPU) and combines the per-GPU
+    tables with NCCL; the dask `client` argument of the reference is accepted
+    and ignored."""
+    indices = list(range(start, end, step))
+    world = wdist.world() if parallel else (0, 1)
+    mine = wdist.shard_frames(indices, *world)
+    eng = _run(system, mine, "interfacial")
+    if world[1] > 1:
+        covariances, hb_labels, frame_solvent_indices = wdist.combine(eng)
+    else:
+        covariances, hb_labels, frame_solvent_indices = eng.covariances(), eng.hb_labels(), eng.frame_solvent_indices()
+    eng.close()
+    n_frames = len(indices)
+    Sorients = Orientations()
+    Sorients.add_data(hb_labels)
+    vibrations = Vibrations(temperature)
+    vibrations.add_data(covariances, diagonalise=True)
+    return Sorients.resid_labelled_Sorient, covariances, vibrations, frame_solvent_indices, n_frames
+
+
+def _entropy_per_step(args):
+    """Reference: `recipes/interfacial_solvent.py:273-345` -- one frame, fresh accumulators.
+    Returns `(frame_solvent_indices, CovarianceCollection, HBLabelCollection, 1)`."""
+    index, system = args
+    eng = _run(system, [index], "interfacial")
+    out = (eng.frame_solvent_indices(), eng.covariances(), eng.hb_labels(), 1)
+    eng.close()
+    return out
+
+
+def get_interfacial_shells(system, start: int, end: int, step: int):
+    """Reference: `recipes/interfacial_solvent.py:104-146` -- RAD shells of the interfacial
+    waters that have a non-like neighbour: `{frame: {water_idx: [shell idx ...]}}`."""
+    indices = list(range(start, end, step))
+    eng = _run(system, indices, "interfacial", keep_debug=True)
+    out = nested_dict()
+    for k, frame in enumerate(eng.frame_ids):
+        shells = eng.shells(k)
+        for atom, _nearest in eng.frame_records(k):
+            out[frame][int(atom)] = shells[int(atom)]
+    eng.close()
+    return out
+
+
+def find_interfacial_solvent(solutes, system, shells=None):
+    """Reference: `recipes/interfacial_solvent.py:25-66` -- waters in the RAD shell of any
+    solute united atom that has a water among its 20 nearest neighbours, for the
+    CURRENT frame of `system`.  `solutes`: atom group (`.indices`) or index list
+    restricting the solute atoms; whole molecules are used, as upstream."""
+    top = SystemTopology.from_universe(system)
+    frame = int(system.trajectory.ts.frame) if hasattr(system, "trajectory") else 0
+    eng = _run(system, [frame], "interfacial", keep_debug=True, keep_records=False)
+    sel = getattr(solutes, "indices", solutes)
+    frag = set(int(top.fragment_id[a]) for a in sel)
+    flags = eng.debug(0, "flags")
+    all_shells = eng.shells(0)
+    slot = {int(a): s for s, a in enumerate(top.heavy_idx)}
+    found = set()
+    for a in top.heavy_idx:
+        a = int(a)
+        if int(top.fragment_id[a]) in frag and (flags[slot[a]] & 1):
+            found.update(n for n in all_shells[a] if top.is_water[n])
+    eng.close()
+    return list(found)
+
+
+def save_solvent_indices(frame, atom_idx, nearest_resid, nearest_resname, frame_solvent_indices):
+    """Reference: `recipes/interfacial_solvent.py:69-88`."""
+    if nearest_resid not in frame_solvent_indices[frame][nearest_resname]:
+        frame_solvent_indices[frame][nearest_resname][nearest_resid] = []
+    frame_solvent_indices[frame][nearest_resname][nearest_resid].append(atom_idx)
+    return frame_solvent_indices
+
+
+def print_frame_solvent_dicts(frame_solvent_indices: dict):
+    """Reference: `recipes/interfacial_solvent.py:91-101`."""
+    for frame, by_name in sorted(list(frame_solvent_indices.items())):
+        for resname, by_resid in sorted(list(by_name.items())):
+            for resid, solvents in sorted(list(by_resid.items())):
+                print(frame, resname, resid, len(solvents), solvents)
+
+
+def print_frame_solvent_shells(frame_solvent_shells: dict):
+    """Reference: `recipes/interfacial_solvent.py:169-178`."""
+    for frame, by_atom in sorted(list(frame_solvent_shells.items())):
+        for atom_idx, shell in sorted(list(by_atom.items())):
+            print(frame, atom_idx, shell, len(shell))
