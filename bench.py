@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- water-molecule.frames/sec of the per-frame hot path (RAD + HB + covariance).
+
+Contract (see the task statement):  python bench.py --gpus N --steps K --warmup W
+prints ONE JSON line on rank 0.  A "step" is one pass of the hot path over one batch
+of synthetic frames of the workload BASELINE.json quotes the metric on (C4: 100k-water
+solvated protein-DNA complex in a triclinic box); per-GPU work is fixed (weak scaling,
+every rank analyses its own frames, tables combined with one NCCL exchange).
+
+  value : whole-job water.frames/s with the frames already resident in HBM, timed with
+          CUDA events on the library's compute stream (max over ranks).
+  e2e   : the same metric through the public host-buffer API (`WaterEntropyEngine.submit`
+          from pinned memory -> sync -> covariance table + label table + recorded-water
+          lists back on the host, plus the cross-rank combine when N > 1).
+  roofline / cpu_baseline : see DESIGN.md "Measurement".
+
+`--impl reference` times the CPU restatement of the reference (oracle/, the reference is
+pure Python on top of an uninstallable MDAnalysis) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+from waterentropy_b200 import synthetic  # noqa: E402
+
+METRIC = "water-molecule.frames/sec (RAD+HB+covariance)"
+UNIT = "water.frames/s"
+
+
+def load_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.device)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["sm_max_mhz"] = max(mx)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ----------------------------------------------------------------------------- CPU arm
+_W = {}
+
+
+def _cpu_init(cfg_name, scale, seed):
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import we_oracle as wo
+
+    s = synthetic.make_config(cfg_name, scale=scale)
+    _W["wo"] = wo
+    _W["sys"] = s
+    _W["top"] = wo.OracleTopology(s.masses, s.charges, s.resids, s.resnames, s.types, s.bonds)
+    _W["seed"] = seed
+
+
+def _cpu_task(args):
+    """Full per-centre cost of the reference algorithm for a random sample of heavy-atom centres
+    of one frame: brute-force neighbour list + stable sort + RAD shell + HB acceptors."""
+    frame, m = args
+    wo, s, top = _W["wo"], _W["sys"], _W["top"]
+    P, F, D = s.frame(frame)
+    rng = np.random.default_rng([_W["seed"], frame])
+    H = len(top.heavy_idx)
+    m = min(m, H)
+    centres = np.sort(rng.choice(top.heavy_idx, size=m, replace=False))
+    t0 = time.perf_counter()
+    r = wo.rad_frame(top, P, D, centres=centres)
+    dx, dh, rows = [], [], []
+    for k, a in enumerate(centres):
+        for h in top.donors[int(a)]:
+            dx.append(int(a))
+            dh.append(h)
+            rows.append(k)
+    if dx:
+        wo.hb_frame(top, P, D, dx, dh, r["shell_n"][rows], r["shell_idx"][rows])
+    waters = [int(a) for a in centres if top.is_water[a]][: max(1, m // 4)]
+    wo.forces_torques(top, P, F, waters)
+    return time.perf_counter() - t0, m, H
+
+
+def cpu_rate(cfg_name, scale, cores, sample_centres, steps, warmup, seed=7):
+    """water.frames/s of the oracle port with `cores` frame-parallel processes."""
+    import multiprocessing as mp
+
+    s = synthetic.make_config(cfg_name, scale=scale)
+    W = s.n_waters
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(cfg_name, scale, seed)) as pool:
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_task, [(it * cores + c, sample_centres) for c in range(cores)])
+            wall = time.perf_counter() - t0
+            if it >= warmup:
+                times.append((wall, res))
+    # every process handled m of H centres of one frame -> fraction m/H of a frame each
+    tot_wall = sum(w for w, _ in times)
+    frames_equiv = sum(sum(m / H for _, m, H in res) for _, res in times)
+    rate = W * frames_equiv / tot_wall
+    m, H = times[0][1][0][1], times[0][1][0][2]
+    return rate, tot_wall / len(times), W, f"{m} of {H} heavy-atom centres of 1 frame per core per step, " \
+        f"full per-centre cost (brute-force neighbours + sort + RAD + HB + F/T), extrapolated linearly in centres"
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = args.cpu_cores or (os.cpu_count() or 1)
+    rate, step_s, W, sample = cpu_rate(args.config, args.scale, cores, args.cpu_sample, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": synthetic.CONFIGS[args.config]["label"], "scale": args.scale},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference = pure Python on MDAnalysis (not installable offline); timed arm is oracle/ (C + NumPy "
+                "restatement of the same algorithm, pinned against the reference's goldens), one process per core",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from waterentropy_b200 import distributed as wdist
+    from waterentropy_b200.engine import WaterEntropyEngine
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    s = synthetic.make_config(args.config, scale=args.scale)
+    N, W = s.n_atoms, s.n_waters
+    Fps = args.frames_per_step
+    # every rank analyses its own frames
+    P, Fr, D = s.frames(rank * Fps, Fps)
+    ids = list(range(rank * Fps, rank * Fps + Fps))
+    input_bytes = P.nbytes + Fr.nbytes
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident arm (value) ----------------
+    eng = WaterEntropyEngine(s, "interfacial", device=local_rank, keep_records=False, chunk_frames=args.chunk)
+    dP, dF = torch.from_numpy(P).cuda(), torch.from_numpy(Fr).cuda()
+    for _ in range(args.warmup):
+        eng.submit_device(dP, dF, D, ids)
+        eng.sync()
+    eng.profile(True)
+    launches0 = eng.diag()["kernel_launches"]
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    eng.span_start()
+    for _ in range(args.steps):
+        eng.submit_device(dP, dF, D, ids)
+    dev_ms = eng.span_stop()
+    eng.sync()
+    barrier()
+    clk = clocks.stop()
+    dev_ms = maxr(dev_ms)
+    diag = eng.diag()
+    launches = diag["kernel_launches"] - launches0
+    ktimes = eng.kernel_times()
+    eng.profile(False)
+    value = world * W * Fps * args.steps / (dev_ms * 1e-3)
+    # roofline of the dominant kernel
+    top_k = max(ktimes, key=lambda k: ktimes[k][0])
+    k_ms, k_n = ktimes[top_k]
+    chunk = max(1, round(Fps * args.steps / max(1, k_n)))
+    alg_bytes = (24 * N + 24) * chunk  # 24 B per atom + 24 B of box per frame
+    peak, peak_src = load_peaks()
+    achieved = alg_bytes / (k_ms / k_n * 1e-3) / 1e9 if k_n else 0.0
+    traffic = None
+    tp = os.path.join(REPO, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            tj = json.load(open(tp))
+            if tj.get("kernel") == top_k and tj.get("config") == args.config and tj.get("frames_per_launch") == chunk:
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    total_k = sum(v[0] for v in ktimes.values())
+    roofline = {"bound": "hbm", "kernel": top_k, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "frames_per_launch": chunk,
+                "kernel_ms_per_launch": k_ms / k_n if k_n else None,
+                "kernel_share_of_step": k_ms / total_k if total_k else None,
+                "kernel_ms": {k: round(v[0] / max(1, v[1]), 4) for k, v in ktimes.items()}}
+    eng.close()
+    del dP, dF
+
+    # ---------------- end-to-end arm (host buffers through the public API) ----------------
+    eng = WaterEntropyEngine(s, "interfacial", device=local_rank, keep_records=True, chunk_frames=args.chunk)
+    hP, hF = torch.from_numpy(P).pin_memory(), torch.from_numpy(Fr).pin_memory()
+    d2h = 0
+
+    def e2e_step():
+        nonlocal d2h
+        eng.submit(hP, hF, D, ids)
+        eng.sync()
+        if world > 1:
+            tables = wdist.allreduce_cov(eng)
+            entries = wdist.merge_label_entries(wdist.allgather_entries(eng.label_entries()))
+        else:
+            tables = eng.cov_tables()
+            entries = eng.label_entries()
+        k0 = len(eng.frame_ids) - Fps
+        nrec = sum(len(eng.frame_records(k0 + k)) for k in range(Fps))
+        d2h = tables[0].nbytes + tables[1].nbytes + entries.nbytes + Fps * (len(eng.top.centres) * 16 + 4)
+        return nrec
+
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    nrec = 0
+    for _ in range(args.steps):
+        nrec = e2e_step()
+    barrier()
+    e2e_s = maxr(time.perf_counter() - t0)
+    e2e_val = world * W * Fps * args.steps / e2e_s
+    eng.close()
+
+    # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = args.cpu_cores or (os.cpu_count() or 1)
+        try:
+            rate, _, _, sample = cpu_rate(args.config, args.scale, cores, args.cpu_sample, 2, 1)
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        except Exception as exc:  # pragma: no cover
+            cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"failed: {exc}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": synthetic.CONFIGS[args.config]["label"], "scale": args.scale,
+                       "n_atoms": N, "n_waters": W, "frames_per_step_per_gpu": Fps,
+                       "recipe": "interfacial", "recorded_waters_per_step": int(nrec),
+                       "l2": f"inputs {input_bytes / 1e6:.0f} MB per step per GPU "
+                             + ("> 126 MB L2 (no flush needed)" if input_bytes > 126e6 else "<= L2: reduce reliance, see DESIGN.md")},
+            "clocks": clk,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(input_bytes + Fps * 32),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s / args.steps * 1e3},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "diag": {k: diag[k] for k in ("ambiguous_rad", "ambiguous_hb", "wide_searches", "shrink_retries", "table_entries")},
+        }
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C4", choices=sorted(synthetic.CONFIGS))
+    ap.add_argument("--scale", type=float, default=1.0, help="scale waters/residues of the config (tests only)")
+    ap.add_argument("--frames-per-step", type=int, default=24)
+    ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=1024, help="centres per core per step of the CPU arm")
+    ap.add_argument("--cpu-cores", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -182,6 +182,25 @@ int we_copy_donors(we_ctx *ctx, int32_t *don_x_atom, int32_t *don_h_atom);
 int64_t we_debug_size(we_ctx *ctx, int64_t k, int32_t field);
 int we_debug_copy(we_ctx *ctx, int64_t k, int32_t field, void *out, int64_t bytes);
 
+/* ---- measurement ------------------------------------------------------------ */
+/* kernel ids for we_kernel_times */
+#define WE_K_BIN 0
+#define WE_K_SCAN 1
+#define WE_K_SCATTER 2
+#define WE_K_RAD 3
+#define WE_K_HB 4
+#define WE_K_FLAG 5
+#define WE_K_LABEL 6
+#define WE_K_COV 7
+#define WE_N_KERNELS 8
+/* Record CUDA events around every kernel launch on the compute stream (the
+ * reference only has wall-clock prints, cli/runWaterEntropy.py:28-29,54). */
+int we_profile(we_ctx *ctx, int32_t enable);
+int we_kernel_times(we_ctx *ctx, double *ms /*[WE_N_KERNELS]*/, uint64_t *launches /*[WE_N_KERNELS]*/);
+/* Device-time span on the compute stream (CUDA events, not wall clock). */
+int we_span_start(we_ctx *ctx);
+int we_span_stop(we_ctx *ctx, double *ms);
+
 /* Clear the accumulators (start a new analysis with the same topology). */
 int we_reset(we_ctx *ctx);
 

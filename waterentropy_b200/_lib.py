@@ -48,6 +48,7 @@ EXPORTS = [
     "we_n_label_entries", "we_copy_label_entries", "we_frame_record_count", "we_copy_frame_records",
     "we_n_heavy", "we_n_donors", "we_copy_heavy_idx", "we_copy_donors", "we_debug_size",
     "we_debug_copy", "we_reset", "we_test_angle_cos", "we_test_powf2", "we_test_distance",
+    "we_profile", "we_kernel_times", "we_span_start", "we_span_stop",
 ]
 
 WE_ERR_DUPLICATE_COORD = -1
@@ -113,6 +114,14 @@ def load():
     L.we_debug_size.argtypes = [V, I64, I]
     L.we_debug_copy.restype = I
     L.we_debug_copy.argtypes = [V, I64, I, V, I64]
+    L.we_profile.restype = I
+    L.we_profile.argtypes = [V, I]
+    L.we_kernel_times.restype = I
+    L.we_kernel_times.argtypes = [V, V, V]
+    L.we_span_start.restype = I
+    L.we_span_start.argtypes = [V]
+    L.we_span_stop.restype = I
+    L.we_span_stop.argtypes = [V, C.POINTER(C.c_double)]
     L.we_test_angle_cos.restype = I
     L.we_test_angle_cos.argtypes = [I, V, V, I, V]
     L.we_test_powf2.restype = I

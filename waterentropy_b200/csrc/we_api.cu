@@ -94,7 +94,40 @@ struct we_ctx {
   std::vector<FrameDebug> debug;
   unsigned long long launches = 0, frames_done = 0, recorded = 0;
   long long chunk_counter = 0;
+  // optional per-kernel CUDA-event timing (we_profile)
+  bool prof = false;
+  struct ProfRec { int id; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_pending;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[WE_N_KERNELS] = {0};
+  unsigned long long prof_n[WE_N_KERNELS] = {0};
+  cudaEvent_t span_a = nullptr, span_b = nullptr;
+  bool span_open = false;
 };
+
+static cudaEvent_t prof_event(we_ctx* c) {
+  if (!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+// record start/stop events around one kernel launch on the compute stream
+struct ProfScope {
+  we_ctx* c; int id; cudaEvent_t a = nullptr, b = nullptr;
+  ProfScope(we_ctx* c_, int id_, cudaStream_t st) : c(c_), id(id_) {
+    if (c->prof) { a = prof_event(c); b = prof_event(c); cudaEventRecord(a, st); }
+  }
+  void stop(cudaStream_t st) { if (c->prof) { cudaEventRecord(b, st); c->prof_pending.push_back({id, a, b}); } }
+};
+static void prof_resolve(we_ctx* c) {
+  for (auto& r : c->prof_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { c->prof_ms[r.id] += ms; c->prof_n[r.id] += 1; }
+    c->prof_pool.push_back(r.a);
+    c->prof_pool.push_back(r.b);
+  }
+  c->prof_pending.clear();
+}
 
 template <typename Tp>
 static int dev_alloc(we_ctx* c, Tp** p, size_t n) {
@@ -448,30 +481,46 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     const WeBox* bx = c->d_boxes[buf];
     const long long* fids = c->d_fids[buf];
     dim3 gH((H + 255) / 256, n);
-    k_bin<<<gH, 256, 0, st>>>(c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_rank_of, c->d_tmp4, c->ncap);
-    k_scan<<<n, 1024, 0, st>>>(bx, c->d_cell_count, c->ncap);
-    k_scatter<<<gH, 256, 0, st>>>(H, c->d_cell_count, c->d_cell_of, c->d_rank_of, c->d_tmp4, c->d_sorted4, c->ncap);
+    { ProfScope ps(c, WE_K_BIN, st);
+      k_bin<<<gH, 256, 0, st>>>(c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_rank_of, c->d_tmp4, c->ncap);
+      ps.stop(st); }
+    { ProfScope ps(c, WE_K_SCAN, st);
+      k_scan<<<n, 1024, 0, st>>>(bx, c->d_cell_count, c->ncap);
+      ps.stop(st); }
+    { ProfScope ps(c, WE_K_SCATTER, st);
+      k_scatter<<<gH, 256, 0, st>>>(H, c->d_cell_count, c->d_cell_of, c->d_rank_of, c->d_tmp4, c->d_sorted4, c->ncap);
+      ps.stop(st); }
     dim3 gR((H + WE_RAD_WARPS - 1) / WE_RAD_WARPS, n);
-    k_rad<<<gR, WE_RAD_WARPS * 32, sizeof(WeRadSmem), st>>>(c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->ncap,
-                                                          c->cell_target, c->d_shell_n, c->d_shell_idx, c->d_nn, c->d_flags,
-                                                          c->d_nbr_idx, c->d_nbr_dist, c->d_diag);
+    { ProfScope ps(c, WE_K_RAD, st);
+      k_rad<<<gR, WE_RAD_WARPS * 32, sizeof(WeRadSmem), st>>>(c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->ncap,
+                                                            c->cell_target, c->d_shell_n, c->d_shell_idx, c->d_nn, c->d_flags,
+                                                            c->d_nbr_idx, c->d_nbr_dist, c->d_diag);
+      ps.stop(st); }
     c->launches += 4;
     if (ND > 0) {
       dim3 gD((ND + 7) / 8, n);
+      ProfScope ps(c, WE_K_HB, st);
       k_hb<<<gD, 256, 0, st>>>(c->T, dp, bx, c->d_shell_n, c->d_shell_idx, c->d_flags, c->d_acceptor, c->d_diag);
+      ps.stop(st);
       c->launches++;
     }
     if (c->recipe == WE_RECIPE_INTERFACIAL && S > 0) {
       dim3 gS((S + 127) / 128, n);
+      ProfScope ps(c, WE_K_FLAG, st);
       k_flag<<<gS, 128, 0, st>>>(c->T, c->d_shell_n, c->d_shell_idx, c->d_flags, c->d_interf, fids, c->d_diag);
+      ps.stop(st);
       c->launches++;
     }
     if (C > 0) {
       dim3 gC((C + 7) / 8, n);
-      k_label<<<gC, 256, 0, st>>>(c->T, c->d_shell_n, c->d_shell_idx, c->d_nn, c->d_flags, c->d_acceptor, c->d_interf, fids,
-                                  c->d_table, c->table_mask, c->d_rec_count, c->d_rec, c->d_diag);
+      { ProfScope ps(c, WE_K_LABEL, st);
+        k_label<<<gC, 256, 0, st>>>(c->T, c->d_shell_n, c->d_shell_idx, c->d_nn, c->d_flags, c->d_acceptor, c->d_interf, fids,
+                                    c->d_table, c->table_mask, c->d_rec_count, c->d_rec, c->d_diag);
+        ps.stop(st); }
       dim3 gV((C + 127) / 128, n);
-      k_cov<<<gV, 128, 0, st>>>(c->T, dp, df, c->d_rec_count, c->d_rec, c->d_centre_of_slot, c->d_cov_sum, c->d_cov_cnt, c->d_ft);
+      { ProfScope ps(c, WE_K_COV, st);
+        k_cov<<<gV, 128, 0, st>>>(c->T, dp, df, c->d_rec_count, c->d_rec, c->d_centre_of_slot, c->d_cov_sum, c->d_cov_cnt, c->d_ft);
+        ps.stop(st); }
       c->launches += 2;
     }
     CK(cudaGetLastError());
@@ -532,6 +581,7 @@ extern "C" int we_sync(we_ctx* c) {
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->s_copy));
   CK(cudaStreamSynchronize(c->s_comp));
+  prof_resolve(c);
   // drain in submission order
   const int older = (int)(c->chunk_counter & 1);
   int rc;
@@ -572,6 +622,38 @@ extern "C" int we_get_diag(we_ctx* c, we_diag* out) {
   out->kernel_launches = c->launches;
   out->frames_done = c->frames_done;
   out->recorded = c->recorded;
+  return WE_OK;
+}
+
+extern "C" int we_profile(we_ctx* c, int32_t enable) {
+  if (!c) return fail(WE_ERR_INVALID, "null context");
+  c->prof = enable != 0;
+  if (enable) { for (int i = 0; i < WE_N_KERNELS; ++i) { c->prof_ms[i] = 0; c->prof_n[i] = 0; } }
+  return WE_OK;
+}
+extern "C" int we_kernel_times(we_ctx* c, double* ms, uint64_t* launches) {
+  if (!c || !ms || !launches) return fail(WE_ERR_INVALID, "null argument");
+  for (int i = 0; i < WE_N_KERNELS; ++i) { ms[i] = c->prof_ms[i]; launches[i] = c->prof_n[i]; }
+  return WE_OK;
+}
+// device-time span of the compute stream: start marks "now" in stream order, stop
+// returns the elapsed milliseconds after everything queued so far has finished
+extern "C" int we_span_start(we_ctx* c) {
+  if (!c) return fail(WE_ERR_INVALID, "null context");
+  CK(cudaSetDevice(c->device));
+  if (!c->span_a) { CK(cudaEventCreate(&c->span_a)); CK(cudaEventCreate(&c->span_b)); }
+  CK(cudaEventRecord(c->span_a, c->s_comp));
+  c->span_open = true;
+  return WE_OK;
+}
+extern "C" int we_span_stop(we_ctx* c, double* ms) {
+  if (!c || !ms || !c->span_open) return fail(WE_ERR_INVALID, "span not started");
+  CK(cudaEventRecord(c->span_b, c->s_comp));
+  CK(cudaEventSynchronize(c->span_b));
+  float f = 0.f;
+  CK(cudaEventElapsedTime(&f, c->span_a, c->span_b));
+  *ms = f;
+  c->span_open = false;
   return WE_OK;
 }
 

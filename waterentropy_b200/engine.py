@@ -117,6 +117,27 @@ class WaterEntropyEngine:
         _lib.check(self.lib.we_get_diag(self._ctx, C.byref(d)))
         return {n: int(getattr(d, n)) for n, _ in d._fields_}
 
+    # ---- measurement ---------------------------------------------------------
+    KERNELS = ["k_bin", "k_scan", "k_scatter", "k_rad", "k_hb", "k_flag", "k_label", "k_cov"]
+
+    def profile(self, enable=True):
+        _lib.check(self.lib.we_profile(self._ctx, int(enable)))
+
+    def kernel_times(self):
+        """{kernel: (total ms, launches)} measured with CUDA events on the compute stream."""
+        ms = np.zeros(8, dtype=np.float64)
+        n = np.zeros(8, dtype=np.uint64)
+        _lib.check(self.lib.we_kernel_times(self._ctx, ms.ctypes.data, n.ctypes.data))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.KERNELS)}
+
+    def span_start(self):
+        _lib.check(self.lib.we_span_start(self._ctx))
+
+    def span_stop(self):
+        ms = C.c_double()
+        _lib.check(self.lib.we_span_stop(self._ctx, C.byref(ms)))
+        return ms.value
+
     # ---- raw tables --------------------------------------------------------
     def cov_tables(self):
         nb = self.lib.we_n_bins(self._ctx)
