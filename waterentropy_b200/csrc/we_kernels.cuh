@@ -186,6 +186,7 @@ struct WeRadSmem {
   int idx[WE_RAD_WARPS][WE_CAND_CAP];
   int src[WE_RAD_WARPS][WE_CAND_CAP];
   int top[WE_RAD_WARPS][32];
+  int stage[WE_RAD_WARPS][64];
   float px[WE_RAD_WARPS][32], py[WE_RAD_WARPS][32], pz[WE_RAD_WARPS][32];
   float e[WE_RAD_WARPS][32], s[WE_RAD_WARPS][32];
   double q[WE_RAD_WARPS][32];
@@ -193,58 +194,87 @@ struct WeRadSmem {
   unsigned long long exp2tab[32];
 };
 
+// Exact phase of the candidate search: lane `lane` < take owns staged candidate
+// stage[(head + lane) & 63] (an index into the cell-sorted array).  Applies the
+// reference's candidate rule (not the centre, not bonded to it), the duplicate-
+// coordinate test and the bit-exact fp64 distance; appends survivors (d <= r).
+__device__ __forceinline__ int we_flush(const WeBox& b, const float4* __restrict__ sorted,
+                                        const int* stage, int head, int take, double r, float mx,
+                                        float my, float mz, int my_atom, const int* ex, double* sd,
+                                        int* si, int* ss, int n, int lane, bool& dup) {
+  bool keep = false;
+  double dd = 0.0;
+  int ai = -1, qi = -1;
+  if (lane < take) {
+    qi = stage[(head + lane) & 63];
+    const float4 c = sorted[qi];
+    ai = __float_as_int(c.w);
+    bool skip = (ai == my_atom);
+#pragma unroll
+    for (int e = 0; e < WE_MAX_EXCL; ++e) skip |= (ex[e] == ai);
+    if (!skip) {
+      if (c.x == mx && c.y == my && c.z == mz) dup = true;
+      dd = we_dist_fast(mx, my, mz, c.x, c.y, c.z, b);
+      keep = (dd <= r);
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, keep);
+  if (keep) {
+    const int p = n + __popc(m & ((1u << lane) - 1u));
+    if (p < WE_CAND_CAP) { sd[p] = dd; si[p] = ai; ss[p] = qi; }
+  }
+  return n + __popc(m);
+}
+
 // visit the cells within +-(wx,wy,wz) of (c0,c1,c2); keep candidates with d <= r.
-// returns the number kept (may exceed WE_CAND_CAP -> caller retries), sets dup.
+// Phase A (all lanes, coalesced float4 loads): float32 nearest-image prefilter,
+// survivors are warp-compacted into a 64-entry ring in shared memory.
+// Phase B (we_flush): every 32 staged survivors get the exact fp64 treatment with all
+// lanes busy.  Returns the number kept (may exceed WE_CAND_CAP -> caller retries).
 __device__ __forceinline__ int we_collect(const WeBox& b, const int* __restrict__ cstart,
                                           const float4* __restrict__ sorted, int c0, int c1, int c2,
                                           int wx, int wy, int wz, double r, float mx, float my,
                                           float mz, int my_atom, const int* ex, double* sd, int* si,
-                                          int* ss, int lane, bool& dup) {
-  int n = 0;
+                                          int* ss, int* stage, int lane, bool& dup) {
+  int n = 0, head = 0, cnt = 0;
   const int n0 = b.nc[0], n1 = b.nc[1], n2 = b.nc[2];
   int z_lo = -wz, z_hi = wz, y_lo = -wy, y_hi = wy;
   if (2 * wz + 1 >= n2) { z_lo = 0; z_hi = n2 - 1; }
   if (2 * wy + 1 >= n1) { y_lo = 0; y_hi = n1 - 1; }
   const bool all_z = (2 * wz + 1 >= n2), all_y = (2 * wy + 1 >= n1), all_x = (2 * wx + 1 >= n0);
-  // float prefilter radius (exact test follows in fp64)
-  float rf = (float)r + 0.02f;
-  float rf2 = rf * rf;
+  const float rf = (float)r + 0.02f;  // float prefilter radius (exact test follows in fp64)
+  const float rf2 = rf * rf;
+  const int mode = !b.triclinic ? 0 : (b.pre_ok ? 1 : 2);
   for (int dz = z_lo; dz <= z_hi; ++dz) {
-    int zc = all_z ? dz : (c2 + dz + n2) % n2;
+    const int zc = all_z ? dz : (c2 + dz + n2) % n2;
     for (int dy = y_lo; dy <= y_hi; ++dy) {
-      int yc = all_y ? dy : (c1 + dy + n1) % n1;
-      int rowbase = (zc * n1 + yc) * n0;
-      // x range: up to two contiguous segments
-      int seg_b[2], seg_e[2], nseg;
+      const int yc = all_y ? dy : (c1 + dy + n1) % n1;
+      const int rowbase = (zc * n1 + yc) * n0;
+      int seg_b[2], seg_e[2], nseg;  // x range: up to two contiguous segments
       if (all_x) { seg_b[0] = 0; seg_e[0] = n0 - 1; nseg = 1; }
       else {
-        int lo = c0 - wx, hi = c0 + wx;
+        const int lo = c0 - wx, hi = c0 + wx;
         if (lo < 0) { seg_b[0] = 0; seg_e[0] = hi; seg_b[1] = lo + n0; seg_e[1] = n0 - 1; nseg = 2; }
         else if (hi >= n0) { seg_b[0] = lo; seg_e[0] = n0 - 1; seg_b[1] = 0; seg_e[1] = hi - n0; nseg = 2; }
         else { seg_b[0] = lo; seg_e[0] = hi; nseg = 1; }
       }
       for (int sgi = 0; sgi < nseg; ++sgi) {
-        int beg = cstart[rowbase + seg_b[sgi]];
-        int end = cstart[rowbase + seg_e[sgi] + 1];
+        const int beg = cstart[rowbase + seg_b[sgi]];
+        const int end = cstart[rowbase + seg_e[sgi] + 1];
         for (int base = beg; base < end; base += 32) {
-          int qi = base + lane;
-          bool keep = false;
-          double dd = 0.0;
-          int ai = -1;
+          const int qi = base + lane;
+          bool pass = false;
           if (qi < end) {
-            float4 c = sorted[qi];
-            ai = __float_as_int(c.w);
-            bool pass;
-            if (!b.triclinic) {
-              float fx = c.x - mx, fy = c.y - my, fz = c.z - mz;
-              fx -= b.box[0] * rintf(fx * b.inv[0]);
-              fy -= b.box[1] * rintf(fy * b.inv[1]);
-              fz -= b.box[2] * rintf(fz * b.inv[2]);
+            const float4 c = sorted[qi];
+            const float ux = c.x - mx, uy = c.y - my, uz = c.z - mz;
+            if (mode == 0) {
+              const float fx = ux - b.box[0] * rintf(ux * b.inv[0]);
+              const float fy = uy - b.box[1] * rintf(uy * b.inv[1]);
+              const float fz = uz - b.box[2] * rintf(uz * b.inv[2]);
               pass = (fx * fx + fy * fy + fz * fz) <= rf2;
-            } else if (b.pre_ok) {
-              // fractional-space nearest image (exact nearest image whenever the
-              // true separation is below half the smallest cell width)
-              const float ux = c.x - mx, uy = c.y - my, uz = c.z - mz;
+            } else if (mode == 1) {
+              // fractional-space nearest image: the exact nearest image whenever the true
+              // separation is below half the smallest cell width (pre_ok guarantees 10 A is)
               float s0 = ux * b.hinvf[0] + uy * b.hinvf[3] + uz * b.hinvf[6];
               float s1 = uy * b.hinvf[4] + uz * b.hinvf[7];
               float s2 = uz * b.hinvf[8];
@@ -256,26 +286,24 @@ __device__ __forceinline__ int we_collect(const WeBox& b, const int* __restrict_
             } else {
               pass = true;
             }
-            if (pass && ai != my_atom) {
-              bool bonded = false;
-#pragma unroll
-              for (int e = 0; e < WE_MAX_EXCL; ++e) bonded |= (ex[e] == ai);
-              if (!bonded) {
-                if (c.x == mx && c.y == my && c.z == mz) dup = true;
-                dd = we_dist(mx, my, mz, c.x, c.y, c.z, b);
-                keep = (dd <= r);
-              }
-            }
           }
-          unsigned m = __ballot_sync(0xffffffffu, keep);
-          if (keep) {
-            int p = n + __popc(m & ((1u << lane) - 1u));
-            if (p < WE_CAND_CAP) { sd[p] = dd; si[p] = ai; ss[p] = qi; }
+          const unsigned m = __ballot_sync(0xffffffffu, pass);
+          if (pass) stage[(head + cnt + __popc(m & ((1u << lane) - 1u))) & 63] = qi;
+          cnt += __popc(m);
+          if (cnt >= 32) {
+            __syncwarp();
+            n = we_flush(b, sorted, stage, head, 32, r, mx, my, mz, my_atom, ex, sd, si, ss, n, lane, dup);
+            head = (head + 32) & 63;
+            cnt -= 32;
+            __syncwarp();
           }
-          n += __popc(m);
         }
       }
     }
+  }
+  if (cnt > 0) {
+    __syncwarp();
+    n = we_flush(b, sorted, stage, head, cnt, r, mx, my, mz, my_atom, ex, sd, si, ss, n, lane, dup);
   }
   dup = __any_sync(0xffffffffu, dup);
   return n;
@@ -324,8 +352,8 @@ k_rad(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxe
   bool wide = false;
   for (int iter = 0; iter < 64; ++iter) {
     dup = false;
-    if (!wide) n = we_collect(b, cstart, sorted, c0, c1, c2, 1, 1, 1, r, mq[0], mq[1], mq[2], my_atom, ex, sd, si, ss, lane, dup);
-    else n = we_collect(b, cstart, sorted, c0, c1, c2, b.wide[0], b.wide[1], b.wide[2], r, mq[0], mq[1], mq[2], my_atom, ex, sd, si, ss, lane, dup);
+    if (!wide) n = we_collect(b, cstart, sorted, c0, c1, c2, 1, 1, 1, r, mq[0], mq[1], mq[2], my_atom, ex, sd, si, ss, S.stage[w], lane, dup);
+    else n = we_collect(b, cstart, sorted, c0, c1, c2, b.wide[0], b.wide[1], b.wide[2], r, mq[0], mq[1], mq[2], my_atom, ex, sd, si, ss, S.stage[w], lane, dup);
     if (n > WE_CAND_CAP) {
       if (n >= WE_MAX_NBR && r > 0.5) { r *= 0.85; if (lane == 0) atomicAdd(&diag->shrink_retries, 1ULL); continue; }
       status = WE_ST_OVERFLOW; break;
@@ -483,7 +511,7 @@ k_hb(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes
     dup = (ax == dx && ay == dy && az == dz);
     float aq[3] = {ax, ay, az};
     if (b.triclinic) we_wrap_tric(ax, ay, az, b.m, aq);
-    dist = we_dist(dq[0], dq[1], dq[2], aq[0], aq[1], aq[2], b);
+    dist = we_dist_fast(dq[0], dq[1], dq[2], aq[0], aq[1], aq[2], b);
     in = dist <= WE_CUTOFF;
     const float dbc = we_angle_sep(ax, ay, az, dx, dy, dz, b.box);
     const float dac = we_angle_sep(ax, ay, az, xx, xy, xz, b.box);

@@ -321,6 +321,40 @@ WE_HD double we_dist_tric(float rx, float ry, float rz, float cx, float cy, floa
   return we_dsqrt(best);
 }
 
+// One-image evaluation of the triclinic distance.  The 27-image minimum of
+// we_dist_tric() is attained at the image chosen by rounding the fractional
+// separation whenever that minimum is below half the smallest perpendicular cell
+// width (any other lattice translate is then longer), and its dsq is computed by
+// the same operation sequence, so the result is bit-identical for every candidate
+// that can pass a d <= 10 A test (b.pre_ok certifies 10 A is below that bound).
+// Candidates beyond the bound return a value > 10 A, which is all callers need.
+WE_HD double we_dist_tric_one(float rx, float ry, float rz, float cx, float cy, float cz,
+                              const WeBox& b) {
+  const double dx = (double)we_fsub(cx, rx);
+  const double dy = (double)we_fsub(cy, ry);
+  const double dz = (double)we_fsub(cz, rz);
+  const double s0 = dx * b.hinv[0] + dy * b.hinv[3] + dz * b.hinv[6];
+  const double s1 = dy * b.hinv[4] + dz * b.hinv[7];
+  const double s2 = dz * b.hinv[8];
+  double ix = -rint(s0), iy = -rint(s1), iz = -rint(s2);
+  ix = fmin(fmax(ix, -1.0), 1.0); iy = fmin(fmax(iy, -1.0), 1.0); iz = fmin(fmax(iz, -1.0), 1.0);
+  const float* m = b.m;
+  const double rx0 = we_add(dx, we_mul((double)m[0], ix));
+  const double ry0 = we_add(rx0, we_mul((double)m[3], iy));
+  const double ry1 = we_add(dy, we_mul((double)m[4], iy));
+  const double rz0 = we_add(ry0, we_mul((double)m[6], iz));
+  const double rz1 = we_add(ry1, we_mul((double)m[7], iz));
+  const double rz2 = we_add(dz, we_mul((double)m[8], iz));
+  return we_dsqrt(we_add(we_add(we_mul(rz0, rz0), we_mul(rz1, rz1)), we_mul(rz2, rz2)));
+}
+
+// distance used by the kernels: exact for everything that can satisfy d <= 10 A
+WE_HD double we_dist_fast(float rx, float ry, float rz, float cx, float cy, float cz, const WeBox& b) {
+  if (!b.triclinic) return we_dist_ortho(rx, ry, rz, cx, cy, cz, b);
+  if (b.pre_ok) return we_dist_tric_one(rx, ry, rz, cx, cy, cz, b);
+  return we_dist_tric(rx, ry, rz, cx, cy, cz, b);
+}
+
 WE_HD double we_dist(float rx, float ry, float rz, float cx, float cy, float cz, const WeBox& b) {
   return b.triclinic ? we_dist_tric(rx, ry, rz, cx, cy, cz, b) : we_dist_ortho(rx, ry, rz, cx, cy, cz, b);
 }
