@@ -242,10 +242,17 @@ def run_ours(args, rank, world, local_rank):
     ktimes = eng.kernel_times()
     eng.profile(False)
     value = world * W * Fps * args.steps / (dev_ms * 1e-3)
-    # roofline of the dominant kernel
-    top_k = max(ktimes, key=lambda k: ktimes[k][0])
-    k_ms, k_n = ktimes[top_k]
-    chunk = max(1, round(Fps * args.steps / max(1, k_n)))
+    # roofline of the dominant kernel.  k_rad runs as up to three dependent passes per batch
+    # (solute atoms -> interfacial waters -> their shell members); they are one kernel and are
+    # accounted together: time per batch = sum of the passes, launches = number of batches.
+    rad_ms = sum(ktimes[k][0] for k in ("k_rad", "k_rad_pass1", "k_rad_pass2"))
+    merged = {k: v for k, v in ktimes.items() if not k.startswith("k_rad")}
+    merged["k_rad"] = (rad_ms, ktimes["k_rad"][1])
+    top_k = max(merged, key=lambda k: merged[k][0])
+    k_ms, k_n = merged[top_k]
+    n_batches = max(1, ktimes["k_bin"][1])
+    chunk = max(1, round(Fps * args.steps / n_batches))
+    k_n = n_batches
     alg_bytes = (24 * N + 24) * chunk  # 24 B per atom + 24 B of box per frame
     peak, peak_src = load_peaks()
     achieved = alg_bytes / (k_ms / k_n * 1e-3) / 1e9 if k_n else 0.0
@@ -258,13 +265,13 @@ def run_ours(args, rank, world, local_rank):
                 traffic = tj.get("dram_bytes_per_launch")
         except Exception:
             pass
-    total_k = sum(v[0] for v in ktimes.values())
+    total_k = sum(v[0] for v in merged.values())
     roofline = {"bound": "hbm", "kernel": top_k, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "frames_per_launch": chunk,
                 "kernel_ms_per_launch": k_ms / k_n if k_n else None,
                 "kernel_share_of_step": k_ms / total_k if total_k else None,
-                "kernel_ms": {k: round(v[0] / max(1, v[1]), 4) for k, v in ktimes.items()}}
+                "kernel_ms_per_batch": {k: round(v[0] / n_batches, 4) for k, v in ktimes.items()}}
     eng.close()
     del dP, dF
 

@@ -39,16 +39,20 @@ def triclinic_vectors(dimensions):
 
 
 def _wrap_triclinic(coords, box):
-    """Move float32 coordinates into the primary triclinic cell (z, y, x order)."""
+    """Move float32 coordinates into the primary triclinic cell: c axis, then b axis, then a
+    axis, each against the slanted bounds of the parallelepiped (`_triclinic_pbc`)."""
     out = np.array(coords, dtype=np.float32, copy=True)
     b = box.astype(np.float64)
+    b_z = b[2, 1] / b[2, 2]
+    a_y = b[1, 0] / b[1, 1]
+    a_z = (b[1, 1] * b[2, 0] - b[1, 0] * b[2, 1]) / (b[1, 1] * b[2, 2])
     for i in range(len(out)):
         c = out[i].astype(np.float64)
         s = np.floor(c[2] / b[2, 2])
         c -= s * b[2]
-        s = np.floor(c[1] / b[1, 1])
+        s = np.floor((c[1] - c[2] * b_z) / b[1, 1])
         c -= s * b[1]
-        s = np.floor(c[0] / b[0, 0])
+        s = np.floor((c[0] - (c[1] * a_y + c[2] * a_z)) / b[0, 0])
         c -= s * b[0]
         out[i] = c.astype(np.float32)
     return out

@@ -74,15 +74,19 @@ static void make_box(const float *dims, box_t *b)
     if (b->triclinic) triclinic_vectors(dims, b->m);
 }
 
-/* wrap one coordinate into the primary triclinic cell (z, then y, then x) */
+/* wrap one coordinate into the primary triclinic cell: c axis, then b axis, then a axis, each
+ * against the slanted bounds of the parallelepiped (MDAnalysis calc_distances.h::_triclinic_pbc) */
 static void wrap_triclinic(const float *in, const float *m, float *out)
 {
     double c0 = in[0], c1 = in[1], c2 = in[2], s;
+    const double b_z = (double)m[7] / (double)m[8];
+    const double a_y = (double)m[3] / (double)m[4];
+    const double a_z = ((double)m[4] * (double)m[6] - (double)m[3] * (double)m[7]) / ((double)m[4] * (double)m[8]);
     s = floor(c2 / (double)m[8]);
     c0 -= s * (double)m[6]; c1 -= s * (double)m[7]; c2 -= s * (double)m[8];
-    s = floor(c1 / (double)m[4]);
+    s = floor((c1 - c2 * b_z) / (double)m[4]);
     c0 -= s * (double)m[3]; c1 -= s * (double)m[4];
-    s = floor(c0 / (double)m[0]);
+    s = floor((c0 - (c1 * a_y + c2 * a_z)) / (double)m[0]);
     c0 -= s * (double)m[0];
     out[0] = (float)c0; out[1] = (float)c1; out[2] = (float)c2;
 }

@@ -11,6 +11,10 @@ void h_powf2(const float* x, int n, float* out) {
   WePowTables T = tabs();
   for (int i = 0; i < n; ++i) out[i] = we_powf2(x[i], T);
 }
+void h_powf2_fast(const float* x, int n, float* out) {
+  WePowTables T = tabs();
+  for (int i = 0; i < n; ++i) out[i] = we_powf2_fast(x[i], T);
+}
 void h_angle_cos(const float* abc, const float* dim, int n, float* out) {
   WePowTables T = tabs();
   for (int i = 0; i < n; ++i) out[i] = we_angle_cos(abc + 9 * i, abc + 9 * i + 3, abc + 9 * i + 6, dim, T);

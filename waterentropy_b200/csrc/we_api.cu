@@ -78,6 +78,10 @@ struct we_ctx {
   float4 *d_tmp4 = nullptr, *d_sorted4 = nullptr;
   int *d_shell_n = nullptr, *d_shell_idx = nullptr, *d_nn = nullptr, *d_flags = nullptr, *d_acceptor = nullptr;
   unsigned char* d_interf = nullptr;
+  unsigned char* d_need_hb = nullptr;
+  int *d_state = nullptr, *d_wl1 = nullptr, *d_wl2 = nullptr, *d_n1 = nullptr, *d_n2 = nullptr;
+  int *d_all_slots = nullptr;
+  int rad_blocks = 0;
   int* d_rec_count = nullptr;
   WeRecord* d_rec = nullptr;
   int* d_nbr_idx = nullptr;
@@ -214,6 +218,9 @@ static int make_box(const float* dims, float cell_target, int ncap, WeBox* b) {
   // inverse of the lower-triangular cell matrix (row-vector convention r = s . M)
   double hi[9] = {1.0 / ax, 0, 0, -bx / (ax * by), 1.0 / by, 0, (bx * cy - by * cx) / (ax * by * cz), -cy / (by * cz), 1.0 / cz};
   for (int i = 0; i < 9; ++i) { b->hinv[i] = hi[i]; b->hinvf[i] = (float)hi[i]; }
+  b->wfac[0] = (double)b->m[3] / (double)b->m[4];
+  b->wfac[1] = ((double)b->m[4] * (double)b->m[6] - (double)b->m[3] * (double)b->m[7]) / ((double)b->m[4] * (double)b->m[8]);
+  b->wfac[2] = (double)b->m[7] / (double)b->m[8];
   b->pre_ok = b->triclinic ? ((WE_CUTOFF + 0.05) < 0.5 * wmin) : 1;
   return 0;
 }
@@ -408,9 +415,21 @@ static int ensure_workspace(we_ctx* c, const float* dims0, bool need_input_buffe
   AL(d_shell_n, F * H) AL(d_shell_idx, F * H * WE_MAX_NBR) AL(d_nn, F * H) AL(d_flags, F * H)
   AL(d_acceptor, F * std::max(1, c->ND)) AL(d_interf, F * H)
   AL(d_rec_count, F) AL(d_rec, F * std::max(1, c->C))
+  AL(d_need_hb, F * H) AL(d_state, F * H) AL(d_wl1, F * std::max(1, c->C)) AL(d_wl2, F * H) AL(d_n1, F) AL(d_n2, F)
   if (c->opt.keep_debug) { AL(d_nbr_idx, F * H * WE_MAX_NBR) AL(d_nbr_dist, F * H * WE_MAX_NBR) AL(d_ft, F * std::max(1, c->C) * 6) }
 #undef AL
   CK(cudaFuncSetAttribute(k_rad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WeRadSmem)));
+  {
+    std::vector<int> all(H);
+    for (int i = 0; i < H; ++i) all[i] = i;
+    const int* p = nullptr;
+    if ((rc = dev_upload(c, &p, all))) return rc;
+    c->d_all_slots = (int*)p;
+    int per_sm = 0, sms = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rad, WE_RAD_WARPS * 32, sizeof(WeRadSmem)));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    c->rad_blocks = std::max(1, per_sm) * std::max(1, sms);
+  }
   c->ws_ready = true;
   return 0;
 }
@@ -478,8 +497,13 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     CK(cudaMemsetAsync(c->d_cell_count, 0, (size_t)n * ((size_t)c->ncap + 1) * sizeof(int), st));
     CK(cudaMemsetAsync(c->d_interf, 0, (size_t)n * H, st));
     CK(cudaMemsetAsync(c->d_rec_count, 0, (size_t)n * sizeof(int), st));
+    CK(cudaMemsetAsync(c->d_state, 0, (size_t)n * H * sizeof(int), st));
+    CK(cudaMemsetAsync(c->d_need_hb, c->opt.keep_debug ? 1 : 0, (size_t)n * H, st));
+    CK(cudaMemsetAsync(c->d_n1, 0, (size_t)n * sizeof(int), st));
+    CK(cudaMemsetAsync(c->d_n2, 0, (size_t)n * sizeof(int), st));
     const WeBox* bx = c->d_boxes[buf];
     const long long* fids = c->d_fids[buf];
+    const bool interfacial = (c->recipe == WE_RECIPE_INTERFACIAL);
     dim3 gH((H + 255) / 256, n);
     { ProfScope ps(c, WE_K_BIN, st);
       k_bin<<<gH, 256, 0, st>>>(c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_rank_of, c->d_tmp4, c->ncap);
@@ -490,24 +514,57 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     { ProfScope ps(c, WE_K_SCATTER, st);
       k_scatter<<<gH, 256, 0, st>>>(H, c->d_cell_count, c->d_cell_of, c->d_rank_of, c->d_tmp4, c->d_sorted4, c->ncap);
       ps.stop(st); }
-    dim3 gR((H + WE_RAD_WARPS - 1) / WE_RAD_WARPS, n);
-    { ProfScope ps(c, WE_K_RAD, st);
-      k_rad<<<gR, WE_RAD_WARPS * 32, sizeof(WeRadSmem), st>>>(c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->ncap,
-                                                            c->cell_target, c->d_shell_n, c->d_shell_idx, c->d_nn, c->d_flags,
-                                                            c->d_nbr_idx, c->d_nbr_dist, c->d_diag);
-      ps.stop(st); }
-    c->launches += 4;
-    if (ND > 0) {
-      dim3 gD((ND + 7) / 8, n);
-      ProfScope ps(c, WE_K_HB, st);
-      k_hb<<<gD, 256, 0, st>>>(c->T, dp, bx, c->d_shell_n, c->d_shell_idx, c->d_flags, c->d_acceptor, c->d_diag);
+    c->launches += 3;
+    // pass-0 centres: every heavy atom (debug), solute united atoms (interfacial), waters (bulk)
+    WeWork w0;
+    w0.count = nullptr; w0.stride = 0;
+    if (c->opt.keep_debug) { w0.list = c->d_all_slots; w0.static_count = H; }
+    else if (interfacial) { w0.list = c->T.solute_ua; w0.static_count = S; }
+    else { w0.list = c->T.centres; w0.static_count = C; }
+    WeRadOut ro{c->d_shell_n, c->d_shell_idx, c->d_nn, c->d_flags, c->d_nbr_idx, c->d_nbr_dist};
+    auto rad_grid = [&](long long items) {
+      long long blocks = (items + WE_RAD_WARPS - 1) / WE_RAD_WARPS;
+      return (int)std::max<long long>(1, std::min<long long>(blocks, c->rad_blocks));
+    };
+    if (w0.static_count > 0) {
+      { ProfScope ps(c, WE_K_MARK, st);
+        k_seed<<<dim3((w0.static_count + 255) / 256, n), 256, 0, st>>>(w0.static_count, w0.list, H, c->d_state);
+        ps.stop(st); }
+      { ProfScope ps(c, WE_K_RAD, st);
+        k_rad<<<rad_grid((long long)w0.static_count * n), WE_RAD_WARPS * 32, sizeof(WeRadSmem), st>>>(
+            c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->ncap, c->cell_target, w0, n, ro, c->d_diag);
+        ps.stop(st); }
+      c->launches += 2;
+    }
+    if (interfacial && S > 0 && C > 0) {
+      dim3 gS((S + 127) / 128, n);
+      { ProfScope ps(c, WE_K_FLAG, st);
+        k_flag<<<gS, 128, 0, st>>>(c->T, c->d_shell_n, c->d_shell_idx, c->d_flags, c->d_interf, c->d_state, c->d_wl1, c->d_n1, fids, c->d_diag);
+        ps.stop(st); }
+      WeWork w1{c->d_wl1, c->d_n1, C, 0};
+      { ProfScope ps(c, WE_K_RAD1, st);
+        k_rad<<<rad_grid((long long)C * n), WE_RAD_WARPS * 32, sizeof(WeRadSmem), st>>>(
+            c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->ncap, c->cell_target, w1, n, ro, c->d_diag);
+        ps.stop(st); }
+      { ProfScope ps(c, WE_K_MARK, st);
+        k_mark<<<dim3((C + 127) / 128, n), 128, 0, st>>>(c->T, c->d_shell_n, c->d_shell_idx, c->d_flags, c->d_wl1, c->d_n1, c->d_state, c->d_wl2, c->d_n2, c->d_need_hb);
+        ps.stop(st); }
+      WeWork w2{c->d_wl2, c->d_n2, H, 0};
+      { ProfScope ps(c, WE_K_RAD2, st);
+        k_rad<<<rad_grid((long long)H * n), WE_RAD_WARPS * 32, sizeof(WeRadSmem), st>>>(
+            c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->ncap, c->cell_target, w2, n, ro, c->d_diag);
+        ps.stop(st); }
+      c->launches += 4;
+    } else if (!interfacial && C > 0) {
+      ProfScope ps(c, WE_K_MARK, st);
+      k_mark_bulk<<<dim3((C + 127) / 128, n), 128, 0, st>>>(c->T, c->d_shell_n, c->d_shell_idx, c->d_flags, c->d_need_hb);
       ps.stop(st);
       c->launches++;
     }
-    if (c->recipe == WE_RECIPE_INTERFACIAL && S > 0) {
-      dim3 gS((S + 127) / 128, n);
-      ProfScope ps(c, WE_K_FLAG, st);
-      k_flag<<<gS, 128, 0, st>>>(c->T, c->d_shell_n, c->d_shell_idx, c->d_flags, c->d_interf, fids, c->d_diag);
+    if (ND > 0) {
+      dim3 gD((ND + 31) / 32, n);
+      ProfScope ps(c, WE_K_HB, st);
+      k_hb<<<gD, 256, 0, st>>>(c->T, dp, bx, c->d_tmp4, c->d_shell_n, c->d_shell_idx, c->d_flags, c->d_need_hb, c->d_acceptor, c->d_diag);
       ps.stop(st);
       c->launches++;
     }
@@ -797,8 +854,8 @@ __global__ void k_test_dist(const float* pairs, WeBox b, int n, double* out) {
   const float* p = pairs + (size_t)i * 6;
   if (b.triclinic) {
     float r[3], c[3];
-    we_wrap_tric(p[0], p[1], p[2], b.m, r);
-    we_wrap_tric(p[3], p[4], p[5], b.m, c);
+    we_wrap_tric(p[0], p[1], p[2], b.m, b.wfac, r);
+    we_wrap_tric(p[3], p[4], p[5], b.m, b.wfac, c);
     out[i] = we_dist_tric(r[0], r[1], r[2], c[0], c[1], c[2], b);
   } else {
     out[i] = we_dist_ortho(p[0], p[1], p[2], p[3], p[4], p[5], b);

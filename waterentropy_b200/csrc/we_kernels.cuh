@@ -104,11 +104,15 @@ __global__ void k_bin(WeTopoDev T, const float* __restrict__ pos, const WeBox* _
   int atom = T.heavy_idx[h];
   const float* p = pos + ((size_t)f * T.n_atoms + atom) * 3;
   float q[3] = {p[0], p[1], p[2]};
-  if (b.triclinic) we_wrap_tric(p[0], p[1], p[2], b.m, q);
+  if (b.triclinic) we_wrap_tric(p[0], p[1], p[2], b.m, b.wfac, q);
   double s[3];
   for (int j = 0; j < 3; ++j) {
     double v = (double)q[0] * b.hinv[j] + (double)q[1] * b.hinv[3 + j] + (double)q[2] * b.hinv[6 + j];
-    v -= floor(v);
+    // triclinic: q is already wrapped, so v is in [0,1) up to float rounding; it is CLAMPED (below)
+    // rather than re-wrapped so that the stored coordinate and the cell stay on the same side of
+    // the boundary (k_rad's per-cell image shift relies on it).  Orthorhombic coordinates are kept
+    // raw (the reference's distance formula needs them) and are wrapped here for binning only.
+    if (!b.triclinic) v -= floor(v);
     s[j] = v;
   }
   int c0 = min((int)(s[0] * b.nc[0]), b.nc[0] - 1);
@@ -185,6 +189,7 @@ struct WeRadSmem {
   double d[WE_RAD_WARPS][WE_CAND_CAP];
   int idx[WE_RAD_WARPS][WE_CAND_CAP];
   int src[WE_RAD_WARPS][WE_CAND_CAP];
+  float f[WE_RAD_WARPS][WE_CAND_CAP + 4];
   int top[WE_RAD_WARPS][32];
   int stage[WE_RAD_WARPS][64];
   float px[WE_RAD_WARPS][32], py[WE_RAD_WARPS][32], pz[WE_RAD_WARPS][32];
@@ -194,6 +199,21 @@ struct WeRadSmem {
   unsigned long long exp2tab[32];
 };
 
+// ---------------------------------------------------------------------------
+// work lists: which heavy-atom centres need a RAD shell in this frame.  The
+// reference memoises shells lazily (analysis/RAD.py:86); the device computes
+// exactly the same closure in three dependent passes:
+//   pass 0  solute united atoms (interfacial) / every water centre (bulk)
+//   pass 1  interfacial waters found from pass 0 (k_flag)
+//   pass 2  shell members of the interfacial waters not yet computed (k_mark)
+// ---------------------------------------------------------------------------
+struct WeWork {
+  const int* list;   // heavy slots; frame f starts at list + f * stride
+  const int* count;  // per-frame count (nullptr -> static_count for every frame)
+  int stride;
+  int static_count;
+};
+
 // Exact phase of the candidate search: lane `lane` < take owns staged candidate
 // stage[(head + lane) & 63] (an index into the cell-sorted array).  Applies the
 // reference's candidate rule (not the centre, not bonded to it), the duplicate-
@@ -201,7 +221,7 @@ struct WeRadSmem {
 __device__ __forceinline__ int we_flush(const WeBox& b, const float4* __restrict__ sorted,
                                         const int* stage, int head, int take, double r, float mx,
                                         float my, float mz, int my_atom, const int* ex, double* sd,
-                                        int* si, int* ss, int n, int lane, bool& dup) {
+                                        float* sf, int* si, int* ss, int n, int lane, bool& dup) {
   bool keep = false;
   double dd = 0.0;
   int ai = -1, qi = -1;
@@ -221,70 +241,87 @@ __device__ __forceinline__ int we_flush(const WeBox& b, const float4* __restrict
   const unsigned m = __ballot_sync(0xffffffffu, keep);
   if (keep) {
     const int p = n + __popc(m & ((1u << lane) - 1u));
-    if (p < WE_CAND_CAP) { sd[p] = dd; si[p] = ai; ss[p] = qi; }
+    if (p < WE_CAND_CAP) { sd[p] = dd; sf[p] = (float)dd; si[p] = ai; ss[p] = qi; }
   }
   return n + __popc(m);
 }
 
 // visit the cells within +-(wx,wy,wz) of (c0,c1,c2); keep candidates with d <= r.
-// Phase A (all lanes, coalesced float4 loads): float32 nearest-image prefilter,
-// survivors are warp-compacted into a 64-entry ring in shared memory.
-// Phase B (we_flush): every 32 staged survivors get the exact fp64 treatment with all
-// lanes busy.  Returns the number kept (may exceed WE_CAND_CAP -> caller retries).
+// Phase A (all lanes, coalesced float4 loads): float32 prefilter.  When every
+// visited cell has one definite periodic image (the usual case) the image shift is
+// a per-row constant and the test is |c + shift - me|^2 <= (r + 0.02)^2; otherwise
+// the generic nearest-image prefilter is used.  Survivors are warp-compacted into a
+// 64-entry ring in shared memory.
+// Phase B (we_flush): every 32 staged survivors get the exact fp64 treatment with
+// all lanes busy.  Returns the number kept (may exceed WE_CAND_CAP -> caller retries).
 __device__ __forceinline__ int we_collect(const WeBox& b, const int* __restrict__ cstart,
                                           const float4* __restrict__ sorted, int c0, int c1, int c2,
                                           int wx, int wy, int wz, double r, float mx, float my,
-                                          float mz, int my_atom, const int* ex, double* sd, int* si,
-                                          int* ss, int* stage, int lane, bool& dup) {
+                                          float mz, int my_atom, const int* ex, double* sd, float* sf,
+                                          int* si, int* ss, int* stage, int lane, bool& dup) {
   int n = 0, head = 0, cnt = 0;
   const int n0 = b.nc[0], n1 = b.nc[1], n2 = b.nc[2];
-  int z_lo = -wz, z_hi = wz, y_lo = -wy, y_hi = wy;
-  if (2 * wz + 1 >= n2) { z_lo = 0; z_hi = n2 - 1; }
-  if (2 * wy + 1 >= n1) { y_lo = 0; y_hi = n1 - 1; }
-  const bool all_z = (2 * wz + 1 >= n2), all_y = (2 * wy + 1 >= n1), all_x = (2 * wx + 1 >= n0);
+  const bool all_z = (2 * wz + 1 > n2), all_y = (2 * wy + 1 > n1), all_x = (2 * wx + 1 > n0);
+  const int z_lo = all_z ? 0 : -wz, z_hi = all_z ? n2 - 1 : wz;
+  const int y_lo = all_y ? 0 : -wy, y_hi = all_y ? n1 - 1 : wy;
   const float rf = (float)r + 0.02f;  // float prefilter radius (exact test follows in fp64)
   const float rf2 = rf * rf;
+  // stored coordinates are wrapped into the cell only for triclinic boxes (ortho keeps the raw
+  // coordinates the exact distance needs), so the per-cell image shift applies there only
+  const bool simple = b.triclinic && !(all_x || all_y || all_z);
   const int mode = !b.triclinic ? 0 : (b.pre_ok ? 1 : 2);
   for (int dz = z_lo; dz <= z_hi; ++dz) {
-    const int zc = all_z ? dz : (c2 + dz + n2) % n2;
+    int zc = all_z ? dz : c2 + dz;
+    const int kz = all_z ? 0 : (zc < 0 ? -1 : (zc >= n2 ? 1 : 0));
+    zc -= kz * n2;
     for (int dy = y_lo; dy <= y_hi; ++dy) {
-      const int yc = all_y ? dy : (c1 + dy + n1) % n1;
+      int yc = all_y ? dy : c1 + dy;
+      const int ky = all_y ? 0 : (yc < 0 ? -1 : (yc >= n1 ? 1 : 0));
+      yc -= ky * n1;
       const int rowbase = (zc * n1 + yc) * n0;
-      int seg_b[2], seg_e[2], nseg;  // x range: up to two contiguous segments
-      if (all_x) { seg_b[0] = 0; seg_e[0] = n0 - 1; nseg = 1; }
+      // centre minus the image shift of this row (lower-triangular cell: a, b, c rows)
+      const float py0 = my - (ky * b.m[4] + kz * b.m[7]);
+      const float pz0 = mz - kz * b.m[8];
+      const float px0 = mx - (ky * b.m[3] + kz * b.m[6]);
+      int seg_b[2], seg_e[2], seg_k[2], nseg;  // x range: up to two contiguous segments
+      if (all_x) { seg_b[0] = 0; seg_e[0] = n0 - 1; seg_k[0] = 0; nseg = 1; }
       else {
         const int lo = c0 - wx, hi = c0 + wx;
-        if (lo < 0) { seg_b[0] = 0; seg_e[0] = hi; seg_b[1] = lo + n0; seg_e[1] = n0 - 1; nseg = 2; }
-        else if (hi >= n0) { seg_b[0] = lo; seg_e[0] = n0 - 1; seg_b[1] = 0; seg_e[1] = hi - n0; nseg = 2; }
-        else { seg_b[0] = lo; seg_e[0] = hi; nseg = 1; }
+        if (lo < 0) { seg_b[0] = 0; seg_e[0] = hi; seg_k[0] = 0; seg_b[1] = lo + n0; seg_e[1] = n0 - 1; seg_k[1] = -1; nseg = 2; }
+        else if (hi >= n0) { seg_b[0] = lo; seg_e[0] = n0 - 1; seg_k[0] = 0; seg_b[1] = 0; seg_e[1] = hi - n0; seg_k[1] = 1; nseg = 2; }
+        else { seg_b[0] = lo; seg_e[0] = hi; seg_k[0] = 0; nseg = 1; }
       }
       for (int sgi = 0; sgi < nseg; ++sgi) {
         const int beg = cstart[rowbase + seg_b[sgi]];
         const int end = cstart[rowbase + seg_e[sgi] + 1];
+        const float px = px0 - seg_k[sgi] * b.m[0];
         for (int base = beg; base < end; base += 32) {
           const int qi = base + lane;
           bool pass = false;
           if (qi < end) {
             const float4 c = sorted[qi];
-            const float ux = c.x - mx, uy = c.y - my, uz = c.z - mz;
-            if (mode == 0) {
-              const float fx = ux - b.box[0] * rintf(ux * b.inv[0]);
-              const float fy = uy - b.box[1] * rintf(uy * b.inv[1]);
-              const float fz = uz - b.box[2] * rintf(uz * b.inv[2]);
-              pass = (fx * fx + fy * fy + fz * fz) <= rf2;
-            } else if (mode == 1) {
-              // fractional-space nearest image: the exact nearest image whenever the true
-              // separation is below half the smallest cell width (pre_ok guarantees 10 A is)
-              float s0 = ux * b.hinvf[0] + uy * b.hinvf[3] + uz * b.hinvf[6];
-              float s1 = uy * b.hinvf[4] + uz * b.hinvf[7];
-              float s2 = uz * b.hinvf[8];
-              s0 -= rintf(s0); s1 -= rintf(s1); s2 -= rintf(s2);
-              const float fx = s0 * b.m[0] + s1 * b.m[3] + s2 * b.m[6];
-              const float fy = s1 * b.m[4] + s2 * b.m[7];
-              const float fz = s2 * b.m[8];
-              pass = (fx * fx + fy * fy + fz * fz) <= rf2;
+            if (simple) {
+              const float ux = c.x - px, uy = c.y - py0, uz = c.z - pz0;
+              pass = __fmaf_rn(ux, ux, __fmaf_rn(uy, uy, uz * uz)) <= rf2;
             } else {
-              pass = true;
+              const float ux = c.x - mx, uy = c.y - my, uz = c.z - mz;
+              if (mode == 0) {
+                const float fx = ux - b.box[0] * rintf(ux * b.inv[0]);
+                const float fy = uy - b.box[1] * rintf(uy * b.inv[1]);
+                const float fz = uz - b.box[2] * rintf(uz * b.inv[2]);
+                pass = (fx * fx + fy * fy + fz * fz) <= rf2;
+              } else if (mode == 1) {
+                float s0 = ux * b.hinvf[0] + uy * b.hinvf[3] + uz * b.hinvf[6];
+                float s1 = uy * b.hinvf[4] + uz * b.hinvf[7];
+                float s2 = uz * b.hinvf[8];
+                s0 -= rintf(s0); s1 -= rintf(s1); s2 -= rintf(s2);
+                const float fx = s0 * b.m[0] + s1 * b.m[3] + s2 * b.m[6];
+                const float fy = s1 * b.m[4] + s2 * b.m[7];
+                const float fz = s2 * b.m[8];
+                pass = (fx * fx + fy * fy + fz * fz) <= rf2;
+              } else {
+                pass = true;
+              }
             }
           }
           const unsigned m = __ballot_sync(0xffffffffu, pass);
@@ -292,7 +329,7 @@ __device__ __forceinline__ int we_collect(const WeBox& b, const int* __restrict_
           cnt += __popc(m);
           if (cnt >= 32) {
             __syncwarp();
-            n = we_flush(b, sorted, stage, head, 32, r, mx, my, mz, my_atom, ex, sd, si, ss, n, lane, dup);
+            n = we_flush(b, sorted, stage, head, 32, r, mx, my, mz, my_atom, ex, sd, sf, si, ss, n, lane, dup);
             head = (head + 32) & 63;
             cnt -= 32;
             __syncwarp();
@@ -303,43 +340,35 @@ __device__ __forceinline__ int we_collect(const WeBox& b, const int* __restrict_
   }
   if (cnt > 0) {
     __syncwarp();
-    n = we_flush(b, sorted, stage, head, cnt, r, mx, my, mz, my_atom, ex, sd, si, ss, n, lane, dup);
+    n = we_flush(b, sorted, stage, head, cnt, r, mx, my, mz, my_atom, ex, sd, sf, si, ss, n, lane, dup);
   }
   dup = __any_sync(0xffffffffu, dup);
   return n;
 }
 
-__global__ void __launch_bounds__(WE_RAD_WARPS * 32)
-k_rad(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes,
-      const int* __restrict__ cell_start, const int* __restrict__ cell_of,
-      const float4* __restrict__ sorted4, int ncap, float search_radius,
-      int* __restrict__ shell_n, int* __restrict__ shell_idx, int* __restrict__ nn_out,
-      int* __restrict__ flags_out, int* __restrict__ nbr_idx_out, double* __restrict__ nbr_dist_out,
-      WeDiag* diag) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  WeRadSmem& S = *reinterpret_cast<WeRadSmem*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  if (tid < 32) { S.log2tab[tid] = ((const double*)we_d_log2tab)[tid]; S.exp2tab[tid] = we_d_exp2tab[tid]; }
-  __syncthreads();
-  WePowTables PT{S.log2tab, S.exp2tab};
-  const int f = blockIdx.y;
-  const int h = blockIdx.x * WE_RAD_WARPS + w;
-  if (h >= T.n_heavy) return;
-  const WeBox& b = boxes[f];
-  const int* cstart = cell_start + (size_t)f * (ncap + 1);
-  const float4* sorted = sorted4 + (size_t)f * T.n_heavy;
-  const float* fpos = pos + (size_t)f * T.n_atoms * 3;
+struct WeRadOut {
+  int* shell_n; int* shell_idx; int* nn; int* flags; int* nbr_idx; double* nbr_dist;
+};
+
+// One centre (heavy slot h of frame f) on one warp.
+__device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __restrict__ fpos,
+                                           const WeBox& b, const int* __restrict__ cstart,
+                                           const int* __restrict__ cell_of_f,
+                                           const float4* __restrict__ sorted, float search_radius,
+                                           int f, int h, const WeRadOut& O, WeDiag* diag,
+                                           WeRadSmem& S, const WePowTables& PT, int lane, int w) {
   const int my_atom = T.heavy_idx[h];
   // raw coordinates (angles, duplicate test) and distance coordinates
   const float rx = fpos[3 * my_atom], ry = fpos[3 * my_atom + 1], rz = fpos[3 * my_atom + 2];
   float mq[3] = {rx, ry, rz};
-  if (b.triclinic) we_wrap_tric(rx, ry, rz, b.m, mq);
+  if (b.triclinic) we_wrap_tric(rx, ry, rz, b.m, b.wfac, mq);
   int ex[WE_MAX_EXCL];
 #pragma unroll
   for (int e = 0; e < WE_MAX_EXCL; ++e) ex[e] = T.excl[(size_t)h * WE_MAX_EXCL + e];
-  const int cell = cell_of[(size_t)f * T.n_heavy + h];
+  const int cell = cell_of_f[h];
   const int c0 = cell % b.nc[0], c1 = (cell / b.nc[0]) % b.nc[1], c2 = cell / (b.nc[0] * b.nc[1]);
   double* sd = S.d[w];
+  float* sf = S.f[w];
   int* si = S.idx[w];
   int* ss = S.src[w];
 
@@ -352,8 +381,8 @@ k_rad(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxe
   bool wide = false;
   for (int iter = 0; iter < 64; ++iter) {
     dup = false;
-    if (!wide) n = we_collect(b, cstart, sorted, c0, c1, c2, 1, 1, 1, r, mq[0], mq[1], mq[2], my_atom, ex, sd, si, ss, S.stage[w], lane, dup);
-    else n = we_collect(b, cstart, sorted, c0, c1, c2, b.wide[0], b.wide[1], b.wide[2], r, mq[0], mq[1], mq[2], my_atom, ex, sd, si, ss, S.stage[w], lane, dup);
+    if (!wide) n = we_collect(b, cstart, sorted, c0, c1, c2, 1, 1, 1, r, mq[0], mq[1], mq[2], my_atom, ex, sd, sf, si, ss, S.stage[w], lane, dup);
+    else n = we_collect(b, cstart, sorted, c0, c1, c2, b.wide[0], b.wide[1], b.wide[2], r, mq[0], mq[1], mq[2], my_atom, ex, sd, sf, si, ss, S.stage[w], lane, dup);
     if (n > WE_CAND_CAP) {
       if (n >= WE_MAX_NBR && r > 0.5) { r *= 0.85; if (lane == 0) atomicAdd(&diag->shrink_retries, 1ULL); continue; }
       status = WE_ST_OVERFLOW; break;
@@ -364,32 +393,50 @@ k_rad(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxe
     if (!wide) { wide = true; if (lane == 0) atomicAdd(&diag->wide_searches, 1ULL); }
     r = fmin(r * 1.3, WE_CUTOFF);
   }
-  // NB: a shrunk radius can in principle leave < 25 candidates only if > CAP
-  // atoms sit in a thin shell; the loop above then grows it again.
   __syncwarp();
   if (status == WE_ST_OK && n > WE_CAND_CAP) status = WE_ST_OVERFLOW;
   if (status == WE_ST_OK && dup) status = WE_ST_DUPLICATE;
   if (status == WE_ST_OK && n == 0) status = WE_ST_NO_NEIGHBOURS;
   const size_t ho = (size_t)f * T.n_heavy + h;
   if (status != WE_ST_OK) {
-    if (lane == 0) { shell_n[ho] = 0; nn_out[ho] = -1; flags_out[ho] = status << 8; }
-    if (nbr_idx_out && lane < WE_MAX_NBR) nbr_idx_out[ho * WE_MAX_NBR + lane] = -1;
+    if (lane == 0) { O.shell_n[ho] = 0; O.nn[ho] = -1; O.flags[ho] = status << 8; }
+    if (O.nbr_idx && lane < WE_MAX_NBR) O.nbr_idx[ho * WE_MAX_NBR + lane] = -1;
     return;
   }
-  // ---- exact ranking: (distance, atom index) lexicographic ------------------
+  // ---- ranking by (distance, atom index) ------------------------------------------
+  // float32 keys first: float(d) is monotone in d, so ranks from float keys are exact
+  // unless two of the 32 smallest keys tie; then the fp64 (d, index) order decides.
   const int n25 = min(n, WE_MAX_NBR);
+  const int npad = (n + 3) & ~3;
+  if (lane < npad - n) sf[n + lane] = 3.0e38f;
+  __syncwarp();
+  unsigned seen = 0u;
   for (int c = lane; c < n; c += 32) {
-    const double dc = sd[c];
-    const int ic = si[c];
+    const float fc = sf[c];
     int rank = 0;
-    for (int m = 0; m < n; ++m) {
-      const double dm = sd[m];
-      rank += (dm < dc) || (dm == dc && si[m] < ic);
+    for (int m = 0; m < npad; m += 4) {
+      const float4 k4 = *reinterpret_cast<const float4*>(sf + m);
+      rank += (k4.x < fc) + (k4.y < fc) + (k4.z < fc) + (k4.w < fc);
     }
-    if (rank < 32) S.top[w][rank] = c;
+    if (rank < 32) { S.top[w][rank] = c; seen |= 1u << rank; }
+  }
+  seen = __reduce_or_sync(0xffffffffu, seen);
+  const int want = min(n, 32);
+  if (__popc(seen) != want) {  // float tie among the leaders: exact path
+    for (int c = lane; c < n; c += 32) {
+      const double dc = sd[c];
+      const int ic = si[c];
+      int rank = 0;
+      for (int m = 0; m < n; ++m) {
+        const double dm = sd[m];
+        rank += (dm < dc) || (dm == dc && si[m] < ic);
+      }
+      if (rank < 32) S.top[w][rank] = c;
+    }
   }
   __syncwarp();
   // ---- per-candidate precomputation ------------------------------------------
+  const float half[3] = {0.5f * b.box[0], 0.5f * b.box[1], 0.5f * b.box[2]};
   const bool act = lane < n25;
   int cidx = -1;
   double dj = 0.0;
@@ -405,16 +452,16 @@ k_rad(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxe
       const float4 c4 = sorted[ss[c]];
       pjx = c4.x; pjy = c4.y; pjz = c4.z;
     }
-    ej = we_angle_sep(pjx, pjy, pjz, rx, ry, rz, b.box);
-    sj = we_powf2(ej, PT);
+    ej = we_angle_sep_h(pjx, pjy, pjz, rx, ry, rz, b.box, half);
+    sj = we_powf2_fast(ej, PT);
     const double inv = we_ddiv(1.0, dj);
     qj = we_mul(inv, inv);  // (1/r)**2 ; libm pow differs from x*x by <= 1 ulp (see diag)
     S.px[w][lane] = pjx; S.py[w][lane] = pjy; S.pz[w][lane] = pjz;
     S.e[w][lane] = ej; S.s[w][lane] = sj; S.q[w][lane] = qj;
   }
-  if (nbr_idx_out && lane < WE_MAX_NBR) {
-    nbr_idx_out[ho * WE_MAX_NBR + lane] = act ? cidx : -1;
-    nbr_dist_out[ho * WE_MAX_NBR + lane] = act ? dj : 0.0;
+  if (O.nbr_idx && lane < WE_MAX_NBR) {
+    O.nbr_idx[ho * WE_MAX_NBR + lane] = act ? cidx : -1;
+    O.nbr_dist[ho * WE_MAX_NBR + lane] = act ? dj : 0.0;
   }
   __syncwarp();
   // ---- RAD blocking test: lane j against closer candidates k = 0..j-1 ---------
@@ -423,15 +470,14 @@ k_rad(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxe
   for (int k = 0; k < n25 - 1; ++k) {
     if (!__any_sync(0xffffffffu, alive)) break;
     if (alive && k < lane) {
-      const float dac = we_angle_sep(S.px[w][k], S.py[w][k], S.pz[w][k], pjx, pjy, pjz, b.box);
+      const float dac = we_angle_sep_h(S.px[w][k], S.py[w][k], S.pz[w][k], pjx, pjy, pjz, b.box, half);
       const float cs = we_angle_cos_from(dac, S.e[w][k], S.s[w][k], ej, sj, PT);
       if (cs != cs) {
         alive = false;  // NaN: stop testing, j stays in the shell (RAD.py:60-61)
       } else {
         const double rhs = we_mul(S.q[w][k], (double)cs);
         if (qj < rhs) { blocked = true; alive = false; }
-        const double gap = fabs(qj - rhs);
-        if (gap <= 8.9e-16 * qj) atomicAdd(&diag->ambiguous_rad, 1ULL);
+        if (fabs(qj - rhs) <= 8.9e-16 * qj) atomicAdd(&diag->ambiguous_rad, 1ULL);
       }
     } else if (alive && k >= lane) {
       alive = false;
@@ -441,7 +487,7 @@ k_rad(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxe
   const bool member = act && !blocked;
   const unsigned mm = __ballot_sync(0xffffffffu, member);
   const int ns = __popc(mm);
-  if (member) shell_idx[ho * WE_MAX_NBR + __popc(mm & ((1u << lane) - 1u))] = cidx;
+  if (member) O.shell_idx[ho * WE_MAX_NBR + __popc(mm & ((1u << lane) - 1u))] = cidx;
   bool nonlike = false, wat = false;
   if (act) {
     nonlike = member && (T.resname_id[cidx] != T.resname_id[my_atom]) && (T.type_id[cidx] != T.type_id[my_atom]);
@@ -452,18 +498,48 @@ k_rad(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxe
   int nn = -1;
   if (nm) nn = __shfl_sync(0xffffffffu, cidx, __ffs(nm) - 1);
   if (lane == 0) {
-    shell_n[ho] = ns;
-    nn_out[ho] = nn;
-    flags_out[ho] = (wm ? 1 : 0);
+    O.shell_n[ho] = ns;
+    O.nn[ho] = nn;
+    O.flags[ho] = (wm ? 1 : 0);
+  }
+  __syncwarp();
+}
+
+// Persistent kernel: gridDim.x blocks of WE_RAD_WARPS warps walk the work list of
+// every frame of the batch with a grid-stride loop (no empty blocks when the list
+// is short, natural load balance when per-centre cost varies).
+__global__ void __launch_bounds__(WE_RAD_WARPS * 32)
+k_rad(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes,
+      const int* __restrict__ cell_start, const int* __restrict__ cell_of,
+      const float4* __restrict__ sorted4, int ncap, float search_radius, WeWork work,
+      int n_frames, WeRadOut O, WeDiag* diag) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WeRadSmem& S = *reinterpret_cast<WeRadSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid < 32) { S.log2tab[tid] = ((const double*)we_d_log2tab)[tid]; S.exp2tab[tid] = we_d_exp2tab[tid]; }
+  __syncthreads();
+  const WePowTables PT{S.log2tab, S.exp2tab};
+  const int stride = gridDim.x * WE_RAD_WARPS;
+  for (int f = 0; f < n_frames; ++f) {
+    const int cnt = work.count ? work.count[f] : work.static_count;
+    const int* list = work.list + (size_t)f * work.stride;
+    const WeBox& b = boxes[f];
+    const int* cstart = cell_start + (size_t)f * (ncap + 1);
+    const float4* sorted = sorted4 + (size_t)f * T.n_heavy;
+    const float* fpos = pos + (size_t)f * T.n_atoms * 3;
+    const int* cof = cell_of + (size_t)f * T.n_heavy;
+    for (int i = blockIdx.x * WE_RAD_WARPS + w; i < cnt; i += stride)
+      we_rad_one(T, fpos, b, cstart, cof, sorted, search_radius, f, list[i], O, diag, S, PT, lane, w);
   }
 }
 
 // ============================================================================
-// K3: hydrogen-bond acceptor of every donor hydrogen, one warp per donor.
+// K3: hydrogen-bond acceptor of donor hydrogens; 8 lanes per donor, 4 donors per warp.
 //   analysis/HB.py:96-139 (get_shell_HB_acceptors), :66-93 (get_HB_terms),
 //   maths/trig.py:71-100 (candidates = heavy atoms of X's shell within 10 A of D,
 //   sorted by distance).  Sequential "rc < current and angle > 90" scan ==
 //   argmin over qualifying candidates of (rc, d, index); default = closest.
+// Only donors of centres whose HBs the recipe touches (need_hb) are evaluated.
 // ============================================================================
 __device__ __forceinline__ bool we_lex_less(double a0, double a1, int a2, double b0, double b1, int b2) {
   if (a0 < b0) return true;
@@ -475,94 +551,174 @@ __device__ __forceinline__ bool we_lex_less(double a0, double a1, int a2, double
 
 __global__ void __launch_bounds__(256)
 k_hb(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes,
-     const int* __restrict__ shell_n, const int* __restrict__ shell_idx,
-     const int* __restrict__ flags, int* __restrict__ acceptor, WeDiag* diag) {
+     const float4* __restrict__ tmp4, const int* __restrict__ shell_n,
+     const int* __restrict__ shell_idx, const int* __restrict__ flags,
+     const unsigned char* __restrict__ need_hb, int* __restrict__ acceptor, WeDiag* diag) {
   __shared__ double s_log2tab[32];
   __shared__ unsigned long long s_exp2tab[32];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (tid < 32) { s_log2tab[tid] = ((const double*)we_d_log2tab)[tid]; s_exp2tab[tid] = we_d_exp2tab[tid]; }
   __syncthreads();
-  WePowTables PT{s_log2tab, s_exp2tab};
+  const WePowTables PT{s_log2tab, s_exp2tab};
   const int f = blockIdx.y;
-  const int d = blockIdx.x * (blockDim.x >> 5) + w;
-  if (d >= T.n_don) return;
+  const int sub = lane & 7;
+  const int d = (blockIdx.x * (blockDim.x >> 5) + w) * 4 + (lane >> 3);
+  const bool have = d < T.n_don;
   const WeBox& b = boxes[f];
   const float* fpos = pos + (size_t)f * T.n_atoms * 3;
-  const int xs = T.don_x[d];
-  const int X = T.heavy_idx[xs];
-  const int D = T.don_h[d];
-  const size_t ho = (size_t)f * T.n_heavy + xs;
-  const size_t dout = (size_t)f * T.n_don + d;
-  if ((flags[ho] >> 8) != WE_ST_OK) { if (lane == 0) acceptor[dout] = -1 - (flags[ho] >> 8); return; }
-  const int ns = shell_n[ho];
-  const float xx = fpos[3 * X], xy = fpos[3 * X + 1], xz = fpos[3 * X + 2];
-  const float dx = fpos[3 * D], dy = fpos[3 * D + 1], dz = fpos[3 * D + 2];
-  float dq[3] = {dx, dy, dz};
-  if (b.triclinic) we_wrap_tric(dx, dy, dz, b.m, dq);
-  const float dba = we_angle_sep(xx, xy, xz, dx, dy, dz, b.box);
-  const float dba2 = we_powf2(dba, PT);
-  const double qD = T.charges[D];
-  bool in = false, ok = false, dup = false;
-  double dist = 0.0, rc = 0.0;
-  int A = -1;
-  if (lane < ns) {
-    A = shell_idx[ho * WE_MAX_NBR + lane];
-    const float ax = fpos[3 * A], ay = fpos[3 * A + 1], az = fpos[3 * A + 2];
-    dup = (ax == dx && ay == dy && az == dz);
-    float aq[3] = {ax, ay, az};
-    if (b.triclinic) we_wrap_tric(ax, ay, az, b.m, aq);
-    dist = we_dist_fast(dq[0], dq[1], dq[2], aq[0], aq[1], aq[2], b);
-    in = dist <= WE_CUTOFF;
-    const float dbc = we_angle_sep(ax, ay, az, dx, dy, dz, b.box);
-    const float dac = we_angle_sep(ax, ay, az, xx, xy, xz, b.box);
-    const float cs = we_angle_cos_from(dac, dbc, we_powf2(dbc, PT), dba, dba2, PT);
-    rc = we_ddiv(we_mul(qD, T.charges[A]), we_mul(dist, dist));
-    ok = in && (rc < 99.0) && we_angle_gt_90(cs);
+  const size_t fo = (size_t)f * T.n_heavy;
+  int xs = 0, X = 0, D = 0, ns = 0, st = WE_ST_OK;
+  bool need = false;
+  if (have) {
+    xs = T.don_x[d];
+    need = need_hb[fo + xs] != 0;
+    if (need) { st = flags[fo + xs] >> 8; ns = (st == WE_ST_OK) ? shell_n[fo + xs] : 0; X = T.heavy_idx[xs]; D = T.don_h[d]; }
   }
-  const bool any_dup = __any_sync(0xffffffffu, dup);
-  const bool any_in = __any_sync(0xffffffffu, in);
-  const bool any_ok = __any_sync(0xffffffffu, ok);
-  if (any_dup || !any_in) {
-    if (lane == 0) acceptor[dout] = -1 - (any_dup ? WE_ST_DUPLICATE : WE_ST_NO_NEIGHBOURS);
-    return;
+  if (!__any_sync(0xffffffffu, need)) return;
+  const size_t ho = fo + xs;
+  const float half[3] = {0.5f * b.box[0], 0.5f * b.box[1], 0.5f * b.box[2]};
+  float xx = 0.f, xy = 0.f, xz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f, dba = 0.f, dba2 = 0.f;
+  float dq[3] = {0.f, 0.f, 0.f};
+  double qD = 0.0;
+  if (need && st == WE_ST_OK) {
+    xx = fpos[3 * X]; xy = fpos[3 * X + 1]; xz = fpos[3 * X + 2];
+    dx = fpos[3 * D]; dy = fpos[3 * D + 1]; dz = fpos[3 * D + 2];
+    dq[0] = dx; dq[1] = dy; dq[2] = dz;
+    if (b.triclinic) we_wrap_tric(dx, dy, dz, b.m, b.wfac, dq);
+    dba = we_angle_sep_h(xx, xy, xz, dx, dy, dz, b.box, half);
+    dba2 = we_powf2_fast(dba, PT);
+    qD = T.charges[D];
   }
-  // argmin: qualifying -> (rc, dist, A); otherwise closest in-range -> (dist, 0, A)
-  const bool part = any_ok ? ok : in;
-  double k0 = part ? (any_ok ? rc : dist) : 1.0e300;
-  double k1 = part ? (any_ok ? dist : 0.0) : 1.0e300;
-  int k2 = part ? A : 0x7fffffff;
-  for (int o = 16; o > 0; o >>= 1) {
-    const double o0 = __shfl_xor_sync(0xffffffffu, k0, o);
-    const double o1 = __shfl_xor_sync(0xffffffffu, k1, o);
-    const int o2 = __shfl_xor_sync(0xffffffffu, k2, o);
-    if (we_lex_less(o0, o1, o2, k0, k1, k2)) { k0 = o0; k1 = o1; k2 = o2; }
+  // group-local best over chunks of 8 shell members
+  double bq0 = 1.0e300, bq1 = 1.0e300, bi0 = 1.0e300;  // qualifying (rc, dist), in-range dist
+  int bq2 = 0x7fffffff, bi2 = 0x7fffffff;
+  bool dup = false;
+  double second_rc = 1.0e300;
+  const int ns_max = __reduce_max_sync(0xffffffffu, ns);
+  for (int m0 = 0; m0 < ns_max; m0 += 8) {
+    const int m = m0 + sub;
+    if (m < ns) {
+      const int A = shell_idx[ho * WE_MAX_NBR + m];
+      const float ax = fpos[3 * A], ay = fpos[3 * A + 1], az = fpos[3 * A + 2];
+      dup |= (ax == dx && ay == dy && az == dz);
+      float aq0 = ax, aq1 = ay, aq2 = az;
+      if (b.triclinic) { const float4 wq = tmp4[fo + T.heavy_slot[A]]; aq0 = wq.x; aq1 = wq.y; aq2 = wq.z; }
+      const double dist = we_dist_fast(dq[0], dq[1], dq[2], aq0, aq1, aq2, b);
+      if (dist <= WE_CUTOFF) {
+        if (we_lex_less(dist, 0.0, A, bi0, 0.0, bi2)) { bi0 = dist; bi2 = A; }
+        const float dbc = we_angle_sep_h(ax, ay, az, dx, dy, dz, b.box, half);
+        const float dac = we_angle_sep_h(ax, ay, az, xx, xy, xz, b.box, half);
+        const float cs = we_angle_cos_from(dac, dbc, we_powf2_fast(dbc, PT), dba, dba2, PT);
+        const double rc = we_ddiv(we_mul(qD, T.charges[A]), we_mul(dist, dist));
+        if ((rc < 99.0) && we_angle_gt_90(cs)) {
+          if (we_lex_less(rc, dist, A, bq0, bq1, bq2)) { second_rc = bq0; bq0 = rc; bq1 = dist; bq2 = A; }
+          else if (rc < second_rc) second_rc = rc;
+        }
+      }
+    }
   }
-  if (lane == 0) acceptor[dout] = k2;
-  // diagnostic: a second candidate whose rc is within 4 ulp of the winner's
-  if (any_ok && ok && A != k2 && fabs(rc - k0) <= 8.9e-16 * fabs(k0)) atomicAdd(&diag->ambiguous_hb, 1ULL);
+  // reduce within the 8-lane group
+  for (int o = 4; o > 0; o >>= 1) {
+    const double q0 = __shfl_xor_sync(0xffffffffu, bq0, o), q1 = __shfl_xor_sync(0xffffffffu, bq1, o);
+    const int q2 = __shfl_xor_sync(0xffffffffu, bq2, o);
+    const double s2 = __shfl_xor_sync(0xffffffffu, second_rc, o);
+    const double i0 = __shfl_xor_sync(0xffffffffu, bi0, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, bi2, o);
+    const bool du = __shfl_xor_sync(0xffffffffu, (int)dup, o) != 0;
+    second_rc = fmin(fmax(bq0, q0), fmin(second_rc, s2));  // second smallest rc of the union
+    if (we_lex_less(q0, q1, q2, bq0, bq1, bq2)) { bq0 = q0; bq1 = q1; bq2 = q2; }
+    if (we_lex_less(i0, 0.0, i2, bi0, 0.0, bi2)) { bi0 = i0; bi2 = i2; }
+    dup |= du;
+  }
+  if (need && sub == 0) {
+    int out;
+    if (st != WE_ST_OK) out = -1 - st;
+    else if (dup) out = -1 - WE_ST_DUPLICATE;
+    else if (bi2 == 0x7fffffff) out = -1 - WE_ST_NO_NEIGHBOURS;
+    else out = (bq2 != 0x7fffffff) ? bq2 : bi2;
+    acceptor[(size_t)f * T.n_don + d] = out;
+    // diagnostic: a runner-up whose rc is within 4 ulp of the winner's
+    if (st == WE_ST_OK && bq2 != 0x7fffffff && second_rc < 1.0e299 && fabs(second_rc - bq0) <= 8.9e-16 * fabs(bq0))
+      atomicAdd(&diag->ambiguous_hb, 1ULL);
+  }
 }
 
 // ============================================================================
-// K4a: interfacial gating (recipes/interfacial_solvent.py:25-66): a solute united
-// atom with a water among its 20 nearest candidates marks the water members of
-// its RAD shell.
+// Work-list kernels.
+// k_seed : pass-0 state (debug mode: every heavy atom is a pass-0 centre)
+// k_flag : K4a interfacial gating (recipes/interfacial_solvent.py:25-66): a solute
+//          united atom with a water among its 20 nearest candidates marks the water
+//          members of its RAD shell; new waters join the pass-1 list.
+// k_mark : shell members of the interfacial waters join the pass-2 list; marks the
+//          centres whose HBs the reference evaluates (analysis/HB.py:142-169).
 // ============================================================================
+__global__ void k_seed(int n, const int* __restrict__ list, int n_heavy, int* __restrict__ state) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = blockIdx.y;
+  if (i < n) state[(size_t)f * n_heavy + list[i]] = 1;
+}
+
 __global__ void k_flag(WeTopoDev T, const int* __restrict__ shell_n, const int* __restrict__ shell_idx,
                        const int* __restrict__ flags, unsigned char* __restrict__ interfacial,
+                       int* __restrict__ state, int* __restrict__ wl1, int* __restrict__ n1,
                        const long long* __restrict__ frame_ids, WeDiag* diag) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   const int f = blockIdx.y;
   if (s >= T.n_solute_ua) return;
   const int hs = T.solute_ua[s];
-  const size_t ho = (size_t)f * T.n_heavy + hs;
-  const int fl = flags[ho];
+  const size_t fo = (size_t)f * T.n_heavy;
+  const int fl = flags[fo + hs];
   if ((fl >> 8) != WE_ST_OK) { we_set_error(diag, fl >> 8, (int)frame_ids[f], T.heavy_idx[hs]); return; }
   if (!(fl & 1)) return;
-  const int ns = shell_n[ho];
+  const int ns = shell_n[fo + hs];
   for (int m = 0; m < ns; ++m) {
-    const int A = shell_idx[ho * WE_MAX_NBR + m];
-    if (T.is_water[A]) interfacial[(size_t)f * T.n_heavy + T.heavy_slot[A]] = 1;
+    const int A = shell_idx[(fo + hs) * WE_MAX_NBR + m];
+    if (!T.is_water[A]) continue;
+    const int as = T.heavy_slot[A];
+    interfacial[fo + as] = 1;
+    // state: 0 untouched, 1 shell computed / queued, 2 queued as interfacial water
+    const int old = atomicMax(&state[fo + as], 2);
+    if (old < 2) wl1[(size_t)f * T.n_centres + atomicAdd(&n1[f], 1)] = as;
   }
+}
+
+// pass-1 entries whose shell was already computed (debug mode / resid overlap) are skipped by
+// k_rad through this filter kernel: it compacts wl1 into the list of centres still to compute.
+__global__ void k_mark(WeTopoDev T, const int* __restrict__ shell_n, const int* __restrict__ shell_idx,
+                       const int* __restrict__ flags, const int* __restrict__ wl1,
+                       const int* __restrict__ n1, int* __restrict__ state, int* __restrict__ wl2,
+                       int* __restrict__ n2, unsigned char* __restrict__ need_hb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = blockIdx.y;
+  if (i >= n1[f]) return;
+  const size_t fo = (size_t)f * T.n_heavy;
+  const int xs = wl1[(size_t)f * T.n_centres + i];
+  need_hb[fo + xs] = 1;
+  if ((flags[fo + xs] >> 8) != WE_ST_OK) return;
+  const int ns = shell_n[fo + xs];
+  for (int m = 0; m < ns; ++m) {
+    const int as = T.heavy_slot[shell_idx[(fo + xs) * WE_MAX_NBR + m]];
+    need_hb[fo + as] = 1;
+    if (atomicCAS(&state[fo + as], 0, 1) == 0) wl2[fo + atomicAdd(&n2[f], 1)] = as;
+  }
+}
+
+// bulk recipe: HBs are evaluated for waters with a pure shell and for their members
+__global__ void k_mark_bulk(WeTopoDev T, const int* __restrict__ shell_n, const int* __restrict__ shell_idx,
+                            const int* __restrict__ flags, unsigned char* __restrict__ need_hb) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = blockIdx.y;
+  if (c >= T.n_centres) return;
+  const size_t fo = (size_t)f * T.n_heavy;
+  const int xs = T.centres[c];
+  if ((flags[fo + xs] >> 8) != WE_ST_OK) return;
+  const int ns = shell_n[fo + xs];
+  if (ns == 0) return;
+  const int my_res = T.resname_id[T.heavy_idx[xs]];
+  for (int m = 0; m < ns; ++m)
+    if (T.resname_id[shell_idx[(fo + xs) * WE_MAX_NBR + m]] != my_res) return;
+  need_hb[fo + xs] = 1;
+  for (int m = 0; m < ns; ++m) need_hb[fo + T.heavy_slot[shell_idx[(fo + xs) * WE_MAX_NBR + m]]] = 1;
 }
 
 // ============================================================================

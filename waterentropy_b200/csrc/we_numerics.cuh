@@ -211,6 +211,23 @@ WE_HD float we_powf2(float x, const WePowTables& T) {
   return (float)yy;
 }
 
+// Fast path of we_powf2.  Enumerating EVERY float in [2^-60, 2^60] (1,006,632,961
+// values, tests/exhaustive_powf2.cpp) shows glibc powf(x, 2) differs from the
+// correctly rounded x*x only when the 29 mantissa bits of the exact double product
+// that float rounding discards lie within 888,704 (< 2^20) of the rounding
+// midpoint 2^28.  Outside that band RN(x*x) IS powf(x, 2); inside it (0.8 % of
+// inputs) the full table emulation runs.
+WE_HD float we_powf2_fast(float x, const WePowTables& T) {
+  const uint32_t ix = we_f2u(x);
+  if (ix - 0x21800000u < 0x5d800000u - 0x21800000u) {  // 2^-60 <= x < 2^60
+    const double p = (double)x * (double)x;            // exact in double
+    const uint32_t low = (uint32_t)we_d2u(p) & 0x1fffffffu;
+    const uint32_t d = low > 0x10000000u ? low - 0x10000000u : 0x10000000u - low;
+    if (d >= (1u << 20)) return (float)p;
+  }
+  return we_powf2(x, T);
+}
+
 // |a-b| with the reference's "box lengths only" wrap, float32
 WE_HD float we_wrap_abs(float a, float b, float dim) {
   float v = fabsf(we_fsub(a, b));
@@ -227,11 +244,20 @@ WE_HD float we_angle_sep(float ax, float ay, float az, float bx, float by, float
   return we_fsqrt(we_fadd(we_fadd(we_fmul(x, x), we_fmul(y, y)), we_fmul(z, z)));
 }
 
+// same with pre-computed 0.5f*dim (exact: a power-of-two scaling)
+WE_HD float we_angle_sep_h(float ax, float ay, float az, float bx, float by, float bz,
+                           const float* dim, const float* half) {
+  float x = fabsf(we_fsub(ax, bx)); if (x > half[0]) x = we_fsub(x, dim[0]);
+  float y = fabsf(we_fsub(ay, by)); if (y > half[1]) y = we_fsub(y, dim[1]);
+  float z = fabsf(we_fsub(az, bz)); if (z > half[2]) z = we_fsub(z, dim[2]);
+  return we_fsqrt(we_fadd(we_fadd(we_fmul(x, x), we_fmul(y, y)), we_fmul(z, z)));
+}
+
 // cosine from the three float32 separations and two pre-computed powf squares:
 //   (powf(dac,2) - powf(dbc,2) - powf(dba,2)) / ((-2*dbc)*dba)
 WE_HD float we_angle_cos_from(float dac, float dbc, float dbc2, float dba, float dba2,
                               const WePowTables& T) {
-  float num = we_fsub(we_fsub(we_powf2(dac, T), dbc2), dba2);
+  float num = we_fsub(we_fsub(we_powf2_fast(dac, T), dbc2), dba2);
   float den = we_fmul(we_fmul(-2.0f, dbc), dba);
   return we_fdiv(num, den);
 }
@@ -259,6 +285,7 @@ struct WeBox {
   int wide[3];    // half-width (in cells) of the wide (10 A) search per axis
   double hinv[9]; // inverse cell matrix: fractional_j = sum_i r_i * hinv[3*i + j]
   float hinvf[9]; // float32 copy (candidate prefilter only)
+  double wfac[3]; // slanted wrap bounds: {m3/m4, (m4*m6 - m3*m7)/(m4*m8), m7/m8}
   float rc_eff;   // radius guaranteed covered by the +-1 cell search
   int pre_ok;     // triclinic float prefilter valid (10 A < half the smallest cell width)
 };
@@ -284,14 +311,16 @@ WE_HD double we_dist_ortho(float rx, float ry, float rz, float cx, float cy, flo
   return we_dsqrt(we_add(we_add(we_mul(dx, dx), we_mul(dy, dy)), we_mul(dz, dz)));
 }
 
-// wrap a coordinate into the primary triclinic cell (z, then y, then x), fp64 then float32
-WE_HD void we_wrap_tric(float x, float y, float z, const float* m, float* out) {
+// wrap a coordinate into the primary triclinic cell: c axis, then b axis, then a axis, each
+// against the slanted bounds of the parallelepiped (MDAnalysis `_triclinic_pbc`); fp64, then float32.
+// wf = {m3/m4, (m4*m6 - m3*m7)/(m4*m8), m7/m8} in double (WeBox.wfac, built on the host).
+WE_HD void we_wrap_tric(float x, float y, float z, const float* m, const double* wf, float* out) {
   double c0 = x, c1 = y, c2 = z, s;
   s = floor(we_ddiv(c2, (double)m[8]));
   c0 = we_add(c0, -we_mul(s, (double)m[6])); c1 = we_add(c1, -we_mul(s, (double)m[7])); c2 = we_add(c2, -we_mul(s, (double)m[8]));
-  s = floor(we_ddiv(c1, (double)m[4]));
+  s = floor(we_ddiv(we_add(c1, -we_mul(c2, wf[2])), (double)m[4]));
   c0 = we_add(c0, -we_mul(s, (double)m[3])); c1 = we_add(c1, -we_mul(s, (double)m[4]));
-  s = floor(we_ddiv(c0, (double)m[0]));
+  s = floor(we_ddiv(we_add(c0, -we_add(we_mul(c1, wf[0]), we_mul(c2, wf[1]))), (double)m[0]));
   c0 = we_add(c0, -we_mul(s, (double)m[0]));
   out[0] = (float)c0; out[1] = (float)c1; out[2] = (float)c2;
 }

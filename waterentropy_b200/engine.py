@@ -118,15 +118,16 @@ class WaterEntropyEngine:
         return {n: int(getattr(d, n)) for n, _ in d._fields_}
 
     # ---- measurement ---------------------------------------------------------
-    KERNELS = ["k_bin", "k_scan", "k_scatter", "k_rad", "k_hb", "k_flag", "k_label", "k_cov"]
+    KERNELS = ["k_bin", "k_scan", "k_scatter", "k_rad", "k_hb", "k_flag", "k_label", "k_cov",
+               "k_rad_pass1", "k_rad_pass2", "k_seed_mark"]
 
     def profile(self, enable=True):
         _lib.check(self.lib.we_profile(self._ctx, int(enable)))
 
     def kernel_times(self):
         """{kernel: (total ms, launches)} measured with CUDA events on the compute stream."""
-        ms = np.zeros(8, dtype=np.float64)
-        n = np.zeros(8, dtype=np.uint64)
+        ms = np.zeros(len(self.KERNELS), dtype=np.float64)
+        n = np.zeros(len(self.KERNELS), dtype=np.uint64)
         _lib.check(self.lib.we_kernel_times(self._ctx, ms.ctypes.data, n.ctypes.data))
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.KERNELS)}
 
