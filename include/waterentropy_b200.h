@@ -78,7 +78,7 @@ typedef struct we_options {
     int32_t table_log2;      /* log2 capacity of the label count table (0 = 16) */
     int32_t keep_records;    /* 1: keep per-frame recorded-water lists (frame_solvent_indices) */
     int32_t keep_debug;      /* 1: keep all-centre shells / neighbours / acceptors / F,T of every frame */
-    float search_radius;     /* first-pass candidate radius in A (0 = 7.0) */
+    float search_radius;     /* first-pass candidate radius in A (0 = 6.6) */
     float max_box;           /* largest box edge expected in A (0 = take from first frame x 1.25) */
 } we_options;
 

@@ -88,7 +88,7 @@ struct we_ctx {
   double* d_nbr_dist = nullptr;
   double* d_ft = nullptr;
   int* h_rec_count[2] = {nullptr, nullptr};
-  WeRecord* h_rec[2] = {nullptr, nullptr};
+  int2* h_rec[2] = {nullptr, nullptr};  // mapped pinned memory written by k_label
   int pending_n[2] = {0, 0};
   cudaStream_t s_copy = nullptr, s_comp = nullptr;
   cudaEvent_t ev_in_ready[2]{}, ev_in_free[2]{}, ev_out_ready[2]{};
@@ -200,7 +200,9 @@ static int make_box(const float* dims, float cell_target, int ncap, WeBox* b) {
   const double w[3] = {vol / std::sqrt(bxc[0] * bxc[0] + bxc[1] * bxc[1] + bxc[2] * bxc[2]),
                        vol / std::sqrt(cxa[0] * cxa[0] + cxa[1] * cxa[1] + cxa[2] * cxa[2]),
                        vol / std::sqrt(axb[0] * axb[0] + axb[1] * axb[1] + axb[2] * axb[2])};
-  for (int i = 0; i < 3; ++i) b->nc[i] = std::max(1, (int)std::floor(w[i] / (double)cell_target));
+  // cells of edge >= cell_target / WE_CELLS_PER_RADIUS, searched +-WE_CELLS_PER_RADIUS cells
+  const double edge = (double)cell_target / WE_CELLS_PER_RADIUS;
+  for (int i = 0; i < 3; ++i) b->nc[i] = std::max(1, (int)std::floor(w[i] / edge));
   while ((long long)b->nc[0] * b->nc[1] * b->nc[2] > (long long)ncap) {
     int big = 0;
     if (b->nc[1] > b->nc[big]) big = 1;
@@ -211,7 +213,9 @@ static int make_box(const float* dims, float cell_target, int ncap, WeBox* b) {
   double rc = 1e30, wmin = std::min(w[0], std::min(w[1], w[2]));
   for (int i = 0; i < 3; ++i) {
     const double cw = w[i] / b->nc[i];
-    if (b->nc[i] >= 3) rc = std::min(rc, cw * (1.0 - 1e-5));
+    b->sw[i] = std::max(1, (int)std::ceil(((double)cell_target * (1.0 + 1e-5)) / cw));
+    // radius guaranteed covered: sw cells on this axis, unless the search covers the whole axis
+    if (2 * b->sw[i] + 1 <= b->nc[i]) rc = std::min(rc, b->sw[i] * cw * (1.0 - 1e-5));
     b->wide[i] = std::max(1, (int)std::ceil((WE_CUTOFF * (1.0 + 1e-5)) / cw));
   }
   b->rc_eff = (float)std::min(rc, 1e30);
@@ -385,9 +389,9 @@ static int ensure_workspace(we_ctx* c, const float* dims0, bool need_input_buffe
   if (c->ws_ready) return 0;
   const int H = c->H, N = c->N;
   int chunk = c->opt.chunk_frames;
-  if (chunk <= 0) chunk = std::max(1, std::min(64, (int)((300000 + H - 1) / std::max(1, H))));
+  if (chunk <= 0) chunk = std::max(1, std::min(64, (int)((800000 + H - 1) / std::max(1, H))));
   c->chunk = chunk;
-  c->cell_target = c->opt.search_radius > 0.f ? c->opt.search_radius : 7.0f;
+  c->cell_target = c->opt.search_radius > 0.f ? c->opt.search_radius : 6.6f;
   // cell capacity from the largest box expected
   WeBox b0;
   float d[6];
@@ -444,8 +448,8 @@ static int drain(we_ctx* c, int buf) {
     c->recorded += (unsigned long long)cnt;
     if (c->opt.keep_records) {
       std::vector<std::pair<int, int>> v((size_t)cnt);
-      const WeRecord* r = c->h_rec[buf] + (size_t)f * std::max(1, c->C);
-      for (int k = 0; k < cnt; ++k) v[k] = {r[k].atom, r[k].nearest};
+      const int2* r = c->h_rec[buf] + (size_t)f * std::max(1, c->C);
+      for (int k = 0; k < cnt; ++k) v[k] = {r[k].x, r[k].y};
       std::sort(v.begin(), v.end());
       std::vector<int> flat((size_t)cnt * 2);
       for (int k = 0; k < cnt; ++k) { flat[2 * k] = v[k].first; flat[2 * k + 1] = v[k].second; }
@@ -572,7 +576,8 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       dim3 gC((C + 7) / 8, n);
       { ProfScope ps(c, WE_K_LABEL, st);
         k_label<<<gC, 256, 0, st>>>(c->T, c->d_shell_n, c->d_shell_idx, c->d_nn, c->d_flags, c->d_acceptor, c->d_interf, fids,
-                                    c->d_table, c->table_mask, c->d_rec_count, c->d_rec, c->d_diag);
+                                    c->d_table, c->table_mask, c->d_rec_count, c->d_rec,
+                                    c->opt.keep_records ? c->h_rec[buf] : nullptr, c->d_diag);
         ps.stop(st); }
       dim3 gV((C + 127) / 128, n);
       { ProfScope ps(c, WE_K_COV, st);
@@ -584,8 +589,6 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     CK(cudaEventRecord(c->ev_in_free[buf], st));
     // results of this chunk -> pinned staging
     CK(cudaMemcpyAsync(c->h_rec_count[buf], c->d_rec_count, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (c->opt.keep_records && C > 0)
-      CK(cudaMemcpyAsync(c->h_rec[buf], c->d_rec, (size_t)n * C * sizeof(WeRecord), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(c->ev_out_ready[buf], st));
     c->pending_n[buf] = n;
     c->out_pending[buf] = true;

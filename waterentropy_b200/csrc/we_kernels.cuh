@@ -20,6 +20,7 @@
 #define WE_CAND_CAP 128
 #define WE_CUTOFF 10.0
 #define WE_RAD_WARPS 8
+#define WE_CELLS_PER_RADIUS 2  // cell edge = search radius / 2, searched +-2 cells
 #define WE_ENTRY_WORDS 64  // 512-byte label-table entries
 
 // status codes (per centre / per donor), also the C-ABI error codes
@@ -185,6 +186,12 @@ __global__ void k_scatter(int n_heavy, const int* __restrict__ cell_start,
 //   gate       : recipes/interfacial_solvent.py:50-56 (water among the 20 nearest)
 //   nearest non-like : analysis/shell_labels.py:90-105
 // ============================================================================
+struct WeRowInfo {  // per-warp description of up to 32 cell rows (+1 sentinel offset)
+  int off[64];
+  int beg0[32], len0[32], beg1[32];
+  float px0[32], px1[32], py[32], pz[32];
+};
+
 struct WeRadSmem {
   double d[WE_RAD_WARPS][WE_CAND_CAP];
   int idx[WE_RAD_WARPS][WE_CAND_CAP];
@@ -192,6 +199,7 @@ struct WeRadSmem {
   float f[WE_RAD_WARPS][WE_CAND_CAP + 4];
   int top[WE_RAD_WARPS][32];
   int stage[WE_RAD_WARPS][64];
+  WeRowInfo rows[WE_RAD_WARPS];
   float px[WE_RAD_WARPS][32], py[WE_RAD_WARPS][32], pz[WE_RAD_WARPS][32];
   float e[WE_RAD_WARPS][32], s[WE_RAD_WARPS][32];
   double q[WE_RAD_WARPS][32];
@@ -246,95 +254,125 @@ __device__ __forceinline__ int we_flush(const WeBox& b, const float4* __restrict
   return n + __popc(m);
 }
 
-// visit the cells within +-(wx,wy,wz) of (c0,c1,c2); keep candidates with d <= r.
-// Phase A (all lanes, coalesced float4 loads): float32 prefilter.  When every
-// visited cell has one definite periodic image (the usual case) the image shift is
-// a per-row constant and the test is |c + shift - me|^2 <= (r + 0.02)^2; otherwise
-// the generic nearest-image prefilter is used.  Survivors are warp-compacted into a
-// 64-entry ring in shared memory.
-// Phase B (we_flush): every 32 staged survivors get the exact fp64 treatment with
-// all lanes busy.  Returns the number kept (may exceed WE_CAND_CAP -> caller retries).
+// visit the cell rows within +-(wx,wy,wz) cells of (c0,c1,c2); keep candidates with d <= r.
+// Rows (runs of cells contiguous in x) are described one per lane, a warp scan turns their
+// lengths into one dense candidate index space, and all 32 lanes walk that space together:
+// Phase A (coalesced float4 loads): float32 prefilter.  For triclinic boxes the stored
+//   coordinates are wrapped, every visited cell has one definite periodic image and the test is
+//   |c + shift(row) - me|^2 <= (r + 0.02)^2; orthorhombic coordinates are kept raw (the
+//   reference's distance formula needs them) and use the rounding nearest image instead.
+//   Survivors are warp-compacted into a 64-entry ring in shared memory.
+// Phase B (we_flush): every 32 staged survivors get the exact fp64 treatment, all lanes busy.
+// Returns the number kept (may exceed WE_CAND_CAP -> caller retries).
 __device__ __forceinline__ int we_collect(const WeBox& b, const int* __restrict__ cstart,
                                           const float4* __restrict__ sorted, int c0, int c1, int c2,
                                           int wx, int wy, int wz, double r, float mx, float my,
                                           float mz, int my_atom, const int* ex, double* sd, float* sf,
-                                          int* si, int* ss, int* stage, int lane, bool& dup) {
+                                          int* si, int* ss, int* stage, WeRowInfo* rows, int lane,
+                                          bool& dup) {
   int n = 0, head = 0, cnt = 0;
   const int n0 = b.nc[0], n1 = b.nc[1], n2 = b.nc[2];
   const bool all_z = (2 * wz + 1 > n2), all_y = (2 * wy + 1 > n1), all_x = (2 * wx + 1 > n0);
-  const int z_lo = all_z ? 0 : -wz, z_hi = all_z ? n2 - 1 : wz;
-  const int y_lo = all_y ? 0 : -wy, y_hi = all_y ? n1 - 1 : wy;
+  const int ny = all_y ? n1 : 2 * wy + 1, nz = all_z ? n2 : 2 * wz + 1;
+  const int nrows = ny * nz;
   const float rf = (float)r + 0.02f;  // float prefilter radius (exact test follows in fp64)
   const float rf2 = rf * rf;
-  // stored coordinates are wrapped into the cell only for triclinic boxes (ortho keeps the raw
-  // coordinates the exact distance needs), so the per-cell image shift applies there only
   const bool simple = b.triclinic && !(all_x || all_y || all_z);
   const int mode = !b.triclinic ? 0 : (b.pre_ok ? 1 : 2);
-  for (int dz = z_lo; dz <= z_hi; ++dz) {
-    int zc = all_z ? dz : c2 + dz;
-    const int kz = all_z ? 0 : (zc < 0 ? -1 : (zc >= n2 ? 1 : 0));
-    zc -= kz * n2;
-    for (int dy = y_lo; dy <= y_hi; ++dy) {
-      int yc = all_y ? dy : c1 + dy;
+  for (int row0 = 0; row0 < nrows; row0 += 32) {
+    // ---- one lane per row: cell ranges and image shift --------------------------------------
+    const int row = row0 + lane;
+    int beg0 = 0, len0 = 0, beg1 = 0, len1 = 0;
+    float px0 = mx, px1 = mx, py = my, pz = mz;
+    if (row < nrows) {
+      const int iy = row % ny, iz = row / ny;
+      int zc = all_z ? iz : c2 + iz - wz;
+      const int kz = all_z ? 0 : (zc < 0 ? -1 : (zc >= n2 ? 1 : 0));
+      zc -= kz * n2;
+      int yc = all_y ? iy : c1 + iy - wy;
       const int ky = all_y ? 0 : (yc < 0 ? -1 : (yc >= n1 ? 1 : 0));
       yc -= ky * n1;
       const int rowbase = (zc * n1 + yc) * n0;
-      // centre minus the image shift of this row (lower-triangular cell: a, b, c rows)
-      const float py0 = my - (ky * b.m[4] + kz * b.m[7]);
-      const float pz0 = mz - kz * b.m[8];
-      const float px0 = mx - (ky * b.m[3] + kz * b.m[6]);
-      int seg_b[2], seg_e[2], seg_k[2], nseg;  // x range: up to two contiguous segments
-      if (all_x) { seg_b[0] = 0; seg_e[0] = n0 - 1; seg_k[0] = 0; nseg = 1; }
+      // centre minus the image shift of this row (lower-triangular cell: rows a, b, c)
+      py = my - (ky * b.m[4] + kz * b.m[7]);
+      pz = mz - kz * b.m[8];
+      px0 = mx - (ky * b.m[3] + kz * b.m[6]);
+      px1 = px0;
+      if (all_x) { beg0 = cstart[rowbase]; len0 = cstart[rowbase + n0] - beg0; }
       else {
         const int lo = c0 - wx, hi = c0 + wx;
-        if (lo < 0) { seg_b[0] = 0; seg_e[0] = hi; seg_k[0] = 0; seg_b[1] = lo + n0; seg_e[1] = n0 - 1; seg_k[1] = -1; nseg = 2; }
-        else if (hi >= n0) { seg_b[0] = lo; seg_e[0] = n0 - 1; seg_k[0] = 0; seg_b[1] = 0; seg_e[1] = hi - n0; seg_k[1] = 1; nseg = 2; }
-        else { seg_b[0] = lo; seg_e[0] = hi; seg_k[0] = 0; nseg = 1; }
+        if (lo < 0) {
+          beg0 = cstart[rowbase]; len0 = cstart[rowbase + hi + 1] - beg0;
+          beg1 = cstart[rowbase + lo + n0]; len1 = cstart[rowbase + n0] - beg1; px1 = px0 + b.m[0];
+        } else if (hi >= n0) {
+          beg0 = cstart[rowbase + lo]; len0 = cstart[rowbase + n0] - beg0;
+          beg1 = cstart[rowbase]; len1 = cstart[rowbase + hi - n0 + 1] - beg1; px1 = px0 - b.m[0];
+        } else {
+          beg0 = cstart[rowbase + lo]; len0 = cstart[rowbase + hi + 1] - beg0;
+        }
       }
-      for (int sgi = 0; sgi < nseg; ++sgi) {
-        const int beg = cstart[rowbase + seg_b[sgi]];
-        const int end = cstart[rowbase + seg_e[sgi] + 1];
-        const float px = px0 - seg_k[sgi] * b.m[0];
-        for (int base = beg; base < end; base += 32) {
-          const int qi = base + lane;
-          bool pass = false;
-          if (qi < end) {
-            const float4 c = sorted[qi];
-            if (simple) {
-              const float ux = c.x - px, uy = c.y - py0, uz = c.z - pz0;
-              pass = __fmaf_rn(ux, ux, __fmaf_rn(uy, uy, uz * uz)) <= rf2;
-            } else {
-              const float ux = c.x - mx, uy = c.y - my, uz = c.z - mz;
-              if (mode == 0) {
-                const float fx = ux - b.box[0] * rintf(ux * b.inv[0]);
-                const float fy = uy - b.box[1] * rintf(uy * b.inv[1]);
-                const float fz = uz - b.box[2] * rintf(uz * b.inv[2]);
-                pass = (fx * fx + fy * fy + fz * fz) <= rf2;
-              } else if (mode == 1) {
-                float s0 = ux * b.hinvf[0] + uy * b.hinvf[3] + uz * b.hinvf[6];
-                float s1 = uy * b.hinvf[4] + uz * b.hinvf[7];
-                float s2 = uz * b.hinvf[8];
-                s0 -= rintf(s0); s1 -= rintf(s1); s2 -= rintf(s2);
-                const float fx = s0 * b.m[0] + s1 * b.m[3] + s2 * b.m[6];
-                const float fy = s1 * b.m[4] + s2 * b.m[7];
-                const float fz = s2 * b.m[8];
-                pass = (fx * fx + fy * fy + fz * fz) <= rf2;
-              } else {
-                pass = true;
-              }
-            }
-          }
-          const unsigned m = __ballot_sync(0xffffffffu, pass);
-          if (pass) stage[(head + cnt + __popc(m & ((1u << lane) - 1u))) & 63] = qi;
-          cnt += __popc(m);
-          if (cnt >= 32) {
-            __syncwarp();
-            n = we_flush(b, sorted, stage, head, 32, r, mx, my, mz, my_atom, ex, sd, sf, si, ss, n, lane, dup);
-            head = (head + 32) & 63;
-            cnt -= 32;
-            __syncwarp();
+    }
+    const int len = len0 + len1;
+    int incl = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    __syncwarp();
+    rows->off[lane] = incl - len;
+    rows->beg0[lane] = beg0; rows->len0[lane] = len0; rows->beg1[lane] = beg1;
+    rows->px0[lane] = px0; rows->px1[lane] = px1; rows->py[lane] = py; rows->pz[lane] = pz;
+    __syncwarp();
+    // ---- dense walk over the candidates of these rows ---------------------------------------
+    for (int base = 0; base < total; base += 32) {
+      const int q = base + lane;
+      bool pass = false;
+      int qi = 0;
+      if (q < total) {
+        int ro = 0;  // largest row with off[row] <= q
+#pragma unroll
+        for (int st = 16; st > 0; st >>= 1) ro += (rows->off[ro + st] <= q) ? st : 0;
+        const int t = q - rows->off[ro];
+        const int l0 = rows->len0[ro];
+        const bool second = t >= l0;
+        qi = second ? rows->beg1[ro] + (t - l0) : rows->beg0[ro] + t;
+        const float4 c = sorted[qi];
+        if (simple) {
+          const float ux = c.x - (second ? rows->px1[ro] : rows->px0[ro]);
+          const float uy = c.y - rows->py[ro], uz = c.z - rows->pz[ro];
+          pass = __fmaf_rn(ux, ux, __fmaf_rn(uy, uy, uz * uz)) <= rf2;
+        } else {
+          const float ux = c.x - mx, uy = c.y - my, uz = c.z - mz;
+          if (mode == 0) {
+            const float fx = __fmaf_rn(-b.box[0], rintf(ux * b.inv[0]), ux);
+            const float fy = __fmaf_rn(-b.box[1], rintf(uy * b.inv[1]), uy);
+            const float fz = __fmaf_rn(-b.box[2], rintf(uz * b.inv[2]), uz);
+            pass = __fmaf_rn(fx, fx, __fmaf_rn(fy, fy, fz * fz)) <= rf2;
+          } else if (mode == 1) {
+            float s0 = ux * b.hinvf[0] + uy * b.hinvf[3] + uz * b.hinvf[6];
+            float s1 = uy * b.hinvf[4] + uz * b.hinvf[7];
+            float s2 = uz * b.hinvf[8];
+            s0 -= rintf(s0); s1 -= rintf(s1); s2 -= rintf(s2);
+            const float fx = s0 * b.m[0] + s1 * b.m[3] + s2 * b.m[6];
+            const float fy = s1 * b.m[4] + s2 * b.m[7];
+            const float fz = s2 * b.m[8];
+            pass = (fx * fx + fy * fy + fz * fz) <= rf2;
+          } else {
+            pass = true;
           }
         }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, pass);
+      if (pass) stage[(head + cnt + __popc(m & ((1u << lane) - 1u))) & 63] = qi;
+      cnt += __popc(m);
+      if (cnt >= 32) {
+        __syncwarp();
+        n = we_flush(b, sorted, stage, head, 32, r, mx, my, mz, my_atom, ex, sd, sf, si, ss, n, lane, dup);
+        head = (head + 32) & 63;
+        cnt -= 32;
+        __syncwarp();
       }
     }
   }
@@ -381,8 +419,8 @@ __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __re
   bool wide = false;
   for (int iter = 0; iter < 64; ++iter) {
     dup = false;
-    if (!wide) n = we_collect(b, cstart, sorted, c0, c1, c2, 1, 1, 1, r, mq[0], mq[1], mq[2], my_atom, ex, sd, sf, si, ss, S.stage[w], lane, dup);
-    else n = we_collect(b, cstart, sorted, c0, c1, c2, b.wide[0], b.wide[1], b.wide[2], r, mq[0], mq[1], mq[2], my_atom, ex, sd, sf, si, ss, S.stage[w], lane, dup);
+    if (!wide) n = we_collect(b, cstart, sorted, c0, c1, c2, b.sw[0], b.sw[1], b.sw[2], r, mq[0], mq[1], mq[2], my_atom, ex, sd, sf, si, ss, S.stage[w], &S.rows[w], lane, dup);
+    else n = we_collect(b, cstart, sorted, c0, c1, c2, b.wide[0], b.wide[1], b.wide[2], r, mq[0], mq[1], mq[2], my_atom, ex, sd, sf, si, ss, S.stage[w], &S.rows[w], lane, dup);
     if (n > WE_CAND_CAP) {
       if (n >= WE_MAX_NBR && r > 0.5) { r *= 0.85; if (lane == 0) atomicAdd(&diag->shrink_retries, 1ULL); continue; }
       status = WE_ST_OVERFLOW; break;
@@ -741,7 +779,7 @@ k_label(WeTopoDev T, const int* __restrict__ shell_n, const int* __restrict__ sh
         const int* __restrict__ acceptor, const unsigned char* __restrict__ interfacial,
         const long long* __restrict__ frame_ids, WeLabelEntry* __restrict__ table,
         unsigned int table_mask, int* __restrict__ rec_count, WeRecord* __restrict__ rec,
-        WeDiag* diag) {
+        int2* __restrict__ rec_host, WeDiag* diag) {
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int f = blockIdx.y;
   const int c = blockIdx.x * (blockDim.x >> 5) + w;
@@ -887,6 +925,8 @@ k_label(WeTopoDev T, const int* __restrict__ shell_n, const int* __restrict__ sh
     rr.bin = bulk ? cls : (T.bin_of_atom[nn] * T.n_classes + cls);
     rr.pad = 0;
     rec[(size_t)f * T.n_centres + r] = rr;
+    // compact copy straight into mapped pinned host memory (frame_solvent_indices)
+    if (rec_host) rec_host[(size_t)f * T.n_centres + r] = make_int2(X, rr.nearest);
   }
   if (sact && sdon) atomicAdd(&e->donates[first_pos], (unsigned int)sdon);
   if (sact && sacc) atomicAdd(&e->accepts[first_pos], (unsigned int)sacc);

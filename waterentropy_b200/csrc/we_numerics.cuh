@@ -283,6 +283,7 @@ struct WeBox {
   // cell grid in fractional coordinates
   int nc[3];      // cells per fractional axis
   int wide[3];    // half-width (in cells) of the wide (10 A) search per axis
+  int sw[3];      // half-width (in cells) of the first-pass search per axis
   double hinv[9]; // inverse cell matrix: fractional_j = sum_i r_i * hinv[3*i + j]
   float hinvf[9]; // float32 copy (candidate prefilter only)
   double wfac[3]; // slanted wrap bounds: {m3/m4, (m4*m6 - m3*m7)/(m4*m8), m7/m8}
