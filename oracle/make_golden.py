@@ -63,6 +63,14 @@ def enc(o):
     return o
 
 
+def write_json(tag, obj):
+    """gzip with mtime=0 so regenerating identical content gives identical bytes"""
+    raw = json.dumps(enc(obj)).encode()
+    with open(os.path.join(GOLD, f"{tag}_reference.json.gz"), "wb") as fh:
+        with gzip.GzipFile(fileobj=fh, mode="wb", mtime=0, compresslevel=9) as gz:
+            gz.write(raw)
+
+
 def cov_dict(cov):
     return {
         "forces": {k: np.array(v) for k, v in cov.forces.items()},
@@ -130,8 +138,7 @@ def record(system, tag, step_frames, centre_frames, bulk_frames, api_runs):
             "frame_solvent_indices": fsi, "n_frames": n,
         }
         ref["shells_api"][key] = Inter.get_interfacial_shells(system, s, e, st)
-    with gzip.open(os.path.join(GOLD, f"{tag}_reference.json.gz"), "wt") as fh:
-        json.dump(enc(ref), fh)
+    write_json(tag, ref)
     print(tag, "reference outputs written")
 
 
@@ -156,6 +163,14 @@ def main():
                 top.charges, top.bonds, tr._pos, tr._frc, tr._dim)
     record(u, "arginine", step_frames=range(10), centre_frames=[0, 2, 7], bulk_frames=[0, 3],
            api_runs=[(0, 4, 2), (0, 10, 1)])
+    # ---- the reference's second fixture (GROMACS TRR + PRMTOP; no reference test uses it) ----
+    from waterentropy_b200.io.gromacs import load_gromacs
+
+    d = "/root/reference/tests/input_files/gromacs/aspirin_solution/"
+    names, types, resnames, resids, masses, charges, bonds, P, F, D = load_gromacs(d + "system.prmtop", d + "system.trr")
+    save_inputs("aspirin", names, types, resnames, resids, masses, charges, bonds, P, F, D)
+    u = MDAnalysis.Universe.from_arrays(names, types, charges, masses, resids, resnames, bonds, P, F, D)
+    record(u, "aspirin", step_frames=range(0, 11, 2), centre_frames=[0, 10], bulk_frames=[5], api_runs=[(0, 11, 3)])
     # ---- small synthetic systems -----------------------------------------
     cases = {
         "synth_ortho": dict(n_waters=420, n_residues=8, n_chains=2, n_ions=2, triclinic=False, seed=11),
@@ -175,8 +190,7 @@ def main():
                    api_runs=[(0, 3, 1)])
         except Exception as exc:  # sparse systems may legitimately raise
             print(tag, "reference raised", type(exc).__name__, exc)
-            with gzip.open(os.path.join(GOLD, f"{tag}_reference.json.gz"), "wt") as fh:
-                json.dump(enc({"raises": type(exc).__name__}), fh)
+            write_json(tag, {"raises": type(exc).__name__})
 
 
 if __name__ == "__main__":

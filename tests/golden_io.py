@@ -48,4 +48,4 @@ def plain(d):
     return d
 
 
-TAGS = ["arginine", "synth_ortho", "synth_tric", "synth_sparse"]
+TAGS = ["arginine", "aspirin", "synth_ortho", "synth_tric", "synth_sparse"]

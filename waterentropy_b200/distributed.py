@@ -75,8 +75,21 @@ def _device_tensor(ptr, n, dtype, device):
     return torch.as_tensor(w, device=f"cuda:{device}")
 
 
+def allreduce_host(s, c):
+    """SUM all-reduce of host copies of the covariance tables (gloo / CPU path)."""
+    import torch
+    import torch.distributed as dist
+
+    ts = torch.from_numpy(s)
+    tc = torch.from_numpy(c.view(np.int64))
+    dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+    dist.all_reduce(tc, op=dist.ReduceOp.SUM)
+    return s, c
+
+
 def allreduce_cov(eng):
-    """In-place SUM all-reduce of the dense covariance tables over the job."""
+    """SUM all-reduce of the dense covariance tables over the job: in place on the device
+    tables through NCCL (NVLink / NVSwitch), or on host copies for non-NCCL backends."""
     import torch
     import torch.distributed as dist
 
@@ -89,12 +102,7 @@ def allreduce_cov(eng):
         dist.all_reduce(t_cnt, op=dist.ReduceOp.SUM)
         torch.cuda.synchronize(eng.device)
         return eng.cov_tables()
-    s, c = eng.cov_tables()
-    ts = torch.from_numpy(s)
-    tc = torch.from_numpy(c.view(np.int64))
-    dist.all_reduce(ts, op=dist.ReduceOp.SUM)
-    dist.all_reduce(tc, op=dist.ReduceOp.SUM)
-    return s, c
+    return allreduce_host(*eng.cov_tables())
 
 
 def allgather_entries(entries):

@@ -40,6 +40,44 @@ def _host_ptr(a):
     return a.ctypes.data
 
 
+def decode_cov_tables(top, recipe, s, c) -> CovarianceCollection:
+    """Dense per-bin sums [B,2,3,3] + counts [B] -> the reference's CovarianceCollection
+    (`entropy/convariances.py:10-19`): key (f"{resname}_{resid}", water resname), mean = sum / count."""
+    out = CovarianceCollection()
+    for b in np.nonzero(c)[0]:
+        cls = int(b) % top.n_classes
+        centre_name = top.resname_table[top.class_resname_ids[cls]]
+        if recipe == RECIPE_BULK:
+            key = (centre_name, centre_name)
+        else:
+            rn, rid = top.pair_bins[int(b) // top.n_classes]
+            key = (f"{top.resname_table[rn]}_{rid}", centre_name)
+        out.set_sums(key, s[b, 0], s[b, 1], int(c[b]))
+    return out
+
+
+def decode_label_entries(top, recipe, entries) -> HBLabelCollection:
+    """Device label-table entries -> the reference's HBLabelCollection
+    (`analysis/HB_labels.py:15-156`).  Label codes become strings, the tuple is sorted the way
+    Python sorts strings, and entries are fed in order of first appearance because N_w is frozen
+    by the first insert (`analysis/HB_labels.py:58,71`)."""
+    out = HBLabelCollection()
+    order = np.argsort(~entries["first_seen_inv"], kind="stable")
+    for e in entries[order]:
+        n = int(e["n_labels"])
+        labels = [top.label_string(int(c)) for c in e["labels"][:n]]
+        don, acc = {}, {}
+        for p in range(n):
+            if e["donates"][p]:
+                don[labels[p]] = don.get(labels[p], 0) + int(e["donates"][p])
+            if e["accepts"][p]:
+                acc[labels[p]] = acc.get(labels[p], 0) + int(e["accepts"][p])
+        resname = top.resname_table[int(e["nearest_resname_id"])]
+        resid = resname if recipe == RECIPE_BULK else int(e["nearest_resid"])
+        out.add_counts(resid, resname, labels, int(e["n_w"]), int(e["shell_count"]), don, acc)
+    return out
+
+
 class WaterEntropyEngine:
     def __init__(self, system, recipe="interfacial", device=0, chunk_frames=0, table_log2=0,
                  keep_records=True, keep_debug=False, search_radius=0.0, max_box=0.0):
@@ -189,38 +227,10 @@ class WaterEntropyEngine:
     def covariances(self, tables=None) -> CovarianceCollection:
         """CovarianceCollection with mean = device sum / count (unscaled units)."""
         s, c = self.cov_tables() if tables is None else tables
-        top = self.top
-        out = CovarianceCollection()
-        for b in np.nonzero(c)[0]:
-            cls = int(b) % top.n_classes
-            centre_name = top.resname_table[top.class_resname_ids[cls]]
-            if self.recipe == RECIPE_BULK:
-                key = (centre_name, centre_name)
-            else:
-                rn, rid = top.pair_bins[int(b) // top.n_classes]
-                key = (f"{top.resname_table[rn]}_{rid}", centre_name)
-            out.set_sums(key, s[b, 0], s[b, 1], int(c[b]))
-        return out
+        return decode_cov_tables(self.top, self.recipe, s, c)
 
     def hb_labels(self, entries=None) -> HBLabelCollection:
-        entries = self.label_entries() if entries is None else entries
-        top = self.top
-        out = HBLabelCollection()
-        # first insert wins for N_w: feed entries in order of first appearance
-        order = np.argsort(~entries["first_seen_inv"], kind="stable")
-        for e in entries[order]:
-            n = int(e["n_labels"])
-            labels = [top.label_string(int(c)) for c in e["labels"][:n]]
-            don, acc = {}, {}
-            for p in range(n):
-                if e["donates"][p]:
-                    don[labels[p]] = don.get(labels[p], 0) + int(e["donates"][p])
-                if e["accepts"][p]:
-                    acc[labels[p]] = acc.get(labels[p], 0) + int(e["accepts"][p])
-            resname = top.resname_table[int(e["nearest_resname_id"])]
-            resid = resname if self.recipe == RECIPE_BULK else int(e["nearest_resid"])
-            out.add_counts(resid, resname, labels, int(e["n_w"]), int(e["shell_count"]), don, acc)
-        return out
+        return decode_label_entries(self.top, self.recipe, self.label_entries() if entries is None else entries)
 
     def frame_solvent_indices(self):
         """frame_solvent_indices[frame][resname][resid] = [water atom idx ...] (ascending)."""
