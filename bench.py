@@ -51,57 +51,64 @@ def load_peaks():
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons of one GPU every 20 ms on a thread (NVML) while the
+    timed region runs; falls back to one `nvidia-smi` query if NVML is unavailable."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, device):
         self.device = device
-        self.proc = None
-        self.path = None
+        self.samples = []
+        self.mask = 0
+        self.max_mhz = None
+        self._stop = None
+        self._thread = None
 
     def start(self):
+        import threading
+
         try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.device)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            return
+        self._stop = threading.Event()
+
+        def loop():
+            while not self._stop.is_set():
+                try:
+                    self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    try:
+                        self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                    except Exception:
+                        pass
+                self._stop.wait(0.02)
+
+        self._thread = threading.Thread(target=loop, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.proc is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+        if not self.samples:
+            try:
+                q = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits",
+                                    "-i", str(self.device)], capture_output=True, text=True, timeout=10).stdout
+                a, b = [float(x) for x in q.strip().split(",")[:2]]
+                out.update(sm_mhz=a, sm_max_mhz=b, samples=1, note="single nvidia-smi sample after the timed region")
+            except Exception:
+                pass
             return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        try:
-            for line in open(self.path):
-                f = [x.strip() for x in line.split(",")]
-                if len(f) < 9:
-                    continue
-                try:
-                    sm.append(float(f[1]))
-                    mx.append(float(f[2]))
-                except ValueError:
-                    continue
-                for nm, v in zip(names, f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        if sm:
-            out["sm_mhz"] = statistics.median(sm)
-            out["sm_max_mhz"] = max(mx)
-            out["samples"] = len(sm)
-        out["reasons"] = sorted(reasons)
+        out["sm_mhz"] = statistics.median(self.samples)
+        out["samples"] = len(self.samples)
+        out["reasons"] = sorted(v for k, v in self.REASONS.items() if self.mask & k)
         return out
 
 
@@ -235,7 +242,6 @@ def run_ours(args, rank, world, local_rank):
     dev_ms = eng.span_stop()
     eng.sync()
     barrier()
-    clk = clocks.stop()
     dev_ms = maxr(dev_ms)
     diag = eng.diag()
     launches = diag["kernel_launches"] - launches0
@@ -310,6 +316,7 @@ def run_ours(args, rank, world, local_rank):
     entries = e2e_finalize()
     barrier()
     e2e_s = maxr(time.perf_counter() - t0)
+    clk = clocks.stop()
     e2e_val = world * W * Fps * args.steps / e2e_s
     final_bytes = int(entries.nbytes)
     eng.close()
@@ -351,8 +358,8 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C4", choices=sorted(synthetic.CONFIGS))
     ap.add_argument("--scale", type=float, default=1.0, help="scale waters/residues of the config (tests only)")

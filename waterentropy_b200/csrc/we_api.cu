@@ -78,8 +78,9 @@ struct we_ctx {
   float4 *d_tmp4 = nullptr, *d_sorted4 = nullptr;
   int *d_shell_n = nullptr, *d_shell_idx = nullptr, *d_nn = nullptr, *d_flags = nullptr, *d_acceptor = nullptr;
   unsigned char* d_interf = nullptr;
-  unsigned char* d_need_hb = nullptr;
   int *d_state = nullptr, *d_wl1 = nullptr, *d_wl2 = nullptr, *d_n1 = nullptr, *d_n2 = nullptr;
+  int *d_hbq = nullptr, *d_wlh = nullptr, *d_nh = nullptr;
+  int hb_blocks = 0, label_blocks = 0;
   int *d_all_slots = nullptr;
   int rad_blocks = 0;
   int* d_rec_count = nullptr;
@@ -419,7 +420,7 @@ static int ensure_workspace(we_ctx* c, const float* dims0, bool need_input_buffe
   AL(d_shell_n, F * H) AL(d_shell_idx, F * H * WE_MAX_NBR) AL(d_nn, F * H) AL(d_flags, F * H)
   AL(d_acceptor, F * std::max(1, c->ND)) AL(d_interf, F * H)
   AL(d_rec_count, F) AL(d_rec, F * std::max(1, c->C))
-  AL(d_need_hb, F * H) AL(d_state, F * H) AL(d_wl1, F * std::max(1, c->C)) AL(d_wl2, F * H) AL(d_n1, F) AL(d_n2, F)
+  AL(d_hbq, F * H) AL(d_wlh, F * H) AL(d_nh, F) AL(d_state, F * H) AL(d_wl1, F * std::max(1, c->C)) AL(d_wl2, F * H) AL(d_n1, F) AL(d_n2, F)
   if (c->opt.keep_debug) { AL(d_nbr_idx, F * H * WE_MAX_NBR) AL(d_nbr_dist, F * H * WE_MAX_NBR) AL(d_ft, F * std::max(1, c->C) * 6) }
 #undef AL
   CK(cudaFuncSetAttribute(k_rad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WeRadSmem)));
@@ -433,6 +434,10 @@ static int ensure_workspace(we_ctx* c, const float* dims0, bool need_input_buffe
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rad, WE_RAD_WARPS * 32, sizeof(WeRadSmem)));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
     c->rad_blocks = std::max(1, per_sm) * std::max(1, sms);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hb, 256, 0));
+    c->hb_blocks = std::max(1, per_sm) * std::max(1, sms);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_label, 256, 0));
+    c->label_blocks = std::max(1, per_sm) * std::max(1, sms);
   }
   c->ws_ready = true;
   return 0;
@@ -502,7 +507,8 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     CK(cudaMemsetAsync(c->d_interf, 0, (size_t)n * H, st));
     CK(cudaMemsetAsync(c->d_rec_count, 0, (size_t)n * sizeof(int), st));
     CK(cudaMemsetAsync(c->d_state, 0, (size_t)n * H * sizeof(int), st));
-    CK(cudaMemsetAsync(c->d_need_hb, c->opt.keep_debug ? 1 : 0, (size_t)n * H, st));
+    CK(cudaMemsetAsync(c->d_hbq, 0, (size_t)n * H * sizeof(int), st));
+    CK(cudaMemsetAsync(c->d_nh, 0, (size_t)n * sizeof(int), st));
     CK(cudaMemsetAsync(c->d_n1, 0, (size_t)n * sizeof(int), st));
     CK(cudaMemsetAsync(c->d_n2, 0, (size_t)n * sizeof(int), st));
     const WeBox* bx = c->d_boxes[buf];
@@ -551,7 +557,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
             c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->ncap, c->cell_target, w1, n, ro, c->d_diag);
         ps.stop(st); }
       { ProfScope ps(c, WE_K_MARK, st);
-        k_mark<<<dim3((C + 127) / 128, n), 128, 0, st>>>(c->T, c->d_shell_n, c->d_shell_idx, c->d_flags, c->d_wl1, c->d_n1, c->d_state, c->d_wl2, c->d_n2, c->d_need_hb);
+        k_mark<<<dim3((C + 127) / 128, n), 128, 0, st>>>(c->T, c->d_shell_n, c->d_shell_idx, c->d_flags, c->d_wl1, c->d_n1, c->d_state, c->d_wl2, c->d_n2, c->d_hbq, c->d_wlh, c->d_nh);
         ps.stop(st); }
       WeWork w2{c->d_wl2, c->d_n2, H, 0};
       { ProfScope ps(c, WE_K_RAD2, st);
@@ -561,23 +567,34 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       c->launches += 4;
     } else if (!interfacial && C > 0) {
       ProfScope ps(c, WE_K_MARK, st);
-      k_mark_bulk<<<dim3((C + 127) / 128, n), 128, 0, st>>>(c->T, c->d_shell_n, c->d_shell_idx, c->d_flags, c->d_need_hb);
+      k_mark_bulk<<<dim3((C + 127) / 128, n), 128, 0, st>>>(c->T, c->d_shell_n, c->d_shell_idx, c->d_flags, c->d_hbq, c->d_wlh, c->d_nh);
       ps.stop(st);
       c->launches++;
     }
+    auto grid_for = [&](long long items, int per_block, int cap) {
+      long long blocks = (items + per_block - 1) / per_block;
+      return (int)std::max<long long>(1, std::min<long long>(blocks, cap));
+    };
     if (ND > 0) {
-      dim3 gD((ND + 31) / 32, n);
+      // HB work list: every heavy atom (debug) or the centres queued by k_mark / k_mark_bulk
+      WeWork wh;
+      if (c->opt.keep_debug) wh = WeWork{c->d_all_slots, nullptr, 0, H};
+      else wh = WeWork{c->d_wlh, c->d_nh, H, 0};
       ProfScope ps(c, WE_K_HB, st);
-      k_hb<<<gD, 256, 0, st>>>(c->T, dp, bx, c->d_tmp4, c->d_shell_n, c->d_shell_idx, c->d_flags, c->d_need_hb, c->d_acceptor, c->d_diag);
+      k_hb<<<grid_for((long long)H * n, 16, c->hb_blocks), 256, 0, st>>>(
+          c->T, dp, bx, c->d_tmp4, c->d_shell_n, c->d_shell_idx, c->d_flags, wh, n, c->d_acceptor, c->d_diag);
       ps.stop(st);
       c->launches++;
     }
     if (C > 0) {
-      dim3 gC((C + 7) / 8, n);
+      WeWork wlab;
+      if (interfacial) wlab = WeWork{c->d_wl1, c->d_n1, C, 0};
+      else wlab = WeWork{c->T.centres, nullptr, 0, C};
       { ProfScope ps(c, WE_K_LABEL, st);
-        k_label<<<gC, 256, 0, st>>>(c->T, c->d_shell_n, c->d_shell_idx, c->d_nn, c->d_flags, c->d_acceptor, c->d_interf, fids,
-                                    c->d_table, c->table_mask, c->d_rec_count, c->d_rec,
-                                    c->opt.keep_records ? c->h_rec[buf] : nullptr, c->d_diag);
+        k_label<<<grid_for((long long)C * n, 8, c->label_blocks), 256, 0, st>>>(
+            c->T, c->d_shell_n, c->d_shell_idx, c->d_nn, c->d_flags, c->d_acceptor, c->d_interf, fids,
+            c->d_table, c->table_mask, c->d_rec_count, c->d_rec,
+            c->opt.keep_records ? c->h_rec[buf] : nullptr, wlab, n, c->d_diag);
         ps.stop(st); }
       dim3 gV((C + 127) / 128, n);
       { ProfScope ps(c, WE_K_COV, st);

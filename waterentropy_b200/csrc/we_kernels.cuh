@@ -587,97 +587,114 @@ __device__ __forceinline__ bool we_lex_less(double a0, double a1, int a2, double
   return a2 < b2;
 }
 
+// Persistent over the list of centres whose HBs the recipe evaluates.  Half a warp per centre,
+// 8 lanes per donor hydrogen (two donors at a time), lanes = shell members in chunks of 8.
 __global__ void __launch_bounds__(256)
 k_hb(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes,
      const float4* __restrict__ tmp4, const int* __restrict__ shell_n,
-     const int* __restrict__ shell_idx, const int* __restrict__ flags,
-     const unsigned char* __restrict__ need_hb, int* __restrict__ acceptor, WeDiag* diag) {
+     const int* __restrict__ shell_idx, const int* __restrict__ flags, WeWork work, int n_frames,
+     int* __restrict__ acceptor, WeDiag* diag) {
   __shared__ double s_log2tab[32];
   __shared__ unsigned long long s_exp2tab[32];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (tid < 32) { s_log2tab[tid] = ((const double*)we_d_log2tab)[tid]; s_exp2tab[tid] = we_d_exp2tab[tid]; }
   __syncthreads();
   const WePowTables PT{s_log2tab, s_exp2tab};
-  const int f = blockIdx.y;
-  const int sub = lane & 7;
-  const int d = (blockIdx.x * (blockDim.x >> 5) + w) * 4 + (lane >> 3);
-  const bool have = d < T.n_don;
-  const WeBox& b = boxes[f];
-  const float* fpos = pos + (size_t)f * T.n_atoms * 3;
-  const size_t fo = (size_t)f * T.n_heavy;
-  int xs = 0, X = 0, D = 0, ns = 0, st = WE_ST_OK;
-  bool need = false;
-  if (have) {
-    xs = T.don_x[d];
-    need = need_hb[fo + xs] != 0;
-    if (need) { st = flags[fo + xs] >> 8; ns = (st == WE_ST_OK) ? shell_n[fo + xs] : 0; X = T.heavy_idx[xs]; D = T.don_h[d]; }
-  }
-  if (!__any_sync(0xffffffffu, need)) return;
-  const size_t ho = fo + xs;
-  const float half[3] = {0.5f * b.box[0], 0.5f * b.box[1], 0.5f * b.box[2]};
-  float xx = 0.f, xy = 0.f, xz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f, dba = 0.f, dba2 = 0.f;
-  float dq[3] = {0.f, 0.f, 0.f};
-  double qD = 0.0;
-  if (need && st == WE_ST_OK) {
-    xx = fpos[3 * X]; xy = fpos[3 * X + 1]; xz = fpos[3 * X + 2];
-    dx = fpos[3 * D]; dy = fpos[3 * D + 1]; dz = fpos[3 * D + 2];
-    dq[0] = dx; dq[1] = dy; dq[2] = dz;
-    if (b.triclinic) we_wrap_tric(dx, dy, dz, b.m, b.wfac, dq);
-    dba = we_angle_sep_h(xx, xy, xz, dx, dy, dz, b.box, half);
-    dba2 = we_powf2_fast(dba, PT);
-    qD = T.charges[D];
-  }
-  // group-local best over chunks of 8 shell members
-  double bq0 = 1.0e300, bq1 = 1.0e300, bi0 = 1.0e300;  // qualifying (rc, dist), in-range dist
-  int bq2 = 0x7fffffff, bi2 = 0x7fffffff;
-  bool dup = false;
-  double second_rc = 1.0e300;
-  const int ns_max = __reduce_max_sync(0xffffffffu, ns);
-  for (int m0 = 0; m0 < ns_max; m0 += 8) {
-    const int m = m0 + sub;
-    if (m < ns) {
-      const int A = shell_idx[ho * WE_MAX_NBR + m];
-      const float ax = fpos[3 * A], ay = fpos[3 * A + 1], az = fpos[3 * A + 2];
-      dup |= (ax == dx && ay == dy && az == dz);
-      float aq0 = ax, aq1 = ay, aq2 = az;
-      if (b.triclinic) { const float4 wq = tmp4[fo + T.heavy_slot[A]]; aq0 = wq.x; aq1 = wq.y; aq2 = wq.z; }
-      const double dist = we_dist_fast(dq[0], dq[1], dq[2], aq0, aq1, aq2, b);
-      if (dist <= WE_CUTOFF) {
-        if (we_lex_less(dist, 0.0, A, bi0, 0.0, bi2)) { bi0 = dist; bi2 = A; }
-        const float dbc = we_angle_sep_h(ax, ay, az, dx, dy, dz, b.box, half);
-        const float dac = we_angle_sep_h(ax, ay, az, xx, xy, xz, b.box, half);
-        const float cs = we_angle_cos_from(dac, dbc, we_powf2_fast(dbc, PT), dba, dba2, PT);
-        const double rc = we_ddiv(we_mul(qD, T.charges[A]), we_mul(dist, dist));
-        if ((rc < 99.0) && we_angle_gt_90(cs)) {
-          if (we_lex_less(rc, dist, A, bq0, bq1, bq2)) { second_rc = bq0; bq0 = rc; bq1 = dist; bq2 = A; }
-          else if (rc < second_rc) second_rc = rc;
+  const int sub = lane & 7, grp = (lane >> 3) & 1, hw = lane >> 4;
+  const int stride = gridDim.x * (blockDim.x >> 5) * 2;
+  for (int f = 0; f < n_frames; ++f) {
+    const int cnt = work.count ? work.count[f] : work.static_count;
+    const int* list = work.list + (size_t)f * work.stride;
+    const WeBox& b = boxes[f];
+    const float* fpos = pos + (size_t)f * T.n_atoms * 3;
+    const size_t fo = (size_t)f * T.n_heavy;
+    const float half[3] = {0.5f * b.box[0], 0.5f * b.box[1], 0.5f * b.box[2]};
+    for (int i0 = (blockIdx.x * (blockDim.x >> 5) + w) * 2; i0 < cnt; i0 += stride) {
+      const int i = i0 + hw;
+      const bool valid = i < cnt;
+      int xs = 0, X = 0, nd = 0, d0 = 0, ns = 0, st = WE_ST_OK;
+      if (valid) {
+        xs = list[i];
+        d0 = T.don_ptr[xs];
+        nd = T.don_ptr[xs + 1] - d0;
+        st = flags[fo + xs] >> 8;
+        ns = (st == WE_ST_OK) ? shell_n[fo + xs] : 0;
+        X = T.heavy_idx[xs];
+      }
+      const size_t ho = fo + xs;
+      for (int it = 0; __any_sync(0xffffffffu, 2 * it < nd); ++it) {
+        const int dn = 2 * it + grp;
+        const bool need = valid && dn < nd;
+        const int d = d0 + dn;
+        float xx = 0.f, xy = 0.f, xz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f, dba = 0.f, dba2 = 0.f;
+        float dq[3] = {0.f, 0.f, 0.f};
+        double qD = 0.0;
+        const bool live = need && st == WE_ST_OK;
+        if (live) {
+          const int D = T.don_h[d];
+          xx = fpos[3 * X]; xy = fpos[3 * X + 1]; xz = fpos[3 * X + 2];
+          dx = fpos[3 * D]; dy = fpos[3 * D + 1]; dz = fpos[3 * D + 2];
+          dq[0] = dx; dq[1] = dy; dq[2] = dz;
+          if (b.triclinic) we_wrap_tric(dx, dy, dz, b.m, b.wfac, dq);
+          dba = we_angle_sep_h(xx, xy, xz, dx, dy, dz, b.box, half);
+          dba2 = we_powf2_fast(dba, PT);
+          qD = T.charges[D];
+        }
+        // group-local best over chunks of 8 shell members
+        double bq0 = 1.0e300, bq1 = 1.0e300, bi0 = 1.0e300;  // qualifying (rc, dist); in-range dist
+        int bq2 = 0x7fffffff, bi2 = 0x7fffffff;
+        bool dup = false;
+        double second_rc = 1.0e300;
+        const int ns_live = live ? ns : 0;
+        const int ns_max = __reduce_max_sync(0xffffffffu, ns_live);
+        for (int m0 = 0; m0 < ns_max; m0 += 8) {
+          const int m = m0 + sub;
+          if (m < ns_live) {
+            const int A = shell_idx[ho * WE_MAX_NBR + m];
+            const float ax = fpos[3 * A], ay = fpos[3 * A + 1], az = fpos[3 * A + 2];
+            dup |= (ax == dx && ay == dy && az == dz);
+            float aq0 = ax, aq1 = ay, aq2 = az;
+            if (b.triclinic) { const float4 wq = tmp4[fo + T.heavy_slot[A]]; aq0 = wq.x; aq1 = wq.y; aq2 = wq.z; }
+            const double dist = we_dist_fast(dq[0], dq[1], dq[2], aq0, aq1, aq2, b);
+            if (dist <= WE_CUTOFF) {
+              if (we_lex_less(dist, 0.0, A, bi0, 0.0, bi2)) { bi0 = dist; bi2 = A; }
+              const float dbc = we_angle_sep_h(ax, ay, az, dx, dy, dz, b.box, half);
+              const float dac = we_angle_sep_h(ax, ay, az, xx, xy, xz, b.box, half);
+              const float cs = we_angle_cos_from(dac, dbc, we_powf2_fast(dbc, PT), dba, dba2, PT);
+              const double rc = we_ddiv(we_mul(qD, T.charges[A]), we_mul(dist, dist));
+              if ((rc < 99.0) && we_angle_gt_90(cs)) {
+                if (we_lex_less(rc, dist, A, bq0, bq1, bq2)) { second_rc = bq0; bq0 = rc; bq1 = dist; bq2 = A; }
+                else if (rc < second_rc) second_rc = rc;
+              }
+            }
+          }
+        }
+        // reduce within the 8-lane group
+        for (int o = 4; o > 0; o >>= 1) {
+          const double q0 = __shfl_xor_sync(0xffffffffu, bq0, o), q1 = __shfl_xor_sync(0xffffffffu, bq1, o);
+          const int q2 = __shfl_xor_sync(0xffffffffu, bq2, o);
+          const double s2 = __shfl_xor_sync(0xffffffffu, second_rc, o);
+          const double i0d = __shfl_xor_sync(0xffffffffu, bi0, o);
+          const int i2 = __shfl_xor_sync(0xffffffffu, bi2, o);
+          const bool du = __shfl_xor_sync(0xffffffffu, (int)dup, o) != 0;
+          second_rc = fmin(fmax(bq0, q0), fmin(second_rc, s2));  // second smallest rc of the union
+          if (we_lex_less(q0, q1, q2, bq0, bq1, bq2)) { bq0 = q0; bq1 = q1; bq2 = q2; }
+          if (we_lex_less(i0d, 0.0, i2, bi0, 0.0, bi2)) { bi0 = i0d; bi2 = i2; }
+          dup |= du;
+        }
+        if (need && sub == 0) {
+          int out;
+          if (st != WE_ST_OK) out = -1 - st;
+          else if (dup) out = -1 - WE_ST_DUPLICATE;
+          else if (bi2 == 0x7fffffff) out = -1 - WE_ST_NO_NEIGHBOURS;
+          else out = (bq2 != 0x7fffffff) ? bq2 : bi2;
+          acceptor[(size_t)f * T.n_don + d] = out;
+          // diagnostic: a runner-up whose rc is within 4 ulp of the winner's
+          if (st == WE_ST_OK && bq2 != 0x7fffffff && second_rc < 1.0e299 && fabs(second_rc - bq0) <= 8.9e-16 * fabs(bq0))
+            atomicAdd(&diag->ambiguous_hb, 1ULL);
         }
       }
     }
-  }
-  // reduce within the 8-lane group
-  for (int o = 4; o > 0; o >>= 1) {
-    const double q0 = __shfl_xor_sync(0xffffffffu, bq0, o), q1 = __shfl_xor_sync(0xffffffffu, bq1, o);
-    const int q2 = __shfl_xor_sync(0xffffffffu, bq2, o);
-    const double s2 = __shfl_xor_sync(0xffffffffu, second_rc, o);
-    const double i0 = __shfl_xor_sync(0xffffffffu, bi0, o);
-    const int i2 = __shfl_xor_sync(0xffffffffu, bi2, o);
-    const bool du = __shfl_xor_sync(0xffffffffu, (int)dup, o) != 0;
-    second_rc = fmin(fmax(bq0, q0), fmin(second_rc, s2));  // second smallest rc of the union
-    if (we_lex_less(q0, q1, q2, bq0, bq1, bq2)) { bq0 = q0; bq1 = q1; bq2 = q2; }
-    if (we_lex_less(i0, 0.0, i2, bi0, 0.0, bi2)) { bi0 = i0; bi2 = i2; }
-    dup |= du;
-  }
-  if (need && sub == 0) {
-    int out;
-    if (st != WE_ST_OK) out = -1 - st;
-    else if (dup) out = -1 - WE_ST_DUPLICATE;
-    else if (bi2 == 0x7fffffff) out = -1 - WE_ST_NO_NEIGHBOURS;
-    else out = (bq2 != 0x7fffffff) ? bq2 : bi2;
-    acceptor[(size_t)f * T.n_don + d] = out;
-    // diagnostic: a runner-up whose rc is within 4 ulp of the winner's
-    if (st == WE_ST_OK && bq2 != 0x7fffffff && second_rc < 1.0e299 && fabs(second_rc - bq0) <= 8.9e-16 * fabs(bq0))
-      atomicAdd(&diag->ambiguous_hb, 1ULL);
   }
 }
 
@@ -720,30 +737,37 @@ __global__ void k_flag(WeTopoDev T, const int* __restrict__ shell_n, const int* 
   }
 }
 
-// pass-1 entries whose shell was already computed (debug mode / resid overlap) are skipped by
-// k_rad through this filter kernel: it compacts wl1 into the list of centres still to compute.
+// HB work list: a centre joins it the first time it is needed and only if it has donors.
+__device__ __forceinline__ void we_queue_hb(const WeTopoDev& T, int f, int slot, int* hbq, int* wlh, int* nh) {
+  if (T.don_ptr[slot + 1] == T.don_ptr[slot]) return;
+  const size_t o = (size_t)f * T.n_heavy + slot;
+  if (atomicExch(&hbq[o], 1) == 0) wlh[(size_t)f * T.n_heavy + atomicAdd(&nh[f], 1)] = slot;
+}
+
 __global__ void k_mark(WeTopoDev T, const int* __restrict__ shell_n, const int* __restrict__ shell_idx,
                        const int* __restrict__ flags, const int* __restrict__ wl1,
                        const int* __restrict__ n1, int* __restrict__ state, int* __restrict__ wl2,
-                       int* __restrict__ n2, unsigned char* __restrict__ need_hb) {
+                       int* __restrict__ n2, int* __restrict__ hbq, int* __restrict__ wlh,
+                       int* __restrict__ nh) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int f = blockIdx.y;
   if (i >= n1[f]) return;
   const size_t fo = (size_t)f * T.n_heavy;
   const int xs = wl1[(size_t)f * T.n_centres + i];
-  need_hb[fo + xs] = 1;
+  we_queue_hb(T, f, xs, hbq, wlh, nh);
   if ((flags[fo + xs] >> 8) != WE_ST_OK) return;
   const int ns = shell_n[fo + xs];
   for (int m = 0; m < ns; ++m) {
     const int as = T.heavy_slot[shell_idx[(fo + xs) * WE_MAX_NBR + m]];
-    need_hb[fo + as] = 1;
+    we_queue_hb(T, f, as, hbq, wlh, nh);
     if (atomicCAS(&state[fo + as], 0, 1) == 0) wl2[fo + atomicAdd(&n2[f], 1)] = as;
   }
 }
 
 // bulk recipe: HBs are evaluated for waters with a pure shell and for their members
 __global__ void k_mark_bulk(WeTopoDev T, const int* __restrict__ shell_n, const int* __restrict__ shell_idx,
-                            const int* __restrict__ flags, unsigned char* __restrict__ need_hb) {
+                            const int* __restrict__ flags, int* __restrict__ hbq, int* __restrict__ wlh,
+                            int* __restrict__ nh) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int f = blockIdx.y;
   if (c >= T.n_centres) return;
@@ -755,8 +779,8 @@ __global__ void k_mark_bulk(WeTopoDev T, const int* __restrict__ shell_n, const 
   const int my_res = T.resname_id[T.heavy_idx[xs]];
   for (int m = 0; m < ns; ++m)
     if (T.resname_id[shell_idx[(fo + xs) * WE_MAX_NBR + m]] != my_res) return;
-  need_hb[fo + xs] = 1;
-  for (int m = 0; m < ns; ++m) need_hb[fo + T.heavy_slot[shell_idx[(fo + xs) * WE_MAX_NBR + m]]] = 1;
+  we_queue_hb(T, f, xs, hbq, wlh, nh);
+  for (int m = 0; m < ns; ++m) we_queue_hb(T, f, T.heavy_slot[shell_idx[(fo + xs) * WE_MAX_NBR + m]], hbq, wlh, nh);
 }
 
 // ============================================================================
@@ -773,18 +797,14 @@ __device__ __forceinline__ unsigned long long we_mix64(unsigned long long x) {
 
 struct WeRecord { int atom; int nearest; int bin; int pad; };
 
-__global__ void __launch_bounds__(256)
-k_label(WeTopoDev T, const int* __restrict__ shell_n, const int* __restrict__ shell_idx,
+// One centre (heavy slot xs of frame f) on one warp.
+__device__ __forceinline__ void we_label_one(const WeTopoDev& T, int f, int xs,
+        const int* __restrict__ shell_n, const int* __restrict__ shell_idx,
         const int* __restrict__ nn_arr, const int* __restrict__ flags,
         const int* __restrict__ acceptor, const unsigned char* __restrict__ interfacial,
         const long long* __restrict__ frame_ids, WeLabelEntry* __restrict__ table,
         unsigned int table_mask, int* __restrict__ rec_count, WeRecord* __restrict__ rec,
-        int2* __restrict__ rec_host, WeDiag* diag) {
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int f = blockIdx.y;
-  const int c = blockIdx.x * (blockDim.x >> 5) + w;
-  if (c >= T.n_centres) return;
-  const int xs = T.centres[c];
+        int2* __restrict__ rec_host, WeDiag* diag, int lane) {
   const size_t fo = (size_t)f * T.n_heavy;
   const size_t ho = fo + xs;
   const bool bulk = (T.recipe == 1);
@@ -930,6 +950,26 @@ k_label(WeTopoDev T, const int* __restrict__ shell_n, const int* __restrict__ sh
   }
   if (sact && sdon) atomicAdd(&e->donates[first_pos], (unsigned int)sdon);
   if (sact && sacc) atomicAdd(&e->accepts[first_pos], (unsigned int)sacc);
+}
+
+// Persistent wrapper: grid-stride over the work list of every frame of the batch
+// (interfacial recipe: the interfacial waters; bulk recipe: every water centre).
+__global__ void __launch_bounds__(256)
+k_label(WeTopoDev T, const int* __restrict__ shell_n, const int* __restrict__ shell_idx,
+        const int* __restrict__ nn_arr, const int* __restrict__ flags,
+        const int* __restrict__ acceptor, const unsigned char* __restrict__ interfacial,
+        const long long* __restrict__ frame_ids, WeLabelEntry* __restrict__ table,
+        unsigned int table_mask, int* __restrict__ rec_count, WeRecord* __restrict__ rec,
+        int2* __restrict__ rec_host, WeWork work, int n_frames, WeDiag* diag) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int stride = gridDim.x * (blockDim.x >> 5);
+  for (int f = 0; f < n_frames; ++f) {
+    const int cnt = work.count ? work.count[f] : work.static_count;
+    const int* list = work.list + (size_t)f * work.stride;
+    for (int i = blockIdx.x * (blockDim.x >> 5) + w; i < cnt; i += stride)
+      we_label_one(T, f, list[i], shell_n, shell_idx, nn_arr, flags, acceptor, interfacial, frame_ids, table,
+                   table_mask, rec_count, rec, rec_host, diag, lane);
+  }
 }
 
 // ============================================================================
