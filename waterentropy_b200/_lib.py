@@ -32,7 +32,7 @@ class we_options(C.Structure):
     _fields_ = [
         ("device", C.c_int32), ("chunk_frames", C.c_int32), ("table_log2", C.c_int32),
         ("keep_records", C.c_int32), ("keep_debug", C.c_int32),
-        ("search_radius", C.c_float), ("max_box", C.c_float),
+        ("search_radius", C.c_float), ("max_box", C.c_float), ("force_upload", C.c_int32),
     ]
 
 

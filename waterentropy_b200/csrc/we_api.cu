@@ -83,8 +83,20 @@ struct we_ctx {
   int hb_blocks = 0, label_blocks = 0;
   int *d_all_slots = nullptr;
   int rad_blocks = 0;
-  int* d_rec_count = nullptr;
-  WeRecord* d_rec = nullptr;
+  int* d_rec_count[2] = {nullptr, nullptr};
+  WeRecord* d_rec[2] = {nullptr, nullptr};
+  // lazy force upload
+  bool lazy = false;
+  int maxfrag = 0;
+  std::vector<int> h_centre_of_atom, h_frag_ptr, h_frag_atoms;
+  float* h_fcomp[2] = {nullptr, nullptr};
+  float* d_fcomp[2] = {nullptr, nullptr};
+  int* h_fbase[2] = {nullptr, nullptr};
+  int* d_fbase[2] = {nullptr, nullptr};
+  bool lazy_pending[2] = {false, false};
+  const float* pend_frc[2] = {nullptr, nullptr};
+  const float* pend_dp[2] = {nullptr, nullptr};
+  cudaEvent_t ev_label[2]{}, ev_f[2]{};
   int* d_nbr_idx = nullptr;
   double* d_nbr_dist = nullptr;
   double* d_ft = nullptr;
@@ -301,6 +313,13 @@ extern "C" int we_create(const we_topology* t, const we_options* opt, we_ctx** o
   c->S = (int)solute.size();
   std::vector<int> frag_ptr(t->frag_ptr, t->frag_ptr + c->C + 1);
   std::vector<int> frag_atoms(t->frag_atoms, t->frag_atoms + frag_ptr[c->C]);
+  c->h_frag_ptr = frag_ptr;
+  c->h_frag_atoms = frag_atoms;
+  c->h_centre_of_atom.assign(N, -1);
+  for (int k = 0; k < c->C; ++k) {
+    c->h_centre_of_atom[t->centres[k]] = k;
+    c->maxfrag = std::max(c->maxfrag, frag_ptr[k + 1] - frag_ptr[k]);
+  }
   if (t->recipe != WE_RECIPE_BULK) {
     for (int i = 0; i < N; ++i)
       if (heavy_slot[i] >= 0 && t->bin_of_atom[i] >= std::max(1, t->n_pair_bins)) { delete c; return fail(WE_ERR_INVALID, "bin_of_atom out of range"); }
@@ -347,6 +366,8 @@ extern "C" int we_create(const we_topology* t, const we_options* opt, we_ctx** o
     CK(cudaEventCreateWithFlags(&c->ev_in_ready[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_in_free[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_out_ready[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_label[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_f[i], cudaEventDisableTiming));
   }
   rc = we_reset(c);
   if (rc) { we_destroy(c); return rc; }
@@ -367,6 +388,7 @@ extern "C" int we_reset(we_ctx* c) {
   c->frames_done = 0;
   c->recorded = 0;
   c->out_pending[0] = c->out_pending[1] = false;
+  c->lazy_pending[0] = c->lazy_pending[1] = false;
   return WE_OK;
 }
 
@@ -382,6 +404,8 @@ extern "C" void we_destroy(we_ctx* c) {
     if (c->ev_in_ready[i]) cudaEventDestroy(c->ev_in_ready[i]);
     if (c->ev_in_free[i]) cudaEventDestroy(c->ev_in_free[i]);
     if (c->ev_out_ready[i]) cudaEventDestroy(c->ev_out_ready[i]);
+    if (c->ev_label[i]) cudaEventDestroy(c->ev_label[i]);
+    if (c->ev_f[i]) cudaEventDestroy(c->ev_f[i]);
   }
   delete c;
 }
@@ -405,21 +429,36 @@ static int ensure_workspace(we_ctx* c, const float* dims0, bool need_input_buffe
   int rc = 0;
   const size_t F = (size_t)chunk;
 #define AL(p, n) if ((rc = dev_alloc(c, &c->p, (n)))) return rc;
+  // forces of recorded waters only (lazy) when frames come from the host, the recipe records a
+  // minority of the waters (interfacial) and nothing else needs whole-frame forces
+  c->lazy = need_input_buffers && !c->opt.keep_debug && c->maxfrag > 0 && c->maxfrag <= 8 &&
+            (c->opt.force_upload == 2 || (c->opt.force_upload == 0 && c->recipe == WE_RECIPE_INTERFACIAL));
   if (need_input_buffers) {
-    for (int i = 0; i < 2; ++i) { AL(d_pos[i], F * N * 3) AL(d_frc[i], F * N * 3) }
+    for (int i = 0; i < 2; ++i) {
+      AL(d_pos[i], F * N * 3)
+      if (!c->lazy) { AL(d_frc[i], F * N * 3) }
+    }
+  }
+  if (c->lazy) {
+    const size_t cap = F * std::max(1, c->C) * (size_t)c->maxfrag * 3;
+    for (int i = 0; i < 2; ++i) {
+      AL(d_fcomp[i], cap) AL(d_fbase[i], F)
+      if ((rc = pin_alloc(c, &c->h_fcomp[i], cap))) return rc;
+      if ((rc = pin_alloc(c, &c->h_fbase[i], F))) return rc;
+    }
   }
   for (int i = 0; i < 2; ++i) {
     AL(d_boxes[i], F) AL(d_fids[i], F)
     if ((rc = pin_alloc(c, &c->h_boxes[i], F))) return rc;
     if ((rc = pin_alloc(c, &c->h_fids[i], F))) return rc;
     if ((rc = pin_alloc(c, &c->h_rec_count[i], F))) return rc;
-    if (c->opt.keep_records) { if ((rc = pin_alloc(c, &c->h_rec[i], F * std::max(1, c->C)))) return rc; }
+    if (c->opt.keep_records || c->lazy) { if ((rc = pin_alloc(c, &c->h_rec[i], F * std::max(1, c->C)))) return rc; }
   }
   AL(d_cell_count, F * ((size_t)c->ncap + 1))
   AL(d_cell_of, F * H) AL(d_rank_of, F * H) AL(d_tmp4, F * H) AL(d_sorted4, F * H)
   AL(d_shell_n, F * H) AL(d_shell_idx, F * H * WE_MAX_NBR) AL(d_nn, F * H) AL(d_flags, F * H)
   AL(d_acceptor, F * std::max(1, c->ND)) AL(d_interf, F * H)
-  AL(d_rec_count, F) AL(d_rec, F * std::max(1, c->C))
+  for (int i = 0; i < 2; ++i) { AL(d_rec_count[i], F) AL(d_rec[i], F * std::max(1, c->C)) }
   AL(d_hbq, F * H) AL(d_wlh, F * H) AL(d_nh, F) AL(d_state, F * H) AL(d_wl1, F * std::max(1, c->C)) AL(d_wl2, F * H) AL(d_n1, F) AL(d_n2, F)
   if (c->opt.keep_debug) { AL(d_nbr_idx, F * H * WE_MAX_NBR) AL(d_nbr_dist, F * H * WE_MAX_NBR) AL(d_ft, F * std::max(1, c->C) * 6) }
 #undef AL
@@ -465,6 +504,53 @@ static int drain(we_ctx* c, int buf) {
   return 0;
 }
 
+// Lazy force upload, second half of a batch: wait for its label kernel, gather the forces of the
+// recorded waters' atoms from the caller's host frames (record order), upload them compactly and
+// launch the covariance kernel.  The recorded-water lists are moved to host vectors here too.
+static int finish_lazy(we_ctx* c, int buf) {
+  if (!c->lazy_pending[buf]) return 0;
+  CK(cudaEventSynchronize(c->ev_label[buf]));
+  const int n = c->pending_n[buf];
+  const int C = std::max(1, c->C), N = c->N, mf = c->maxfrag;
+  size_t total = 0;
+  for (int f = 0; f < n; ++f) { c->h_fbase[buf][f] = (int)total; total += (size_t)c->h_rec_count[buf][f]; }
+  float* out = c->h_fcomp[buf];
+  for (int f = 0; f < n; ++f) {
+    const int cnt = c->h_rec_count[buf][f];
+    const int2* r = c->h_rec[buf] + (size_t)f * C;
+    const float* ff = c->pend_frc[buf] + (size_t)f * N * 3;
+    float* o = out + (size_t)c->h_fbase[buf][f] * mf * 3;
+    for (int k = 0; k < cnt; ++k) {
+      const int ce = c->h_centre_of_atom[r[k].x];
+      const int a0 = c->h_frag_ptr[ce], a1 = c->h_frag_ptr[ce + 1];
+      for (int a = a0; a < a1; ++a) {
+        const float* src = ff + (size_t)c->h_frag_atoms[a] * 3;
+        float* dst = o + ((size_t)k * mf + (a - a0)) * 3;
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+      }
+    }
+  }
+  if (total) CK(cudaMemcpyAsync(c->d_fcomp[buf], out, total * mf * 3 * sizeof(float), cudaMemcpyHostToDevice, c->s_copy));
+  CK(cudaMemcpyAsync(c->d_fbase[buf], c->h_fbase[buf], (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->s_copy));
+  CK(cudaEventRecord(c->ev_f[buf], c->s_copy));
+  cudaStream_t st = c->s_comp;
+  CK(cudaStreamWaitEvent(st, c->ev_f[buf], 0));
+  {
+    dim3 gV((c->C + 127) / 128, n);
+    ProfScope ps(c, WE_K_COV, st);
+    k_cov<<<gV, 128, 0, st>>>(c->T, c->pend_dp[buf], nullptr, c->d_rec_count[buf], c->d_rec[buf], c->d_centre_of_slot,
+                              c->d_cov_sum, c->d_cov_cnt, nullptr, c->d_fcomp[buf], c->d_fbase[buf], mf);
+    ps.stop(st);
+    c->launches += 1;
+  }
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(c->ev_in_free[buf], st));
+  CK(cudaEventRecord(c->ev_out_ready[buf], st));
+  c->lazy_pending[buf] = false;
+  c->out_pending[buf] = true;
+  return 0;
+}
+
 static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_device, const float* dims,
                        const int64_t* frame_ids, int n_frames) {
   if (!c || !pos || !frc || !dims || !frame_ids) return fail(WE_ERR_INVALID, "null argument");
@@ -480,6 +566,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     const int buf = (int)(c->chunk_counter & 1);
     c->chunk_counter++;
     // staging buffers of this slot were last used two chunks ago
+    if ((rc = finish_lazy(c, buf))) return rc;
     if ((rc = drain(c, buf))) return rc;
     CK(cudaEventSynchronize(c->ev_in_free[buf]));
     for (int f = 0; f < n; ++f) {
@@ -491,7 +578,8 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     const float* df;
     if (!on_device) {
       CK(cudaMemcpyAsync(c->d_pos[buf], pos + (size_t)f0 * frame_floats, (size_t)n * frame_floats * sizeof(float), cudaMemcpyHostToDevice, c->s_copy));
-      CK(cudaMemcpyAsync(c->d_frc[buf], frc + (size_t)f0 * frame_floats, (size_t)n * frame_floats * sizeof(float), cudaMemcpyHostToDevice, c->s_copy));
+      if (!c->lazy)
+        CK(cudaMemcpyAsync(c->d_frc[buf], frc + (size_t)f0 * frame_floats, (size_t)n * frame_floats * sizeof(float), cudaMemcpyHostToDevice, c->s_copy));
       dp = c->d_pos[buf];
       df = c->d_frc[buf];
     } else {
@@ -505,7 +593,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     CK(cudaStreamWaitEvent(st, c->ev_in_ready[buf], 0));
     CK(cudaMemsetAsync(c->d_cell_count, 0, (size_t)n * ((size_t)c->ncap + 1) * sizeof(int), st));
     CK(cudaMemsetAsync(c->d_interf, 0, (size_t)n * H, st));
-    CK(cudaMemsetAsync(c->d_rec_count, 0, (size_t)n * sizeof(int), st));
+    CK(cudaMemsetAsync(c->d_rec_count[buf], 0, (size_t)n * sizeof(int), st));
     CK(cudaMemsetAsync(c->d_state, 0, (size_t)n * H * sizeof(int), st));
     CK(cudaMemsetAsync(c->d_hbq, 0, (size_t)n * H * sizeof(int), st));
     CK(cudaMemsetAsync(c->d_nh, 0, (size_t)n * sizeof(int), st));
@@ -593,29 +681,43 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       { ProfScope ps(c, WE_K_LABEL, st);
         k_label<<<grid_for((long long)C * n, 8, c->label_blocks), 256, 0, st>>>(
             c->T, c->d_shell_n, c->d_shell_idx, c->d_nn, c->d_flags, c->d_acceptor, c->d_interf, fids,
-            c->d_table, c->table_mask, c->d_rec_count, c->d_rec,
-            c->opt.keep_records ? c->h_rec[buf] : nullptr, wlab, n, c->d_diag);
+            c->d_table, c->table_mask, c->d_rec_count[buf], c->d_rec[buf],
+            (c->opt.keep_records || c->lazy) ? c->h_rec[buf] : nullptr, wlab, n, c->d_diag);
         ps.stop(st); }
-      dim3 gV((C + 127) / 128, n);
-      { ProfScope ps(c, WE_K_COV, st);
-        k_cov<<<gV, 128, 0, st>>>(c->T, dp, df, c->d_rec_count, c->d_rec, c->d_centre_of_slot, c->d_cov_sum, c->d_cov_cnt, c->d_ft);
-        ps.stop(st); }
-      c->launches += 2;
+      c->launches += 1;
+      if (!c->lazy) {
+        dim3 gV((C + 127) / 128, n);
+        ProfScope ps(c, WE_K_COV, st);
+        k_cov<<<gV, 128, 0, st>>>(c->T, dp, df, c->d_rec_count[buf], c->d_rec[buf], c->d_centre_of_slot, c->d_cov_sum,
+                                  c->d_cov_cnt, c->d_ft, nullptr, nullptr, 0);
+        ps.stop(st);
+        c->launches += 1;
+      }
     }
     CK(cudaGetLastError());
-    CK(cudaEventRecord(c->ev_in_free[buf], st));
-    // results of this chunk -> pinned staging
-    CK(cudaMemcpyAsync(c->h_rec_count[buf], c->d_rec_count, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(c->ev_out_ready[buf], st));
+    // per-frame record counts -> pinned staging (the records themselves are already in mapped memory)
+    CK(cudaMemcpyAsync(c->h_rec_count[buf], c->d_rec_count[buf], (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
     c->pending_n[buf] = n;
-    c->out_pending[buf] = true;
     c->frames_done += (unsigned long long)n;
+    if (c->lazy && C > 0) {
+      // the covariance kernel of this batch runs one batch later, after the host has gathered
+      // the forces of the recorded waters (finish_lazy); until then its inputs stay alive
+      CK(cudaEventRecord(c->ev_label[buf], st));
+      c->lazy_pending[buf] = true;
+      c->pend_frc[buf] = frc + (size_t)f0 * frame_floats;
+      c->pend_dp[buf] = dp;
+      if ((rc = finish_lazy(c, buf ^ 1))) return rc;
+    } else {
+      CK(cudaEventRecord(c->ev_in_free[buf], st));
+      CK(cudaEventRecord(c->ev_out_ready[buf], st));
+      c->out_pending[buf] = true;
+    }
     if (c->opt.keep_debug) {
       CK(cudaStreamSynchronize(st));
       if ((rc = drain(c, buf ^ 1))) return rc;  // keep frame order in frame_records
       if ((rc = drain(c, buf))) return rc;
       std::vector<int> rc_h(n);
-      CK(cudaMemcpy(rc_h.data(), c->d_rec_count, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(rc_h.data(), c->d_rec_count[buf], (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
       for (int f = 0; f < n; ++f) {
         FrameDebug D;
         D.shell_n.resize(H); D.shell_idx.resize((size_t)H * WE_MAX_NBR); D.nn.resize(H); D.flags.resize(H);
@@ -630,7 +732,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
         CK(cudaMemcpy(D.nbr_dist.data(), c->d_nbr_dist + (size_t)f * H * WE_MAX_NBR, (size_t)H * WE_MAX_NBR * 8, cudaMemcpyDeviceToHost));
         if (rc_h[f]) {
           CK(cudaMemcpy(D.ft.data(), c->d_ft + (size_t)f * C * 6, (size_t)rc_h[f] * 6 * 8, cudaMemcpyDeviceToHost));
-          CK(cudaMemcpy(D.rec.data(), c->d_rec + (size_t)f * C, (size_t)rc_h[f] * sizeof(WeRecord), cudaMemcpyDeviceToHost));
+          CK(cudaMemcpy(D.rec.data(), c->d_rec[buf] + (size_t)f * C, (size_t)rc_h[f] * sizeof(WeRecord), cudaMemcpyDeviceToHost));
         }
         c->debug.push_back(std::move(D));
       }
@@ -656,6 +758,12 @@ static int read_diag(we_ctx* c, WeDiag* d) {
 extern "C" int we_sync(we_ctx* c) {
   if (!c) return fail(WE_ERR_INVALID, "null context");
   CK(cudaSetDevice(c->device));
+  {
+    const int older0 = (int)(c->chunk_counter & 1);
+    int rc0;
+    if ((rc0 = finish_lazy(c, older0))) return rc0;
+    if ((rc0 = finish_lazy(c, older0 ^ 1))) return rc0;
+  }
   CK(cudaStreamSynchronize(c->s_copy));
   CK(cudaStreamSynchronize(c->s_comp));
   prof_resolve(c);

@@ -1017,7 +1017,8 @@ __global__ void __launch_bounds__(128)
 k_cov(WeTopoDev T, const float* __restrict__ pos, const float* __restrict__ frc,
       const int* __restrict__ rec_count, const WeRecord* __restrict__ rec,
       const int* __restrict__ centre_of_slot, double* __restrict__ cov_sum,
-      unsigned long long* __restrict__ cov_cnt, double* __restrict__ ft_out) {
+      unsigned long long* __restrict__ cov_cnt, double* __restrict__ ft_out,
+      const float* __restrict__ fcomp, const int* __restrict__ fbase, int maxfrag) {
   const int f = blockIdx.y;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -1033,7 +1034,9 @@ k_cov(WeTopoDev T, const float* __restrict__ pos, const float* __restrict__ frc,
     const int c = centre_of_slot[T.heavy_slot[rr.atom]];
     const int a0 = T.frag_ptr[c], a1 = T.frag_ptr[c + 1];
     const float* fp = pos + (size_t)f * T.n_atoms * 3;
-    const float* ff = frc + (size_t)f * T.n_atoms * 3;
+    // forces: the whole frame (eager upload) or only the recorded molecules, gathered by the
+    // host in record order (lazy upload: fcomp[(fbase[f] + r) * maxfrag + k][3])
+    const float* ff = fcomp ? fcomp + ((size_t)(fbase[f] + r) * maxfrag) * 3 : frc + (size_t)f * T.n_atoms * 3;
     // centre of mass (mass-weighted, fp64, no unwrapping: forces_torques.py:40)
     double mtot = 0.0, cx = 0.0, cy = 0.0, cz = 0.0;
     for (int k = a0; k < a1; ++k) {
@@ -1088,7 +1091,8 @@ k_cov(WeTopoDev T, const float* __restrict__ pos, const float* __restrict__ frc,
     for (int k = a0; k < a1; ++k) {
       const int at = T.frag_atoms[k];
       const double p[3] = {(double)fp[3 * at] - cx, (double)fp[3 * at + 1] - cy, (double)fp[3 * at + 2] - cz};
-      const double g[3] = {(double)ff[3 * at], (double)ff[3 * at + 1], (double)ff[3 * at + 2]};
+      const int fa = fcomp ? (k - a0) : at;
+      const double g[3] = {(double)ff[3 * fa], (double)ff[3 * fa + 1], (double)ff[3 * fa + 2]};
       double rp[3], rg[3];
       for (int i = 0; i < 3; ++i) {
         rp[i] = ax[i][0] * p[0] + ax[i][1] * p[1] + ax[i][2] * p[2];
@@ -1097,8 +1101,8 @@ k_cov(WeTopoDev T, const float* __restrict__ pos, const float* __restrict__ frc,
       tq[0] += (rp[1] * rg[2] - rp[2] * rg[1]) / sq[0];
       tq[1] += (rp[2] * rg[0] - rp[0] * rg[2]) / sq[1];
       tq[2] += (rp[0] * rg[1] - rp[1] * rg[0]) / sq[2];
-      if (k == a0) { fsx = ff[3 * at]; fsy = ff[3 * at + 1]; fsz = ff[3 * at + 2]; }
-      else { fsx = we_fadd(fsx, ff[3 * at]); fsy = we_fadd(fsy, ff[3 * at + 1]); fsz = we_fadd(fsz, ff[3 * at + 2]); }  // float32 sum (transformations.py:48)
+      if (k == a0) { fsx = ff[3 * fa]; fsy = ff[3 * fa + 1]; fsz = ff[3 * fa + 2]; }
+      else { fsx = we_fadd(fsx, ff[3 * fa]); fsy = we_fadd(fsy, ff[3 * fa + 1]); fsz = we_fadd(fsz, ff[3 * fa + 2]); }  // float32 sum (transformations.py:48)
     }
     const double msq = sqrt(mtot);
     double F[3];

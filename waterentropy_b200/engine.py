@@ -80,14 +80,14 @@ def decode_label_entries(top, recipe, entries) -> HBLabelCollection:
 
 class WaterEntropyEngine:
     def __init__(self, system, recipe="interfacial", device=0, chunk_frames=0, table_log2=0,
-                 keep_records=True, keep_debug=False, search_radius=0.0, max_box=0.0):
+                 keep_records=True, keep_debug=False, search_radius=0.0, max_box=0.0, force_upload=0):
         self.lib = _lib.load()
         self.top = SystemTopology.from_universe(system)
         self.recipe = RECIPE_BULK if recipe in ("bulk", RECIPE_BULK) else RECIPE_INTERFACIAL
         t, self._keep = self.top.c_struct(self.recipe)
         o = _lib.we_options(device=device, chunk_frames=chunk_frames, table_log2=table_log2,
                             keep_records=int(keep_records), keep_debug=int(keep_debug),
-                            search_radius=search_radius, max_box=max_box)
+                            search_radius=search_radius, max_box=max_box, force_upload=force_upload)
         self._ctx = C.c_void_p()
         _lib.check(self.lib.we_create(C.byref(t), C.byref(o), C.byref(self._ctx)))
         self.device = device
