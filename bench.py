@@ -282,7 +282,8 @@ def run_ours(args, rank, world, local_rank):
     del dP, dF
 
     # ---------------- end-to-end arm (host buffers through the public API) ----------------
-    eng = WaterEntropyEngine(s, "interfacial", device=local_rank, keep_records=True, chunk_frames=args.chunk)
+    eng = WaterEntropyEngine(s, "interfacial", device=local_rank, keep_records=True, chunk_frames=args.chunk,
+                             force_upload=args.force_upload)
     hP, hF = torch.from_numpy(P).pin_memory(), torch.from_numpy(Fr).pin_memory()
     d2h = 0
 
@@ -358,16 +359,17 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C4", choices=sorted(synthetic.CONFIGS))
     ap.add_argument("--scale", type=float, default=1.0, help="scale waters/residues of the config (tests only)")
-    ap.add_argument("--frames-per-step", type=int, default=24)
+    ap.add_argument("--frames-per-step", type=int, default=96)
     ap.add_argument("--chunk", type=int, default=0)
-    ap.add_argument("--cpu-sample", type=int, default=1024, help="centres per core per step of the CPU arm")
+    ap.add_argument("--cpu-sample", type=int, default=512, help="centres per core per step of the CPU arm")
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--force-upload", type=int, default=0, help="e2e arm: 0 auto, 1 whole frames, 2 recorded waters only")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -103,7 +103,7 @@ struct we_ctx {
   int* h_rec_count[2] = {nullptr, nullptr};
   int2* h_rec[2] = {nullptr, nullptr};  // mapped pinned memory written by k_label
   int pending_n[2] = {0, 0};
-  cudaStream_t s_copy = nullptr, s_comp = nullptr;
+  cudaStream_t s_copy = nullptr, s_comp = nullptr, s_cov = nullptr;
   cudaEvent_t ev_in_ready[2]{}, ev_in_free[2]{}, ev_out_ready[2]{};
   bool out_pending[2] = {false, false};
   // results on host
@@ -362,6 +362,7 @@ extern "C" int we_create(const we_topology* t, const we_options* opt, we_ctx** o
   if ((rc = dev_alloc(c, &c->d_diag, 1))) { we_destroy(c); return rc; }
   CK(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->s_cov, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {
     CK(cudaEventCreateWithFlags(&c->ev_in_ready[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_in_free[i], cudaEventDisableTiming));
@@ -400,6 +401,7 @@ extern "C" void we_destroy(we_ctx* c) {
   for (void* p : c->pinned) cudaFreeHost(p);
   if (c->s_copy) cudaStreamDestroy(c->s_copy);
   if (c->s_comp) cudaStreamDestroy(c->s_comp);
+  if (c->s_cov) cudaStreamDestroy(c->s_cov);
   for (int i = 0; i < 2; ++i) {
     if (c->ev_in_ready[i]) cudaEventDestroy(c->ev_in_ready[i]);
     if (c->ev_in_free[i]) cudaEventDestroy(c->ev_in_free[i]);
@@ -533,7 +535,10 @@ static int finish_lazy(we_ctx* c, int buf) {
   if (total) CK(cudaMemcpyAsync(c->d_fcomp[buf], out, total * mf * 3 * sizeof(float), cudaMemcpyHostToDevice, c->s_copy));
   CK(cudaMemcpyAsync(c->d_fbase[buf], c->h_fbase[buf], (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->s_copy));
   CK(cudaEventRecord(c->ev_f[buf], c->s_copy));
-  cudaStream_t st = c->s_comp;
+  // own stream: the covariance kernel of batch k must not queue behind the kernels of batch k+1
+  // (its completion frees this slot's input buffers for the H2D copy of batch k+2)
+  cudaStream_t st = c->s_cov;
+  CK(cudaStreamWaitEvent(st, c->ev_label[buf], 0));
   CK(cudaStreamWaitEvent(st, c->ev_f[buf], 0));
   {
     dim3 gV((c->C + 127) / 128, n);
@@ -766,6 +771,7 @@ extern "C" int we_sync(we_ctx* c) {
   }
   CK(cudaStreamSynchronize(c->s_copy));
   CK(cudaStreamSynchronize(c->s_comp));
+  CK(cudaStreamSynchronize(c->s_cov));
   prof_resolve(c);
   // drain in submission order
   const int older = (int)(c->chunk_counter & 1);
