@@ -58,7 +58,7 @@ _lib = None
 
 
 def library_path() -> str:
-    return _build.SO
+    return os.environ.get("WE_LIB_PATH") or _build.SO  # WE_LIB_PATH: tuning builds only
 
 
 def load():

@@ -21,6 +21,9 @@
 #define WE_CUTOFF 10.0
 #define WE_RAD_WARPS 8
 #define WE_CELLS_PER_RADIUS 2  // cell edge = search radius / 2, searched +-2 cells
+#ifndef WE_RAD_MINBLOCKS
+#define WE_RAD_MINBLOCKS 3    // resident blocks per SM the register allocator must allow for k_rad
+#endif
 #define WE_ENTRY_WORDS 64  // 512-byte label-table entries
 
 // status codes (per centre / per donor), also the C-ABI error codes
@@ -326,44 +329,41 @@ __device__ __forceinline__ int we_collect(const WeBox& b, const int* __restrict_
     rows->px0[lane] = px0; rows->px1[lane] = px1; rows->py[lane] = py; rows->pz[lane] = pz;
     __syncwarp();
     // ---- dense walk over the candidates of these rows ---------------------------------------
-    for (int base = 0; base < total; base += 32) {
-      const int q = base + lane;
-      bool pass = false;
-      int qi = 0;
-      if (q < total) {
-        int ro = 0;  // largest row with off[row] <= q
+    auto probe = [&](int q, int& qi) -> bool {
+      if (q >= total) return false;
+      int ro = 0;  // largest row with off[row] <= q
 #pragma unroll
-        for (int st = 16; st > 0; st >>= 1) ro += (rows->off[ro + st] <= q) ? st : 0;
-        const int t = q - rows->off[ro];
-        const int l0 = rows->len0[ro];
-        const bool second = t >= l0;
-        qi = second ? rows->beg1[ro] + (t - l0) : rows->beg0[ro] + t;
-        const float4 c = sorted[qi];
-        if (simple) {
-          const float ux = c.x - (second ? rows->px1[ro] : rows->px0[ro]);
-          const float uy = c.y - rows->py[ro], uz = c.z - rows->pz[ro];
-          pass = __fmaf_rn(ux, ux, __fmaf_rn(uy, uy, uz * uz)) <= rf2;
-        } else {
-          const float ux = c.x - mx, uy = c.y - my, uz = c.z - mz;
-          if (mode == 0) {
-            const float fx = __fmaf_rn(-b.box[0], rintf(ux * b.inv[0]), ux);
-            const float fy = __fmaf_rn(-b.box[1], rintf(uy * b.inv[1]), uy);
-            const float fz = __fmaf_rn(-b.box[2], rintf(uz * b.inv[2]), uz);
-            pass = __fmaf_rn(fx, fx, __fmaf_rn(fy, fy, fz * fz)) <= rf2;
-          } else if (mode == 1) {
-            float s0 = ux * b.hinvf[0] + uy * b.hinvf[3] + uz * b.hinvf[6];
-            float s1 = uy * b.hinvf[4] + uz * b.hinvf[7];
-            float s2 = uz * b.hinvf[8];
-            s0 -= rintf(s0); s1 -= rintf(s1); s2 -= rintf(s2);
-            const float fx = s0 * b.m[0] + s1 * b.m[3] + s2 * b.m[6];
-            const float fy = s1 * b.m[4] + s2 * b.m[7];
-            const float fz = s2 * b.m[8];
-            pass = (fx * fx + fy * fy + fz * fz) <= rf2;
-          } else {
-            pass = true;
-          }
-        }
+      for (int st = 16; st > 0; st >>= 1) ro += (rows->off[ro + st] <= q) ? st : 0;
+      const int t = q - rows->off[ro];
+      const int l0 = rows->len0[ro];
+      const bool second = t >= l0;
+      qi = second ? rows->beg1[ro] + (t - l0) : rows->beg0[ro] + t;
+      const float4 c = sorted[qi];
+      if (simple) {
+        const float ux = c.x - (second ? rows->px1[ro] : rows->px0[ro]);
+        const float uy = c.y - rows->py[ro], uz = c.z - rows->pz[ro];
+        return __fmaf_rn(ux, ux, __fmaf_rn(uy, uy, uz * uz)) <= rf2;
       }
+      const float ux = c.x - mx, uy = c.y - my, uz = c.z - mz;
+      if (mode == 0) {
+        const float fx = __fmaf_rn(-b.box[0], rintf(ux * b.inv[0]), ux);
+        const float fy = __fmaf_rn(-b.box[1], rintf(uy * b.inv[1]), uy);
+        const float fz = __fmaf_rn(-b.box[2], rintf(uz * b.inv[2]), uz);
+        return __fmaf_rn(fx, fx, __fmaf_rn(fy, fy, fz * fz)) <= rf2;
+      }
+      if (mode == 1) {
+        float s0 = ux * b.hinvf[0] + uy * b.hinvf[3] + uz * b.hinvf[6];
+        float s1 = uy * b.hinvf[4] + uz * b.hinvf[7];
+        float s2 = uz * b.hinvf[8];
+        s0 -= rintf(s0); s1 -= rintf(s1); s2 -= rintf(s2);
+        const float fx = s0 * b.m[0] + s1 * b.m[3] + s2 * b.m[6];
+        const float fy = s1 * b.m[4] + s2 * b.m[7];
+        const float fz = s2 * b.m[8];
+        return (fx * fx + fy * fy + fz * fz) <= rf2;
+      }
+      return true;
+    };
+    auto push = [&](bool pass, int qi) {
       const unsigned m = __ballot_sync(0xffffffffu, pass);
       if (pass) stage[(head + cnt + __popc(m & ((1u << lane) - 1u))) & 63] = qi;
       cnt += __popc(m);
@@ -374,6 +374,11 @@ __device__ __forceinline__ int we_collect(const WeBox& b, const int* __restrict_
         cnt -= 32;
         __syncwarp();
       }
+    };
+    for (int base = 0; base < total; base += 32) {
+      int qa = 0;
+      const bool pa = probe(base + lane, qa);
+      push(pa, qa);
     }
   }
   if (cnt > 0) {
@@ -503,6 +508,7 @@ __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __re
   }
   __syncwarp();
   // ---- RAD blocking test: lane j against closer candidates k = 0..j-1 ---------
+  // (evaluating two k per iteration or two scan candidates per lane was measured: no gain)
   bool blocked = false;
   bool alive = act && lane > 0;
   for (int k = 0; k < n25 - 1; ++k) {
@@ -546,7 +552,7 @@ __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __re
 // Persistent kernel: gridDim.x blocks of WE_RAD_WARPS warps walk the work list of
 // every frame of the batch with a grid-stride loop (no empty blocks when the list
 // is short, natural load balance when per-centre cost varies).
-__global__ void __launch_bounds__(WE_RAD_WARPS * 32)
+__global__ void __launch_bounds__(WE_RAD_WARPS * 32, WE_RAD_MINBLOCKS)
 k_rad(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes,
       const int* __restrict__ cell_start, const int* __restrict__ cell_of,
       const float4* __restrict__ sorted4, int ncap, float search_radius, WeWork work,
