@@ -301,14 +301,14 @@ def run_ours(args, rank, world, local_rank):
 
     def e2e_finalize():
         """end of job, inside the timed region: the label count table (and its cross-rank merge)"""
-        entries = eng.label_entries()
         if world > 1:
-            entries = wdist.merge_label_entries(wdist.allgather_entries(entries))
-        return entries
+            return wdist.merge_labels_nccl(eng)
+        return eng.label_entries()
 
     for _ in range(args.warmup):
         e2e_step()
     e2e_finalize()
+    eng.reset()  # the warm-up merge folded the other ranks' tables into this one
     barrier()
     t0 = time.perf_counter()
     nrec = 0

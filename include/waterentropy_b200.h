@@ -158,6 +158,13 @@ typedef struct we_label_entry {
 } we_label_entry;
 int we_n_label_entries(we_ctx *ctx);
 int we_copy_label_entries(we_ctx *ctx, we_label_entry *out, int32_t capacity);
+/* Cross-rank merge on the device (replaces HBLabelCollection.merge, analysis/HB_labels.py:158-296):
+ * `we_label_entries_device` compacts this rank's entries into a device buffer owned by the context
+ * (valid until the next call) and returns their number; after an all-gather of those buffers
+ * `we_merge_label_entries` adds another rank's entries (device pointer) into this context's table:
+ * counts add, N_w / first-seen follow the "first insert wins" rule. */
+int we_label_entries_device(we_ctx *ctx, void **d_entries);
+int we_merge_label_entries(we_ctx *ctx, const void *d_entries, int32_t n);
 
 /* Per-frame recorded waters (frame_solvent_indices, recipes/interfacial_solvent.py:69-88);
  * needs we_options.keep_records.  `k` counts submitted frames from 0.

@@ -391,3 +391,49 @@ def test_chunking_and_device_resident_inputs_agree():
         assert np.allclose(outs[0][5], o[5], rtol=1e-12)
         for a, b in zip(outs[0][6], o[6]):
             assert np.array_equal(a, b)
+
+
+def test_label_table_grows_and_rehashes():
+    """A tiny initial table must grow (device rehash) without changing any count."""
+    inp = gio.load_inputs("arginine")
+    F = inp["positions"].shape[0]
+    outs = []
+    for log2, chunk in ((4, 1), (17, 8)):
+        eng = _engine(inp, table_log2=log2, chunk_frames=chunk)
+        for f in range(F):  # one submit per frame: growth is decided between batches
+            eng.submit(inp["positions"][f:f + 1], inp["forces"][f:f + 1], inp["dimensions"][f:f + 1], [f])
+        eng.sync()
+        e = eng.label_entries()
+        e = e[np.lexsort((e["hash2"], e["hash"]))]
+        outs.append(e)
+        eng.close()
+    a, b = outs
+    assert len(a) == len(b) and len(a) > 100
+    for field in ("hash", "hash2", "shell_count", "n_w", "n_labels", "labels", "donates", "accepts", "first_seen_inv"):
+        assert np.array_equal(a[field], b[field]), field
+
+
+def test_device_merge_of_label_entries_equals_single_pass():
+    """we_merge_label_entries (the cross-rank merge of analysis/HB_labels.py:158-296 on the device):
+    frames 0-4 on one context + frames 5-9 on another, merged == all ten frames on one context."""
+    inp = gio.load_inputs("arginine")
+
+    def run(frames):
+        eng = _engine(inp)
+        eng.submit(inp["positions"][frames], inp["forces"][frames], inp["dimensions"][frames], list(frames))
+        eng.sync()
+        return eng
+
+    a, b, c = run(range(0, 5)), run(range(5, 10)), run(range(0, 10))
+    ptr, n = b.label_entries_device()
+    assert n == len(b.label_entries())
+    a.merge_label_entries_device(ptr, n)
+    ea, ec = a.label_entries(), c.label_entries()
+    ea, ec = ea[np.lexsort((ea["hash2"], ea["hash"]))], ec[np.lexsort((ec["hash2"], ec["hash"]))]
+    assert len(ea) == len(ec)
+    for field in ("hash", "hash2", "shell_count", "n_w", "n_labels", "labels", "donates", "accepts", "first_seen_inv",
+                  "nearest_resid", "nearest_resname_id"):
+        assert np.array_equal(ea[field], ec[field]), field
+    assert gio.plain(a.hb_labels().resid_labelled_shell_counts) == gio.plain(c.hb_labels().resid_labelled_shell_counts)
+    for e in (a, b, c):
+        e.close()

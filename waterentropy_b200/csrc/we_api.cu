@@ -61,8 +61,11 @@ struct we_ctx {
   unsigned long long* d_cov_cnt = nullptr;
   WeLabelEntry* d_table = nullptr;
   WeLabelEntry* d_compact = nullptr;
+  size_t compact_cap = 0;
   int* d_compact_n = nullptr;
   unsigned int table_mask = 0;
+  WeDiag* h_diag = nullptr;            // pinned mirror refreshed after every batch
+  unsigned long long seen_entries = 0, max_new = 0;
   WeDiag* d_diag = nullptr;
   // workspace
   bool ws_ready = false;
@@ -352,12 +355,16 @@ extern "C" int we_create(const we_topology* t, const we_options* opt, we_ctx** o
   if ((rc = dev_upload(c, &cos_p, centre_of_slot))) { we_destroy(c); return rc; }
   c->d_centre_of_slot = (int*)cos_p;
   // accumulators
-  const int tl = c->opt.table_log2 > 0 ? c->opt.table_log2 : 16;
+  const int tl = c->opt.table_log2 > 0 ? c->opt.table_log2 : 17;
   if (tl < 4 || tl > 24) { we_destroy(c); return fail(WE_ERR_INVALID, "table_log2 must be in [4,24]"); }
   c->table_mask = (1u << tl) - 1u;
   if ((rc = dev_alloc(c, &c->d_cov_sum, (size_t)c->B * 18))) { we_destroy(c); return rc; }
   if ((rc = dev_alloc(c, &c->d_cov_cnt, (size_t)c->B))) { we_destroy(c); return rc; }
-  if ((rc = dev_alloc(c, &c->d_table, (size_t)c->table_mask + 1))) { we_destroy(c); return rc; }
+  {
+    void* q = nullptr;
+    if (cudaMalloc(&q, ((size_t)c->table_mask + 1) * sizeof(WeLabelEntry)) != cudaSuccess) { we_destroy(c); return fail(WE_ERR_CUDA, "label table allocation failed"); }
+    c->d_table = (WeLabelEntry*)q;
+  }
   if ((rc = dev_alloc(c, &c->d_compact_n, 1))) { we_destroy(c); return rc; }
   if ((rc = dev_alloc(c, &c->d_diag, 1))) { we_destroy(c); return rc; }
   CK(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
@@ -370,6 +377,8 @@ extern "C" int we_create(const we_topology* t, const we_options* opt, we_ctx** o
     CK(cudaEventCreateWithFlags(&c->ev_label[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_f[i], cudaEventDisableTiming));
   }
+  if ((rc = pin_alloc(c, &c->h_diag, 1))) { we_destroy(c); return rc; }
+  memset(c->h_diag, 0, sizeof(WeDiag));
   rc = we_reset(c);
   if (rc) { we_destroy(c); return rc; }
   *out = c;
@@ -390,6 +399,9 @@ extern "C" int we_reset(we_ctx* c) {
   c->recorded = 0;
   c->out_pending[0] = c->out_pending[1] = false;
   c->lazy_pending[0] = c->lazy_pending[1] = false;
+  c->seen_entries = 0;
+  c->max_new = 0;
+  if (c->h_diag) memset(c->h_diag, 0, sizeof(WeDiag));
   return WE_OK;
 }
 
@@ -398,6 +410,8 @@ extern "C" void we_destroy(we_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   for (void* p : c->allocs) cudaFree(p);
+  if (c->d_table) cudaFree(c->d_table);
+  if (c->d_compact) cudaFree(c->d_compact);
   for (void* p : c->pinned) cudaFreeHost(p);
   if (c->s_copy) cudaStreamDestroy(c->s_copy);
   if (c->s_comp) cudaStreamDestroy(c->s_comp);
@@ -506,6 +520,50 @@ static int drain(we_ctx* c, int buf) {
   return 0;
 }
 
+// ---- label table growth ---------------------------------------------------------------------
+__global__ void k_rehash(const WeLabelEntry* __restrict__ old_t, unsigned int old_n,
+                         WeLabelEntry* __restrict__ new_t, unsigned int new_mask) {
+  const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= old_n) return;
+  const unsigned long long h = old_t[i].hash;
+  if (h == 0ULL) return;
+  unsigned int s = (unsigned int)h & new_mask;
+  while (atomicCAS(&new_t[s].hash, 0ULL, h) != 0ULL) s = (s + 1) & new_mask;
+  const uint4* src = reinterpret_cast<const uint4*>(old_t + i);
+  uint4* dst = reinterpret_cast<uint4*>(new_t + s);
+#pragma unroll
+  for (int k = 0; k < 32; ++k) dst[k] = src[k];
+}
+
+// Keep the open-addressing table below ~50 % load: called between batches with the entry count
+// mirrored after the previous batch plus the largest per-batch growth seen so far (x4 margin).
+static int grow_table_to(we_ctx* c, unsigned long long need);
+static int maybe_grow_table(we_ctx* c) {
+  const unsigned long long entries = c->h_diag->table_entries;
+  if (entries > c->seen_entries) c->max_new = std::max(c->max_new, entries - c->seen_entries);
+  c->seen_entries = entries;
+  return grow_table_to(c, entries + 4 * c->max_new + 1024);
+}
+static int grow_table_to(we_ctx* c, unsigned long long need) {
+  unsigned long long cap = (unsigned long long)c->table_mask + 1;
+  if (need * 2 <= cap) return 0;
+  unsigned long long ncap = cap;
+  while (need * 2 > ncap) ncap <<= 1;
+  if (ncap > (1ULL << 24)) return fail(WE_ERR_TABLE_FULL, "label count table would exceed 2^24 entries");
+  CK(cudaStreamSynchronize(c->s_comp));
+  CK(cudaStreamSynchronize(c->s_cov));
+  WeLabelEntry* nt = nullptr;
+  CK(cudaMalloc((void**)&nt, ncap * sizeof(WeLabelEntry)));
+  CK(cudaMemsetAsync(nt, 0, ncap * sizeof(WeLabelEntry), c->s_comp));
+  k_rehash<<<(unsigned int)((cap + 255) / 256), 256, 0, c->s_comp>>>(c->d_table, (unsigned int)cap, nt, (unsigned int)(ncap - 1));
+  c->launches++;
+  CK(cudaStreamSynchronize(c->s_comp));
+  CK(cudaFree(c->d_table));
+  c->d_table = nt;
+  c->table_mask = (unsigned int)(ncap - 1);
+  return 0;
+}
+
 // Lazy force upload, second half of a batch: wait for its label kernel, gather the forces of the
 // recorded waters' atoms from the caller's host frames (record order), upload them compactly and
 // launch the covariance kernel.  The recorded-water lists are moved to host vectors here too.
@@ -574,6 +632,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     if ((rc = finish_lazy(c, buf))) return rc;
     if ((rc = drain(c, buf))) return rc;
     CK(cudaEventSynchronize(c->ev_in_free[buf]));
+    if ((rc = maybe_grow_table(c))) return rc;
     for (int f = 0; f < n; ++f) {
       if (make_box(dims + (size_t)(f0 + f) * 6, c->cell_target, c->ncap, &c->h_boxes[buf][f]))
         return fail(WE_ERR_INVALID, "frame %lld: box dimensions must be positive and finite", (long long)frame_ids[f0 + f]);
@@ -700,6 +759,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       }
     }
     CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c->h_diag, c->d_diag, sizeof(WeDiag), cudaMemcpyDeviceToHost, st));  // table load mirror
     // per-frame record counts -> pinned staging (the records themselves are already in mapped memory)
     CK(cudaMemcpyAsync(c->h_rec_count[buf], c->d_rec_count[buf], (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
     c->pending_n[buf] = n;
@@ -915,6 +975,70 @@ extern "C" int we_copy_label_entries(we_ctx* c, we_label_entry* out, int32_t cap
   cudaFree(tmp);
   if (e != cudaSuccess) return fail(WE_ERR_CUDA, "copy of label entries failed: %s", cudaGetErrorString(e));
   return n;
+}
+
+extern "C" int we_label_entries_device(we_ctx* c, void** d_entries) {
+  if (!c || !d_entries) return fail(WE_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  const int n = we_n_label_entries(c);
+  if (n < 0) return n;
+  if ((size_t)n > c->compact_cap) {
+    if (c->d_compact) cudaFree(c->d_compact);
+    c->d_compact = nullptr;
+    c->compact_cap = (size_t)n + 1024;
+    CK(cudaMalloc((void**)&c->d_compact, c->compact_cap * sizeof(WeLabelEntry)));
+  }
+  CK(cudaMemset(c->d_compact_n, 0, sizeof(int)));
+  const unsigned int tn = c->table_mask + 1;
+  if (n) { k_compact<<<(tn + 255) / 256, 256>>>(c->d_table, tn, c->d_compact, c->d_compact_n); c->launches++; }
+  CK(cudaDeviceSynchronize());
+  *d_entries = c->d_compact;
+  return n;
+}
+
+__global__ void k_merge(const WeLabelEntry* __restrict__ src, int n, WeLabelEntry* __restrict__ table,
+                        unsigned int mask, WeDiag* diag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const WeLabelEntry& e = src[i];
+  unsigned int s = (unsigned int)e.hash & mask;
+  bool won = false;
+  for (unsigned int probe = 0; probe <= mask; ++probe) {
+    const unsigned long long old = atomicCAS(&table[s].hash, 0ULL, e.hash);
+    if (old == 0ULL) { won = true; break; }
+    if (old == e.hash) break;
+    s = (s + 1) & mask;
+  }
+  WeLabelEntry* t = table + s;
+  const unsigned long long old2 = atomicCAS(&t->hash2, 0ULL, e.hash2);
+  if (old2 != 0ULL && old2 != e.hash2) { we_set_error(diag, 5, -1, -1); return; }
+  if (won) {
+    t->nearest_resid = e.nearest_resid; t->nearest_resname_id = e.nearest_resname_id;
+    t->n_labels = e.n_labels; t->n_w = e.n_w;
+    for (int k = 0; k < 32; ++k) t->labels[k] = e.labels[k];
+    atomicAdd(&diag->table_entries, 1ULL);
+  }
+  atomicAdd(&t->shell_count, e.shell_count);
+  atomicMax(&t->first_seen_inv, e.first_seen_inv);
+  for (int k = 0; k < WE_MAX_NBR; ++k) {
+    if (e.donates[k]) atomicAdd(&t->donates[k], e.donates[k]);
+    if (e.accepts[k]) atomicAdd(&t->accepts[k], e.accepts[k]);
+  }
+}
+
+extern "C" int we_merge_label_entries(we_ctx* c, const void* d_entries, int32_t n) {
+  if (!c || (!d_entries && n > 0)) return fail(WE_ERR_INVALID, "null argument");
+  if (n <= 0) return WE_OK;
+  CK(cudaSetDevice(c->device));
+  const int have = we_n_label_entries(c);
+  if (have < 0) return have;
+  int rc = grow_table_to(c, (unsigned long long)have + (unsigned long long)n + 1024);
+  if (rc) return rc;
+  k_merge<<<(n + 127) / 128, 128, 0, c->s_comp>>>((const WeLabelEntry*)d_entries, n, c->d_table, c->table_mask, c->d_diag);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->s_comp));
+  return WE_OK;
 }
 
 extern "C" int we_frame_record_count(we_ctx* c, int64_t k) {

@@ -41,24 +41,23 @@ def shard_frames(indices, rank, world_size):
 
 
 def merge_label_entries(entry_arrays):
-    """Merge structured label-entry arrays (one per rank) by (hash, hash2)."""
-    allv = np.concatenate([e for e in entry_arrays if len(e)]) if any(len(e) for e in entry_arrays) else None
-    if allv is None:
+    """Merge structured label-entry arrays (one per rank) by their 128-bit key (hash, hash2):
+    counts add, `first_seen_inv` takes the maximum (= earliest first appearance), the key
+    fields come from any member of the group.  Vectorised (sort + reduceat)."""
+    parts = [e for e in entry_arrays if len(e)]
+    if not parts:
         return entry_arrays[0][:0]
-    keys = np.stack([allv["hash"], allv["hash2"]], axis=1)
-    uniq, inv = np.unique(keys, axis=0, return_inverse=True)
-    inv = inv.reshape(-1)
-    out = np.zeros(len(uniq), dtype=allv.dtype)
-    first = np.full(len(uniq), -1, dtype=np.int64)
-    for i, g in enumerate(inv):
-        if first[g] < 0:
-            first[g] = i
-            out[g] = allv[i]
-        else:
-            out[g]["shell_count"] += allv[i]["shell_count"]
-            out[g]["donates"] += allv[i]["donates"]
-            out[g]["accepts"] += allv[i]["accepts"]
-            out[g]["first_seen_inv"] = max(out[g]["first_seen_inv"], allv[i]["first_seen_inv"])
+    allv = np.concatenate(parts)
+    order = np.lexsort((allv["hash2"], allv["hash"]))
+    allv = allv[order]
+    new = np.ones(len(allv), dtype=bool)
+    new[1:] = (allv["hash"][1:] != allv["hash"][:-1]) | (allv["hash2"][1:] != allv["hash2"][:-1])
+    starts = np.nonzero(new)[0]
+    out = allv[starts].copy()
+    out["shell_count"] = np.add.reduceat(allv["shell_count"], starts)
+    out["donates"] = np.add.reduceat(allv["donates"], starts, axis=0)
+    out["accepts"] = np.add.reduceat(allv["accepts"], starts, axis=0)
+    out["first_seen_inv"] = np.maximum.reduceat(allv["first_seen_inv"], starts)
     return out
 
 
@@ -125,12 +124,41 @@ def allgather_entries(entries):
     return [o.cpu().numpy().view(entries.dtype)[:k] for o, k in zip(outs, sizes)]
 
 
+def merge_labels_nccl(eng):
+    """Job-wide label table on every rank, merged on the device: all-gather of the compacted
+    entries over NCCL, then `we_merge_label_entries` folds the other ranks' entries into this
+    rank's table.  Returns the merged entries (host structured array)."""
+    import torch
+    import torch.distributed as dist
+
+    ws, rank = dist.get_world_size(), dist.get_rank()
+    dev = torch.device("cuda", eng.device)
+    ptr, n = eng.label_entries_device()
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(ws)]
+    dist.all_gather(sizes, torch.tensor([n], dtype=torch.int64, device=dev))
+    sizes = [int(x.item()) for x in sizes]
+    cap = max(max(sizes), 1)
+    mine = torch.zeros(cap * 512, dtype=torch.uint8, device=dev)
+    if n:
+        mine[: n * 512].copy_(_device_tensor(ptr, n * 512, np.uint8, eng.device))
+    outs = [torch.empty_like(mine) for _ in range(ws)]
+    dist.all_gather(outs, mine)
+    torch.cuda.synchronize(dev)
+    for r in range(ws):
+        if r != rank and sizes[r]:
+            eng.merge_label_entries_device(outs[r].data_ptr(), sizes[r])
+    return eng.label_entries()
+
+
 def combine(eng):
     """(CovarianceCollection, HBLabelCollection, frame_solvent_indices) of the whole job."""
     import torch.distributed as dist
 
     tables = allreduce_cov(eng)
-    merged = merge_label_entries(allgather_entries(eng.label_entries()))
+    if dist.get_backend() == "nccl":
+        merged = merge_labels_nccl(eng)
+    else:
+        merged = merge_label_entries(allgather_entries(eng.label_entries()))
     fsi_local = {k: {a: dict(b) for a, b in v.items()} for k, v in eng.frame_solvent_indices().items()}
     gathered = [None] * dist.get_world_size()
     dist.all_gather_object(gathered, fsi_local)

@@ -196,6 +196,15 @@ class WaterEntropyEngine:
         got = _lib.check(self.lib.we_copy_label_entries(self._ctx, out.ctypes.data, len(out)))
         return out[:got]
 
+    def label_entries_device(self):
+        """(device pointer, count) of this rank's compacted label entries (512 B each)."""
+        p = C.c_void_p()
+        n = _lib.check(self.lib.we_label_entries_device(self._ctx, C.byref(p)))
+        return p.value, n
+
+    def merge_label_entries_device(self, ptr, n):
+        _lib.check(self.lib.we_merge_label_entries(self._ctx, ptr, n))
+
     def frame_records(self, k):
         n = _lib.check(self.lib.we_frame_record_count(self._ctx, k))
         out = np.zeros((max(n, 1), 2), dtype=np.int32)
