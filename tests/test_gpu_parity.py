@@ -437,3 +437,97 @@ def test_device_merge_of_label_entries_equals_single_pass():
     assert gio.plain(a.hb_labels().resid_labelled_shell_counts) == gio.plain(c.hb_labels().resid_labelled_shell_counts)
     for e in (a, b, c):
         e.close()
+
+
+# ------------------------------------------------ BASELINE.json configurations at full size
+def test_c2_full_size_bulk_vs_oracle():
+    """C2 (pure TIP3P, 10k waters): two frames of the bulk recipe against the full CPU oracle."""
+    from waterentropy_b200 import synthetic
+    from waterentropy_b200.engine import WaterEntropyEngine
+
+    s = synthetic.make_config("C2")
+    assert s.n_waters == 10_000
+    P, Fr, D = s.frames(0, 2)
+    eng = WaterEntropyEngine(s, "bulk", device=0)
+    eng.submit(P, Fr, D, [0, 1])
+    eng.sync()
+    top = wo.OracleTopology(s.masses, s.charges, s.resids, s.resnames, s.types, s.bonds)
+    cov, lab = wo.bulk_run(top, P, Fr, D, [0, 1])
+    got = eng.hb_labels()
+    assert gio.plain(got.labelled_shell_counts) == gio.plain(lab.labelled_shell_counts)
+    mine = eng.covariances()
+    k = ("WAT", "WAT")
+    assert mine.counts[k] == cov.counts[k]
+    assert np.allclose(np.diag(mine.forces[k]), np.diag(cov.forces[k]), rtol=RTOL)
+    assert np.allclose(np.diag(mine.torques[k]), np.diag(cov.torques[k]), rtol=RTOL)
+    d = eng.diag()
+    assert d["ambiguous_rad"] == 0 and d["ambiguous_hb"] == 0
+    eng.close()
+
+
+def test_c4_full_size_properties_and_sampled_oracle():
+    """C4 (100k waters, 314k atoms, triclinic): one frame.  Shells / acceptors of 1,500 random centres
+    against the oracle, plus size-independent invariants of the whole frame."""
+    from waterentropy_b200 import synthetic
+    from waterentropy_b200.engine import WaterEntropyEngine
+
+    s = synthetic.make_config("C4")
+    assert s.n_waters == 100_000
+    P, Fr, D = s.frames(3, 1)
+    top = wo.OracleTopology(s.masses, s.charges, s.resids, s.resnames, s.types, s.bonds)
+    dbg = WaterEntropyEngine(s, "interfacial", device=0, keep_debug=True, chunk_frames=1)
+    dbg.submit(P, Fr, D, [3])
+    dbg.sync()
+    rng = np.random.default_rng(5)
+    centres = np.sort(rng.choice(top.heavy_idx, size=1500, replace=False))
+    r = wo.rad_frame(top, P[0], D[0], centres=centres)
+    slots = top.heavy_slot[centres]
+    sn, si = dbg.debug(0, "shell_n"), dbg.debug(0, "shell_idx")
+    nd = dbg.debug(0, "nbr_dist")
+    assert np.array_equal(sn[slots], r["shell_n"])
+    valid = np.arange(25)[None, :] < r["shell_n"][:, None]
+    assert np.array_equal(np.where(valid, si[slots], -1), r["shell_idx"])
+    assert np.array_equal(nd[slots], r["nbr_dist"])  # bit-exact fp64 distances, triclinic
+    assert np.array_equal(dbg.debug(0, "flags")[slots] & 1, r["gate"])
+    # the production path (needed-set work lists, lazy forces) gives the same tables as the
+    # all-centres debug path
+    prod = WaterEntropyEngine(s, "interfacial", device=0)
+    prod.submit(P, Fr, D, [3])
+    prod.sync()
+    ea, eb = dbg.label_entries(), prod.label_entries()
+    ea, eb = ea[np.lexsort((ea["hash2"], ea["hash"]))], eb[np.lexsort((eb["hash2"], eb["hash"]))]
+    for field in ("hash", "hash2", "shell_count", "donates", "accepts", "n_w"):
+        assert np.array_equal(ea[field], eb[field]), field
+    rec = prod.frame_records(0)
+    assert np.array_equal(rec, dbg.frame_records(0))
+    assert len(rec) > 500 and np.all(np.diff(rec[:, 0]) > 0)            # ascending, unique waters
+    assert int(eb["shell_count"].sum()) == len(rec)                        # every recorded water counted once
+    sa, ca = dbg.cov_tables()
+    sb, cb = prod.cov_tables()
+    assert int(cb.sum()) == len(rec) and np.array_equal(ca, cb)
+    assert np.allclose(sa, sb, rtol=1e-12, atol=0)
+    assert np.all(top.is_water[rec[:, 0]] == 1) and np.all(top.is_water[rec[:, 1]] == 0)
+    # donated labels: at most two per water; accepted: bounded by shell size x 4 donors
+    assert int(eb["donates"].sum()) <= 2 * len(rec)
+    for e in (dbg, prod):
+        assert e.diag()["ambiguous_rad"] == 0
+        e.close()
+
+
+def test_cli_prints_reference_tables(monkeypatch, capsys):
+    """`waterEntropy` console entry: same flags and printed tables as cli/runWaterEntropy.py:24-54."""
+    from waterentropy_b200.cli import runWaterEntropy as cli
+    from waterentropy_b200.io import Universe
+
+    inp = gio.load_inputs("arginine")
+    u = Universe.from_arrays(inp["names"], inp["types"], inp["resnames"], inp["resids"], inp["masses"],
+                             inp["charges"], inp["bonds"], inp["positions"], inp["forces"], inp["dimensions"])
+    monkeypatch.setattr(cli, "load_universe", lambda top, crd: u)
+    args = cli.build_parser().parse_args(["-top", "system.prmtop", "-crd", "system.nc", "-s", "0", "-e", "4", "-dt", "2"])
+    cli.run_waterEntropy(args)
+    out = capsys.readouterr().out
+    assert "Number of frames analysed: 2" in out
+    assert "resid resname Sor count N_c N_w Nc_eff pbias Sor_Nc Sor_Nw" in out
+    assert "1 ACE 2.2474 13 6.4679 5.2571 2.9595 0.1077 10.6703 8.1831" in out   # test_interfacial_solvent.py:62-73
+    assert "resid resname solvent_name Strans Srot Svib counts" in out
+    assert "1 ACE WAT 50.6287 23.7537 74.3825 13" in out                          # :141-146
