@@ -80,7 +80,7 @@ typedef struct we_options {
     int32_t keep_debug;      /* 1: keep all-centre shells / neighbours / acceptors / F,T of every frame */
     float search_radius;     /* first-pass candidate radius in A (0 = 6.6) */
     float max_box;           /* largest box edge expected in A (0 = take from first frame x 1.25) */
-    int32_t force_upload;    /* we_submit: 0 auto, 1 whole frames, 2 only the recorded waters' forces
+    int32_t force_upload;    /* we_submit: 0/1 whole frames (default), 2 only the recorded waters' forces
                                 (gathered on the host from the record lists one batch later) */
 } we_options;
 

@@ -364,14 +364,15 @@ def test_empty_submit_and_reset():
 
 
 def test_chunking_and_device_resident_inputs_agree():
-    """Same frames through 1-frame chunks, one big chunk, and device-resident buffers."""
+    """Same frames through 1-frame chunks, one big chunk, device-resident buffers, and the lazy
+    force upload (only the recorded waters' forces cross PCIe)."""
     import torch
 
     inp = gio.load_inputs("synth_tric")
     F = inp["positions"].shape[0]
     outs = []
-    for mode in ("chunk1", "chunkall", "device"):
-        eng = _engine(inp, chunk_frames=1 if mode == "chunk1" else 8)
+    for mode in ("chunk1", "chunkall", "device", "lazy"):
+        eng = _engine(inp, chunk_frames=1 if mode in ("chunk1", "lazy") else 8, force_upload=2 if mode == "lazy" else 0)
         if mode == "device":
             dp = torch.from_numpy(inp["positions"]).cuda()
             df = torch.from_numpy(inp["forces"]).cuda()

@@ -445,10 +445,12 @@ static int ensure_workspace(we_ctx* c, const float* dims0, bool need_input_buffe
   int rc = 0;
   const size_t F = (size_t)chunk;
 #define AL(p, n) if ((rc = dev_alloc(c, &c->p, (n)))) return rc;
-  // forces of recorded waters only (lazy) when frames come from the host, the recipe records a
-  // minority of the waters (interfacial) and nothing else needs whole-frame forces
+  // optional (force_upload = 2): upload only the forces of the recorded waters, gathered by the
+  // host one batch later.  Halves PCIe traffic, but puts host-side gathers on the critical path;
+  // measured on this pool it is within 5 % of the whole-frame upload and much more sensitive to
+  // a busy host, so whole frames (copy engine only, no CPU touch) are the default.
   c->lazy = need_input_buffers && !c->opt.keep_debug && c->maxfrag > 0 && c->maxfrag <= 8 &&
-            (c->opt.force_upload == 2 || (c->opt.force_upload == 0 && c->recipe == WE_RECIPE_INTERFACIAL));
+            c->opt.force_upload == 2;
   if (need_input_buffers) {
     for (int i = 0; i < 2; ++i) {
       AL(d_pos[i], F * N * 3)
@@ -674,7 +676,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       k_scan<<<n, 1024, 0, st>>>(bx, c->d_cell_count, c->ncap);
       ps.stop(st); }
     { ProfScope ps(c, WE_K_SCATTER, st);
-      k_scatter<<<gH, 256, 0, st>>>(H, c->d_cell_count, c->d_cell_of, c->d_rank_of, c->d_tmp4, c->d_sorted4, c->ncap);
+      k_scatter<<<gH, 256, 0, st>>>(H, bx, c->d_cell_count, c->d_cell_of, c->d_rank_of, c->d_tmp4, c->d_sorted4, c->ncap);
       ps.stop(st); }
     c->launches += 3;
     // pass-0 centres: every heavy atom (debug), solute united atoms (interfacial), waters (bulk)
@@ -694,7 +696,8 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
         ps.stop(st); }
       { ProfScope ps(c, WE_K_RAD, st);
         k_rad<<<rad_grid((long long)w0.static_count * n), WE_RAD_WARPS * 32, sizeof(WeRadSmem), st>>>(
-            c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->ncap, c->cell_target, w0, n, ro, c->d_diag);
+            c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->d_tmp4, c->ncap, c->cell_target, w0, n, ro,
+            (interfacial && !c->opt.keep_debug) ? c->d_state : nullptr, c->d_diag);
         ps.stop(st); }
       c->launches += 2;
     }
@@ -706,7 +709,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       WeWork w1{c->d_wl1, c->d_n1, C, 0};
       { ProfScope ps(c, WE_K_RAD1, st);
         k_rad<<<rad_grid((long long)C * n), WE_RAD_WARPS * 32, sizeof(WeRadSmem), st>>>(
-            c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->ncap, c->cell_target, w1, n, ro, c->d_diag);
+            c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->d_tmp4, c->ncap, c->cell_target, w1, n, ro, nullptr, c->d_diag);
         ps.stop(st); }
       { ProfScope ps(c, WE_K_MARK, st);
         k_mark<<<dim3((C + 127) / 128, n), 128, 0, st>>>(c->T, c->d_shell_n, c->d_shell_idx, c->d_flags, c->d_wl1, c->d_n1, c->d_state, c->d_wl2, c->d_n2, c->d_hbq, c->d_wlh, c->d_nh);
@@ -714,7 +717,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       WeWork w2{c->d_wl2, c->d_n2, H, 0};
       { ProfScope ps(c, WE_K_RAD2, st);
         k_rad<<<rad_grid((long long)H * n), WE_RAD_WARPS * 32, sizeof(WeRadSmem), st>>>(
-            c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->ncap, c->cell_target, w2, n, ro, c->d_diag);
+            c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->d_tmp4, c->ncap, c->cell_target, w2, n, ro, nullptr, c->d_diag);
         ps.stop(st); }
       c->launches += 4;
     } else if (!interfacial && C > 0) {

@@ -125,7 +125,7 @@ __global__ void k_bin(WeTopoDev T, const float* __restrict__ pos, const WeBox* _
   c0 = max(c0, 0); c1 = max(c1, 0); c2 = max(c2, 0);
   int cell = (c2 * b.nc[1] + c1) * b.nc[0] + c0;
   size_t o = (size_t)f * T.n_heavy + h;
-  cell_of[o] = cell;
+  cell_of[o] = (c2 << 20) | (c1 << 10) | c0;  // packed coordinates (<= 1023 cells per axis)
   rank_of[o] = atomicAdd(&cell_count[(size_t)f * (ncap + 1) + cell], 1);
   tmp4[o] = make_float4(q[0], q[1], q[2], __int_as_float(atom));
 }
@@ -170,14 +170,16 @@ __global__ void k_scan(const WeBox* __restrict__ boxes, int* __restrict__ cell_c
   }
 }
 
-__global__ void k_scatter(int n_heavy, const int* __restrict__ cell_start,
+__global__ void k_scatter(int n_heavy, const WeBox* __restrict__ boxes, const int* __restrict__ cell_start,
                           const int* __restrict__ cell_of, const int* __restrict__ rank_of,
                           const float4* __restrict__ tmp4, float4* __restrict__ sorted4, int ncap) {
   int h = blockIdx.x * blockDim.x + threadIdx.x;
   int f = blockIdx.y;
   if (h >= n_heavy) return;
   size_t o = (size_t)f * n_heavy + h;
-  int dst = cell_start[(size_t)f * (ncap + 1) + cell_of[o]] + rank_of[o];
+  const int pc = cell_of[o];
+  const int cell = ((pc >> 20) * boxes[f].nc[1] + ((pc >> 10) & 1023)) * boxes[f].nc[0] + (pc & 1023);
+  int dst = cell_start[(size_t)f * (ncap + 1) + cell] + rank_of[o];
   sorted4[(size_t)f * n_heavy + dst] = tmp4[o];
 }
 
@@ -397,19 +399,21 @@ struct WeRadOut {
 __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __restrict__ fpos,
                                            const WeBox& b, const int* __restrict__ cstart,
                                            const int* __restrict__ cell_of_f,
-                                           const float4* __restrict__ sorted, float search_radius,
-                                           int f, int h, const WeRadOut& O, WeDiag* diag,
-                                           WeRadSmem& S, const WePowTables& PT, int lane, int w) {
+                                           const float4* __restrict__ sorted,
+                                           const float4* __restrict__ tmp4_f, float search_radius,
+                                           int f, int h, const WeRadOut& O, int* gate_only_state,
+                                           WeDiag* diag, WeRadSmem& S, const WePowTables& PT, int lane,
+                                           int w) {
   const int my_atom = T.heavy_idx[h];
-  // raw coordinates (angles, duplicate test) and distance coordinates
+  // raw coordinates (angles, duplicate test) and distance coordinates (k_bin wrapped them already)
   const float rx = fpos[3 * my_atom], ry = fpos[3 * my_atom + 1], rz = fpos[3 * my_atom + 2];
-  float mq[3] = {rx, ry, rz};
-  if (b.triclinic) we_wrap_tric(rx, ry, rz, b.m, b.wfac, mq);
+  const float4 mq4 = tmp4_f[h];
+  const float mq[3] = {mq4.x, mq4.y, mq4.z};
   int ex[WE_MAX_EXCL];
 #pragma unroll
   for (int e = 0; e < WE_MAX_EXCL; ++e) ex[e] = T.excl[(size_t)h * WE_MAX_EXCL + e];
   const int cell = cell_of_f[h];
-  const int c0 = cell % b.nc[0], c1 = (cell / b.nc[0]) % b.nc[1], c2 = cell / (b.nc[0] * b.nc[1]);
+  const int c0 = cell & 1023, c1 = (cell >> 10) & 1023, c2 = cell >> 20;
   double* sd = S.d[w];
   float* sf = S.f[w];
   int* si = S.idx[w];
@@ -478,6 +482,18 @@ __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __re
     }
   }
   __syncwarp();
+  // ---- solute atoms without a water among their 20 nearest candidates need no RAD shell
+  // (recipes/interfacial_solvent.py:50-56).  Their state goes back to "not computed", so
+  // that k_mark queues them again should an interfacial water hold them in its shell.
+  if (gate_only_state) {
+    bool wat0 = false;
+    if (lane < min(n25, WE_GATE_NBR)) wat0 = T.is_water[si[S.top[w][lane]]] != 0;
+    if (!__any_sync(0xffffffffu, wat0)) {
+      if (lane == 0) { O.shell_n[ho] = 0; O.nn[ho] = -1; O.flags[ho] = 0; gate_only_state[ho] = 0; }
+      __syncwarp();
+      return;
+    }
+  }
   // ---- per-candidate precomputation ------------------------------------------
   const float half[3] = {0.5f * b.box[0], 0.5f * b.box[1], 0.5f * b.box[2]};
   const bool act = lane < n25;
@@ -555,8 +571,8 @@ __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __re
 __global__ void __launch_bounds__(WE_RAD_WARPS * 32, WE_RAD_MINBLOCKS)
 k_rad(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes,
       const int* __restrict__ cell_start, const int* __restrict__ cell_of,
-      const float4* __restrict__ sorted4, int ncap, float search_radius, WeWork work,
-      int n_frames, WeRadOut O, WeDiag* diag) {
+      const float4* __restrict__ sorted4, const float4* __restrict__ tmp4, int ncap,
+      float search_radius, WeWork work, int n_frames, WeRadOut O, int* gate_only_state, WeDiag* diag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WeRadSmem& S = *reinterpret_cast<WeRadSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -572,8 +588,9 @@ k_rad(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxe
     const float4* sorted = sorted4 + (size_t)f * T.n_heavy;
     const float* fpos = pos + (size_t)f * T.n_atoms * 3;
     const int* cof = cell_of + (size_t)f * T.n_heavy;
+    const float4* t4 = tmp4 + (size_t)f * T.n_heavy;
     for (int i = blockIdx.x * WE_RAD_WARPS + w; i < cnt; i += stride)
-      we_rad_one(T, fpos, b, cstart, cof, sorted, search_radius, f, list[i], O, diag, S, PT, lane, w);
+      we_rad_one(T, fpos, b, cstart, cof, sorted, t4, search_radius, f, list[i], O, gate_only_state, diag, S, PT, lane, w);
   }
 }
 
