@@ -532,3 +532,53 @@ def test_cli_prints_reference_tables(monkeypatch, capsys):
     assert "1 ACE 2.2474 13 6.4679 5.2571 2.9595 0.1077 10.6703 8.1831" in out   # test_interfacial_solvent.py:62-73
     assert "resid resname solvent_name Strans Srot Svib counts" in out
     assert "1 ACE WAT 50.6287 23.7537 74.3825 13" in out                          # :141-146
+
+
+@pytest.mark.parametrize("name,n_sample", [("C3", 1200), ("C5", 800)])
+def test_other_baseline_configs_full_size(name, n_sample):
+    """C3 (30k waters, orthorhombic) and C5 (300k waters, 1M atoms): one frame at full size.
+    Sampled centres against the oracle (bit-exact), production path == all-centres debug path."""
+    from waterentropy_b200 import synthetic
+    from waterentropy_b200.engine import WaterEntropyEngine
+
+    s = synthetic.make_config(name)
+    P, Fr, D = s.frames(1, 1)
+    top = wo.OracleTopology(s.masses, s.charges, s.resids, s.resnames, s.types, s.bonds)
+    dbg = WaterEntropyEngine(s, "interfacial", device=0, keep_debug=True, chunk_frames=1)
+    dbg.submit(P, Fr, D, [1])
+    dbg.sync()
+    rng = np.random.default_rng(9)
+    # half of the sample near the solute (where shells are mixed), half anywhere
+    near = top.solute_UAs[rng.choice(len(top.solute_UAs), size=n_sample // 2, replace=False)]
+    anyw = rng.choice(top.heavy_idx, size=n_sample // 2, replace=False)
+    centres = np.unique(np.concatenate([near, anyw]))
+    r = wo.rad_frame(top, P[0], D[0], centres=centres)
+    slots = top.heavy_slot[centres]
+    sn, si = dbg.debug(0, "shell_n"), dbg.debug(0, "shell_idx")
+    assert np.array_equal(sn[slots], r["shell_n"])
+    valid = np.arange(25)[None, :] < r["shell_n"][:, None]
+    assert np.array_equal(np.where(valid, si[slots], -1), r["shell_idx"])
+    assert np.array_equal(dbg.debug(0, "nbr_dist")[slots], r["nbr_dist"])
+    # HB acceptors of the sampled centres' donors
+    don_x = np.zeros(dbg.lib.we_n_donors(dbg._ctx), dtype=np.int32)
+    don_h = np.zeros_like(don_x)
+    dbg.lib.we_copy_donors(dbg._ctx, _p(don_x), _p(don_h))
+    sel = np.nonzero(np.isin(don_x, centres))[0]
+    row = np.searchsorted(centres, don_x[sel])
+    acc, st = wo.hb_frame(top, P[0], D[0], don_x[sel], don_h[sel], r["shell_n"][row], r["shell_idx"][row])
+    assert np.array_equal(dbg.debug(0, "acceptor")[sel], acc)
+    prod = WaterEntropyEngine(s, "interfacial", device=0)
+    prod.submit(P, Fr, D, [1])
+    prod.sync()
+    ea, eb = dbg.label_entries(), prod.label_entries()
+    ea, eb = ea[np.lexsort((ea["hash2"], ea["hash"]))], eb[np.lexsort((eb["hash2"], eb["hash"]))]
+    for field in ("hash", "hash2", "shell_count", "donates", "accepts", "n_w"):
+        assert np.array_equal(ea[field], eb[field]), field
+    assert np.array_equal(prod.frame_records(0), dbg.frame_records(0))
+    (sa, ca), (sb, cb) = dbg.cov_tables(), prod.cov_tables()
+    assert np.array_equal(ca, cb) and np.allclose(sa, sb, rtol=1e-12, atol=0)
+    assert int(cb.sum()) == len(prod.frame_records(0)) == int(eb["shell_count"].sum())
+    for e in (dbg, prod):
+        d = e.diag()
+        assert d["ambiguous_rad"] == 0 and d["ambiguous_hb"] == 0
+        e.close()
