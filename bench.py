@@ -287,33 +287,46 @@ def run_ours(args, rank, world, local_rank):
     hP, hF = torch.from_numpy(P).pin_memory(), torch.from_numpy(Fr).pin_memory()
     d2h = 0
 
-    def e2e_step():
-        """one batch through the host API: H2D from pinned memory, kernels, this batch's results back
-        on the host (covariance table + recorded-water lists; cross-rank all-reduce when N > 1)"""
+    def read_step(ticket, k0):
+        """host read of one finished step: its covariance snapshot + its recorded-water lists"""
         nonlocal d2h
-        eng.submit(hP, hF, D, ids)
-        eng.sync()
-        tables = wdist.allreduce_cov(eng) if world > 1 else eng.cov_tables()
-        k0 = len(eng.frame_ids) - Fps
+        tables = eng.wait_cov(ticket)
         nrec = sum(len(eng.frame_records(k0 + k)) for k in range(Fps))
         d2h = tables[0].nbytes + tables[1].nbytes + Fps * 4 + nrec * 8
         return nrec
 
+    def e2e_steps(k_steps):
+        """K steps through the host API.  Every step copies its frames host -> device from pinned
+        memory and its result (stream-ordered covariance snapshot + recorded-water lists) is read
+        back on the host; the read of step k overlaps the kernels of step k+1, as in a real run
+        that streams a long trajectory."""
+        prev, nrec = None, 0
+        for _ in range(k_steps):
+            k0 = len(eng.frame_ids)
+            eng.submit(hP, hF, D, ids)
+            ticket = eng.snapshot_cov()
+            if prev is not None:
+                nrec = read_step(*prev)
+            prev = (ticket, k0)
+        eng.sync()  # drains the last batches' recorded-water lists
+        if prev is not None:
+            nrec = read_step(*prev)
+        return nrec
+
     def e2e_finalize():
-        """end of job, inside the timed region: the label count table (and its cross-rank merge)"""
+        """end of job, inside the timed region: the cross-rank combine (one NCCL all-reduce of the
+        covariance tables, all-gather + device merge of the label entries) and the label table read"""
         if world > 1:
+            wdist.allreduce_cov(eng)
             return wdist.merge_labels_nccl(eng)
         return eng.label_entries()
 
-    for _ in range(args.warmup):
-        e2e_step()
+    e2e_steps(args.warmup)
     e2e_finalize()
     eng.reset()  # the warm-up merge folded the other ranks' tables into this one
     barrier()
     t0 = time.perf_counter()
-    nrec = 0
-    for _ in range(args.steps):
-        nrec = e2e_step()
+    nrec = e2e_steps(args.steps)
     entries = e2e_finalize()
     barrier()
     e2e_s = maxr(time.perf_counter() - t0)
@@ -346,8 +359,8 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(input_bytes + Fps * 32),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s / args.steps * 1e3,
                     "d2h_bytes_at_end_of_job": final_bytes,
-                    "timed": "K x (submit from pinned host memory + sync + covariance table + recorded-water "
-                             "lists on the host) + one label-table read at the end of the job"},
+                    "timed": "K x (submit from pinned host memory; stream-ordered covariance snapshot + recorded-water "
+                             "lists read on the host, overlapping the next step) + end-of-job combine and label-table read"},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
@@ -369,7 +382,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=512, help="centres per core per step of the CPU arm")
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--force-upload", type=int, default=0, help="e2e arm: 0 auto, 1 whole frames, 2 recorded waters only")
+    ap.add_argument("--force-upload", type=int, default=0, help="e2e arm: 0 auto, 1 whole frames, 2 host gather, 3 zero-copy")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -80,8 +80,10 @@ typedef struct we_options {
     int32_t keep_debug;      /* 1: keep all-centre shells / neighbours / acceptors / F,T of every frame */
     float search_radius;     /* first-pass candidate radius in A (0 = 6.6) */
     float max_box;           /* largest box edge expected in A (0 = take from first frame x 1.25) */
-    int32_t force_upload;    /* we_submit: 0/1 whole frames (default), 2 only the recorded waters' forces
-                                (gathered on the host from the record lists one batch later) */
+    int32_t force_upload;    /* we_submit, how forces reach k_cov: 0 auto (zero-copy for the interfacial recipe
+                                when the buffer is pinned, else whole frames), 1 whole frames, 2 recorded
+                                waters only, gathered by the host one batch later, 3 zero-copy: k_cov reads
+                                the recorded waters' forces straight from pinned host memory */
 } we_options;
 
 typedef struct we_ctx we_ctx;
@@ -137,6 +139,12 @@ int we_error_location(we_ctx *ctx, int64_t *frame_id, int32_t *atom);
  *   n_bins = n_pair_bins * n_classes (interfacial) or n_classes (bulk). */
 int we_n_bins(we_ctx *ctx);
 int we_copy_cov(we_ctx *ctx, double *cov_sum, uint64_t *cov_cnt);
+/* Stream-ordered snapshot of the covariance tables: `we_snapshot_cov` enqueues a copy into pinned
+ * memory behind everything submitted so far and returns a ticket (>= 0) without waiting;
+ * `we_wait_cov` waits for that copy only, so later batches keep running while the host reads the
+ * result of an earlier one (4 snapshots may be outstanding). */
+int we_snapshot_cov(we_ctx *ctx);
+int we_wait_cov(we_ctx *ctx, int32_t ticket, double *cov_sum, uint64_t *cov_cnt);
 /* device pointers of the same tables, for an NCCL all-reduce across ranks
  * (replaces CovarianceCollection.merge, entropy/convariances.py:86-108) */
 int we_device_tables(we_ctx *ctx, void **d_cov_sum, void **d_cov_cnt);

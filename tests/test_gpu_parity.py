@@ -364,16 +364,21 @@ def test_empty_submit_and_reset():
 
 
 def test_chunking_and_device_resident_inputs_agree():
-    """Same frames through 1-frame chunks, one big chunk, device-resident buffers, and the lazy
-    force upload (only the recorded waters' forces cross PCIe)."""
+    """Same frames through 1-frame chunks, one big chunk, device-resident buffers, the lazy force
+    upload and zero-copy forces (only the recorded waters' forces cross PCIe)."""
     import torch
 
     inp = gio.load_inputs("synth_tric")
     F = inp["positions"].shape[0]
     outs = []
-    for mode in ("chunk1", "chunkall", "device", "lazy"):
-        eng = _engine(inp, chunk_frames=1 if mode in ("chunk1", "lazy") else 8, force_upload=2 if mode == "lazy" else 0)
-        if mode == "device":
+    for mode in ("chunk1", "chunkall", "device", "lazy", "zerocopy"):
+        fu = {"lazy": 2, "zerocopy": 3}.get(mode, 1)
+        eng = _engine(inp, chunk_frames=1 if mode in ("chunk1", "lazy") else 8, force_upload=fu)
+        if mode == "zerocopy":
+            hp = torch.from_numpy(inp["positions"]).pin_memory()
+            hf = torch.from_numpy(inp["forces"]).pin_memory()
+            eng.submit(hp, hf, inp["dimensions"], list(range(F)))
+        elif mode == "device":
             dp = torch.from_numpy(inp["positions"]).cuda()
             df = torch.from_numpy(inp["forces"]).cuda()
             eng.submit_device(dp, df, inp["dimensions"], list(range(F)))
@@ -581,4 +586,29 @@ def test_other_baseline_configs_full_size(name, n_sample):
     for e in (dbg, prod):
         d = e.diag()
         assert d["ambiguous_rad"] == 0 and d["ambiguous_hb"] == 0
+        e.close()
+
+
+def test_cov_snapshots_are_stream_ordered():
+    """we_snapshot_cov / we_wait_cov: the snapshot taken after batch k holds exactly the sums of
+    batches 0..k even though later batches were already queued."""
+    inp = gio.load_inputs("arginine")
+    eng = _engine(inp, chunk_frames=2)
+    tickets = []
+    for f0 in (0, 4):
+        fr = list(range(f0, f0 + 4))
+        eng.submit(inp["positions"][fr], inp["forces"][fr], inp["dimensions"][fr], fr)
+        tickets.append(eng.snapshot_cov())
+    s0, c0 = eng.wait_cov(tickets[0])
+    s1, c1 = eng.wait_cov(tickets[1])
+    eng.sync()
+    sf, cf = eng.cov_tables()
+    ref = _engine(inp)
+    ref.submit(inp["positions"][:4], inp["forces"][:4], inp["dimensions"][:4], [0, 1, 2, 3])
+    ref.sync()
+    sr, cr = ref.cov_tables()
+    assert np.array_equal(c0, cr) and np.allclose(s0, sr, rtol=1e-12, atol=0)
+    assert np.array_equal(c1, cf) and np.allclose(s1, sf, rtol=1e-12, atol=0)
+    assert c1.sum() > c0.sum() > 0
+    for e in (eng, ref):
         e.close()

@@ -49,7 +49,7 @@ EXPORTS = [
     "we_n_heavy", "we_n_donors", "we_copy_heavy_idx", "we_copy_donors", "we_debug_size",
     "we_debug_copy", "we_reset", "we_test_angle_cos", "we_test_powf2", "we_test_distance",
     "we_profile", "we_kernel_times", "we_span_start", "we_span_stop",
-    "we_label_entries_device", "we_merge_label_entries",
+    "we_label_entries_device", "we_merge_label_entries", "we_snapshot_cov", "we_wait_cov",
 ]
 
 WE_ERR_DUPLICATE_COORD = -1
@@ -103,6 +103,10 @@ def load():
     L.we_device_tables.argtypes = [V, C.POINTER(V), C.POINTER(V)]
     L.we_copy_label_entries.restype = I
     L.we_copy_label_entries.argtypes = [V, V, I]
+    L.we_snapshot_cov.restype = I
+    L.we_snapshot_cov.argtypes = [V]
+    L.we_wait_cov.restype = I
+    L.we_wait_cov.argtypes = [V, I, V, V]
     L.we_label_entries_device.restype = I
     L.we_label_entries_device.argtypes = [V, C.POINTER(V)]
     L.we_merge_label_entries.restype = I

@@ -65,6 +65,10 @@ struct we_ctx {
   int* d_compact_n = nullptr;
   unsigned int table_mask = 0;
   WeDiag* h_diag = nullptr;            // pinned mirror refreshed after every batch
+  unsigned char* h_snap[4] = {nullptr, nullptr, nullptr, nullptr};  // pinned covariance snapshots
+  cudaEvent_t ev_snap[4]{};
+  cudaEvent_t ev_cov = nullptr;
+  long long snap_counter = 0;
   unsigned long long seen_entries = 0, max_new = 0;
   WeDiag* d_diag = nullptr;
   // workspace
@@ -416,12 +420,15 @@ extern "C" void we_destroy(we_ctx* c) {
   if (c->s_copy) cudaStreamDestroy(c->s_copy);
   if (c->s_comp) cudaStreamDestroy(c->s_comp);
   if (c->s_cov) cudaStreamDestroy(c->s_cov);
+  if (c->ev_cov) cudaEventDestroy(c->ev_cov);
   for (int i = 0; i < 2; ++i) {
     if (c->ev_in_ready[i]) cudaEventDestroy(c->ev_in_ready[i]);
     if (c->ev_in_free[i]) cudaEventDestroy(c->ev_in_free[i]);
     if (c->ev_out_ready[i]) cudaEventDestroy(c->ev_out_ready[i]);
     if (c->ev_label[i]) cudaEventDestroy(c->ev_label[i]);
     if (c->ev_f[i]) cudaEventDestroy(c->ev_f[i]);
+    if (c->ev_snap[i]) cudaEventDestroy(c->ev_snap[i]);
+    if (c->ev_snap[i + 2]) cudaEventDestroy(c->ev_snap[i + 2]);
   }
   delete c;
 }
@@ -452,10 +459,7 @@ static int ensure_workspace(we_ctx* c, const float* dims0, bool need_input_buffe
   c->lazy = need_input_buffers && !c->opt.keep_debug && c->maxfrag > 0 && c->maxfrag <= 8 &&
             c->opt.force_upload == 2;
   if (need_input_buffers) {
-    for (int i = 0; i < 2; ++i) {
-      AL(d_pos[i], F * N * 3)
-      if (!c->lazy) { AL(d_frc[i], F * N * 3) }
-    }
+    for (int i = 0; i < 2; ++i) { AL(d_pos[i], F * N * 3) }  // d_frc: allocated on first whole-frame upload
   }
   if (c->lazy) {
     const size_t cap = F * std::max(1, c->C) * (size_t)c->maxfrag * 3;
@@ -626,6 +630,25 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
   if (!on_device && !c->d_pos[0]) return fail(WE_ERR_INVALID, "context was first used with device buffers; create a new context for host frames");
   const int H = c->H, N = c->N, ND = c->ND, C = c->C, S = c->S;
   const size_t frame_floats = (size_t)N * 3;
+  // Forces are only read by k_cov, for the recorded waters (1-2 % of the atoms in the interfacial
+  // recipe).  If the caller's force buffer is pinned (UVA-mapped) the kernel reads exactly those
+  // atoms straight from host memory over PCIe and the whole-frame upload is skipped.
+  const float* frc_zero_copy = nullptr;
+  if (!on_device && !c->lazy && !c->opt.keep_debug &&
+      (c->opt.force_upload == 3 || (c->opt.force_upload == 0 && c->recipe == WE_RECIPE_INTERFACIAL))) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, frc) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+      frc_zero_copy = (const float*)at.devicePointer;
+    else
+      cudaGetLastError();
+    if (!frc_zero_copy && c->opt.force_upload == 3)
+      return fail(WE_ERR_INVALID, "force_upload = 3 needs the force buffer in pinned (page-locked) host memory");
+  }
+  if (!on_device && !c->lazy && !frc_zero_copy && !c->d_frc[0]) {
+    for (int i = 0; i < 2; ++i) {
+      if ((rc = dev_alloc(c, &c->d_frc[i], (size_t)c->chunk * N * 3))) return rc;
+    }
+  }
   for (int f0 = 0; f0 < n_frames; f0 += c->chunk) {
     const int n = std::min(c->chunk, n_frames - f0);
     const int buf = (int)(c->chunk_counter & 1);
@@ -644,10 +667,14 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     const float* df;
     if (!on_device) {
       CK(cudaMemcpyAsync(c->d_pos[buf], pos + (size_t)f0 * frame_floats, (size_t)n * frame_floats * sizeof(float), cudaMemcpyHostToDevice, c->s_copy));
-      if (!c->lazy)
-        CK(cudaMemcpyAsync(c->d_frc[buf], frc + (size_t)f0 * frame_floats, (size_t)n * frame_floats * sizeof(float), cudaMemcpyHostToDevice, c->s_copy));
       dp = c->d_pos[buf];
-      df = c->d_frc[buf];
+      if (frc_zero_copy) {
+        df = frc_zero_copy + (size_t)f0 * frame_floats;
+      } else {
+        if (!c->lazy)
+          CK(cudaMemcpyAsync(c->d_frc[buf], frc + (size_t)f0 * frame_floats, (size_t)n * frame_floats * sizeof(float), cudaMemcpyHostToDevice, c->s_copy));
+        df = c->d_frc[buf];
+      }
     } else {
       dp = pos + (size_t)f0 * frame_floats;
       df = frc + (size_t)f0 * frame_floats;
@@ -931,6 +958,41 @@ extern "C" int we_copy_cov(we_ctx* c, double* cov_sum, uint64_t* cov_cnt) {
   CK(cudaSetDevice(c->device));
   CK(cudaMemcpy(cov_sum, c->d_cov_sum, (size_t)c->B * 18 * sizeof(double), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(cov_cnt, c->d_cov_cnt, (size_t)c->B * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return WE_OK;
+}
+
+extern "C" int we_snapshot_cov(we_ctx* c) {
+  if (!c) return fail(WE_ERR_INVALID, "null context");
+  CK(cudaSetDevice(c->device));
+  int rc;
+  // lazy-upload batches still waiting for their covariance kernel must run it first
+  const int older = (int)(c->chunk_counter & 1);
+  if ((rc = finish_lazy(c, older))) return rc;
+  if ((rc = finish_lazy(c, older ^ 1))) return rc;
+  const int slot = (int)(c->snap_counter & 3);
+  const size_t bs = (size_t)c->B * 18 * sizeof(double), bc = (size_t)c->B * sizeof(unsigned long long);
+  if (!c->h_snap[slot]) {
+    if ((rc = pin_alloc(c, &c->h_snap[slot], bs + bc))) return rc;
+    CK(cudaEventCreateWithFlags(&c->ev_snap[slot], cudaEventDisableTiming));
+  }
+  if (!c->ev_cov) CK(cudaEventCreateWithFlags(&c->ev_cov, cudaEventDisableTiming));
+  CK(cudaEventRecord(c->ev_cov, c->s_cov));
+  CK(cudaStreamWaitEvent(c->s_comp, c->ev_cov, 0));
+  CK(cudaMemcpyAsync(c->h_snap[slot], c->d_cov_sum, bs, cudaMemcpyDeviceToHost, c->s_comp));
+  CK(cudaMemcpyAsync(c->h_snap[slot] + bs, c->d_cov_cnt, bc, cudaMemcpyDeviceToHost, c->s_comp));
+  CK(cudaEventRecord(c->ev_snap[slot], c->s_comp));
+  return (int)(c->snap_counter++ & 0x7fffffff);
+}
+
+extern "C" int we_wait_cov(we_ctx* c, int32_t ticket, double* cov_sum, uint64_t* cov_cnt) {
+  if (!c || !cov_sum || !cov_cnt) return fail(WE_ERR_INVALID, "null argument");
+  if (ticket < 0 || (long long)ticket >= c->snap_counter || (long long)ticket + 4 < c->snap_counter)
+    return fail(WE_ERR_INVALID, "snapshot ticket %d is not outstanding", ticket);
+  const int slot = ticket & 3;
+  CK(cudaEventSynchronize(c->ev_snap[slot]));
+  const size_t bs = (size_t)c->B * 18 * sizeof(double), bc = (size_t)c->B * sizeof(unsigned long long);
+  memcpy(cov_sum, c->h_snap[slot], bs);
+  memcpy(cov_cnt, c->h_snap[slot] + bs, bc);
   return WE_OK;
 }
 

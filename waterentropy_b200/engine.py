@@ -185,6 +185,18 @@ class WaterEntropyEngine:
         _lib.check(self.lib.we_copy_cov(self._ctx, s.ctypes.data, c.ctypes.data))
         return s, c
 
+    def snapshot_cov(self):
+        """Enqueue a stream-ordered copy of the covariance tables (state after everything submitted
+        so far); returns a ticket for `wait_cov`.  Does not wait."""
+        return _lib.check(self.lib.we_snapshot_cov(self._ctx))
+
+    def wait_cov(self, ticket):
+        nb = self.lib.we_n_bins(self._ctx)
+        s = np.zeros((nb, 2, 3, 3), dtype=np.float64)
+        c = np.zeros(nb, dtype=np.uint64)
+        _lib.check(self.lib.we_wait_cov(self._ctx, ticket, s.ctypes.data, c.ctypes.data))
+        return s, c
+
     def device_table_ptrs(self):
         a, b = C.c_void_p(), C.c_void_p()
         _lib.check(self.lib.we_device_tables(self._ctx, C.byref(a), C.byref(b)))
