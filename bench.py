@@ -318,7 +318,7 @@ def run_ours(args, rank, world, local_rank):
         covariance tables, all-gather + device merge of the label entries) and the label table read"""
         if world > 1:
             wdist.allreduce_cov(eng)
-            return wdist.merge_labels_nccl(eng)
+            return wdist.merge_labels_nccl(eng, root_only=True)
         return eng.label_entries()
 
     e2e_steps(args.warmup)

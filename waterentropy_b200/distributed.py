@@ -124,10 +124,11 @@ def allgather_entries(entries):
     return [o.cpu().numpy().view(entries.dtype)[:k] for o, k in zip(outs, sizes)]
 
 
-def merge_labels_nccl(eng):
-    """Job-wide label table on every rank, merged on the device: all-gather of the compacted
-    entries over NCCL, then `we_merge_label_entries` folds the other ranks' entries into this
-    rank's table.  Returns the merged entries (host structured array)."""
+def merge_labels_nccl(eng, root_only=False):
+    """Job-wide label table, merged on the device: all-gather of the compacted entries over NCCL,
+    then `we_merge_label_entries` folds the other ranks' entries into this rank's table.
+    Returns the merged entries (host structured array); with `root_only` only rank 0 merges and
+    downloads (the other ranks return their own entries)."""
     import torch
     import torch.distributed as dist
 
@@ -144,6 +145,8 @@ def merge_labels_nccl(eng):
     outs = [torch.empty_like(mine) for _ in range(ws)]
     dist.all_gather(outs, mine)
     torch.cuda.synchronize(dev)
+    if root_only and rank != 0:
+        return eng.label_entries()[:0]
     for r in range(ws):
         if r != rank and sizes[r]:
             eng.merge_label_entries_device(outs[r].data_ptr(), sizes[r])
