@@ -80,6 +80,7 @@ typedef struct we_options {
     int32_t keep_debug;      /* 1: keep all-centre shells / neighbours / acceptors / F,T of every frame */
     float search_radius;     /* first-pass candidate radius in A (0 = 6.6) */
     float max_box;           /* largest box edge expected in A (0 = take from first frame x 1.25) */
+    int32_t keep_shells;     /* 1: also keep the RAD shell of every recorded water (get_interfacial_shells) */
     int32_t force_upload;    /* we_submit, how forces reach k_cov: 0 auto (zero-copy for the interfacial recipe
                                 when the buffer is pinned, else whole frames), 1 whole frames, 2 recorded
                                 waters only, gathered by the host one batch later, 3 zero-copy: k_cov reads
@@ -179,6 +180,9 @@ int we_merge_label_entries(we_ctx *ctx, const void *d_entries, int32_t n);
  * out = int32 [count][2] = (water atom index, nearest non-like atom index or -1), ascending. */
 int we_frame_record_count(we_ctx *ctx, int64_t k);
 int we_copy_frame_records(we_ctx *ctx, int64_t k, int32_t *out, int32_t capacity);
+/* RAD shells of the recorded waters of frame k, same order as we_copy_frame_records
+ * (needs we_options.keep_shells): out = int32 [count][26] = (n, member 0 .. member 24). */
+int we_copy_frame_shells(we_ctx *ctx, int64_t k, int32_t *out, int32_t capacity);
 
 /* All-centre per-frame state (needs we_options.keep_debug); used by
  * get_interfacial_shells (recipes/interfacial_solvent.py:104-146) and by the

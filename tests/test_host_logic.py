@@ -240,3 +240,31 @@ def test_shard_frames_and_merge():
     got = {int(e["hash"]): e for e in m}
     assert sorted(got) == [1, 2, 3, 4]
     assert got[2]["shell_count"] == 16 and got[2]["donates"][0] == 7 and got[2]["first_seen_inv"] == 200
+
+
+REF_FILES = "/root/reference/tests/input_files"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_FILES), reason="reference fixtures only exist in the build container")
+def test_streaming_readers_reproduce_golden_inputs():
+    """io.Universe (prmtop + NetCDF, prmtop + TRR; memory-mapped, frames on demand) vs the committed inputs."""
+    from waterentropy_b200.frames import iter_batches
+    from waterentropy_b200.io import Universe
+
+    for tag, top, crd in (("arginine", "amber/arginine_solution/system.prmtop", "amber/arginine_solution/system.nc"),
+                          ("aspirin", "gromacs/aspirin_solution/system.prmtop", "gromacs/aspirin_solution/system.trr")):
+        u = Universe(os.path.join(REF_FILES, top), os.path.join(REF_FILES, crd))
+        g = gio.load_inputs(tag)
+        n = g["positions"].shape[0]
+        assert u.trajectory.n_frames == n
+        P, F, D = u.frame_arrays(range(n))
+        assert np.array_equal(P, g["positions"]) and np.array_equal(F, g["forces"]) and np.array_equal(D, g["dimensions"])
+        ts = u.trajectory[n - 1]
+        assert ts.frame == n - 1 and np.array_equal(u.atoms.positions, g["positions"][n - 1])
+        got = [ids for _, _, _, ids in iter_batches(u, range(0, n, 2), 3)]
+        assert sum(got, []) == list(range(0, n, 2))
+        st = SystemTopology.from_universe(u)
+        assert st.n_atoms == len(g["masses"]) and np.allclose(st.charges, g["charges"])
+    with pytest.raises(NotImplementedError):
+        Universe(os.path.join(REF_FILES, "gromacs/aspirin_solution/system.gro"),
+                 os.path.join(REF_FILES, "gromacs/aspirin_solution/system.trr"))

@@ -32,7 +32,8 @@ class we_options(C.Structure):
     _fields_ = [
         ("device", C.c_int32), ("chunk_frames", C.c_int32), ("table_log2", C.c_int32),
         ("keep_records", C.c_int32), ("keep_debug", C.c_int32),
-        ("search_radius", C.c_float), ("max_box", C.c_float), ("force_upload", C.c_int32),
+        ("search_radius", C.c_float), ("max_box", C.c_float), ("keep_shells", C.c_int32),
+        ("force_upload", C.c_int32),
     ]
 
 
@@ -50,6 +51,7 @@ EXPORTS = [
     "we_debug_copy", "we_reset", "we_test_angle_cos", "we_test_powf2", "we_test_distance",
     "we_profile", "we_kernel_times", "we_span_start", "we_span_stop",
     "we_label_entries_device", "we_merge_label_entries", "we_snapshot_cov", "we_wait_cov",
+    "we_copy_frame_shells",
 ]
 
 WE_ERR_DUPLICATE_COORD = -1
@@ -115,6 +117,8 @@ def load():
     L.we_frame_record_count.argtypes = [V, I64]
     L.we_copy_frame_records.restype = I
     L.we_copy_frame_records.argtypes = [V, I64, V, I]
+    L.we_copy_frame_shells.restype = I
+    L.we_copy_frame_shells.argtypes = [V, I64, V, I]
     L.we_copy_heavy_idx.restype = I
     L.we_copy_heavy_idx.argtypes = [V, V]
     L.we_copy_donors.restype = I

@@ -109,6 +109,8 @@ struct we_ctx {
   double* d_ft = nullptr;
   int* h_rec_count[2] = {nullptr, nullptr};
   int2* h_rec[2] = {nullptr, nullptr};  // mapped pinned memory written by k_label
+  int* h_shell[2] = {nullptr, nullptr};  // mapped pinned: RAD shells of recorded waters (keep_shells)
+  std::vector<std::vector<int>> frame_shells;
   int pending_n[2] = {0, 0};
   cudaStream_t s_copy = nullptr, s_comp = nullptr, s_cov = nullptr;
   cudaEvent_t ev_in_ready[2]{}, ev_in_free[2]{}, ev_out_ready[2]{};
@@ -398,6 +400,7 @@ extern "C" int we_reset(we_ctx* c) {
   CK(cudaMemset(c->d_table, 0, ((size_t)c->table_mask + 1) * sizeof(WeLabelEntry)));
   CK(cudaMemset(c->d_diag, 0, sizeof(WeDiag)));
   c->frame_records.clear();
+  c->frame_shells.clear();
   c->debug.clear();
   c->frames_done = 0;
   c->recorded = 0;
@@ -474,7 +477,8 @@ static int ensure_workspace(we_ctx* c, const float* dims0, bool need_input_buffe
     if ((rc = pin_alloc(c, &c->h_boxes[i], F))) return rc;
     if ((rc = pin_alloc(c, &c->h_fids[i], F))) return rc;
     if ((rc = pin_alloc(c, &c->h_rec_count[i], F))) return rc;
-    if (c->opt.keep_records || c->lazy) { if ((rc = pin_alloc(c, &c->h_rec[i], F * std::max(1, c->C)))) return rc; }
+    if (c->opt.keep_records || c->lazy || c->opt.keep_shells) { if ((rc = pin_alloc(c, &c->h_rec[i], F * std::max(1, c->C)))) return rc; }
+    if (c->opt.keep_shells) { if ((rc = pin_alloc(c, &c->h_shell[i], F * std::max(1, c->C) * (WE_MAX_NBR + 1)))) return rc; }
   }
   AL(d_cell_count, F * ((size_t)c->ncap + 1))
   AL(d_cell_of, F * H) AL(d_rank_of, F * H) AL(d_tmp4, F * H) AL(d_sorted4, F * H)
@@ -512,14 +516,21 @@ static int drain(we_ctx* c, int buf) {
   for (int f = 0; f < n; ++f) {
     const int cnt = c->h_rec_count[buf][f];
     c->recorded += (unsigned long long)cnt;
-    if (c->opt.keep_records) {
-      std::vector<std::pair<int, int>> v((size_t)cnt);
+    if (c->opt.keep_records || c->opt.keep_shells) {
       const int2* r = c->h_rec[buf] + (size_t)f * std::max(1, c->C);
-      for (int k = 0; k < cnt; ++k) v[k] = {r[k].x, r[k].y};
-      std::sort(v.begin(), v.end());
+      std::vector<int> order((size_t)cnt);
+      for (int k = 0; k < cnt; ++k) order[k] = k;
+      std::sort(order.begin(), order.end(), [&](int a, int b) { return r[a].x < r[b].x; });
       std::vector<int> flat((size_t)cnt * 2);
-      for (int k = 0; k < cnt; ++k) { flat[2 * k] = v[k].first; flat[2 * k + 1] = v[k].second; }
+      for (int k = 0; k < cnt; ++k) { flat[2 * k] = r[order[k]].x; flat[2 * k + 1] = r[order[k]].y; }
       c->frame_records.push_back(std::move(flat));
+      if (c->opt.keep_shells) {
+        const int W = WE_MAX_NBR + 1;
+        const int* sh = c->h_shell[buf] + (size_t)f * std::max(1, c->C) * W;
+        std::vector<int> fs((size_t)cnt * W);
+        for (int k = 0; k < cnt; ++k) memcpy(fs.data() + (size_t)k * W, sh + (size_t)order[k] * W, W * sizeof(int));
+        c->frame_shells.push_back(std::move(fs));
+      }
     }
   }
   c->out_pending[buf] = false;
@@ -776,7 +787,8 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
         k_label<<<grid_for((long long)C * n, 8, c->label_blocks), 256, 0, st>>>(
             c->T, c->d_shell_n, c->d_shell_idx, c->d_nn, c->d_flags, c->d_acceptor, c->d_interf, fids,
             c->d_table, c->table_mask, c->d_rec_count[buf], c->d_rec[buf],
-            (c->opt.keep_records || c->lazy) ? c->h_rec[buf] : nullptr, wlab, n, c->d_diag);
+            (c->opt.keep_records || c->lazy || c->opt.keep_shells) ? c->h_rec[buf] : nullptr,
+            c->opt.keep_shells ? c->h_shell[buf] : nullptr, wlab, n, c->d_diag);
         ps.stop(st); }
       c->launches += 1;
       if (!c->lazy) {
@@ -1115,6 +1127,14 @@ extern "C" int we_copy_frame_records(we_ctx* c, int64_t k, int32_t* out, int32_t
   if (n < 0) return n;
   if (n > capacity) return fail(WE_ERR_INVALID, "capacity too small");
   memcpy(out, c->frame_records[(size_t)k].data(), (size_t)n * 2 * sizeof(int));
+  return n;
+}
+
+extern "C" int we_copy_frame_shells(we_ctx* c, int64_t k, int32_t* out, int32_t capacity) {
+  if (!c || k < 0 || k >= (int64_t)c->frame_shells.size()) return fail(WE_ERR_INVALID, "frame ordinal out of range (keep_shells set?)");
+  const int n = (int)(c->frame_shells[(size_t)k].size() / (WE_MAX_NBR + 1));
+  if (n > capacity) return fail(WE_ERR_INVALID, "capacity too small");
+  memcpy(out, c->frame_shells[(size_t)k].data(), c->frame_shells[(size_t)k].size() * sizeof(int));
   return n;
 }
 

@@ -827,7 +827,7 @@ __device__ __forceinline__ void we_label_one(const WeTopoDev& T, int f, int xs,
         const int* __restrict__ acceptor, const unsigned char* __restrict__ interfacial,
         const long long* __restrict__ frame_ids, WeLabelEntry* __restrict__ table,
         unsigned int table_mask, int* __restrict__ rec_count, WeRecord* __restrict__ rec,
-        int2* __restrict__ rec_host, WeDiag* diag, int lane) {
+        int2* __restrict__ rec_host, int* __restrict__ shell_host, WeDiag* diag, int lane) {
   const size_t fo = (size_t)f * T.n_heavy;
   const size_t ho = fo + xs;
   const bool bulk = (T.recipe == 1);
@@ -957,10 +957,11 @@ __device__ __forceinline__ void we_label_one(const WeTopoDev& T, int f, int xs,
       atomicAdd(&diag->table_entries, 1ULL);
     }
   }
+  int r = 0;
   if (lane == 0) {
     atomicAdd(&e->shell_count, 1ULL);
     atomicMax(&e->first_seen_inv, ~((unsigned long long)frame_ids[f] * (unsigned long long)T.n_atoms + (unsigned long long)X));
-    const int r = atomicAdd(&rec_count[f], 1);
+    r = atomicAdd(&rec_count[f], 1);
     WeRecord rr;
     rr.atom = X;
     rr.nearest = bulk ? -1 : nn;
@@ -970,6 +971,14 @@ __device__ __forceinline__ void we_label_one(const WeTopoDev& T, int f, int xs,
     rec[(size_t)f * T.n_centres + r] = rr;
     // compact copy straight into mapped pinned host memory (frame_solvent_indices)
     if (rec_host) rec_host[(size_t)f * T.n_centres + r] = make_int2(X, rr.nearest);
+  }
+  if (shell_host) {
+    // RAD shell of the recorded water (distance order) for get_interfacial_shells:
+    // [count, member 0 .. member 24] per record, in mapped pinned host memory
+    r = __shfl_sync(0xffffffffu, r, 0);
+    int* o = shell_host + ((size_t)f * T.n_centres + r) * (WE_MAX_NBR + 1);
+    if (lane == 0) o[0] = ns;
+    if (act) o[1 + lane] = A;
   }
   if (sact && sdon) atomicAdd(&e->donates[first_pos], (unsigned int)sdon);
   if (sact && sacc) atomicAdd(&e->accepts[first_pos], (unsigned int)sacc);
@@ -983,7 +992,7 @@ k_label(WeTopoDev T, const int* __restrict__ shell_n, const int* __restrict__ sh
         const int* __restrict__ acceptor, const unsigned char* __restrict__ interfacial,
         const long long* __restrict__ frame_ids, WeLabelEntry* __restrict__ table,
         unsigned int table_mask, int* __restrict__ rec_count, WeRecord* __restrict__ rec,
-        int2* __restrict__ rec_host, WeWork work, int n_frames, WeDiag* diag) {
+        int2* __restrict__ rec_host, int* __restrict__ shell_host, WeWork work, int n_frames, WeDiag* diag) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int stride = gridDim.x * (blockDim.x >> 5);
   for (int f = 0; f < n_frames; ++f) {
@@ -991,7 +1000,7 @@ k_label(WeTopoDev T, const int* __restrict__ shell_n, const int* __restrict__ sh
     const int* list = work.list + (size_t)f * work.stride;
     for (int i = blockIdx.x * (blockDim.x >> 5) + w; i < cnt; i += stride)
       we_label_one(T, f, list[i], shell_n, shell_idx, nn_arr, flags, acceptor, interfacial, frame_ids, table,
-                   table_mask, rec_count, rec, rec_host, diag, lane);
+                   table_mask, rec_count, rec, rec_host, shell_host, diag, lane);
   }
 }
 

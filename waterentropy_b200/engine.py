@@ -80,14 +80,16 @@ def decode_label_entries(top, recipe, entries) -> HBLabelCollection:
 
 class WaterEntropyEngine:
     def __init__(self, system, recipe="interfacial", device=0, chunk_frames=0, table_log2=0,
-                 keep_records=True, keep_debug=False, search_radius=0.0, max_box=0.0, force_upload=0):
+                 keep_records=True, keep_debug=False, search_radius=0.0, max_box=0.0, force_upload=0,
+                 keep_shells=False):
         self.lib = _lib.load()
         self.top = SystemTopology.from_universe(system)
         self.recipe = RECIPE_BULK if recipe in ("bulk", RECIPE_BULK) else RECIPE_INTERFACIAL
         t, self._keep = self.top.c_struct(self.recipe)
         o = _lib.we_options(device=device, chunk_frames=chunk_frames, table_log2=table_log2,
                             keep_records=int(keep_records), keep_debug=int(keep_debug),
-                            search_radius=search_radius, max_box=max_box, force_upload=force_upload)
+                            search_radius=search_radius, max_box=max_box, force_upload=force_upload,
+                            keep_shells=int(keep_shells))
         self._ctx = C.c_void_p()
         _lib.check(self.lib.we_create(C.byref(t), C.byref(o), C.byref(self._ctx)))
         self.device = device
@@ -222,6 +224,14 @@ class WaterEntropyEngine:
         out = np.zeros((max(n, 1), 2), dtype=np.int32)
         _lib.check(self.lib.we_copy_frame_records(self._ctx, k, out.ctypes.data, len(out)))
         return out[:n]
+
+    def frame_shells(self, k):
+        """{water atom: [shell atoms, distance order]} of the recorded waters of submitted frame k."""
+        n = _lib.check(self.lib.we_frame_record_count(self._ctx, k))
+        out = np.zeros((max(n, 1), 26), dtype=np.int32)
+        _lib.check(self.lib.we_copy_frame_shells(self._ctx, k, out.ctypes.data, len(out)))
+        rec = self.frame_records(k)
+        return {int(rec[i, 0]): [int(v) for v in out[i, 1:1 + out[i, 0]]] for i in range(n)}
 
     def debug(self, k, field):
         fid, dt = DBG[field]

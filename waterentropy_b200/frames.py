@@ -28,12 +28,12 @@ def iter_batches(system, indices, batch):
     n_atoms = system.n_atoms if hasattr(system, "n_atoms") else len(system.atoms)
     for b0 in range(0, len(indices), batch):
         sel = indices[b0 : b0 + batch]
-        if hasattr(system, "frame_arrays"):  # waterentropy_b200.io.Universe
-            P, F, D = system.frame_arrays(sel)
-            yield np.ascontiguousarray(P), np.ascontiguousarray(F), np.ascontiguousarray(D), sel
-            continue
         P, keepP = _pinned((len(sel), n_atoms, 3), np.float32)
         F, keepF = _pinned((len(sel), n_atoms, 3), np.float32)
+        if hasattr(system, "frame_arrays"):  # waterentropy_b200.io.Universe: read into pinned memory
+            _, _, D = system.frame_arrays(sel, P, F)
+            yield keepP, keepF, np.ascontiguousarray(D), sel
+            continue
         D = np.empty((len(sel), 6), dtype=np.float32)
         ids = []
         for k, i in enumerate(sel):

@@ -91,27 +91,59 @@ class AmberTopology:
 
 
 class NetCDFTrajectory:
-    """AMBER NetCDF3 trajectory: coordinates, forces (optional), cell."""
+    """AMBER NetCDF3 trajectory: coordinates, forces, cell.  Frames are read on demand from a
+    memory-mapped file (`read(indices)`), so trajectories larger than RAM can be streamed."""
 
     def __init__(self, path: str):
         from scipy.io import netcdf_file
 
-        nc = netcdf_file(path, "r", mmap=False)
-        var = nc.variables
-        self.positions = np.array(var["coordinates"][:], dtype=np.float32)
-        self.n_frames = self.positions.shape[0]
-        if "forces" in var:
-            frc = np.array(var["forces"][:], dtype=np.float32)
-            frc *= np.float32(4.184)  # kcal -> kJ, float32 like MDAnalysis
-            self.forces = frc
-        else:
-            self.forces = None
+        self._nc = netcdf_file(path, "r", mmap=True)
+        var = self._nc.variables
+        self._xyz = var["coordinates"]
+        self.n_frames, self.n_atoms = int(self._xyz.shape[0]), int(self._xyz.shape[1])
+        self._frc = var["forces"] if "forces" in var else None
+        self.has_forces = self._frc is not None
         if "cell_lengths" in var:
             lengths = np.array(var["cell_lengths"][:], dtype=np.float64)
             angles = np.array(var["cell_angles"][:], dtype=np.float64)
-            self.dimensions = np.concatenate([lengths, angles], axis=1).astype(
-                np.float32
-            )
+            self.dimensions = np.concatenate([lengths, angles], axis=1).astype(np.float32)
         else:
             self.dimensions = np.zeros((self.n_frames, 6), dtype=np.float32)
-        nc.close()
+
+    def read(self, indices, out_pos=None, out_frc=None):
+        """float32 native-endian (positions, forces, dimensions) of the given frames."""
+        idx = np.asarray(list(indices), dtype=np.int64)
+        n = len(idx)
+        P = out_pos if out_pos is not None else np.empty((n, self.n_atoms, 3), dtype=np.float32)
+        F = out_frc if out_frc is not None else np.empty((n, self.n_atoms, 3), dtype=np.float32)
+        for k, i in enumerate(idx):
+            P[k] = self._xyz[int(i)]  # big-endian file -> native float32
+            if self._frc is not None:
+                F[k] = self._frc[int(i)]
+        if self._frc is not None:
+            F[:n] *= np.float32(4.184)  # kcal -> kJ, float32 like MDAnalysis
+        return P[:n], (F[:n] if self._frc is not None else None), self.dimensions[idx]
+
+    def close(self):
+        self._xyz = self._frc = None  # drop the memory-mapped views before closing the file
+        nc, self._nc = getattr(self, "_nc", None), None
+        if nc is not None:
+            import warnings
+
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", RuntimeWarning)
+                nc.close()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def positions(self):
+        return self.read(range(self.n_frames))[0]
+
+    @property
+    def forces(self):
+        return self.read(range(self.n_frames))[1]

@@ -38,8 +38,8 @@ class _Atoms:
     names = property(lambda s: s._u._names)
     indices = property(lambda s: np.arange(s._u.n_atoms))
     bonds = property(lambda s: s._u.bonds)
-    positions = property(lambda s: s._u._positions[s._u._frame])
-    forces = property(lambda s: s._u._forces[s._u._frame])
+    positions = property(lambda s: s._u._current()[0])
+    forces = property(lambda s: s._u._current()[1])
 
 
 class _Trajectory:
@@ -48,7 +48,7 @@ class _Trajectory:
 
     @property
     def n_frames(self):
-        return self._u._positions.shape[0]
+        return self._u._source.n_frames
 
     def __len__(self):
         return self.n_frames
@@ -72,9 +72,31 @@ class _Trajectory:
         return self[0 : self.n_frames]
 
 
+class _ArraySource:
+    """Frames held in memory."""
+
+    def __init__(self, positions, forces, dimensions):
+        self.P = np.ascontiguousarray(positions, dtype=np.float32)
+        self.F = np.ascontiguousarray(forces, dtype=np.float32)
+        self.dimensions = np.ascontiguousarray(dimensions, dtype=np.float32)
+        self.n_frames = self.P.shape[0]
+
+    def read(self, indices, out_pos=None, out_frc=None):
+        idx = np.asarray(list(indices), dtype=np.int64)
+        if out_pos is not None:
+            out_pos[: len(idx)] = self.P[idx]
+            out_frc[: len(idx)] = self.F[idx]
+            return out_pos[: len(idx)], out_frc[: len(idx)], self.dimensions[idx]
+        return self.P[idx], self.F[idx], self.dimensions[idx]
+
+
 class Universe:
+    """`Universe(topology, coordinates)` for AMBER prmtop + NetCDF and prmtop + GROMACS TRR
+    (frames streamed from memory-mapped files), or `Universe.from_arrays(...)`."""
+
     def __init__(self, topology=None, coordinates=None):
         self._frame = 0
+        self._cache = (-1, None, None)
         if topology is None:
             return
         ext_t = os.path.splitext(str(topology))[1].lower()
@@ -84,24 +106,31 @@ class Universe:
 
             t = AmberTopology(topology)
             x = NetCDFTrajectory(coordinates)
-            self._set(t.names, t.types, t.resnames, t.resids, t.masses, t.charges, t.bonds,
-                      x.positions, x.forces, x.dimensions)
         elif ext_c == ".trr":
-            from .gromacs import load_gromacs
+            from .gromacs import open_gromacs
 
-            self._set(*load_gromacs(topology, coordinates))
+            t, x = open_gromacs(topology, coordinates)
         else:
             raise NotImplementedError(
                 f"no reader for topology {ext_t!r} + coordinates {ext_c!r} "
-                "(supported: AMBER prmtop + NetCDF, GROMACS gro/prmtop + TRR)")
+                "(supported: AMBER prmtop + NetCDF, prmtop + GROMACS TRR)")
+        if not x.has_forces:
+            raise ValueError("the trajectory holds no forces; the covariance path needs them")
+        if x.n_atoms != t.n_atoms:
+            raise ValueError(f"trajectory has {x.n_atoms} atoms, topology {t.n_atoms}")
+        self._set_topology(t.names, t.types, t.resnames, t.resids, t.masses, t.charges, t.bonds)
+        self._source = x
 
     @classmethod
     def from_arrays(cls, names, types, resnames, resids, masses, charges, bonds, positions, forces, dimensions):
         u = cls()
-        u._set(names, types, resnames, resids, masses, charges, bonds, positions, forces, dimensions)
+        if forces is None:
+            raise ValueError("the trajectory holds no forces; the covariance path needs them")
+        u._set_topology(names, types, resnames, resids, masses, charges, bonds)
+        u._source = _ArraySource(positions, forces, dimensions)
         return u
 
-    def _set(self, names, types, resnames, resids, masses, charges, bonds, positions, forces, dimensions):
+    def _set_topology(self, names, types, resnames, resids, masses, charges, bonds):
         self._names = np.asarray(names, dtype=object)
         self._types = np.asarray(types, dtype=object)
         self._resnames = np.asarray(resnames, dtype=object)
@@ -109,20 +138,20 @@ class Universe:
         self._masses = np.asarray(masses, dtype=np.float64)
         self._charges = np.asarray(charges, dtype=np.float64)
         self.bonds = _Bonds(bonds)
-        self._positions = np.ascontiguousarray(positions, dtype=np.float32)
-        if forces is None:
-            raise ValueError("the trajectory holds no forces; the covariance path needs them")
-        self._forces = np.ascontiguousarray(forces, dtype=np.float32)
-        self._dimensions = np.ascontiguousarray(dimensions, dtype=np.float32)
         self.n_atoms = len(self._masses)
         self.atoms = _Atoms(self)
         self.trajectory = _Trajectory(self)
 
+    def _current(self):
+        if self._cache[0] != self._frame:
+            P, F, _ = self._source.read([self._frame])
+            self._cache = (self._frame, P[0], F[0])
+        return self._cache[1], self._cache[2]
+
     @property
     def dimensions(self):
-        return self._dimensions[self._frame]
+        return self._source.dimensions[self._frame]
 
-    # fast path used by waterentropy_b200.frames: all frames as arrays
-    def frame_arrays(self, indices):
-        idx = np.asarray(list(indices), dtype=np.int64)
-        return self._positions[idx], self._forces[idx], self._dimensions[idx]
+    # fast path used by waterentropy_b200.frames: a batch of frames straight into (pinned) buffers
+    def frame_arrays(self, indices, out_pos=None, out_frc=None):
+        return self._source.read(indices, out_pos, out_frc)

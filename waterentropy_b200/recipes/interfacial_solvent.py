@@ -29,9 +29,9 @@ def _device():
     return 0
 
 
-def _run(system, indices, recipe, keep_debug=False, keep_records=True):
+def _run(system, indices, recipe, keep_debug=False, keep_records=True, keep_shells=False):
     eng = WaterEntropyEngine(system, recipe, device=_device(), keep_records=keep_records,
-                             keep_debug=keep_debug)
+                             keep_debug=keep_debug, keep_shells=keep_shells)
     batch = max(1, min(64, 400_000 // max(1, len(eng.top.heavy_idx))))
     for P, F, D, ids in iter_batches(system, indices, batch):
         eng.submit(P, F, D, ids)
@@ -79,12 +79,11 @@ def get_interfacial_shells(system, start: int, end: int, step: int):
     """Reference: `recipes/interfacial_solvent.py:104-146` -- RAD shells of the interfacial
     waters that have a non-like neighbour: `{frame: {water_idx: [shell idx ...]}}`."""
     indices = list(range(start, end, step))
-    eng = _run(system, indices, "interfacial", keep_debug=True)
+    eng = _run(system, indices, "interfacial", keep_shells=True)
     out = nested_dict()
     for k, frame in enumerate(eng.frame_ids):
-        shells = eng.shells(k)
-        for atom, _nearest in eng.frame_records(k):
-            out[frame][int(atom)] = shells[int(atom)]
+        for atom, shell in eng.frame_shells(k).items():
+            out[frame][atom] = shell
     eng.close()
     return out
 
