@@ -612,3 +612,37 @@ def test_cov_snapshots_are_stream_ordered():
     assert c1.sum() > c0.sum() > 0
     for e in (eng, ref):
         e.close()
+
+
+def test_degenerate_systems():
+    """No solute, no waters: the engine returns empty tables; the interfacial recipe refuses a
+    solute-free system like upstream does (select_atoms("resid ") fails there)."""
+    from waterentropy_b200 import synthetic
+    from waterentropy_b200.engine import WaterEntropyEngine
+    from waterentropy_b200.recipes.interfacial_solvent import get_interfacial_water_orient_entropy
+
+    pure = synthetic.make_system(n_waters=300, n_residues=0, seed=41)
+    P, Fr, D = pure.frames(0, 2)
+    eng = WaterEntropyEngine(pure, "interfacial", device=0)
+    eng.submit(P, Fr, D, [0, 1])
+    eng.sync()
+    assert len(eng.label_entries()) == 0 and eng.cov_tables()[1].sum() == 0 and len(eng.frame_records(1)) == 0
+    eng.close()
+    with pytest.raises(ValueError, match="no solute"):
+        get_interfacial_water_orient_entropy(pure, 0, 2, 1)
+    # a "solute only" system: drop the waters of a small solvated peptide
+    full = synthetic.make_system(n_waters=8, n_residues=12, n_chains=1, seed=42, density=0.0005)
+    n_sol = len(full.solute_atoms)
+    keep = np.arange(n_sol)
+    b = full.bonds[(full.bonds < n_sol).all(axis=1)]
+    top_only = type("S", (), {})()
+    top_only.masses, top_only.charges = full.masses[keep], full.charges[keep]
+    top_only.resids, top_only.resnames = full.resids[keep], [full.resnames[i] for i in keep]
+    top_only.types, top_only.bonds, top_only.names = [full.types[i] for i in keep], b, None
+    Pf, Ff, Df = full.frames(0, 1)
+    eng = WaterEntropyEngine(top_only, "interfacial", device=0, keep_debug=True)
+    eng.submit(Pf[:, keep], Ff[:, keep], Df, [0])
+    eng.sync()
+    assert eng.cov_tables()[1].sum() == 0 and len(eng.label_entries()) == 0
+    assert (eng.debug(0, "shell_n") >= 0).all()
+    eng.close()

@@ -30,6 +30,11 @@ def _device():
 
 
 def _run(system, indices, recipe, keep_debug=False, keep_records=True, keep_shells=False):
+    if recipe == "interfacial" and len(SystemTopology.from_universe(system).solute_ua) == 0:
+        # upstream ends in MDAnalysis' SelectionError here: `select_atoms("resid ")` with an empty
+        # residue list (utils/selections.py:19-20); use the bulk recipe for solute-free systems
+        raise ValueError("no solute molecules in the system: the interfacial recipe needs a solute "
+                         "(use get_bulk_water_orient_entropy for pure water)")
     eng = WaterEntropyEngine(system, recipe, device=_device(), keep_records=keep_records,
                              keep_debug=keep_debug, keep_shells=keep_shells)
     batch = max(1, min(64, 400_000 // max(1, len(eng.top.heavy_idx))))
