@@ -1,14 +1,20 @@
 // Hand-written sm_100a kernels for the waterEntropy per-frame hot path.
 //
-// One launch of each kernel processes a *batch* of frames (grid.y = frame).
-//   K1  k_bin / k_scan / k_scatter   cell list over heavy atoms (float4 packed)
-//   K2  k_rad        warp per centre: cell search -> exact top-25 -> RAD shell
-//   K3  k_hb         warp per donor hydrogen: acceptor argmin
-//   K4  k_flag       interfacial gating from solute-atom shells
-//       k_label      warp per water: labels, HB labels, count-table key + insert
-//   K5  k_cov        principal-axis force/torque, outer products
-//   K6  (fused in k_label / k_cov)  warp-aggregated atomics into the label hash
-//       table and the dense per-bin covariance sums
+// One launch of each kernel processes a *batch* of frames.
+//   K1  k_bin / k_scan / k_scatter   cell list over heavy atoms: cells of edge >= r/2 in
+//                    fractional coordinates, float4 (x, y, z, atom) records in cell order
+//   K2  k_rad        persistent, one warp per centre of a work list: flattened warp-dense
+//                    cell scan -> float32 prefilter -> exact fp64 distances -> exact top-25
+//                    -> RAD blocking test with the reference's float32 cosine
+//       k_seed / k_flag / k_mark / k_mark_bulk   the work lists: solute atoms -> interfacial
+//                    waters -> their shell members (the closure the reference memoises lazily)
+//   K3  k_hb         persistent over the centres whose HBs are needed: 8 lanes per donor
+//                    hydrogen, acceptor = argmin over the donor's RAD shell
+//   K4  k_label      persistent, warp per water: labels, HB labels, sorted key, hash-table
+//                    insert, record of the water (also into mapped pinned host memory)
+//   K5  k_cov        principal-axis force / torque, outer products
+//   K6  (fused in k_label / k_cov)  atomics into the label hash table and warp-aggregated
+//                    fp64 atomics into the dense per-bin covariance sums
 // Reference lines each kernel replaces are cited at the kernel.
 #pragma once
 #include <cuda_runtime.h>
@@ -24,7 +30,6 @@
 #ifndef WE_RAD_MINBLOCKS
 #define WE_RAD_MINBLOCKS 3    // resident blocks per SM the register allocator must allow for k_rad
 #endif
-#define WE_ENTRY_WORDS 64  // 512-byte label-table entries
 
 // status codes (per centre / per donor), also the C-ABI error codes
 #define WE_ST_OK 0
