@@ -206,6 +206,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     s = synthetic.make_config(args.config, scale=args.scale)
     N, W = s.n_atoms, s.n_waters
+    recipe = "interfacial" if len(s.solute_atoms) else "bulk"  # solute-free configs (C2): bulk recipe
     Fps = args.frames_per_step
     # every rank analyses its own frames
     P, Fr, D = s.frames(rank * Fps, Fps)
@@ -226,7 +227,7 @@ def run_ours(args, rank, world, local_rank):
         return float(t.item())
 
     # ---------------- device-resident arm (value) ----------------
-    eng = WaterEntropyEngine(s, "interfacial", device=local_rank, keep_records=False, chunk_frames=args.chunk)
+    eng = WaterEntropyEngine(s, recipe, device=local_rank, keep_records=False, chunk_frames=args.chunk)
     dP, dF = torch.from_numpy(P).cuda(), torch.from_numpy(Fr).cuda()
     for _ in range(args.warmup):
         eng.submit_device(dP, dF, D, ids)
@@ -282,7 +283,7 @@ def run_ours(args, rank, world, local_rank):
     del dP, dF
 
     # ---------------- end-to-end arm (host buffers through the public API) ----------------
-    eng = WaterEntropyEngine(s, "interfacial", device=local_rank, keep_records=True, chunk_frames=args.chunk,
+    eng = WaterEntropyEngine(s, recipe, device=local_rank, keep_records=(recipe == "interfacial"), chunk_frames=args.chunk,
                              force_upload=args.force_upload)
     hP, hF = torch.from_numpy(P).pin_memory(), torch.from_numpy(Fr).pin_memory()
     d2h = 0
@@ -291,7 +292,8 @@ def run_ours(args, rank, world, local_rank):
         """host read of one finished step: its covariance snapshot + its recorded-water lists"""
         nonlocal d2h
         tables = eng.wait_cov(ticket)
-        nrec = sum(len(eng.frame_records(k0 + k)) for k in range(Fps))
+        # the bulk recipe returns no per-frame lists (recipes/bulk_water.py:86-90)
+        nrec = sum(len(eng.frame_records(k0 + k)) for k in range(Fps)) if recipe == "interfacial" else 0
         d2h = tables[0].nbytes + tables[1].nbytes + Fps * 4 + nrec * 8
         return nrec
 
@@ -352,7 +354,7 @@ def run_ours(args, rank, world, local_rank):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": synthetic.CONFIGS[args.config]["label"], "scale": args.scale,
                        "n_atoms": N, "n_waters": W, "frames_per_step_per_gpu": Fps,
-                       "recipe": "interfacial", "recorded_waters_per_step": int(nrec),
+                       "recipe": recipe, "recorded_waters_per_step": int(nrec),
                        "l2": f"inputs {input_bytes / 1e6:.0f} MB per step per GPU "
                              + ("> 126 MB L2 (no flush needed)" if input_bytes > 126e6 else "<= L2: reduce reliance, see DESIGN.md")},
             "clocks": clk,

@@ -616,10 +616,9 @@ static int finish_lazy(we_ctx* c, int buf) {
   CK(cudaStreamWaitEvent(st, c->ev_label[buf], 0));
   CK(cudaStreamWaitEvent(st, c->ev_f[buf], 0));
   {
-    dim3 gV((c->C + 127) / 128, n);
     ProfScope ps(c, WE_K_COV, st);
-    k_cov<<<gV, 128, 0, st>>>(c->T, c->pend_dp[buf], nullptr, c->d_rec_count[buf], c->d_rec[buf], c->d_centre_of_slot,
-                              c->d_cov_sum, c->d_cov_cnt, nullptr, c->d_fcomp[buf], c->d_fbase[buf], mf);
+    k_cov<<<dim3((c->C + 511) / 512, n), 128, 0, st>>>(c->T, c->pend_dp[buf], nullptr, c->d_rec_count[buf], c->d_rec[buf], c->d_centre_of_slot,
+                                       c->d_cov_sum, c->d_cov_cnt, nullptr, c->d_fcomp[buf], c->d_fbase[buf], mf, n);
     ps.stop(st);
     c->launches += 1;
   }
@@ -792,10 +791,10 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
         ps.stop(st); }
       c->launches += 1;
       if (!c->lazy) {
-        dim3 gV((C + 127) / 128, n);
         ProfScope ps(c, WE_K_COV, st);
-        k_cov<<<gV, 128, 0, st>>>(c->T, dp, df, c->d_rec_count[buf], c->d_rec[buf], c->d_centre_of_slot, c->d_cov_sum,
-                                  c->d_cov_cnt, c->d_ft, nullptr, nullptr, 0);
+        k_cov<<<dim3((C + 511) / 512, n), 128, 0, st>>>(
+            c->T, dp, df, c->d_rec_count[buf], c->d_rec[buf], c->d_centre_of_slot, c->d_cov_sum,
+            c->d_cov_cnt, c->d_ft, nullptr, nullptr, 0, n);
         ps.stop(st);
         c->launches += 1;
       }

@@ -135,42 +135,51 @@ __global__ void k_bin(WeTopoDev T, const float* __restrict__ pos, const WeBox* _
   tmp4[o] = make_float4(q[0], q[1], q[2], __int_as_float(atom));
 }
 
-// exclusive scan of the per-frame cell counts, in place; [ncell] receives the total
+// exclusive scan of the per-frame cell counts, in place; [ncell] receives the total.
+// One 1024-thread block per frame; every thread owns 8 consecutive cells per sweep.
+#define WE_SCAN_PER_THREAD 8
 __global__ void k_scan(const WeBox* __restrict__ boxes, int* __restrict__ cell_count, int ncap) {
   __shared__ int s_part[32];
   __shared__ int s_carry;
-  int f = blockIdx.x;
+  const int f = blockIdx.x;
   const WeBox& b = boxes[f];
-  int ncell = b.nc[0] * b.nc[1] * b.nc[2];
+  const int ncell = b.nc[0] * b.nc[1] * b.nc[2];
   int* cnt = cell_count + (size_t)f * (ncap + 1);
-  int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (tid == 0) s_carry = 0;
   __syncthreads();
-  for (int base = 0; base < ncell + 1; base += blockDim.x) {
-    int i = base + tid;
-    int v = (i < ncell) ? cnt[i] : 0;
-    int incl = v;
+  const int span = blockDim.x * WE_SCAN_PER_THREAD;
+  for (int base = 0; base < ncell + 1; base += span) {
+    const int i0 = base + tid * WE_SCAN_PER_THREAD;
+    int v[WE_SCAN_PER_THREAD];
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < WE_SCAN_PER_THREAD; ++k) { v[k] = (i0 + k < ncell) ? cnt[i0 + k] : 0; sum += v[k]; }
+    int incl = sum;
     for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, incl, o);
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += t;
     }
     if (lane == 31) s_part[w] = incl;
     __syncthreads();
     if (w == 0) {
-      int pv = (lane < (blockDim.x >> 5)) ? s_part[lane] : 0;
+      const int pv = (lane < (blockDim.x >> 5)) ? s_part[lane] : 0;
       int pi = pv;
       for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, pi, o);
+        const int t = __shfl_up_sync(0xffffffffu, pi, o);
         if (lane >= o) pi += t;
       }
       s_part[lane] = pi - pv;  // exclusive prefix of warp totals
     }
     __syncthreads();
-    int carry = s_carry;
-    int excl = carry + s_part[w] + incl - v;
-    if (i <= ncell) cnt[i] = excl;
+    int run = s_carry + s_part[w] + incl - sum;  // exclusive prefix of this thread's first cell
+#pragma unroll
+    for (int k = 0; k < WE_SCAN_PER_THREAD; ++k) {
+      if (i0 + k <= ncell) cnt[i0 + k] = run;
+      run += v[k];
+    }
     __syncthreads();
-    if (tid == blockDim.x - 1) s_carry = excl + v;
+    if (tid == blockDim.x - 1) s_carry = run;
     __syncthreads();
   }
 }
@@ -825,6 +834,19 @@ __device__ __forceinline__ unsigned long long we_mix64(unsigned long long x) {
 
 struct WeRecord { int atom; int nearest; int bin; int pad; };
 
+// K6 for the integer label histograms: per-block staging table in shared memory.  Waters of one
+// block that share a label key (the bulk recipe has a few dozen keys for all waters) add their
+// counts with shared-memory atomics; the block folds each staged key into the global table once.
+#define WE_STAGE_SLOTS 64
+struct WeLabelStage {
+  unsigned long long hash[WE_STAGE_SLOTS];       // 0 = free
+  unsigned long long first_inv[WE_STAGE_SLOTS];
+  int gslot[WE_STAGE_SLOTS];                     // slot in the global table (-1: insert failed)
+  unsigned int shell_count[WE_STAGE_SLOTS];
+  unsigned int don[WE_STAGE_SLOTS][WE_MAX_NBR];
+  unsigned int acc[WE_STAGE_SLOTS][WE_MAX_NBR];
+};
+
 // One centre (heavy slot xs of frame f) on one warp.
 __device__ __forceinline__ void we_label_one(const WeTopoDev& T, int f, int xs,
         const int* __restrict__ shell_n, const int* __restrict__ shell_idx,
@@ -832,7 +854,8 @@ __device__ __forceinline__ void we_label_one(const WeTopoDev& T, int f, int xs,
         const int* __restrict__ acceptor, const unsigned char* __restrict__ interfacial,
         const long long* __restrict__ frame_ids, WeLabelEntry* __restrict__ table,
         unsigned int table_mask, int* __restrict__ rec_count, WeRecord* __restrict__ rec,
-        int2* __restrict__ rec_host, int* __restrict__ shell_host, WeDiag* diag, int lane) {
+        int2* __restrict__ rec_host, int* __restrict__ shell_host, WeLabelStage* stage,
+        WeDiag* diag, int lane) {
   const size_t fo = (size_t)f * T.n_heavy;
   const size_t ho = fo + xs;
   const bool bulk = (T.recipe == 1);
@@ -930,42 +953,69 @@ __device__ __forceinline__ void we_label_one(const WeTopoDev& T, int f, int xs,
   h2 = we_mix64(h2 + we_mix64(head ^ 0xA5A5A5A5A5A5A5A5ULL));
   if (h1 == 0ULL) h1 = 1ULL;
   if (h2 == 0ULL) h2 = 1ULL;
-  // ---- insert / find (lane 0), open addressing ---------------------------------------
-  int slot = -1;
-  int won = 0;
+  // ---- block-level staging: find / claim the key in shared memory (lane 0) --------------------
+  int sidx = -1, claimed = 0;
   if (lane == 0) {
-    unsigned int s = (unsigned int)h1 & table_mask;
-    for (unsigned int probe = 0; probe <= table_mask; ++probe) {
-      const unsigned long long old = atomicCAS(&table[s].hash, 0ULL, h1);
-      if (old == 0ULL) { slot = (int)s; won = 1; break; }
-      if (old == h1) { slot = (int)s; break; }
-      s = (s + 1) & table_mask;
-    }
-    if (slot >= 0) {
-      const unsigned long long old2 = atomicCAS(&table[slot].hash2, 0ULL, h2);
-      if (old2 != 0ULL && old2 != h2) { we_set_error(diag, 5, frame_id, X); slot = -1; }
-    } else {
-      we_set_error(diag, 4, frame_id, X);  // table full
+    unsigned int s = (unsigned int)h1 & (WE_STAGE_SLOTS - 1);
+    for (int probe = 0; probe < 4; ++probe) {
+      const unsigned long long old = atomicCAS(&stage->hash[s], 0ULL, h1);
+      if (old == 0ULL) { sidx = (int)s; claimed = 1; break; }
+      if (old == h1) { sidx = (int)s; break; }
+      s = (s + 1) & (WE_STAGE_SLOTS - 1);
     }
   }
-  slot = __shfl_sync(0xffffffffu, slot, 0);
-  won = __shfl_sync(0xffffffffu, won, 0);
-  if (slot < 0) return;
-  WeLabelEntry* e = table + slot;
-  if (won) {
-    e->labels[lane] = sact ? (unsigned short)scode : (unsigned short)0xffff;
+  sidx = __shfl_sync(0xffffffffu, sidx, 0);
+  claimed = __shfl_sync(0xffffffffu, claimed, 0);
+  const unsigned long long stamp_inv = ~((unsigned long long)frame_ids[f] * (unsigned long long)T.n_atoms + (unsigned long long)X);
+  // ---- global insert / find (lane 0), open addressing: for newly staged keys and for waters
+  // that found no staging slot --------------------------------------------------------------
+  int slot = -1;
+  if (sidx < 0 || claimed) {
+    int won = 0;
     if (lane == 0) {
-      e->nearest_resid = key_resid;
-      e->nearest_resname_id = key_resname;
-      e->n_labels = ns;
-      e->n_w = n_w;
-      atomicAdd(&diag->table_entries, 1ULL);
+      unsigned int s = (unsigned int)h1 & table_mask;
+      for (unsigned int probe = 0; probe <= table_mask; ++probe) {
+        const unsigned long long old = atomicCAS(&table[s].hash, 0ULL, h1);
+        if (old == 0ULL) { slot = (int)s; won = 1; break; }
+        if (old == h1) { slot = (int)s; break; }
+        s = (s + 1) & table_mask;
+      }
+      if (slot >= 0) {
+        const unsigned long long old2 = atomicCAS(&table[slot].hash2, 0ULL, h2);
+        if (old2 != 0ULL && old2 != h2) { we_set_error(diag, 5, frame_id, X); slot = -1; }
+      } else {
+        we_set_error(diag, 4, frame_id, X);  // table full
+      }
+      if (claimed) stage->gslot[sidx] = slot;
     }
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    won = __shfl_sync(0xffffffffu, won, 0);
+    if (slot >= 0 && won) {
+      WeLabelEntry* e = table + slot;
+      e->labels[lane] = sact ? (unsigned short)scode : (unsigned short)0xffff;
+      if (lane == 0) {
+        e->nearest_resid = key_resid;
+        e->nearest_resname_id = key_resname;
+        e->n_labels = ns;
+        e->n_w = n_w;
+        atomicAdd(&diag->table_entries, 1ULL);
+      }
+    }
+    if (slot < 0 && sidx < 0) return;  // not recorded: the error flag is set
+  }
+  // ---- counts: shared-memory stage, or straight to the global entry ----------------------------
+  if (sidx >= 0) {
+    if (lane == 0) { atomicAdd(&stage->shell_count[sidx], 1u); atomicMax(&stage->first_inv[sidx], stamp_inv); }
+    if (sact && sdon) atomicAdd(&stage->don[sidx][first_pos], (unsigned int)sdon);
+    if (sact && sacc) atomicAdd(&stage->acc[sidx][first_pos], (unsigned int)sacc);
+  } else {
+    WeLabelEntry* e = table + slot;
+    if (lane == 0) { atomicAdd(&e->shell_count, 1ULL); atomicMax(&e->first_seen_inv, stamp_inv); }
+    if (sact && sdon) atomicAdd(&e->donates[first_pos], (unsigned int)sdon);
+    if (sact && sacc) atomicAdd(&e->accepts[first_pos], (unsigned int)sacc);
   }
   int r = 0;
   if (lane == 0) {
-    atomicAdd(&e->shell_count, 1ULL);
-    atomicMax(&e->first_seen_inv, ~((unsigned long long)frame_ids[f] * (unsigned long long)T.n_atoms + (unsigned long long)X));
     r = atomicAdd(&rec_count[f], 1);
     WeRecord rr;
     rr.atom = X;
@@ -985,8 +1035,6 @@ __device__ __forceinline__ void we_label_one(const WeTopoDev& T, int f, int xs,
     if (lane == 0) o[0] = ns;
     if (act) o[1 + lane] = A;
   }
-  if (sact && sdon) atomicAdd(&e->donates[first_pos], (unsigned int)sdon);
-  if (sact && sacc) atomicAdd(&e->accepts[first_pos], (unsigned int)sacc);
 }
 
 // Persistent wrapper: grid-stride over the work list of every frame of the batch
@@ -998,6 +1046,9 @@ k_label(WeTopoDev T, const int* __restrict__ shell_n, const int* __restrict__ sh
         const long long* __restrict__ frame_ids, WeLabelEntry* __restrict__ table,
         unsigned int table_mask, int* __restrict__ rec_count, WeRecord* __restrict__ rec,
         int2* __restrict__ rec_host, int* __restrict__ shell_host, WeWork work, int n_frames, WeDiag* diag) {
+  __shared__ WeLabelStage stage;
+  for (int t = threadIdx.x; t < (int)(sizeof(WeLabelStage) / 4); t += blockDim.x) reinterpret_cast<unsigned int*>(&stage)[t] = 0u;
+  __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int stride = gridDim.x * (blockDim.x >> 5);
   for (int f = 0; f < n_frames; ++f) {
@@ -1005,7 +1056,22 @@ k_label(WeTopoDev T, const int* __restrict__ shell_n, const int* __restrict__ sh
     const int* list = work.list + (size_t)f * work.stride;
     for (int i = blockIdx.x * (blockDim.x >> 5) + w; i < cnt; i += stride)
       we_label_one(T, f, list[i], shell_n, shell_idx, nn_arr, flags, acceptor, interfacial, frame_ids, table,
-                   table_mask, rec_count, rec, rec_host, shell_host, diag, lane);
+                   table_mask, rec_count, rec, rec_host, shell_host, &stage, diag, lane);
+  }
+  // ---- fold the staged keys into the global table ----------------------------------------------
+  __syncthreads();
+  for (int t = threadIdx.x; t < WE_STAGE_SLOTS * (2 * WE_MAX_NBR + 1); t += blockDim.x) {
+    const int sl = t / (2 * WE_MAX_NBR + 1), i = t % (2 * WE_MAX_NBR + 1);
+    if (stage.hash[sl] == 0ULL || stage.gslot[sl] < 0) continue;
+    WeLabelEntry* e = table + stage.gslot[sl];
+    if (i == 2 * WE_MAX_NBR) {
+      atomicAdd(&e->shell_count, (unsigned long long)stage.shell_count[sl]);
+      atomicMax(&e->first_seen_inv, stage.first_inv[sl]);
+    } else if (i < WE_MAX_NBR) {
+      if (stage.don[sl][i]) atomicAdd(&e->donates[i], stage.don[sl][i]);
+    } else {
+      if (stage.acc[sl][i - WE_MAX_NBR]) atomicAdd(&e->accepts[i - WE_MAX_NBR], stage.acc[sl][i - WE_MAX_NBR]);
+    }
   }
 }
 
@@ -1050,16 +1116,29 @@ __device__ __forceinline__ void we_jacobi3(double a[3][3], double v[3][3], doubl
   ev[0] = a[0][0]; ev[1] = a[1][1]; ev[2] = a[2][2];
 }
 
+// grid = (blocks per frame, frames); the blocks of a frame walk its recorded waters with a
+// grid-stride loop (about four warp-iterations each when every water is recorded).
+// K6: per-block shared-memory staging of the covariance sums (16 bin slots), flushed with one
+// global atomic per value per block; warps whose waters share one bin reduce with shuffles first.
+#define WE_COV_SLOTS 16
 __global__ void __launch_bounds__(128)
 k_cov(WeTopoDev T, const float* __restrict__ pos, const float* __restrict__ frc,
       const int* __restrict__ rec_count, const WeRecord* __restrict__ rec,
       const int* __restrict__ centre_of_slot, double* __restrict__ cov_sum,
       unsigned long long* __restrict__ cov_cnt, double* __restrict__ ft_out,
-      const float* __restrict__ fcomp, const int* __restrict__ fbase, int maxfrag) {
-  const int f = blockIdx.y;
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+      const float* __restrict__ fcomp, const int* __restrict__ fbase, int maxfrag, int n_frames) {
+  __shared__ int s_bin[WE_COV_SLOTS];
+  __shared__ double s_sum[WE_COV_SLOTS][18];
+  __shared__ unsigned long long s_cnt[WE_COV_SLOTS];
   const int lane = threadIdx.x & 31;
+  for (int t = threadIdx.x; t < WE_COV_SLOTS * 18; t += blockDim.x) s_sum[t / 18][t % 18] = 0.0;
+  if (threadIdx.x < WE_COV_SLOTS) { s_bin[threadIdx.x] = -1; s_cnt[threadIdx.x] = 0ULL; }
+  __syncthreads();
+  const int f = blockIdx.y;
+  {
   const int nrec = rec_count[f];
+  for (int r0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); r0 < nrec; r0 += gridDim.x * blockDim.x) {
+  const int r = r0 + lane;
   const bool act = r < nrec;
   double val[18];
 #pragma unroll
@@ -1153,23 +1232,43 @@ k_cov(WeTopoDev T, const float* __restrict__ pos, const float* __restrict__ frc,
       o[0] = F[0]; o[1] = F[1]; o[2] = F[2]; o[3] = tq[0]; o[4] = tq[1]; o[5] = tq[2];
     }
   }
-  // ---- K6: warp-aggregated accumulation into the dense per-bin table -----------
+  // ---- K6: accumulate ---------------------------------------------------------------
   const unsigned actm = __ballot_sync(0xffffffffu, act);
-  if (!actm) return;
   const int lead = __ffs(actm) - 1;
   const int b0 = __shfl_sync(0xffffffffu, bin, lead);
   const bool uniform = __all_sync(0xffffffffu, !act || bin == b0);
   if (uniform) {
+    double mine = 0.0;  // after the butterflies lane i keeps the warp total of value i
 #pragma unroll
     for (int i = 0; i < 18; ++i) {
       double v = val[i];
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) atomicAdd(&cov_sum[(size_t)b0 * 18 + i], v);
+      if (lane == i) mine = v;
     }
-    if (lane == 0) atomicAdd(&cov_cnt[b0], (unsigned long long)__popc(actm));
+    const int slot = b0 & (WE_COV_SLOTS - 1);
+    int owner = 0;
+    if (lane == 0) { const int old = atomicCAS(&s_bin[slot], -1, b0); owner = (old == -1 || old == b0); }
+    owner = __shfl_sync(0xffffffffu, owner, 0);
+    if (owner) {
+      if (lane < 18) atomicAdd(&s_sum[slot][lane], mine);
+      else if (lane == 18) atomicAdd(&s_cnt[slot], (unsigned long long)__popc(actm));
+    } else {
+      if (lane < 18) atomicAdd(&cov_sum[(size_t)b0 * 18 + lane], mine);
+      else if (lane == 18) atomicAdd(&cov_cnt[b0], (unsigned long long)__popc(actm));
+    }
   } else if (act) {
 #pragma unroll
     for (int i = 0; i < 18; ++i) atomicAdd(&cov_sum[(size_t)bin * 18 + i], val[i]);
     atomicAdd(&cov_cnt[bin], 1ULL);
+  }
+  }  // records
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < WE_COV_SLOTS * 19; t += blockDim.x) {
+    const int slot = t / 19, i = t % 19;
+    const int bb = s_bin[slot];
+    if (bb < 0) continue;
+    if (i < 18) { if (s_sum[slot][i] != 0.0) atomicAdd(&cov_sum[(size_t)bb * 18 + i], s_sum[slot][i]); }
+    else if (s_cnt[slot]) atomicAdd(&cov_cnt[bb], s_cnt[slot]);
   }
 }
