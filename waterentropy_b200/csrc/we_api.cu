@@ -87,6 +87,8 @@ struct we_ctx {
   unsigned char* d_interf = nullptr;
   int *d_state = nullptr, *d_wl1 = nullptr, *d_wl2 = nullptr, *d_n1 = nullptr, *d_n2 = nullptr;
   int *d_hbq = nullptr, *d_wlh = nullptr, *d_nh = nullptr;
+  int* d_zero = nullptr;
+  size_t zero_ints = 0;
   int hb_blocks = 0, label_blocks = 0;
   int *d_all_slots = nullptr;
   int rad_blocks = 0;
@@ -452,6 +454,7 @@ static int ensure_workspace(we_ctx* c, const float* dims0, bool need_input_buffe
   if (make_box(d, c->cell_target, 1 << 30, &b0)) return fail(WE_ERR_INVALID, "invalid box dimensions");
   long long ncell = (long long)b0.nc[0] * b0.nc[1] * b0.nc[2];
   c->ncap = (int)std::min<long long>(std::max<long long>(ncell, 8), 1LL << 26);
+  c->ncap = ((c->ncap + 1 + 7) & ~7) - 1;  // per-frame stride ncap + 1 is a multiple of 8 ints (int4 scans)
   int rc = 0;
   const size_t F = (size_t)chunk;
 #define AL(p, n) if ((rc = dev_alloc(c, &c->p, (n)))) return rc;
@@ -480,12 +483,25 @@ static int ensure_workspace(we_ctx* c, const float* dims0, bool need_input_buffe
     if (c->opt.keep_records || c->lazy || c->opt.keep_shells) { if ((rc = pin_alloc(c, &c->h_rec[i], F * std::max(1, c->C)))) return rc; }
     if (c->opt.keep_shells) { if ((rc = pin_alloc(c, &c->h_shell[i], F * std::max(1, c->C) * (WE_MAX_NBR + 1)))) return rc; }
   }
-  AL(d_cell_count, F * ((size_t)c->ncap + 1))
   AL(d_cell_of, F * H) AL(d_rank_of, F * H) AL(d_tmp4, F * H) AL(d_sorted4, F * H)
   AL(d_shell_n, F * H) AL(d_shell_idx, F * H * WE_MAX_NBR) AL(d_nn, F * H) AL(d_flags, F * H)
-  AL(d_acceptor, F * std::max(1, c->ND)) AL(d_interf, F * H)
+  AL(d_acceptor, F * std::max(1, c->ND))
   for (int i = 0; i < 2; ++i) { AL(d_rec_count[i], F) AL(d_rec[i], F * std::max(1, c->C)) }
-  AL(d_hbq, F * H) AL(d_wlh, F * H) AL(d_nh, F) AL(d_state, F * H) AL(d_wl1, F * std::max(1, c->C)) AL(d_wl2, F * H) AL(d_n1, F) AL(d_n2, F)
+  AL(d_wlh, F * H) AL(d_wl1, F * std::max(1, c->C)) AL(d_wl2, F * H)
+  {
+    // everything that must be zero at the start of a batch lives in one block: one memset per batch
+    const size_t n_cells = F * ((size_t)c->ncap + 1), n_fh = F * (size_t)H;
+    c->zero_ints = n_cells + 2 * n_fh + 3 * F + (n_fh + 3) / 4;
+    AL(d_zero, c->zero_ints)
+    int* p = c->d_zero;
+    c->d_cell_count = p; p += n_cells;
+    c->d_state = p; p += n_fh;
+    c->d_hbq = p; p += n_fh;
+    c->d_nh = p; p += F;
+    c->d_n1 = p; p += F;
+    c->d_n2 = p; p += F;
+    c->d_interf = reinterpret_cast<unsigned char*>(p);
+  }
   if (c->opt.keep_debug) { AL(d_nbr_idx, F * H * WE_MAX_NBR) AL(d_nbr_dist, F * H * WE_MAX_NBR) AL(d_ft, F * std::max(1, c->C) * 6) }
 #undef AL
   CK(cudaFuncSetAttribute(k_rad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WeRadSmem)));
@@ -694,14 +710,8 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     CK(cudaEventRecord(c->ev_in_ready[buf], c->s_copy));
     cudaStream_t st = c->s_comp;
     CK(cudaStreamWaitEvent(st, c->ev_in_ready[buf], 0));
-    CK(cudaMemsetAsync(c->d_cell_count, 0, (size_t)n * ((size_t)c->ncap + 1) * sizeof(int), st));
-    CK(cudaMemsetAsync(c->d_interf, 0, (size_t)n * H, st));
+    CK(cudaMemsetAsync(c->d_zero, 0, c->zero_ints * sizeof(int), st));  // cells, state, queues, counters, flags
     CK(cudaMemsetAsync(c->d_rec_count[buf], 0, (size_t)n * sizeof(int), st));
-    CK(cudaMemsetAsync(c->d_state, 0, (size_t)n * H * sizeof(int), st));
-    CK(cudaMemsetAsync(c->d_hbq, 0, (size_t)n * H * sizeof(int), st));
-    CK(cudaMemsetAsync(c->d_nh, 0, (size_t)n * sizeof(int), st));
-    CK(cudaMemsetAsync(c->d_n1, 0, (size_t)n * sizeof(int), st));
-    CK(cudaMemsetAsync(c->d_n2, 0, (size_t)n * sizeof(int), st));
     const WeBox* bx = c->d_boxes[buf];
     const long long* fids = c->d_fids[buf];
     const bool interfacial = (c->recipe == WE_RECIPE_INTERFACIAL);

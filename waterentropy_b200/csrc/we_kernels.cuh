@@ -153,8 +153,15 @@ __global__ void k_scan(const WeBox* __restrict__ boxes, int* __restrict__ cell_c
     const int i0 = base + tid * WE_SCAN_PER_THREAD;
     int v[WE_SCAN_PER_THREAD];
     int sum = 0;
+    if (i0 + WE_SCAN_PER_THREAD <= ncell) {  // 32-byte aligned: ncap + 1 is a multiple of 8
+      const int4 a = *reinterpret_cast<const int4*>(cnt + i0), c4 = *reinterpret_cast<const int4*>(cnt + i0 + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c4.x; v[5] = c4.y; v[6] = c4.z; v[7] = c4.w;
 #pragma unroll
-    for (int k = 0; k < WE_SCAN_PER_THREAD; ++k) { v[k] = (i0 + k < ncell) ? cnt[i0 + k] : 0; sum += v[k]; }
+      for (int k = 0; k < WE_SCAN_PER_THREAD; ++k) sum += v[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < WE_SCAN_PER_THREAD; ++k) { v[k] = (i0 + k < ncell) ? cnt[i0 + k] : 0; sum += v[k]; }
+    }
     int incl = sum;
     for (int o = 1; o < 32; o <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -173,10 +180,18 @@ __global__ void k_scan(const WeBox* __restrict__ boxes, int* __restrict__ cell_c
     }
     __syncthreads();
     int run = s_carry + s_part[w] + incl - sum;  // exclusive prefix of this thread's first cell
+    if (i0 + WE_SCAN_PER_THREAD <= ncell) {
+      int4 a, c4;
+      a.x = run; run += v[0]; a.y = run; run += v[1]; a.z = run; run += v[2]; a.w = run; run += v[3];
+      c4.x = run; run += v[4]; c4.y = run; run += v[5]; c4.z = run; run += v[6]; c4.w = run; run += v[7];
+      *reinterpret_cast<int4*>(cnt + i0) = a;
+      *reinterpret_cast<int4*>(cnt + i0 + 4) = c4;
+    } else {
 #pragma unroll
-    for (int k = 0; k < WE_SCAN_PER_THREAD; ++k) {
-      if (i0 + k <= ncell) cnt[i0 + k] = run;
-      run += v[k];
+      for (int k = 0; k < WE_SCAN_PER_THREAD; ++k) {
+        if (i0 + k <= ncell) cnt[i0 + k] = run;
+        run += v[k];
+      }
     }
     __syncthreads();
     if (tid == blockDim.x - 1) s_carry = run;
