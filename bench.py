@@ -366,7 +366,7 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "diag": {k: diag[k] for k in ("ambiguous_rad", "ambiguous_hb", "wide_searches", "shrink_retries", "table_entries")},
+            "diag": {k: diag[k] for k in ("wide_searches", "shrink_retries", "table_entries")},
         }
         print(json.dumps(line), flush=True)
 

@@ -90,8 +90,6 @@ typedef struct we_options {
 typedef struct we_ctx we_ctx;
 
 typedef struct we_diag {
-    uint64_t ambiguous_rad;   /* RAD comparisons within 4 ulp (libm pow vs x*x could differ) */
-    uint64_t ambiguous_hb;
     uint64_t wide_searches;   /* centres that needed the 10 A wide search */
     uint64_t shrink_retries;
     uint64_t table_entries;
@@ -230,9 +228,11 @@ int we_reset(we_ctx *ctx);
 
 /* Scalar arithmetic hooks (device-executed) so the float32 angle / powf
  * replay and the distance formula can be pinned directly in tests:
- *   maths/trig.py:103-122 (get_angle), MDAnalysis capped_distance formula. */
+ *   maths/trig.py:103-122 (get_angle), MDAnalysis capped_distance formula,
+ *   and the float64 `x ** 2` of neighbours/RAD.py:53-57 / analysis/HB.py:96 (libm pow(x, 2.0)). */
 int we_test_angle_cos(int32_t device, const float *abc /*[n][9]*/, const float *dim3, int32_t n, float *out);
 int we_test_powf2(int32_t device, const float *x, int32_t n, float *out);
+int we_test_pow2(int32_t device, const double *x, int32_t n, double *out);
 int we_test_distance(int32_t device, const float *pairs /*[n][6]*/, const float *dims6, int32_t n, double *out);
 
 #ifdef __cplusplus

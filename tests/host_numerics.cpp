@@ -30,3 +30,6 @@ void h_dist_ortho(const float* pairs, const float* dims, int n, double* out) {
 }
 int h_angle_gt_90(float c) { return we_angle_gt_90(c) ? 1 : 0; }
 }
+extern "C" void h_pow2(const double* x, int n, double* out) {
+  for (int i = 0; i < n; ++i) out[i] = we_pow2(x[i]);
+}

@@ -51,6 +51,25 @@ def test_powf2_matches_libm(hostlib):
     assert all(np.float32(v) ** 2 == r for v, r in zip(x[:20000], ref[:20000]))
 
 
+def test_pow2_f64_matches_libm_and_numpy(hostlib):
+    """we_pow2 (we_numerics.cuh) == glibc pow(x, 2.0) == NumPy's float64 scalar `x ** 2` (RAD.py:53-57, HB.py:96)."""
+    rng = np.random.default_rng(11)
+    x = np.concatenate([
+        np.exp(rng.uniform(-7, 7, 150_000)),
+        rng.uniform(0.05, 12.0, 150_000),                 # distances / inverse distances in Angstrom
+        1.0 + rng.uniform(-1e-12, 1e-12, 1000), [1.0, 0.5, 2.0, float.fromhex("0x1.b0860c015e44p-9")],
+    ]).astype(np.float64)
+    out = np.empty_like(x)
+    hostlib.h_pow2(_p(x), len(x), _p(out))
+    libm = ctypes.CDLL("libm.so.6")
+    libm.pow.restype = ctypes.c_double
+    libm.pow.argtypes = [ctypes.c_double, ctypes.c_double]
+    ref = np.array([libm.pow(float(v), 2.0) for v in x])
+    assert np.array_equal(out.view(np.uint64), ref.view(np.uint64))
+    assert (ref != x * x).sum() > 50                      # the emulation is not just x*x
+    assert all(np.float64(v) ** 2 == r for v, r in zip(x[:20000], ref[:20000]))
+
+
 def test_angle_matches_oracle_and_numpy(hostlib):
     rng = np.random.default_rng(2)
     n = 50_000

@@ -39,7 +39,7 @@ class we_options(C.Structure):
 
 class we_diag(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
-        "ambiguous_rad", "ambiguous_hb", "wide_searches", "shrink_retries", "table_entries",
+        "wide_searches", "shrink_retries", "table_entries",
         "kernel_launches", "frames_done", "recorded")]
 
 
@@ -48,7 +48,7 @@ EXPORTS = [
     "we_sync", "we_get_diag", "we_error_location", "we_n_bins", "we_copy_cov", "we_device_tables",
     "we_n_label_entries", "we_copy_label_entries", "we_frame_record_count", "we_copy_frame_records",
     "we_n_heavy", "we_n_donors", "we_copy_heavy_idx", "we_copy_donors", "we_debug_size",
-    "we_debug_copy", "we_reset", "we_test_angle_cos", "we_test_powf2", "we_test_distance",
+    "we_debug_copy", "we_reset", "we_test_angle_cos", "we_test_powf2", "we_test_pow2", "we_test_distance",
     "we_profile", "we_kernel_times", "we_span_start", "we_span_stop",
     "we_label_entries_device", "we_merge_label_entries", "we_snapshot_cov", "we_wait_cov",
     "we_copy_frame_shells",
@@ -139,6 +139,8 @@ def load():
     L.we_test_angle_cos.argtypes = [I, V, V, I, V]
     L.we_test_powf2.restype = I
     L.we_test_powf2.argtypes = [I, V, I, V]
+    L.we_test_pow2.restype = I
+    L.we_test_pow2.argtypes = [I, V, I, V]
     L.we_test_distance.restype = I
     L.we_test_distance.argtypes = [I, V, V, I, V]
     _lib = L

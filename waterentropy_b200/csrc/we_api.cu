@@ -916,8 +916,6 @@ extern "C" int we_get_diag(we_ctx* c, we_diag* out) {
   WeDiag d;
   int rc = read_diag(c, &d);
   if (rc) return rc;
-  out->ambiguous_rad = d.ambiguous_rad;
-  out->ambiguous_hb = d.ambiguous_hb;
   out->wide_searches = d.wide_searches;
   out->shrink_retries = d.shrink_retries;
   out->table_entries = d.table_entries;
@@ -1200,6 +1198,10 @@ __global__ void k_test_powf2(const float* x, int n, float* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = we_powf2(x[i], PT);
 }
+__global__ void k_test_pow2(const double* x, int n, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = we_pow2(x[i]);
+}
 __global__ void k_test_dist(const float* pairs, WeBox b, int n, double* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -1243,6 +1245,11 @@ extern "C" int we_test_angle_cos(int32_t device, const float* abc, const float* 
 extern "C" int we_test_powf2(int32_t device, const float* x, int32_t n, float* out) {
   return run_test(device, x, (size_t)n * 4, out, (size_t)n * 4, [&](void* di, void* dout) {
     k_test_powf2<<<(n + 127) / 128, 128>>>((const float*)di, n, (float*)dout);
+  });
+}
+extern "C" int we_test_pow2(int32_t device, const double* x, int32_t n, double* out) {
+  return run_test(device, x, (size_t)n * 8, out, (size_t)n * 8, [&](void* di, void* dout) {
+    k_test_pow2<<<(n + 127) / 128, 128>>>((const double*)di, n, (double*)dout);
   });
 }
 extern "C" int we_test_distance(int32_t device, const float* pairs, const float* dims6, int32_t n, double* out) {

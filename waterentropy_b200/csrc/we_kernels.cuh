@@ -68,8 +68,6 @@ struct WeTopoDev {
 };
 
 struct WeDiag {
-  unsigned long long ambiguous_rad;  // RAD decisions within 4 ulp (pow vs x*x could differ)
-  unsigned long long ambiguous_hb;
   unsigned long long wide_searches;
   unsigned long long shrink_retries;
   unsigned long long table_entries;
@@ -542,8 +540,7 @@ __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __re
     }
     ej = we_angle_sep_h(pjx, pjy, pjz, rx, ry, rz, b.box, half);
     sj = we_powf2_fast(ej, PT);
-    const double inv = we_ddiv(1.0, dj);
-    qj = we_mul(inv, inv);  // (1/r)**2 ; libm pow differs from x*x by <= 1 ulp (see diag)
+    qj = we_pow2(we_ddiv(1.0, dj));  // (1/r)**2 as libm pow(x, 2.0) evaluates it
     S.px[w][lane] = pjx; S.py[w][lane] = pjy; S.pz[w][lane] = pjz;
     S.e[w][lane] = ej; S.s[w][lane] = sj; S.q[w][lane] = qj;
   }
@@ -566,7 +563,6 @@ __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __re
       } else {
         const double rhs = we_mul(S.q[w][k], (double)cs);
         if (qj < rhs) { blocked = true; alive = false; }
-        if (fabs(qj - rhs) <= 8.9e-16 * qj) atomicAdd(&diag->ambiguous_rad, 1ULL);
       }
     } else if (alive && k >= lane) {
       alive = false;
@@ -696,7 +692,6 @@ k_hb(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes
         double bq0 = 1.0e300, bq1 = 1.0e300, bi0 = 1.0e300;  // qualifying (rc, dist); in-range dist
         int bq2 = 0x7fffffff, bi2 = 0x7fffffff;
         bool dup = false;
-        double second_rc = 1.0e300;
         const int ns_live = live ? ns : 0;
         const int ns_max = __reduce_max_sync(0xffffffffu, ns_live);
         for (int m0 = 0; m0 < ns_max; m0 += 8) {
@@ -713,10 +708,11 @@ k_hb(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes
               const float dbc = we_angle_sep_h(ax, ay, az, dx, dy, dz, b.box, half);
               const float dac = we_angle_sep_h(ax, ay, az, xx, xy, xz, b.box, half);
               const float cs = we_angle_cos_from(dac, dbc, we_powf2_fast(dbc, PT), dba, dba2, PT);
-              const double rc = we_ddiv(we_mul(qD, T.charges[A]), we_mul(dist, dist));
-              if ((rc < 99.0) && we_angle_gt_90(cs)) {
-                if (we_lex_less(rc, dist, A, bq0, bq1, bq2)) { second_rc = bq0; bq0 = rc; bq1 = dist; bq2 = A; }
-                else if (rc < second_rc) second_rc = rc;
+              if (we_angle_gt_90(cs)) {  // dist**2 is libm pow(dist, 2.0): only evaluated past the angle test
+                const double rc = we_ddiv(we_mul(qD, T.charges[A]), we_pow2(dist));
+                if (rc < 99.0) {
+                  if (we_lex_less(rc, dist, A, bq0, bq1, bq2)) { bq0 = rc; bq1 = dist; bq2 = A; }
+                }
               }
             }
           }
@@ -725,11 +721,9 @@ k_hb(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes
         for (int o = 4; o > 0; o >>= 1) {
           const double q0 = __shfl_xor_sync(0xffffffffu, bq0, o), q1 = __shfl_xor_sync(0xffffffffu, bq1, o);
           const int q2 = __shfl_xor_sync(0xffffffffu, bq2, o);
-          const double s2 = __shfl_xor_sync(0xffffffffu, second_rc, o);
           const double i0d = __shfl_xor_sync(0xffffffffu, bi0, o);
           const int i2 = __shfl_xor_sync(0xffffffffu, bi2, o);
           const bool du = __shfl_xor_sync(0xffffffffu, (int)dup, o) != 0;
-          second_rc = fmin(fmax(bq0, q0), fmin(second_rc, s2));  // second smallest rc of the union
           if (we_lex_less(q0, q1, q2, bq0, bq1, bq2)) { bq0 = q0; bq1 = q1; bq2 = q2; }
           if (we_lex_less(i0d, 0.0, i2, bi0, 0.0, bi2)) { bi0 = i0d; bi2 = i2; }
           dup |= du;
@@ -741,9 +735,6 @@ k_hb(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes
           else if (bi2 == 0x7fffffff) out = -1 - WE_ST_NO_NEIGHBOURS;
           else out = (bq2 != 0x7fffffff) ? bq2 : bi2;
           acceptor[(size_t)f * T.n_don + d] = out;
-          // diagnostic: a runner-up whose rc is within 4 ulp of the winner's
-          if (st == WE_ST_OK && bq2 != 0x7fffffff && second_rc < 1.0e299 && fabs(second_rc - bq0) <= 8.9e-16 * fabs(bq0))
-            atomicAdd(&diag->ambiguous_hb, 1ULL);
         }
       }
     }

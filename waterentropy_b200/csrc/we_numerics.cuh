@@ -274,6 +274,83 @@ WE_HD float we_angle_cos(const float* a, const float* b, const float* c, const f
 // float(degrees(arccos(c))) > 90 evaluated in float32  <=>  -1 <= c <= -2^-24
 WE_HD bool we_angle_gt_90(float c) { return (c >= -1.0f) && (c <= -5.9604644775390625e-08f); }
 
+// ---- glibc pow(x, 2.0) in double precision ------------------------------------
+// The reference squares float64 scalars with `**2` (neighbours/RAD.py:53-57 `(1/r)**2`, analysis/HB.py:96
+// `dist**2`), which NumPy hands to libm pow().  pow(x, 2.0) is correctly rounded in ~99.92 % of the cases
+// and one ulp off x*x otherwise, so the device follows glibc (>= 2.28, e_pow.c as built for FMA CPUs;
+// the contraction pattern below is the one of libm 2.39's __pow_fma, read from its disassembly)
+// step by step: log_inline() -> (hi, lo), y = 2 -> exp_inline().  Valid for
+// finite normal x > 0 with |2 ln x| < 512, which covers every distance and inverse distance (Angstrom)
+// the path produces.  tests/host_numerics.cpp checks the host build against libm on 10^7 arguments; the
+// GPU parity suite checks the device build against NumPy.
+#include "we_pow64_tables.h"
+#ifdef __CUDACC__
+__device__ const double we_d_powlog[128][3] = {WE_POW_LOG_TAB};
+__device__ const unsigned long long we_d_exptab[256] = {WE_EXP_TAB};
+#endif
+static const double we_h_powlog[128][3] = {WE_POW_LOG_TAB};
+static const unsigned long long we_h_exptab[256] = {WE_EXP_TAB};
+
+WE_HD double we_fma(double a, double b, double c) {
+#ifdef __CUDA_ARCH__
+  return __fma_rn(a, b, c);
+#else
+  return fma(a, b, c);
+#endif
+}
+
+WE_HD double we_pow2(double x) {
+#ifdef __CUDA_ARCH__
+  const double(*LT)[3] = we_d_powlog;
+  const unsigned long long* ET = we_d_exptab;
+#else
+  const double(*LT)[3] = we_h_powlog;
+  const unsigned long long* ET = we_h_exptab;
+#endif
+  const double A[7] = WE_POW_A;
+  const double C[4] = WE_EXP_C;
+  // log_inline: x = 2^k z, z in [0x1.69555p-1, 0x1.69555p0), log(x) = k ln2 + log(c) + log1p(z/c - 1)
+  const uint64_t ix = we_d2u(x);
+  const uint64_t tmp = ix - 0x3fe6955500000000ULL;
+  const int i = (int)((tmp >> 45) & 127);
+  const int k = (int)((int64_t)tmp >> 52);
+  const double z = we_u2d(ix - (tmp & (0xfffULL << 52)));
+  const double kd = (double)k;
+  const double invc = LT[i][0], logc = LT[i][1], logctail = LT[i][2];
+  const double r = we_fma(z, invc, -1.0);
+  const double t1 = we_fma(kd, WE_POW_LN2HI, logc);
+  const double t2 = we_add(t1, r);
+  const double lo1 = we_fma(kd, WE_POW_LN2LO, logctail);
+  const double lo2 = we_add(we_add(t1, -t2), r);
+  const double ar = we_mul(A[0], r);
+  const double ar2 = we_mul(r, ar);
+  const double ar3 = we_mul(r, ar2);
+  const double hi = we_add(t2, ar2);
+  const double lo3 = we_fma(ar, r, -ar2);
+  const double lo4 = we_add(we_add(t2, -hi), ar2);
+  double q = we_fma(ar2, we_fma(r, A[6], A[5]), we_fma(r, A[4], A[3]));
+  q = we_fma(ar2, q, we_fma(r, A[2], A[1]));
+  const double lo = we_fma(ar3, q, we_add(we_add(we_add(lo1, lo2), lo3), lo4));
+  const double y = we_add(hi, lo);
+  const double tail = we_add(we_add(hi, -y), lo);
+  // y = 2: ehi = 2*log(x) and its rounding error are exact
+  const double ehi = we_mul(2.0, y);
+  const double elo = we_fma(2.0, tail, we_fma(2.0, y, -ehi));
+  // exp_inline: exp(ehi + elo) = 2^(kk/128) exp(rr)
+  double kd2 = we_fma(WE_EXP_INVLN2N, ehi, WE_EXP_SHIFT);
+  const uint64_t ki = we_d2u(kd2);
+  kd2 = we_add(kd2, -(WE_EXP_SHIFT));
+  double rr = we_fma(kd2, WE_EXP_NEGLN2LON, we_fma(kd2, WE_EXP_NEGLN2HIN, ehi));
+  rr = we_add(rr, elo);
+  const uint64_t idx = 2 * (ki & 127);
+  const double tl = we_u2d(ET[idx]);
+  const double scale = we_u2d(ET[idx + 1] + (ki << 45));
+  const double r2 = we_mul(rr, rr);
+  double s = we_fma(r2, we_fma(rr, C[1], C[0]), we_add(tl, rr));
+  s = we_fma(we_mul(r2, r2), we_fma(rr, C[3], C[2]), s);
+  return we_fma(scale, s, scale);
+}
+
 // per-frame box description (built on the host by we_submit, see we_api.cu)
 struct WeBox {
   float box[3];   // dimensions[:3]
