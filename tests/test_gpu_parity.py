@@ -415,6 +415,31 @@ def test_chunking_and_device_resident_inputs_agree():
             assert np.array_equal(a, b)
 
 
+def test_records_of_frames_in_flight_are_readable_without_sync():
+    """Batches sit in a ring of four slots; asking for the recorded waters of a frame whose batch is still
+    in flight waits for that batch only, and the lists keep submission order over many ring turns."""
+    inp = gio.load_inputs("synth_tric")
+    F = inp["positions"].shape[0]
+    ref_eng = _engine(inp, chunk_frames=8)
+    ref_eng.submit(inp["positions"], inp["forces"], inp["dimensions"], list(range(F)))
+    ref_eng.sync()
+    ref = [ref_eng.frame_records(k).copy() for k in range(F)]
+    ref_cov = ref_eng.cov_tables()
+    ref_eng.close()
+    for fu in (1, 2):
+        eng = _engine(inp, chunk_frames=1, force_upload=fu)
+        for rep in range(3):                       # 3 x F one-frame batches: the ring wraps many times
+            eng.submit(inp["positions"], inp["forces"], inp["dimensions"], list(range(F)))
+            last = rep * F + F - 1
+            assert np.array_equal(eng.frame_records(last), ref[F - 1])      # newest batch, no sync
+            for k in range(F):
+                assert np.array_equal(eng.frame_records(rep * F + k), ref[k])
+        eng.sync()
+        s, c = eng.cov_tables()
+        assert np.array_equal(c, 3 * ref_cov[1]) and np.allclose(s, 3 * ref_cov[0], rtol=1e-12)
+        eng.close()
+
+
 def test_label_table_grows_and_rehashes():
     """A tiny initial table must grow (device rehash) without changing any count."""
     inp = gio.load_inputs("arginine")

@@ -47,6 +47,13 @@ struct FrameDebug {
   std::vector<double> nbr_dist, ft;
 };
 
+// Batches in flight: input staging buffers, record buffers and their events form a ring of WE_NBUF
+// slots, so the device always has a few milliseconds of queued work while the host reads results.
+#ifndef WE_NBUF_SLOTS
+#define WE_NBUF_SLOTS 4
+#endif
+static const int WE_NBUF = WE_NBUF_SLOTS;
+
 struct we_ctx {
   int device = 0;
   we_options opt{};
@@ -75,12 +82,12 @@ struct we_ctx {
   bool ws_ready = false;
   int chunk = 0, ncap = 0;
   float cell_target = 7.0f;
-  float* d_pos[2] = {nullptr, nullptr};
-  float* d_frc[2] = {nullptr, nullptr};
-  WeBox* d_boxes[2] = {nullptr, nullptr};
-  long long* d_fids[2] = {nullptr, nullptr};
-  WeBox* h_boxes[2] = {nullptr, nullptr};
-  long long* h_fids[2] = {nullptr, nullptr};
+  float* d_pos[WE_NBUF] = {};
+  float* d_frc[WE_NBUF] = {};
+  WeBox* d_boxes[WE_NBUF] = {};
+  long long* d_fids[WE_NBUF] = {};
+  WeBox* h_boxes[WE_NBUF] = {};
+  long long* h_fids[WE_NBUF] = {};
   int *d_cell_count = nullptr, *d_cell_of = nullptr, *d_rank_of = nullptr;
   float4 *d_tmp4 = nullptr, *d_sorted4 = nullptr;
   int *d_shell_n = nullptr, *d_shell_idx = nullptr, *d_nn = nullptr, *d_flags = nullptr, *d_acceptor = nullptr;
@@ -92,31 +99,32 @@ struct we_ctx {
   int hb_blocks = 0, label_blocks = 0;
   int *d_all_slots = nullptr;
   int rad_blocks = 0;
-  int* d_rec_count[2] = {nullptr, nullptr};
-  WeRecord* d_rec[2] = {nullptr, nullptr};
+  int* d_rec_count[WE_NBUF] = {};
+  WeRecord* d_rec[WE_NBUF] = {};
   // lazy force upload
   bool lazy = false;
   int maxfrag = 0;
   std::vector<int> h_centre_of_atom, h_frag_ptr, h_frag_atoms;
-  float* h_fcomp[2] = {nullptr, nullptr};
-  float* d_fcomp[2] = {nullptr, nullptr};
-  int* h_fbase[2] = {nullptr, nullptr};
-  int* d_fbase[2] = {nullptr, nullptr};
-  bool lazy_pending[2] = {false, false};
-  const float* pend_frc[2] = {nullptr, nullptr};
-  const float* pend_dp[2] = {nullptr, nullptr};
-  cudaEvent_t ev_label[2]{}, ev_f[2]{};
+  float* h_fcomp[WE_NBUF] = {};
+  float* d_fcomp[WE_NBUF] = {};
+  int* h_fbase[WE_NBUF] = {};
+  int* d_fbase[WE_NBUF] = {};
+  bool lazy_pending[WE_NBUF] = {};
+  const float* pend_frc[WE_NBUF] = {};
+  const float* pend_dp[WE_NBUF] = {};
+  cudaEvent_t ev_label[WE_NBUF]{}, ev_f[WE_NBUF]{};
   int* d_nbr_idx = nullptr;
   double* d_nbr_dist = nullptr;
   double* d_ft = nullptr;
-  int* h_rec_count[2] = {nullptr, nullptr};
-  int2* h_rec[2] = {nullptr, nullptr};  // mapped pinned memory written by k_label
-  int* h_shell[2] = {nullptr, nullptr};  // mapped pinned: RAD shells of recorded waters (keep_shells)
+  int* h_rec_count[WE_NBUF] = {};
+  int2* h_rec[WE_NBUF] = {};  // mapped pinned memory written by k_label
+  int* h_shell[WE_NBUF] = {};  // mapped pinned: RAD shells of recorded waters (keep_shells)
   std::vector<std::vector<int>> frame_shells;
-  int pending_n[2] = {0, 0};
+  int pending_n[WE_NBUF] = {};
   cudaStream_t s_copy = nullptr, s_comp = nullptr, s_cov = nullptr;
-  cudaEvent_t ev_in_ready[2]{}, ev_in_free[2]{}, ev_out_ready[2]{};
-  bool out_pending[2] = {false, false};
+  cudaEvent_t ev_in_ready[WE_NBUF]{}, ev_in_free[WE_NBUF]{}, ev_out_ready[WE_NBUF]{}, ev_p0[WE_NBUF]{};
+  int copy_gate = 1, cov_stream = 1;
+  bool out_pending[WE_NBUF] = {};
   // results on host
   std::vector<std::vector<int>> frame_records;  // per submitted frame: (atom, nearest) pairs sorted by atom
   std::vector<FrameDebug> debug;
@@ -378,15 +386,18 @@ extern "C" int we_create(const we_topology* t, const we_options* opt, we_ctx** o
   CK(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->s_cov, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < WE_NBUF; ++i) {
     CK(cudaEventCreateWithFlags(&c->ev_in_ready[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_in_free[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_out_ready[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_p0[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_label[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_f[i], cudaEventDisableTiming));
   }
   if ((rc = pin_alloc(c, &c->h_diag, 1))) { we_destroy(c); return rc; }
   memset(c->h_diag, 0, sizeof(WeDiag));
+  if (const char* g = getenv("WE_COPY_GATE")) c->copy_gate = atoi(g);
+  if (const char* g = getenv("WE_COV_STREAM")) c->cov_stream = atoi(g);
   rc = we_reset(c);
   if (rc) { we_destroy(c); return rc; }
   *out = c;
@@ -426,14 +437,14 @@ extern "C" void we_destroy(we_ctx* c) {
   if (c->s_comp) cudaStreamDestroy(c->s_comp);
   if (c->s_cov) cudaStreamDestroy(c->s_cov);
   if (c->ev_cov) cudaEventDestroy(c->ev_cov);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < WE_NBUF; ++i) {
     if (c->ev_in_ready[i]) cudaEventDestroy(c->ev_in_ready[i]);
     if (c->ev_in_free[i]) cudaEventDestroy(c->ev_in_free[i]);
     if (c->ev_out_ready[i]) cudaEventDestroy(c->ev_out_ready[i]);
+    if (c->ev_p0[i]) cudaEventDestroy(c->ev_p0[i]);
     if (c->ev_label[i]) cudaEventDestroy(c->ev_label[i]);
     if (c->ev_f[i]) cudaEventDestroy(c->ev_f[i]);
-    if (c->ev_snap[i]) cudaEventDestroy(c->ev_snap[i]);
-    if (c->ev_snap[i + 2]) cudaEventDestroy(c->ev_snap[i + 2]);
+    if (i < 4 && c->ev_snap[i]) cudaEventDestroy(c->ev_snap[i]);
   }
   delete c;
 }
@@ -465,17 +476,17 @@ static int ensure_workspace(we_ctx* c, const float* dims0, bool need_input_buffe
   c->lazy = need_input_buffers && !c->opt.keep_debug && c->maxfrag > 0 && c->maxfrag <= 8 &&
             c->opt.force_upload == 2;
   if (need_input_buffers) {
-    for (int i = 0; i < 2; ++i) { AL(d_pos[i], F * N * 3) }  // d_frc: allocated on first whole-frame upload
+    for (int i = 0; i < WE_NBUF; ++i) { AL(d_pos[i], F * N * 3) }  // d_frc: allocated on first whole-frame upload
   }
   if (c->lazy) {
     const size_t cap = F * std::max(1, c->C) * (size_t)c->maxfrag * 3;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < WE_NBUF; ++i) {
       AL(d_fcomp[i], cap) AL(d_fbase[i], F)
       if ((rc = pin_alloc(c, &c->h_fcomp[i], cap))) return rc;
       if ((rc = pin_alloc(c, &c->h_fbase[i], F))) return rc;
     }
   }
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < WE_NBUF; ++i) {
     AL(d_boxes[i], F) AL(d_fids[i], F)
     if ((rc = pin_alloc(c, &c->h_boxes[i], F))) return rc;
     if ((rc = pin_alloc(c, &c->h_fids[i], F))) return rc;
@@ -486,7 +497,7 @@ static int ensure_workspace(we_ctx* c, const float* dims0, bool need_input_buffe
   AL(d_cell_of, F * H) AL(d_rank_of, F * H) AL(d_tmp4, F * H) AL(d_sorted4, F * H)
   AL(d_shell_n, F * H) AL(d_shell_idx, F * H * WE_MAX_NBR) AL(d_nn, F * H) AL(d_flags, F * H)
   AL(d_acceptor, F * std::max(1, c->ND))
-  for (int i = 0; i < 2; ++i) { AL(d_rec_count[i], F) AL(d_rec[i], F * std::max(1, c->C)) }
+  for (int i = 0; i < WE_NBUF; ++i) { AL(d_rec_count[i], F) AL(d_rec[i], F * std::max(1, c->C)) }
   AL(d_wlh, F * H) AL(d_wl1, F * std::max(1, c->C)) AL(d_wl2, F * H)
   {
     // everything that must be zero at the start of a batch lives in one block: one memset per batch
@@ -646,6 +657,15 @@ static int finish_lazy(we_ctx* c, int buf) {
   return 0;
 }
 
+// the slot chunk_counter % WE_NBUF holds the oldest batch in flight
+static int finish_lazy_all(we_ctx* c) {
+  for (int i = 0; i < WE_NBUF; ++i) {
+    const int rc = finish_lazy(c, (int)((c->chunk_counter + i) % WE_NBUF));
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_device, const float* dims,
                        const int64_t* frame_ids, int n_frames) {
   if (!c || !pos || !frc || !dims || !frame_ids) return fail(WE_ERR_INVALID, "null argument");
@@ -671,15 +691,15 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       return fail(WE_ERR_INVALID, "force_upload = 3 needs the force buffer in pinned (page-locked) host memory");
   }
   if (!on_device && !c->lazy && !frc_zero_copy && !c->d_frc[0]) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < WE_NBUF; ++i) {
       if ((rc = dev_alloc(c, &c->d_frc[i], (size_t)c->chunk * N * 3))) return rc;
     }
   }
   for (int f0 = 0; f0 < n_frames; f0 += c->chunk) {
     const int n = std::min(c->chunk, n_frames - f0);
-    const int buf = (int)(c->chunk_counter & 1);
+    const int buf = (int)(c->chunk_counter % WE_NBUF);
     c->chunk_counter++;
-    // staging buffers of this slot were last used two chunks ago
+    // staging buffers of this slot were last used WE_NBUF chunks ago
     if ((rc = finish_lazy(c, buf))) return rc;
     if ((rc = drain(c, buf))) return rc;
     CK(cudaEventSynchronize(c->ev_in_free[buf]));
@@ -692,6 +712,11 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     const float* dp;
     const float* df;
     if (!on_device) {
+      // While a host->device DMA is in flight every kernel launch of the compute stream takes 20-40 us
+      // longer (measured: the short kernels of a batch appear 2-3x slower, the 0.4 ms first neighbour
+      // pass +3 %).  So the upload of this batch starts when the first pass of the previous batch
+      // starts and is over before the run of short kernels that follows it (WE_COPY_GATE=0: ungated).
+      if (c->copy_gate) CK(cudaStreamWaitEvent(c->s_copy, c->ev_p0[(buf + WE_NBUF - 1) % WE_NBUF], 0));
       CK(cudaMemcpyAsync(c->d_pos[buf], pos + (size_t)f0 * frame_floats, (size_t)n * frame_floats * sizeof(float), cudaMemcpyHostToDevice, c->s_copy));
       dp = c->d_pos[buf];
       if (frc_zero_copy) {
@@ -708,7 +733,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     CK(cudaMemcpyAsync(c->d_boxes[buf], c->h_boxes[buf], (size_t)n * sizeof(WeBox), cudaMemcpyHostToDevice, c->s_copy));
     CK(cudaMemcpyAsync(c->d_fids[buf], c->h_fids[buf], (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, c->s_copy));
     CK(cudaEventRecord(c->ev_in_ready[buf], c->s_copy));
-    cudaStream_t st = c->s_comp;
+    cudaStream_t st = c->s_comp, cov_st = c->s_comp;
     CK(cudaStreamWaitEvent(st, c->ev_in_ready[buf], 0));
     CK(cudaMemsetAsync(c->d_zero, 0, c->zero_ints * sizeof(int), st));  // cells, state, queues, counters, flags
     CK(cudaMemsetAsync(c->d_rec_count[buf], 0, (size_t)n * sizeof(int), st));
@@ -741,6 +766,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       { ProfScope ps(c, WE_K_MARK, st);
         k_seed<<<dim3((w0.static_count + 255) / 256, n), 256, 0, st>>>(w0.static_count, w0.list, H, c->d_state);
         ps.stop(st); }
+      CK(cudaEventRecord(c->ev_p0[buf], st));
       { ProfScope ps(c, WE_K_RAD, st);
         k_rad<<<rad_grid((long long)w0.static_count * n), WE_RAD_WARPS * 32, sizeof(WeRadSmem), st>>>(
             c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->d_tmp4, c->ncap, c->cell_target, w0, n, ro,
@@ -801,11 +827,17 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
         ps.stop(st); }
       c->launches += 1;
       if (!c->lazy) {
-        ProfScope ps(c, WE_K_COV, st);
-        k_cov<<<dim3((C + 511) / 512, n), 128, 0, st>>>(
+        // zero-copy forces: the kernel waits on PCIe reads, so it runs beside the next batch's kernels
+        cov_st = (frc_zero_copy && c->cov_stream) ? c->s_cov : st;
+        if (cov_st != st) {
+          CK(cudaEventRecord(c->ev_label[buf], st));
+          CK(cudaStreamWaitEvent(cov_st, c->ev_label[buf], 0));
+        }
+        ProfScope ps(c, WE_K_COV, cov_st);
+        k_cov<<<dim3((C + 511) / 512, n), 128, 0, cov_st>>>(
             c->T, dp, df, c->d_rec_count[buf], c->d_rec[buf], c->d_centre_of_slot, c->d_cov_sum,
             c->d_cov_cnt, c->d_ft, nullptr, nullptr, 0, n);
-        ps.stop(st);
+        ps.stop(cov_st);
         c->launches += 1;
       }
     }
@@ -822,16 +854,20 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       c->lazy_pending[buf] = true;
       c->pend_frc[buf] = frc + (size_t)f0 * frame_floats;
       c->pend_dp[buf] = dp;
-      if ((rc = finish_lazy(c, buf ^ 1))) return rc;
+      if ((rc = finish_lazy(c, (buf + WE_NBUF - 1) % WE_NBUF))) return rc;
     } else {
-      CK(cudaEventRecord(c->ev_in_free[buf], st));
-      CK(cudaEventRecord(c->ev_out_ready[buf], st));
+      if (cov_st != st) {  // both events must also cover the record-count copy queued on the compute stream
+        CK(cudaEventRecord(c->ev_f[buf], st));
+        CK(cudaStreamWaitEvent(cov_st, c->ev_f[buf], 0));
+      }
+      CK(cudaEventRecord(c->ev_in_free[buf], cov_st));
+      CK(cudaEventRecord(c->ev_out_ready[buf], cov_st));
       c->out_pending[buf] = true;
     }
     if (c->opt.keep_debug) {
       CK(cudaStreamSynchronize(st));
-      if ((rc = drain(c, buf ^ 1))) return rc;  // keep frame order in frame_records
-      if ((rc = drain(c, buf))) return rc;
+      for (int i = 1; i <= WE_NBUF; ++i)  // oldest first: keeps frame order in frame_records
+        if ((rc = drain(c, (buf + i) % WE_NBUF))) return rc;
       std::vector<int> rc_h(n);
       CK(cudaMemcpy(rc_h.data(), c->d_rec_count[buf], (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
       for (int f = 0; f < n; ++f) {
@@ -875,20 +911,17 @@ extern "C" int we_sync(we_ctx* c) {
   if (!c) return fail(WE_ERR_INVALID, "null context");
   CK(cudaSetDevice(c->device));
   {
-    const int older0 = (int)(c->chunk_counter & 1);
     int rc0;
-    if ((rc0 = finish_lazy(c, older0))) return rc0;
-    if ((rc0 = finish_lazy(c, older0 ^ 1))) return rc0;
+    if ((rc0 = finish_lazy_all(c))) return rc0;
   }
   CK(cudaStreamSynchronize(c->s_copy));
   CK(cudaStreamSynchronize(c->s_comp));
   CK(cudaStreamSynchronize(c->s_cov));
   prof_resolve(c);
   // drain in submission order
-  const int older = (int)(c->chunk_counter & 1);
   int rc;
-  if ((rc = drain(c, older))) return rc;
-  if ((rc = drain(c, older ^ 1))) return rc;
+  for (int i = 0; i < WE_NBUF; ++i)
+    if ((rc = drain(c, (int)((c->chunk_counter + i) % WE_NBUF)))) return rc;
   WeDiag d;
   if ((rc = read_diag(c, &d))) return rc;
   switch (d.err_code) {
@@ -985,9 +1018,7 @@ extern "C" int we_snapshot_cov(we_ctx* c) {
   CK(cudaSetDevice(c->device));
   int rc;
   // lazy-upload batches still waiting for their covariance kernel must run it first
-  const int older = (int)(c->chunk_counter & 1);
-  if ((rc = finish_lazy(c, older))) return rc;
-  if ((rc = finish_lazy(c, older ^ 1))) return rc;
+  if ((rc = finish_lazy_all(c))) return rc;
   const int slot = (int)(c->snap_counter & 3);
   const size_t bs = (size_t)c->B * 18 * sizeof(double), bc = (size_t)c->B * sizeof(unsigned long long);
   if (!c->h_snap[slot]) {
@@ -1125,7 +1156,22 @@ extern "C" int we_merge_label_entries(we_ctx* c, const void* d_entries, int32_t 
   return WE_OK;
 }
 
+// Frames of batches still in flight: wait for (only) the batches up to the one holding frame k.
+static int drain_until(we_ctx* c, size_t have, int64_t k) {
+  if (!c || k < 0 || (size_t)k < have || (unsigned long long)k >= c->frames_done) return 0;
+  cudaSetDevice(c->device);
+  for (int i = 0; i < WE_NBUF; ++i) {
+    const int buf = (int)((c->chunk_counter + i) % WE_NBUF);
+    int rc;
+    if ((rc = finish_lazy(c, buf))) return rc;
+    if ((rc = drain(c, buf))) return rc;
+    if ((size_t)k < c->frame_records.size()) break;
+  }
+  return 0;
+}
+
 extern "C" int we_frame_record_count(we_ctx* c, int64_t k) {
+  if (c && (c->opt.keep_records || c->opt.keep_shells)) { const int rc = drain_until(c, c->frame_records.size(), k); if (rc) return rc; }
   if (!c || k < 0 || k >= (int64_t)c->frame_records.size()) return fail(WE_ERR_INVALID, "frame ordinal out of range (keep_records set?)");
   return (int)(c->frame_records[(size_t)k].size() / 2);
 }
@@ -1138,6 +1184,7 @@ extern "C" int we_copy_frame_records(we_ctx* c, int64_t k, int32_t* out, int32_t
 }
 
 extern "C" int we_copy_frame_shells(we_ctx* c, int64_t k, int32_t* out, int32_t capacity) {
+  if (c && c->opt.keep_shells) { const int rc = drain_until(c, c->frame_shells.size(), k); if (rc) return rc; }
   if (!c || k < 0 || k >= (int64_t)c->frame_shells.size()) return fail(WE_ERR_INVALID, "frame ordinal out of range (keep_shells set?)");
   const int n = (int)(c->frame_shells[(size_t)k].size() / (WE_MAX_NBR + 1));
   if (n > capacity) return fail(WE_ERR_INVALID, "capacity too small");
