@@ -334,6 +334,19 @@ def run_ours(args, rank, world, local_rank):
     e2e_s = maxr(time.perf_counter() - t0)
     clk = clocks.stop()
     e2e_val = world * W * Fps * args.steps / e2e_s
+    # bytes that cross PCIe per step: positions, boxes and frame ids are copied; the forces either are
+    # copied whole (force_upload 1 / bulk recipe) or stay in pinned host memory and k_cov reads the atoms
+    # of the recorded waters in place (zero-copy, the default for the interfacial recipe)
+    zero_copy = recipe == "interfacial" and args.force_upload in (0, 3)
+    if zero_copy:
+        h2d = P.nbytes + Fps * 32 + int(nrec) * 3 * 12
+        force_path = "zero-copy: recorded waters' atoms read in place from pinned host memory"
+    elif args.force_upload == 2:
+        h2d = P.nbytes + Fps * 32 + int(nrec) * 3 * 12
+        force_path = "recorded waters' atoms gathered by the host, uploaded compactly"
+    else:
+        h2d = input_bytes + Fps * 32
+        force_path = "whole force frames copied"
     final_bytes = int(entries.nbytes)
     eng.close()
 
@@ -358,7 +371,8 @@ def run_ours(args, rank, world, local_rank):
                        "l2": f"inputs {input_bytes / 1e6:.0f} MB per step per GPU "
                              + ("> 126 MB L2 (no flush needed)" if input_bytes > 126e6 else "<= L2: reduce reliance, see DESIGN.md")},
             "clocks": clk,
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(input_bytes + Fps * 32),
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "host_input_bytes_per_step": int(input_bytes + Fps * 32), "force_path": force_path,
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s / args.steps * 1e3,
                     "d2h_bytes_at_end_of_job": final_bytes,
                     "timed": "K x (submit from pinned host memory; stream-ordered covariance snapshot + recorded-water "
