@@ -70,6 +70,19 @@ def test_pow2_f64_matches_libm_and_numpy(hostlib):
     assert all(np.float64(v) ** 2 == r for v, r in zip(x[:20000], ref[:20000]))
 
 
+def test_pow_tables_are_this_libms():
+    """csrc/we_pow64_tables.h holds exactly the constants of the libm the reference would run on here."""
+    import importlib.util
+
+    libm_path = "/lib/x86_64-linux-gnu/libm.so.6"
+    if not os.path.exists(libm_path):
+        pytest.skip("no x86-64 glibc libm at the usual path")
+    spec = importlib.util.spec_from_file_location("make_pow_tables", os.path.join(REPO, "tools", "make_pow_tables.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.render(libm_path) == open(mod.DST).read()
+
+
 def test_angle_matches_oracle_and_numpy(hostlib):
     rng = np.random.default_rng(2)
     n = 50_000
