@@ -218,10 +218,9 @@ __global__ void k_scatter(int n_heavy, const WeBox* __restrict__ boxes, const in
 //   gate       : recipes/interfacial_solvent.py:50-56 (water among the 20 nearest)
 //   nearest non-like : analysis/shell_labels.py:90-105
 // ============================================================================
-struct WeRowInfo {  // per-warp description of up to 32 cell rows (+1 sentinel offset)
-  int off[64];
-  int beg0[32], len0[32], beg1[32];
-  float px0[32], px1[32], py[32], pz[32];
+struct WeRowInfo {  // per-warp description of up to 32 non-empty cell rows, compacted
+  int4 ri[32];      // beg0, len0, beg1, first dense candidate index of the row
+  float4 rp[32];    // centre minus image shift: x (first run), y, z, x (second run)
 };
 
 struct WeRadSmem {
@@ -352,25 +351,36 @@ __device__ __forceinline__ int we_collect(const WeBox& b, const int* __restrict_
       if (lane >= o) incl += t;
     }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
+    // non-empty rows, compacted: their first dense indices are strictly increasing
+    const unsigned nonempty = __ballot_sync(0xffffffffu, len > 0);
+    const int nr = __popc(nonempty);
     __syncwarp();
-    rows->off[lane] = incl - len;
-    rows->beg0[lane] = beg0; rows->len0[lane] = len0; rows->beg1[lane] = beg1;
-    rows->px0[lane] = px0; rows->px1[lane] = px1; rows->py[lane] = py; rows->pz[lane] = pz;
+    if (len > 0) {
+      const int ci = __popc(nonempty & ((1u << lane) - 1u));
+      rows->ri[ci] = make_int4(beg0, len0, beg1, incl - len);
+      rows->rp[ci] = make_float4(px0, py, pz, px1);
+    }
     __syncwarp();
+    const int coff = (lane < nr) ? rows->ri[lane].w : 0x7fffffff;  // lane r holds the start of compact row r
     // ---- dense walk over the candidates of these rows ---------------------------------------
-    auto probe = [&](int q, int& qi) -> bool {
+    // Row of dense index q = base + lane: rows that start at or before `base` are counted by one
+    // ballot, rows that start inside the 32-wide window set bit (start - base) of a warp-wide OR.
+    auto probe = [&](int base, int& qi) -> bool {
+      const int rel = coff - base;
+      const unsigned starts = __reduce_or_sync(0xffffffffu, (rel > 0 && rel < 32) ? (1u << rel) : 0u);
+      const int r0 = __popc(__ballot_sync(0xffffffffu, rel <= 0)) - 1;
+      const int q = base + lane;
       if (q >= total) return false;
-      int ro = 0;  // largest row with off[row] <= q
-#pragma unroll
-      for (int st = 16; st > 0; st >>= 1) ro += (rows->off[ro + st] <= q) ? st : 0;
-      const int t = q - rows->off[ro];
-      const int l0 = rows->len0[ro];
-      const bool second = t >= l0;
-      qi = second ? rows->beg1[ro] + (t - l0) : rows->beg0[ro] + t;
+      const int ro = r0 + __popc(starts & (0xffffffffu >> (31 - lane)));
+      const int4 ri = rows->ri[ro];
+      const float4 rp = rows->rp[ro];
+      const int t = q - ri.w;
+      const bool second = t >= ri.y;
+      qi = second ? ri.z + (t - ri.y) : ri.x + t;
       const float4 c = sorted[qi];
       if (simple) {
-        const float ux = c.x - (second ? rows->px1[ro] : rows->px0[ro]);
-        const float uy = c.y - rows->py[ro], uz = c.z - rows->pz[ro];
+        const float ux = c.x - (second ? rp.w : rp.x);
+        const float uy = c.y - rp.y, uz = c.z - rp.z;
         return __fmaf_rn(ux, ux, __fmaf_rn(uy, uy, uz * uz)) <= rf2;
       }
       const float ux = c.x - mx, uy = c.y - my, uz = c.z - mz;
@@ -406,7 +416,7 @@ __device__ __forceinline__ int we_collect(const WeBox& b, const int* __restrict_
     };
     for (int base = 0; base < total; base += 32) {
       int qa = 0;
-      const bool pa = probe(base + lane, qa);
+      const bool pa = probe(base, qa);
       push(pa, qa);
     }
   }
