@@ -96,6 +96,8 @@ typedef struct we_diag {
     uint64_t kernel_launches; /* kernels launched so far by this context */
     uint64_t frames_done;
     uint64_t recorded;        /* recorded (water, frame) pairs so far */
+    uint64_t fast_path_mismatches; /* keep_debug contexts replay every float32 fast-path decision of the RAD
+                                      test exactly and count contradictions: must stay 0 */
 } we_diag;
 
 const char *we_last_error(void);

@@ -143,7 +143,7 @@ def test_all_centres(tag):
             cen = ref["centres"][f]
             shells = eng.shells(f)
             assert all(shells[a] == cen["shell"][a] for a in shells)
-    d = eng.diag()
+    assert eng.diag()["fast_path_mismatches"] == 0   # every float32 fast-path RAD decision replayed exactly
     eng.close()
 
 
@@ -327,7 +327,7 @@ def test_seeded_systems_vs_oracle(cfg):
         assert mine.counts[k] == cov.counts[k]
         assert np.allclose(np.diag(mine.forces[k]), np.diag(cov.forces[k]), rtol=RTOL)
         assert np.allclose(np.diag(mine.torques[k]), np.diag(cov.torques[k]), rtol=RTOL)
-    d = eng.diag()
+    assert eng.diag()["fast_path_mismatches"] == 0   # every float32 fast-path RAD decision replayed exactly
     eng.close()
 
 
@@ -507,7 +507,7 @@ def test_c2_full_size_bulk_vs_oracle():
     assert mine.counts[k] == cov.counts[k]
     assert np.allclose(np.diag(mine.forces[k]), np.diag(cov.forces[k]), rtol=RTOL)
     assert np.allclose(np.diag(mine.torques[k]), np.diag(cov.torques[k]), rtol=RTOL)
-    d = eng.diag()
+    assert eng.diag()["fast_path_mismatches"] == 0   # every float32 fast-path RAD decision replayed exactly
     eng.close()
 
 
@@ -524,6 +524,7 @@ def test_c4_full_size_properties_and_sampled_oracle():
     dbg = WaterEntropyEngine(s, "interfacial", device=0, keep_debug=True, chunk_frames=1)
     dbg.submit(P, Fr, D, [3])
     dbg.sync()
+    assert dbg.diag()["fast_path_mismatches"] == 0   # all ~1e5 centres of the frame, every (j, k) pair replayed
     rng = np.random.default_rng(5)
     centres = np.sort(rng.choice(top.heavy_idx, size=1500, replace=False))
     r = wo.rad_frame(top, P[0], D[0], centres=centres)
@@ -591,6 +592,7 @@ def test_other_baseline_configs_full_size(name, n_sample):
     dbg = WaterEntropyEngine(s, "interfacial", device=0, keep_debug=True, chunk_frames=1)
     dbg.submit(P, Fr, D, [1])
     dbg.sync()
+    assert dbg.diag()["fast_path_mismatches"] == 0
     rng = np.random.default_rng(9)
     # half of the sample near the solute (where shells are mixed), half anywhere
     near = top.solute_UAs[rng.choice(len(top.solute_UAs), size=n_sample // 2, replace=False)]

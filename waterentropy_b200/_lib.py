@@ -40,7 +40,7 @@ class we_options(C.Structure):
 class we_diag(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "wide_searches", "shrink_retries", "table_entries",
-        "kernel_launches", "frames_done", "recorded")]
+        "kernel_launches", "frames_done", "recorded", "fast_path_mismatches")]
 
 
 EXPORTS = [

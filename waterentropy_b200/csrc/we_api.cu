@@ -955,6 +955,7 @@ extern "C" int we_get_diag(we_ctx* c, we_diag* out) {
   out->kernel_launches = c->launches;
   out->frames_done = c->frames_done;
   out->recorded = c->recorded;
+  out->fast_path_mismatches = d.fast_path_mismatches;
   return WE_OK;
 }
 

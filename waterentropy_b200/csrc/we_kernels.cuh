@@ -71,6 +71,7 @@ struct WeDiag {
   unsigned long long wide_searches;
   unsigned long long shrink_retries;
   unsigned long long table_entries;
+  unsigned long long fast_path_mismatches;  // debug contexts: float32 fast-path decisions the exact replay contradicts
   int err_code, err_frame, err_atom, pad;
 };
 
@@ -231,9 +232,9 @@ struct WeRadSmem {
   int top[WE_RAD_WARPS][32];
   int stage[WE_RAD_WARPS][64];
   WeRowInfo rows[WE_RAD_WARPS];
-  float px[WE_RAD_WARPS][32], py[WE_RAD_WARPS][32], pz[WE_RAD_WARPS][32];
-  float e[WE_RAD_WARPS][32], s[WE_RAD_WARPS][32];
-  double q[WE_RAD_WARPS][32];
+  float4 p4[WE_RAD_WARPS][32];  // ranked candidate k: position, separation e_k from the centre (float32)
+  float4 q4[WE_RAD_WARPS][32];  // powf(e_k, 2), (float)q_k, 2 e_k
+  double q[WE_RAD_WARPS][32];   // q_k = (1 / r_k)**2 in fp64
   double log2tab[32];
   unsigned long long exp2tab[32];
 };
@@ -551,8 +552,9 @@ __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __re
     ej = we_angle_sep_h(pjx, pjy, pjz, rx, ry, rz, b.box, half);
     sj = we_powf2_fast(ej, PT);
     qj = we_pow2(we_ddiv(1.0, dj));  // (1/r)**2 as libm pow(x, 2.0) evaluates it
-    S.px[w][lane] = pjx; S.py[w][lane] = pjy; S.pz[w][lane] = pjz;
-    S.e[w][lane] = ej; S.s[w][lane] = sj; S.q[w][lane] = qj;
+    S.p4[w][lane] = make_float4(pjx, pjy, pjz, ej);
+    S.q4[w][lane] = make_float4(sj, (float)qj, we_fmul(2.0f, ej), 0.f);
+    S.q[w][lane] = qj;
   }
   if (O.nbr_idx && lane < WE_MAX_NBR) {
     O.nbr_idx[ho * WE_MAX_NBR + lane] = act ? cidx : -1;
@@ -560,20 +562,41 @@ __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __re
   }
   __syncwarp();
   // ---- RAD blocking test: lane j against closer candidates k = 0..j-1 ---------
+  // j is blocked by k when q_j < q_k cos(jik), i.e. cos > rho = q_j / q_k  (RAD.py:63-67).
+  // Fast path, float32: with s2 = |p_k - p_j|^2 (same min-image components as get_angle),
+  // A = e_k^2 + e_j^2 - s2 and D = 2 e_k e_j the reference's cosine is A / D to within 5e-6
+  // (it rounds sqrt, powf and the division; A and D see the same inputs), so the sign of
+  // A q_k - q_j D decides unless it is within 1e-3 q_k D of zero (200x that error); those
+  // pairs, and anything non-finite, replay the reference's float32/fp64 arithmetic exactly.
+  // Debug contexts replay every pair and count contradictions (we_diag.fast_path_mismatches).
   // (evaluating two k per iteration or two scan candidates per lane was measured: no gain)
   bool blocked = false;
   bool alive = act && lane > 0;
+  const float qjf = (float)qj;
+  const bool check = (O.nbr_idx != nullptr);
   for (int k = 0; k < n25 - 1; ++k) {
     if (!__any_sync(0xffffffffu, alive)) break;
     if (alive && k < lane) {
-      const float dac = we_angle_sep_h(S.px[w][k], S.py[w][k], S.pz[w][k], pjx, pjy, pjz, b.box, half);
-      const float cs = we_angle_cos_from(dac, S.e[w][k], S.s[w][k], ej, sj, PT);
-      if (cs != cs) {
-        alive = false;  // NaN: stop testing, j stays in the shell (RAD.py:60-61)
-      } else {
-        const double rhs = we_mul(S.q[w][k], (double)cs);
-        if (qj < rhs) { blocked = true; alive = false; }
+      const float4 pk = S.p4[w][k], qk = S.q4[w][k];
+      float x = fabsf(we_fsub(pk.x, pjx)); if (x > half[0]) x = we_fsub(x, b.box[0]);
+      float y = fabsf(we_fsub(pk.y, pjy)); if (y > half[1]) y = we_fsub(y, b.box[1]);
+      float z = fabsf(we_fsub(pk.z, pjz)); if (z > half[2]) z = we_fsub(z, b.box[2]);
+      const float s2 = __fmaf_rn(x, x, __fmaf_rn(y, y, we_fmul(z, z)));
+      const float A = we_fsub(we_fadd(qk.x, sj), s2);
+      const float D = we_fmul(qk.z, ej);
+      const float df = we_fsub(we_fmul(A, qk.y), we_fmul(qjf, D));
+      const bool decided = (D > 0.f) && (fabsf(df) > we_fmul(1.0e-3f, we_fmul(qk.y, D)));
+      bool blk = df > 0.f;
+      if (!decided || check) {
+        const float dac = we_fsqrt(we_fadd(we_fadd(we_fmul(x, x), we_fmul(y, y)), we_fmul(z, z)));
+        const float cs = we_angle_cos_from(dac, pk.w, qk.x, ej, sj, PT);
+        bool eb = false;
+        if (cs != cs) alive = false;  // NaN: stop testing, j stays in the shell (RAD.py:60-61)
+        else eb = qj < we_mul(S.q[w][k], (double)cs);
+        if (decided && (eb != blk || cs != cs)) atomicAdd(&diag->fast_path_mismatches, 1ULL);
+        blk = eb;
       }
+      if (blk) { blocked = true; alive = false; }
     } else if (alive && k >= lane) {
       alive = false;
     }
