@@ -233,8 +233,8 @@ struct WeRadSmem {
   int stage[WE_RAD_WARPS][64];
   WeRowInfo rows[WE_RAD_WARPS];
   float4 p4[WE_RAD_WARPS][32];  // ranked candidate k: position, separation e_k from the centre (float32)
-  float4 q4[WE_RAD_WARPS][32];  // powf(e_k, 2), (float)q_k, 2 e_k
-  double q[WE_RAD_WARPS][32];   // q_k = (1 / r_k)**2 in fp64
+  float4 q4[WE_RAD_WARPS][32];  // float32 e_k^2, 1 / r_k^2, 2 e_k
+  double q[WE_RAD_WARPS][32];   // r_k, the exact fp64 distance of ranked candidate k
   double log2tab[32];
   unsigned long long exp2tab[32];
 };
@@ -537,8 +537,7 @@ __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __re
   const bool act = lane < n25;
   int cidx = -1;
   double dj = 0.0;
-  float pjx = 0.f, pjy = 0.f, pjz = 0.f, ej = 0.f, sj = 0.f;
-  double qj = 0.0;
+  float pjx = 0.f, pjy = 0.f, pjz = 0.f, ej = 0.f, sj = 0.f, qjf = 0.f;
   if (act) {
     const int c = S.top[w][lane];
     cidx = si[c];
@@ -550,11 +549,14 @@ __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __re
       pjx = c4.x; pjy = c4.y; pjz = c4.z;
     }
     ej = we_angle_sep_h(pjx, pjy, pjz, rx, ry, rz, b.box, half);
-    sj = we_powf2_fast(ej, PT);
-    qj = we_pow2(we_ddiv(1.0, dj));  // (1/r)**2 as libm pow(x, 2.0) evaluates it
+    // float32 stand-ins for the fast path of the blocking test (relative error <= 3e-7); the exact
+    // powf(e, 2) and (1/r)**2 = libm pow(1/r, 2.0) are evaluated only by the pairs that need them
+    sj = we_fmul(ej, ej);
+    const float rinv = __fdividef(1.0f, (float)dj);
+    qjf = we_fmul(rinv, rinv);
     S.p4[w][lane] = make_float4(pjx, pjy, pjz, ej);
-    S.q4[w][lane] = make_float4(sj, (float)qj, we_fmul(2.0f, ej), 0.f);
-    S.q[w][lane] = qj;
+    S.q4[w][lane] = make_float4(sj, qjf, we_fmul(2.0f, ej), 0.f);
+    S.q[w][lane] = dj;
   }
   if (O.nbr_idx && lane < WE_MAX_NBR) {
     O.nbr_idx[ho * WE_MAX_NBR + lane] = act ? cidx : -1;
@@ -566,13 +568,12 @@ __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __re
   // Fast path, float32: with s2 = |p_k - p_j|^2 (same min-image components as get_angle),
   // A = e_k^2 + e_j^2 - s2 and D = 2 e_k e_j the reference's cosine is A / D to within 5e-6
   // (it rounds sqrt, powf and the division; A and D see the same inputs), so the sign of
-  // A q_k - q_j D decides unless it is within 1e-3 q_k D of zero (200x that error); those
+  // A q_k - q_j D decides unless it is within 1e-3 q_k D of zero (>100x that error); those
   // pairs, and anything non-finite, replay the reference's float32/fp64 arithmetic exactly.
   // Debug contexts replay every pair and count contradictions (we_diag.fast_path_mismatches).
   // (evaluating two k per iteration or two scan candidates per lane was measured: no gain)
   bool blocked = false;
   bool alive = act && lane > 0;
-  const float qjf = (float)qj;
   const bool check = (O.nbr_idx != nullptr);
   for (int k = 0; k < n25 - 1; ++k) {
     if (!__any_sync(0xffffffffu, alive)) break;
@@ -589,10 +590,10 @@ __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __re
       bool blk = df > 0.f;
       if (!decided || check) {
         const float dac = we_fsqrt(we_fadd(we_fadd(we_fmul(x, x), we_fmul(y, y)), we_fmul(z, z)));
-        const float cs = we_angle_cos_from(dac, pk.w, qk.x, ej, sj, PT);
+        const float cs = we_angle_cos_from(dac, pk.w, we_powf2_fast(pk.w, PT), ej, we_powf2_fast(ej, PT), PT);
         bool eb = false;
         if (cs != cs) alive = false;  // NaN: stop testing, j stays in the shell (RAD.py:60-61)
-        else eb = qj < we_mul(S.q[w][k], (double)cs);
+        else eb = we_pow2(we_ddiv(1.0, dj)) < we_mul(we_pow2(we_ddiv(1.0, S.q[w][k])), (double)cs);
         if (decided && (eb != blk || cs != cs)) atomicAdd(&diag->fast_path_mismatches, 1ULL);
         blk = eb;
       }
