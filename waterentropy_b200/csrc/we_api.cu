@@ -810,7 +810,8 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       else wh = WeWork{c->d_wlh, c->d_nh, H, 0};
       ProfScope ps(c, WE_K_HB, st);
       k_hb<<<grid_for((long long)H * n, 16, c->hb_blocks), 256, 0, st>>>(
-          c->T, dp, bx, c->d_tmp4, c->d_shell_n, c->d_shell_idx, c->d_flags, wh, n, c->d_acceptor, c->d_diag);
+          c->T, dp, bx, c->d_tmp4, c->d_shell_n, c->d_shell_idx, c->d_flags, wh, n, c->d_acceptor, c->d_diag,
+          c->opt.keep_debug ? 1 : 0);
       ps.stop(st);
       c->launches++;
     }

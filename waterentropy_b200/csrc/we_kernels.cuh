@@ -675,7 +675,7 @@ __global__ void __launch_bounds__(256)
 k_hb(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes,
      const float4* __restrict__ tmp4, const int* __restrict__ shell_n,
      const int* __restrict__ shell_idx, const int* __restrict__ flags, WeWork work, int n_frames,
-     int* __restrict__ acceptor, WeDiag* diag) {
+     int* __restrict__ acceptor, WeDiag* diag, int check) {
   __shared__ double s_log2tab[32];
   __shared__ unsigned long long s_exp2tab[32];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -708,7 +708,7 @@ k_hb(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes
         const int dn = 2 * it + grp;
         const bool need = valid && dn < nd;
         const int d = d0 + dn;
-        float xx = 0.f, xy = 0.f, xz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f, dba = 0.f, dba2 = 0.f;
+        float xx = 0.f, xy = 0.f, xz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f, dba = 0.f, dba2 = 0.f, dba2f = 0.f;
         float dq[3] = {0.f, 0.f, 0.f};
         double qD = 0.0;
         const bool live = need && st == WE_ST_OK;
@@ -720,6 +720,7 @@ k_hb(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes
           if (b.triclinic) we_wrap_tric(dx, dy, dz, b.m, b.wfac, dq);
           dba = we_angle_sep_h(xx, xy, xz, dx, dy, dz, b.box, half);
           dba2 = we_powf2_fast(dba, PT);
+          dba2f = we_fmul(dba, dba);
           qD = T.charges[D];
         }
         // group-local best over chunks of 8 shell members
@@ -739,10 +740,27 @@ k_hb(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes
             const double dist = we_dist_fast(dq[0], dq[1], dq[2], aq0, aq1, aq2, b);
             if (dist <= WE_CUTOFF) {
               if (we_lex_less(dist, 0.0, A, bi0, 0.0, bi2)) { bi0 = dist; bi2 = A; }
-              const float dbc = we_angle_sep_h(ax, ay, az, dx, dy, dz, b.box, half);
-              const float dac = we_angle_sep_h(ax, ay, az, xx, xy, xz, b.box, half);
-              const float cs = we_angle_cos_from(dac, dbc, we_powf2_fast(dbc, PT), dba, dba2, PT);
-              if (we_angle_gt_90(cs)) {  // dist**2 is libm pow(dist, 2.0): only evaluated past the angle test
+              // angle X-D-A > 90 degrees  <=>  -1 <= cos <= -2^-24 (we_angle_gt_90).  Fast path as in the
+              // RAD test: cos = A2 / D2 with A2 = dbc^2 + dba^2 - dac^2, D2 = 2 dbc dba from the squared
+              // float32 separations (error <= 5e-6); compared through squares, so no sqrt, powf or
+              // division unless cos is within 1e-3 of 0 or of -1.
+              const float sbc = we_angle_sep2_h(ax, ay, az, dx, dy, dz, b.box, half);
+              const float sac = we_angle_sep2_h(ax, ay, az, xx, xy, xz, b.box, half);
+              const float A2 = we_fsub(we_fadd(sbc, dba2f), sac);
+              const float D2sq = we_fmul(4.0f, we_fmul(sbc, dba2f));     // (2 dbc dba)^2
+              const float A2sq = we_fmul(A2, A2);
+              const bool off_zero = A2sq > we_fmul(1.0e-6f, D2sq);        // |cos| > 1e-3
+              const bool decided = off_zero && (A2 > 0.f || A2sq < we_fmul(0.998f, D2sq));  // cos > -0.999
+              bool gt90 = A2 < 0.f;
+              if (!decided || check) {
+                const float dbc = we_fsqrt(we_angle_sep2_exact_h(ax, ay, az, dx, dy, dz, b.box, half));
+                const float dac = we_fsqrt(we_angle_sep2_exact_h(ax, ay, az, xx, xy, xz, b.box, half));
+                const float cs = we_angle_cos_from(dac, dbc, we_powf2_fast(dbc, PT), dba, dba2, PT);
+                const bool eg = we_angle_gt_90(cs);
+                if (decided && eg != gt90) atomicAdd(&diag->fast_path_mismatches, 1ULL);
+                gt90 = eg;
+              }
+              if (gt90) {  // dist**2 is libm pow(dist, 2.0): only evaluated past the angle test
                 const double rc = we_ddiv(we_mul(qD, T.charges[A]), we_pow2(dist));
                 if (rc < 99.0) {
                   if (we_lex_less(rc, dist, A, bq0, bq1, bq2)) { bq0 = rc; bq1 = dist; bq2 = A; }

@@ -253,6 +253,23 @@ WE_HD float we_angle_sep_h(float ax, float ay, float az, float bx, float by, flo
   return we_fsqrt(we_fadd(we_fadd(we_fmul(x, x), we_fmul(y, y)), we_fmul(z, z)));
 }
 
+// squared separation: the argument of the square root above, same operations (exact variant), and
+// with the sum contracted (fast-path variant, relative error <= 2 ulp)
+WE_HD float we_angle_sep2_exact_h(float ax, float ay, float az, float bx, float by, float bz,
+                                  const float* dim, const float* half) {
+  float x = fabsf(we_fsub(ax, bx)); if (x > half[0]) x = we_fsub(x, dim[0]);
+  float y = fabsf(we_fsub(ay, by)); if (y > half[1]) y = we_fsub(y, dim[1]);
+  float z = fabsf(we_fsub(az, bz)); if (z > half[2]) z = we_fsub(z, dim[2]);
+  return we_fadd(we_fadd(we_fmul(x, x), we_fmul(y, y)), we_fmul(z, z));
+}
+WE_HD float we_angle_sep2_h(float ax, float ay, float az, float bx, float by, float bz,
+                            const float* dim, const float* half) {
+  float x = fabsf(we_fsub(ax, bx)); if (x > half[0]) x = we_fsub(x, dim[0]);
+  float y = fabsf(we_fsub(ay, by)); if (y > half[1]) y = we_fsub(y, dim[1]);
+  float z = fabsf(we_fsub(az, bz)); if (z > half[2]) z = we_fsub(z, dim[2]);
+  return fmaf(x, x, fmaf(y, y, we_fmul(z, z)));
+}
+
 // cosine from the three float32 separations and two pre-computed powf squares:
 //   (powf(dac,2) - powf(dbc,2) - powf(dba,2)) / ((-2*dbc)*dba)
 WE_HD float we_angle_cos_from(float dac, float dbc, float dbc2, float dba, float dba2,
