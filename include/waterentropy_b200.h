@@ -210,12 +210,12 @@ int we_debug_copy(we_ctx *ctx, int64_t k, int32_t field, void *out, int64_t byte
 #define WE_K_SCATTER 2
 #define WE_K_RAD 3
 #define WE_K_HB 4
-#define WE_K_FLAG 5
+#define WE_K_LIST1 5  /* k_list1: pass-1 list from the interfacial marks */
 #define WE_K_LABEL 6
 #define WE_K_COV 7
 #define WE_K_RAD1 8   /* k_rad, pass 1: interfacial waters */
 #define WE_K_RAD2 9   /* k_rad, pass 2: their shell members */
-#define WE_K_MARK 10  /* k_seed + k_mark / k_mark_bulk */
+#define WE_K_LIST2 10 /* k_seed + k_list2 (pass-2 and HB lists) */
 #define WE_N_KERNELS 11
 /* Record CUDA events around every kernel launch on the compute stream (the
  * reference only has wall-clock prints, cli/runWaterEntropy.py:28-29,54). */

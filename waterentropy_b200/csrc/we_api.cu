@@ -762,49 +762,60 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       long long blocks = (items + WE_RAD_WARPS - 1) / WE_RAD_WARPS;
       return (int)std::max<long long>(1, std::min<long long>(blocks, c->rad_blocks));
     };
-    if (w0.static_count > 0) {
-      { ProfScope ps(c, WE_K_MARK, st);
-        k_seed<<<dim3((w0.static_count + 255) / 256, n), 256, 0, st>>>(w0.static_count, w0.list, H, c->d_state);
-        ps.stop(st); }
-      CK(cudaEventRecord(c->ev_p0[buf], st));
-      { ProfScope ps(c, WE_K_RAD, st);
-        k_rad<<<rad_grid((long long)w0.static_count * n), WE_RAD_WARPS * 32, sizeof(WeRadSmem), st>>>(
-            c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->d_tmp4, c->ncap, c->cell_target, w0, n, ro,
-            (interfacial && !c->opt.keep_debug) ? c->d_state : nullptr, c->d_diag);
-        ps.stop(st); }
-      c->launches += 2;
-    }
-    if (interfacial && S > 0 && C > 0) {
-      dim3 gS((S + 127) / 128, n);
-      { ProfScope ps(c, WE_K_FLAG, st);
-        k_flag<<<gS, 128, 0, st>>>(c->T, c->d_shell_n, c->d_shell_idx, c->d_flags, c->d_interf, c->d_state, c->d_wl1, c->d_n1, fids, c->d_diag);
-        ps.stop(st); }
-      WeWork w1{c->d_wl1, c->d_n1, C, 0};
-      { ProfScope ps(c, WE_K_RAD1, st);
-        k_rad<<<rad_grid((long long)C * n), WE_RAD_WARPS * 32, sizeof(WeRadSmem), st>>>(
-            c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->d_tmp4, c->ncap, c->cell_target, w1, n, ro, nullptr, c->d_diag);
-        ps.stop(st); }
-      { ProfScope ps(c, WE_K_MARK, st);
-        k_mark<<<dim3((C + 127) / 128, n), 128, 0, st>>>(c->T, c->d_shell_n, c->d_shell_idx, c->d_flags, c->d_wl1, c->d_n1, c->d_state, c->d_wl2, c->d_n2, c->d_hbq, c->d_wlh, c->d_nh);
-        ps.stop(st); }
-      WeWork w2{c->d_wl2, c->d_n2, H, 0};
-      { ProfScope ps(c, WE_K_RAD2, st);
-        k_rad<<<rad_grid((long long)H * n), WE_RAD_WARPS * 32, sizeof(WeRadSmem), st>>>(
-            c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->d_tmp4, c->ncap, c->cell_target, w2, n, ro, nullptr, c->d_diag);
-        ps.stop(st); }
-      c->launches += 4;
-    } else if (!interfacial && C > 0) {
-      ProfScope ps(c, WE_K_MARK, st);
-      k_mark_bulk<<<dim3((C + 127) / 128, n), 128, 0, st>>>(c->T, c->d_shell_n, c->d_shell_idx, c->d_flags, c->d_hbq, c->d_wlh, c->d_nh);
-      ps.stop(st);
-      c->launches++;
-    }
     auto grid_for = [&](long long items, int per_block, int cap) {
       long long blocks = (items + per_block - 1) / per_block;
       return (int)std::max<long long>(1, std::min<long long>(blocks, cap));
     };
+    // marks written by the passes (bytes inside the zero block): see WeMarks
+    unsigned char* mark_hb = reinterpret_cast<unsigned char*>(c->d_hbq);
+    unsigned char* mark_shell = mark_hb + (size_t)c->chunk * H;
+    const WeMarks no_marks{nullptr, nullptr, nullptr, nullptr, 0};
+    // pass 0 of the recipe: solute united atoms mark interfacial waters / bulk waters mark their HB centres
+    const WeMarks m0 = interfacial ? WeMarks{c->d_interf, nullptr, nullptr, fids, 0}
+                                   : WeMarks{nullptr, mark_hb, nullptr, nullptr, 1};
+    auto rad = [&](int id, const WeWork& wk, long long items, int* gate_state, const WeMarks& mk) {
+      ProfScope ps(c, id, st);
+      k_rad<<<rad_grid(items), WE_RAD_WARPS * 32, sizeof(WeRadSmem), st>>>(
+          c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->d_tmp4, c->ncap, c->cell_target, wk, n, ro,
+          gate_state, mk, c->d_diag);
+      ps.stop(st);
+      c->launches++;
+    };
+    if (w0.static_count > 0) {
+      { ProfScope ps(c, WE_K_LIST2, st);
+        k_seed<<<dim3((w0.static_count + 255) / 256, n), 256, 0, st>>>(w0.static_count, w0.list, H, c->d_state);
+        ps.stop(st); }
+      c->launches++;
+      CK(cudaEventRecord(c->ev_p0[buf], st));
+      if (!c->opt.keep_debug) {
+        rad(WE_K_RAD, w0, (long long)w0.static_count * n, interfacial ? c->d_state : nullptr, m0);
+      } else {
+        // debug contexts evaluate every heavy atom first (no marks), then the recipe's own pass 0
+        rad(WE_K_RAD, w0, (long long)w0.static_count * n, nullptr, no_marks);
+        WeWork wr{interfacial ? c->T.solute_ua : c->T.centres, nullptr, 0, interfacial ? S : C};
+        if (wr.static_count > 0) rad(WE_K_RAD, wr, (long long)wr.static_count * n, nullptr, m0);
+      }
+    }
+    if (interfacial && S > 0 && C > 0) {
+      { ProfScope ps(c, WE_K_LIST1, st);
+        k_list1<<<dim3((C + 255) / 256, n), 256, 0, st>>>(c->T, c->d_interf, c->d_state, c->d_wl1, c->d_n1);
+        ps.stop(st); }
+      WeWork w1{c->d_wl1, c->d_n1, C, 0};
+      rad(WE_K_RAD1, w1, (long long)C * n, nullptr, WeMarks{nullptr, mark_hb, mark_shell, nullptr, 0});
+      { ProfScope ps(c, WE_K_LIST2, st);
+        k_list2<<<gH, 256, 0, st>>>(c->T, mark_shell, mark_hb, c->d_state, c->d_wl2, c->d_n2, c->d_wlh, c->d_nh);
+        ps.stop(st); }
+      WeWork w2{c->d_wl2, c->d_n2, H, 0};
+      rad(WE_K_RAD2, w2, (long long)H * n, nullptr, no_marks);
+      c->launches += 2;
+    } else if (!interfacial && C > 0) {
+      ProfScope ps(c, WE_K_LIST2, st);
+      k_list2<<<gH, 256, 0, st>>>(c->T, nullptr, mark_hb, c->d_state, c->d_wl2, c->d_n2, c->d_wlh, c->d_nh);
+      ps.stop(st);
+      c->launches++;
+    }
     if (ND > 0) {
-      // HB work list: every heavy atom (debug) or the centres queued by k_mark / k_mark_bulk
+      // HB work list: every heavy atom (debug) or the centres marked by the passes (k_list2)
       WeWork wh;
       if (c->opt.keep_debug) wh = WeWork{c->d_all_slots, nullptr, 0, H};
       else wh = WeWork{c->d_wlh, c->d_nh, H, 0};

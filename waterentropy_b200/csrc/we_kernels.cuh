@@ -433,6 +433,18 @@ struct WeRadOut {
   int* shell_n; int* shell_idx; int* nn; int* flags; int* nbr_idx; double* nbr_dist;
 };
 
+// What a pass of k_rad marks for the next work lists (bytes, plain stores; k_list1 / k_list2 compact them):
+//   interf : pass 0 of the interfacial recipe - water members of the shell of a solute united atom that
+//            has a water among its 20 nearest candidates (recipes/interfacial_solvent.py:50-65)
+//   hb     : centres whose hydrogen bonds the reference evaluates - the centre and every shell member
+//            (analysis/HB.py:142-169); bulk recipe: only for pure shells (recipes/bulk_water.py:49-51)
+//   shell  : shell members whose own RAD shell the labels need (analysis/shell_labels.py:55-76)
+struct WeMarks {
+  unsigned char* interf; unsigned char* hb; unsigned char* shell;
+  const long long* frame_ids;  // non-null: report search errors of the centres of this pass
+  int bulk;
+};
+
 // One centre (heavy slot h of frame f) on one warp.
 __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __restrict__ fpos,
                                            const WeBox& b, const int* __restrict__ cstart,
@@ -440,7 +452,7 @@ __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __re
                                            const float4* __restrict__ sorted,
                                            const float4* __restrict__ tmp4_f, float search_radius,
                                            int f, int h, const WeRadOut& O, int* gate_only_state,
-                                           WeDiag* diag, WeRadSmem& S, const WePowTables& PT, int lane,
+                                           const WeMarks& M, WeDiag* diag, WeRadSmem& S, const WePowTables& PT, int lane,
                                            int w) {
   const int my_atom = T.heavy_idx[h];
   // raw coordinates (angles, duplicate test) and distance coordinates (k_bin wrapped them already)
@@ -484,7 +496,11 @@ __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __re
   if (status == WE_ST_OK && n == 0) status = WE_ST_NO_NEIGHBOURS;
   const size_t ho = (size_t)f * T.n_heavy + h;
   if (status != WE_ST_OK) {
-    if (lane == 0) { O.shell_n[ho] = 0; O.nn[ho] = -1; O.flags[ho] = status << 8; }
+    if (lane == 0) {
+      O.shell_n[ho] = 0; O.nn[ho] = -1; O.flags[ho] = status << 8;
+      if (M.frame_ids) we_set_error(diag, status, (int)M.frame_ids[f], my_atom);
+      if (M.hb && !M.bulk) M.hb[ho] = 1;
+    }
     if (O.nbr_idx && lane < WE_MAX_NBR) O.nbr_idx[ho * WE_MAX_NBR + lane] = -1;
     return;
   }
@@ -621,6 +637,26 @@ __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __re
     O.nn[ho] = nn;
     O.flags[ho] = (wm ? 1 : 0);
   }
+  // ---- marks for the next work lists ----------------------------------------------
+  const size_t fo = (size_t)f * T.n_heavy;
+  if (M.interf && wm) {
+    if (member && T.is_water[cidx]) M.interf[fo + T.heavy_slot[cidx]] = 1;
+  }
+  if (M.hb) {
+    bool go = true;
+    if (M.bulk) {
+      const bool other = member && (T.resname_id[cidx] != T.resname_id[my_atom]);
+      go = ns > 0 && !__any_sync(0xffffffffu, other);
+    }
+    if (go) {
+      if (lane == 0) M.hb[ho] = 1;
+      if (member) {
+        const int sl = T.heavy_slot[cidx];
+        M.hb[fo + sl] = 1;
+        if (M.shell) M.shell[fo + sl] = 1;
+      }
+    }
+  }
   __syncwarp();
 }
 
@@ -631,7 +667,8 @@ __global__ void __launch_bounds__(WE_RAD_WARPS * 32, WE_RAD_MINBLOCKS)
 k_rad(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes,
       const int* __restrict__ cell_start, const int* __restrict__ cell_of,
       const float4* __restrict__ sorted4, const float4* __restrict__ tmp4, int ncap,
-      float search_radius, WeWork work, int n_frames, WeRadOut O, int* gate_only_state, WeDiag* diag) {
+      float search_radius, WeWork work, int n_frames, WeRadOut O, int* gate_only_state, WeMarks M,
+      WeDiag* diag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WeRadSmem& S = *reinterpret_cast<WeRadSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -649,7 +686,7 @@ k_rad(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxe
     const int* cof = cell_of + (size_t)f * T.n_heavy;
     const float4* t4 = tmp4 + (size_t)f * T.n_heavy;
     for (int i = blockIdx.x * WE_RAD_WARPS + w; i < cnt; i += stride)
-      we_rad_one(T, fpos, b, cstart, cof, sorted, t4, search_radius, f, list[i], O, gate_only_state, diag, S, PT, lane, w);
+      we_rad_one(T, fpos, b, cstart, cof, sorted, t4, search_radius, f, list[i], O, gate_only_state, M, diag, S, PT, lane, w);
   }
 }
 
@@ -796,11 +833,12 @@ k_hb(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes
 // ============================================================================
 // Work-list kernels.
 // k_seed : pass-0 state (debug mode: every heavy atom is a pass-0 centre)
-// k_flag : K4a interfacial gating (recipes/interfacial_solvent.py:25-66): a solute
-//          united atom with a water among its 20 nearest candidates marks the water
-//          members of its RAD shell; new waters join the pass-1 list.
-// k_mark : shell members of the interfacial waters join the pass-2 list; marks the
-//          centres whose HBs the reference evaluates (analysis/HB.py:142-169).
+// k_rad itself marks what the next pass needs (WeMarks: plain byte stores from the warp that
+// holds the shell in registers); the list kernels turn the marks into dense work lists:
+// k_list1: K4a interfacial gating (recipes/interfacial_solvent.py:25-66): the water members of
+//          the shells of gated solute united atoms form the pass-1 list.
+// k_list2: shell members of the interfacial waters form the pass-2 list; the centres whose HBs
+//          the reference evaluates (analysis/HB.py:142-169) form the HB list.
 // ============================================================================
 __global__ void k_seed(int n, const int* __restrict__ list, int n_heavy, int* __restrict__ state) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -808,74 +846,46 @@ __global__ void k_seed(int n, const int* __restrict__ list, int n_heavy, int* __
   if (i < n) state[(size_t)f * n_heavy + list[i]] = 1;
 }
 
-__global__ void k_flag(WeTopoDev T, const int* __restrict__ shell_n, const int* __restrict__ shell_idx,
-                       const int* __restrict__ flags, unsigned char* __restrict__ interfacial,
-                       int* __restrict__ state, int* __restrict__ wl1, int* __restrict__ n1,
-                       const long long* __restrict__ frame_ids, WeDiag* diag) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  const int f = blockIdx.y;
-  if (s >= T.n_solute_ua) return;
-  const int hs = T.solute_ua[s];
-  const size_t fo = (size_t)f * T.n_heavy;
-  const int fl = flags[fo + hs];
-  if ((fl >> 8) != WE_ST_OK) { we_set_error(diag, fl >> 8, (int)frame_ids[f], T.heavy_idx[hs]); return; }
-  if (!(fl & 1)) return;
-  const int ns = shell_n[fo + hs];
-  for (int m = 0; m < ns; ++m) {
-    const int A = shell_idx[(fo + hs) * WE_MAX_NBR + m];
-    if (!T.is_water[A]) continue;
-    const int as = T.heavy_slot[A];
-    interfacial[fo + as] = 1;
-    // state: 0 untouched, 1 shell computed / queued, 2 queued as interfacial water
-    const int old = atomicMax(&state[fo + as], 2);
-    if (old < 2) wl1[(size_t)f * T.n_centres + atomicAdd(&n1[f], 1)] = as;
-  }
+// Warp-aggregated append: the lanes with `want` get consecutive slots of a per-frame list whose
+// length counter sees one atomicAdd per warp.
+__device__ __forceinline__ int we_append_slot(bool want, int* counter, int lane) {
+  const unsigned m = __ballot_sync(0xffffffffu, want);
+  if (!m) return -1;
+  const int leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(counter, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return want ? base + __popc(m & ((1u << lane) - 1u)) : -1;
 }
 
-// HB work list: a centre joins it the first time it is needed and only if it has donors.
-__device__ __forceinline__ void we_queue_hb(const WeTopoDev& T, int f, int slot, int* hbq, int* wlh, int* nh) {
-  if (T.don_ptr[slot + 1] == T.don_ptr[slot]) return;
-  const size_t o = (size_t)f * T.n_heavy + slot;
-  if (atomicExch(&hbq[o], 1) == 0) wlh[(size_t)f * T.n_heavy + atomicAdd(&nh[f], 1)] = slot;
+// pass-1 list: the waters marked interfacial by pass 0 (state 2 = queued as interfacial water)
+__global__ void k_list1(WeTopoDev T, const unsigned char* __restrict__ interfacial, int* __restrict__ state,
+                        int* __restrict__ wl1, int* __restrict__ n1) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+  const int f = blockIdx.y;
+  const size_t fo = (size_t)f * T.n_heavy;
+  const int h = (c < T.n_centres) ? T.centres[c] : 0;
+  const bool want = (c < T.n_centres) && interfacial[fo + h];
+  const int slot = we_append_slot(want, &n1[f], lane);
+  if (want) { wl1[(size_t)f * T.n_centres + slot] = h; state[fo + h] = 2; }
 }
 
-__global__ void k_mark(WeTopoDev T, const int* __restrict__ shell_n, const int* __restrict__ shell_idx,
-                       const int* __restrict__ flags, const int* __restrict__ wl1,
-                       const int* __restrict__ n1, int* __restrict__ state, int* __restrict__ wl2,
-                       int* __restrict__ n2, int* __restrict__ hbq, int* __restrict__ wlh,
-                       int* __restrict__ nh) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// pass-2 list (marked shell members whose shell is not computed yet) and the HB list (marked
+// centres that have donor hydrogens)
+__global__ void k_list2(WeTopoDev T, const unsigned char* __restrict__ mark_shell,
+                        const unsigned char* __restrict__ mark_hb, int* __restrict__ state,
+                        int* __restrict__ wl2, int* __restrict__ n2, int* __restrict__ wlh,
+                        int* __restrict__ nh) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
   const int f = blockIdx.y;
-  if (i >= n1[f]) return;
   const size_t fo = (size_t)f * T.n_heavy;
-  const int xs = wl1[(size_t)f * T.n_centres + i];
-  we_queue_hb(T, f, xs, hbq, wlh, nh);
-  if ((flags[fo + xs] >> 8) != WE_ST_OK) return;
-  const int ns = shell_n[fo + xs];
-  for (int m = 0; m < ns; ++m) {
-    const int as = T.heavy_slot[shell_idx[(fo + xs) * WE_MAX_NBR + m]];
-    we_queue_hb(T, f, as, hbq, wlh, nh);
-    if (atomicCAS(&state[fo + as], 0, 1) == 0) wl2[fo + atomicAdd(&n2[f], 1)] = as;
-  }
-}
-
-// bulk recipe: HBs are evaluated for waters with a pure shell and for their members
-__global__ void k_mark_bulk(WeTopoDev T, const int* __restrict__ shell_n, const int* __restrict__ shell_idx,
-                            const int* __restrict__ flags, int* __restrict__ hbq, int* __restrict__ wlh,
-                            int* __restrict__ nh) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const int f = blockIdx.y;
-  if (c >= T.n_centres) return;
-  const size_t fo = (size_t)f * T.n_heavy;
-  const int xs = T.centres[c];
-  if ((flags[fo + xs] >> 8) != WE_ST_OK) return;
-  const int ns = shell_n[fo + xs];
-  if (ns == 0) return;
-  const int my_res = T.resname_id[T.heavy_idx[xs]];
-  for (int m = 0; m < ns; ++m)
-    if (T.resname_id[shell_idx[(fo + xs) * WE_MAX_NBR + m]] != my_res) return;
-  we_queue_hb(T, f, xs, hbq, wlh, nh);
-  for (int m = 0; m < ns; ++m) we_queue_hb(T, f, T.heavy_slot[shell_idx[(fo + xs) * WE_MAX_NBR + m]], hbq, wlh, nh);
+  const bool valid = h < T.n_heavy;
+  const bool w2 = valid && mark_shell && mark_shell[fo + h] && state[fo + h] == 0;
+  const bool wh = valid && mark_hb[fo + h] && T.don_ptr[h + 1] != T.don_ptr[h];
+  const int p2 = we_append_slot(w2, &n2[f], lane);
+  if (w2) { wl2[fo + p2] = h; state[fo + h] = 1; }
+  const int ph = we_append_slot(wh, &nh[f], lane);
+  if (wh) wlh[fo + ph] = h;
 }
 
 // ============================================================================

@@ -158,8 +158,8 @@ class WaterEntropyEngine:
         return {n: int(getattr(d, n)) for n, _ in d._fields_}
 
     # ---- measurement ---------------------------------------------------------
-    KERNELS = ["k_bin", "k_scan", "k_scatter", "k_rad", "k_hb", "k_flag", "k_label", "k_cov",
-               "k_rad_pass1", "k_rad_pass2", "k_seed_mark"]
+    KERNELS = ["k_bin", "k_scan", "k_scatter", "k_rad", "k_hb", "k_list1", "k_label", "k_cov",
+               "k_rad_pass1", "k_rad_pass2", "k_seed_list2"]
 
     def profile(self, enable=True):
         _lib.check(self.lib.we_profile(self._ctx, int(enable)))
