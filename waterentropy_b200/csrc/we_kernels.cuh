@@ -27,8 +27,15 @@
 #define WE_CUTOFF 10.0
 #define WE_RAD_WARPS 8
 #define WE_CELLS_PER_RADIUS 2  // cell edge = search radius / 2, searched +-2 cells
+// resident blocks per SM the register allocator must allow for (tuned on B200)
 #ifndef WE_RAD_MINBLOCKS
-#define WE_RAD_MINBLOCKS 3    // resident blocks per SM the register allocator must allow for k_rad
+#define WE_RAD_MINBLOCKS 3
+#endif
+#ifndef WE_HB_MINBLOCKS
+#define WE_HB_MINBLOCKS 3
+#endif
+#ifndef WE_LABEL_MINBLOCKS
+#define WE_LABEL_MINBLOCKS 4
 #endif
 
 // status codes (per centre / per donor), also the C-ABI error codes
@@ -708,7 +715,7 @@ __device__ __forceinline__ bool we_lex_less(double a0, double a1, int a2, double
 
 // Persistent over the list of centres whose HBs the recipe evaluates.  Half a warp per centre,
 // 8 lanes per donor hydrogen (two donors at a time), lanes = shell members in chunks of 8.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, WE_HB_MINBLOCKS)
 k_hb(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes,
      const float4* __restrict__ tmp4, const int* __restrict__ shell_n,
      const int* __restrict__ shell_idx, const int* __restrict__ flags, WeWork work, int n_frames,
@@ -1107,7 +1114,7 @@ __device__ __forceinline__ void we_label_one(const WeTopoDev& T, int f, int xs,
 
 // Persistent wrapper: grid-stride over the work list of every frame of the batch
 // (interfacial recipe: the interfacial waters; bulk recipe: every water centre).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, WE_LABEL_MINBLOCKS)
 k_label(WeTopoDev T, const int* __restrict__ shell_n, const int* __restrict__ shell_idx,
         const int* __restrict__ nn_arr, const int* __restrict__ flags,
         const int* __restrict__ acceptor, const unsigned char* __restrict__ interfacial,
