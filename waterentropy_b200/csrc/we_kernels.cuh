@@ -853,45 +853,57 @@ __global__ void k_seed(int n, const int* __restrict__ list, int n_heavy, int* __
   if (i < n) state[(size_t)f * n_heavy + list[i]] = 1;
 }
 
-// Warp-aggregated append: the lanes with `want` get consecutive slots of a per-frame list whose
-// length counter sees one atomicAdd per warp.
-__device__ __forceinline__ int we_append_slot(bool want, int* counter, int lane) {
+// Block-aggregated append for 256-thread blocks: the threads with `want` get consecutive slots of a
+// per-frame list whose length counter sees one atomicAdd per block (same-address atomics serialise).
+__device__ __forceinline__ int we_append_block(bool want, int* counter, int* s_cnt /*[9]*/) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const unsigned m = __ballot_sync(0xffffffffu, want);
-  if (!m) return -1;
-  const int leader = __ffs(m) - 1;
-  int base = 0;
-  if (lane == leader) base = atomicAdd(counter, __popc(m));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  return want ? base + __popc(m & ((1u << lane) - 1u)) : -1;
+  if (lane == 0) s_cnt[w] = __popc(m);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const int c = s_cnt[i]; s_cnt[i] = tot; tot += c; }
+    const int base = tot ? atomicAdd(counter, tot) : 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_cnt[i] += base;
+  }
+  __syncthreads();
+  const int slot = s_cnt[w] + __popc(m & ((1u << lane) - 1u));
+  __syncthreads();  // s_cnt is reused by the next append
+  return want ? slot : -1;
 }
 
 // pass-1 list: the waters marked interfacial by pass 0 (state 2 = queued as interfacial water)
-__global__ void k_list1(WeTopoDev T, const unsigned char* __restrict__ interfacial, int* __restrict__ state,
-                        int* __restrict__ wl1, int* __restrict__ n1) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(256)
+k_list1(WeTopoDev T, const unsigned char* __restrict__ interfacial, int* __restrict__ state,
+        int* __restrict__ wl1, int* __restrict__ n1) {
+  __shared__ int s_cnt[8];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int f = blockIdx.y;
   const size_t fo = (size_t)f * T.n_heavy;
   const int h = (c < T.n_centres) ? T.centres[c] : 0;
   const bool want = (c < T.n_centres) && interfacial[fo + h];
-  const int slot = we_append_slot(want, &n1[f], lane);
+  const int slot = we_append_block(want, &n1[f], s_cnt);
   if (want) { wl1[(size_t)f * T.n_centres + slot] = h; state[fo + h] = 2; }
 }
 
 // pass-2 list (marked shell members whose shell is not computed yet) and the HB list (marked
 // centres that have donor hydrogens)
-__global__ void k_list2(WeTopoDev T, const unsigned char* __restrict__ mark_shell,
-                        const unsigned char* __restrict__ mark_hb, int* __restrict__ state,
-                        int* __restrict__ wl2, int* __restrict__ n2, int* __restrict__ wlh,
-                        int* __restrict__ nh) {
-  const int h = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(256)
+k_list2(WeTopoDev T, const unsigned char* __restrict__ mark_shell,
+        const unsigned char* __restrict__ mark_hb, int* __restrict__ state, int* __restrict__ wl2,
+        int* __restrict__ n2, int* __restrict__ wlh, int* __restrict__ nh) {
+  __shared__ int s_cnt[8];
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
   const int f = blockIdx.y;
   const size_t fo = (size_t)f * T.n_heavy;
   const bool valid = h < T.n_heavy;
   const bool w2 = valid && mark_shell && mark_shell[fo + h] && state[fo + h] == 0;
   const bool wh = valid && mark_hb[fo + h] && T.don_ptr[h + 1] != T.don_ptr[h];
-  const int p2 = we_append_slot(w2, &n2[f], lane);
+  const int p2 = we_append_block(w2, &n2[f], s_cnt);
   if (w2) { wl2[fo + p2] = h; state[fo + h] = 1; }
-  const int ph = we_append_slot(wh, &nh[f], lane);
+  const int ph = we_append_block(wh, &nh[f], s_cnt);
   if (wh) wlh[fo + ph] = h;
 }
 
