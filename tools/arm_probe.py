@@ -9,11 +9,11 @@ s = synthetic.make_config("C4"); F = 96
 P, Fr, D = s.frames(0, F); ids = list(range(F))
 hP, hF = torch.from_numpy(P).pin_memory(), torch.from_numpy(Fr).pin_memory()
 dP, dF = hP.cuda(), hF.cuda()
-for name, kw, dev, gate, cov in (("host zero-copy gate1 cov1", dict(keep_records=True), False, 1, 1),
-                                 ("host zero-copy gate2 cov1", dict(keep_records=True), False, 2, 1),
-                                 ("host zero-copy gate2 cov0", dict(keep_records=True), False, 2, 0),
-                                 ("host zero-copy gate1 cov1 again", dict(keep_records=True), False, 1, 1),
-                                 ("host zero-copy gate2 cov1 again", dict(keep_records=True), False, 2, 1)):
+for name, kw, dev, gate, cov in (("device, no records", dict(keep_records=False), True, 1, 1),
+                                 ("device + records", dict(keep_records=True), True, 1, 1),
+                                 ("host zero-copy + records", dict(keep_records=True), False, 1, 1),
+                                 ("host zero-copy, no records", dict(keep_records=False), False, 1, 1),
+                                 ("host zero-copy + records, ungated", dict(keep_records=True), False, 0, 1)):
     os.environ["WE_COPY_GATE"] = str(gate); os.environ["WE_COV_STREAM"] = str(cov)
     for prof in (False, True):
         eng = WaterEntropyEngine(s, "interfacial", device=0, **kw)

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <map>
 #include <vector>
 
 #include "../../include/waterentropy_b200.h"
@@ -123,10 +124,15 @@ struct we_ctx {
   int pending_n[WE_NBUF] = {};
   cudaStream_t s_copy = nullptr, s_comp = nullptr, s_cov = nullptr;
   cudaEvent_t ev_in_ready[WE_NBUF]{}, ev_in_free[WE_NBUF]{}, ev_out_ready[WE_NBUF]{}, ev_p0[WE_NBUF]{};
-  int copy_gate = 1, cov_stream = 1;
+  int copy_gate = 1, cov_stream = 1, use_graphs = 1, n_sm = 148;
+  // CUDA graphs of the two kernel runs of a batch (before / after the pass-0 event), per ring slot and
+  // frame count; host-buffer submissions only (the device pointers of a slot are fixed)
+  struct BatchGraph { cudaGraphExec_t exec = nullptr; unsigned long long launches = 0; };
+  std::map<long long, BatchGraph> graphs;
   bool out_pending[WE_NBUF] = {};
   // results on host
   std::vector<std::vector<int>> frame_records;  // per submitted frame: (atom, nearest) pairs sorted by atom
+  std::vector<unsigned long long> sort_keys;
   std::vector<FrameDebug> debug;
   unsigned long long launches = 0, frames_done = 0, recorded = 0;
   long long chunk_counter = 0;
@@ -383,9 +389,15 @@ extern "C" int we_create(const we_topology* t, const we_options* opt, we_ctx** o
   }
   if ((rc = dev_alloc(c, &c->d_compact_n, 1))) { we_destroy(c); return rc; }
   if ((rc = dev_alloc(c, &c->d_diag, 1))) { we_destroy(c); return rc; }
-  CK(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&c->s_cov, cudaStreamNonBlocking));
+  {
+    // the covariance kernel of batch k runs beside the kernels of batch k+1: it must only fill the
+    // SM slots they leave free, so its stream has the lowest priority and the compute stream the highest
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CK(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithPriority(&c->s_comp, cudaStreamNonBlocking, prio_hi));
+    CK(cudaStreamCreateWithPriority(&c->s_cov, cudaStreamNonBlocking, prio_lo));
+  }
   for (int i = 0; i < WE_NBUF; ++i) {
     CK(cudaEventCreateWithFlags(&c->ev_in_ready[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_in_free[i], cudaEventDisableTiming));
@@ -398,6 +410,7 @@ extern "C" int we_create(const we_topology* t, const we_options* opt, we_ctx** o
   memset(c->h_diag, 0, sizeof(WeDiag));
   if (const char* g = getenv("WE_COPY_GATE")) c->copy_gate = atoi(g);
   if (const char* g = getenv("WE_COV_STREAM")) c->cov_stream = atoi(g);
+  if (const char* g = getenv("WE_GRAPHS")) c->use_graphs = atoi(g);
   rc = we_reset(c);
   if (rc) { we_destroy(c); return rc; }
   *out = c;
@@ -425,6 +438,7 @@ extern "C" int we_reset(we_ctx* c) {
   return WE_OK;
 }
 
+static void drop_graphs(we_ctx* c);
 extern "C" void we_destroy(we_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
@@ -433,6 +447,7 @@ extern "C" void we_destroy(we_ctx* c) {
   if (c->d_table) cudaFree(c->d_table);
   if (c->d_compact) cudaFree(c->d_compact);
   for (void* p : c->pinned) cudaFreeHost(p);
+  drop_graphs(c);
   if (c->s_copy) cudaStreamDestroy(c->s_copy);
   if (c->s_comp) cudaStreamDestroy(c->s_comp);
   if (c->s_cov) cudaStreamDestroy(c->s_cov);
@@ -532,6 +547,7 @@ static int ensure_workspace(we_ctx* c, const float* dims0, bool need_input_buffe
     int per_sm = 0, sms = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rad, WE_RAD_WARPS * 32, sizeof(WeRadSmem)));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    c->n_sm = std::max(1, sms);
     c->rad_blocks = std::max(1, per_sm) * std::max(1, sms);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hb, 256, 0));
     c->hb_blocks = std::max(1, per_sm) * std::max(1, sms);
@@ -550,19 +566,22 @@ static int drain(we_ctx* c, int buf) {
   for (int f = 0; f < n; ++f) {
     const int cnt = c->h_rec_count[buf][f];
     c->recorded += (unsigned long long)cnt;
-    if (c->opt.keep_records || c->opt.keep_shells) {
+    if ((c->opt.keep_records || c->opt.keep_shells)) {
+      // ascending atom index (recipes/interfacial_solvent.py:66,303): sort (atom, position) packed in
+      // 64-bit keys - this runs on the submitting thread, between two batch submissions
       const int2* r = c->h_rec[buf] + (size_t)f * std::max(1, c->C);
-      std::vector<int> order((size_t)cnt);
-      for (int k = 0; k < cnt; ++k) order[k] = k;
-      std::sort(order.begin(), order.end(), [&](int a, int b) { return r[a].x < r[b].x; });
+      std::vector<unsigned long long>& order = c->sort_keys;
+      order.resize((size_t)cnt);
+      for (int k = 0; k < cnt; ++k) order[k] = ((unsigned long long)(unsigned int)r[k].x << 32) | (unsigned int)k;
+      std::sort(order.begin(), order.end());
       std::vector<int> flat((size_t)cnt * 2);
-      for (int k = 0; k < cnt; ++k) { flat[2 * k] = r[order[k]].x; flat[2 * k + 1] = r[order[k]].y; }
+      for (int k = 0; k < cnt; ++k) { const int2 v = r[order[k] & 0xffffffffULL]; flat[2 * k] = v.x; flat[2 * k + 1] = v.y; }
       c->frame_records.push_back(std::move(flat));
       if (c->opt.keep_shells) {
         const int W = WE_MAX_NBR + 1;
         const int* sh = c->h_shell[buf] + (size_t)f * std::max(1, c->C) * W;
         std::vector<int> fs((size_t)cnt * W);
-        for (int k = 0; k < cnt; ++k) memcpy(fs.data() + (size_t)k * W, sh + (size_t)order[k] * W, W * sizeof(int));
+        for (int k = 0; k < cnt; ++k) memcpy(fs.data() + (size_t)k * W, sh + (size_t)(order[k] & 0xffffffffULL) * W, W * sizeof(int));
         c->frame_shells.push_back(std::move(fs));
       }
     }
@@ -610,6 +629,7 @@ static int grow_table_to(we_ctx* c, unsigned long long need) {
   c->launches++;
   CK(cudaStreamSynchronize(c->s_comp));
   CK(cudaFree(c->d_table));
+  drop_graphs(c);  // k_label's table pointer and mask are baked into the captured launches
   c->d_table = nt;
   c->table_mask = (unsigned int)(ncap - 1);
   return 0;
@@ -663,6 +683,49 @@ static int finish_lazy(we_ctx* c, int buf) {
   c->out_pending[buf] = true;
   return 0;
 }
+
+static void drop_graphs(we_ctx* c) {
+  for (auto& kv : c->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  c->graphs.clear();
+}
+
+// One run of kernels of a batch as a CUDA graph: the first time a (slot, frames, part) key is seen the
+// launches between begin() and end() are captured from the compute stream and instantiated; afterwards
+// begin() replays the graph and tells the caller to skip the launches.  While host->device uploads are
+// in flight every individual launch costs 20-40 us extra (see the upload gating above); a graph is one
+// submission for the whole run.
+struct GraphRegion {
+  we_ctx* c; cudaStream_t st; long long key; bool on; bool capturing = false; unsigned long long l0 = 0;
+  GraphRegion(we_ctx* c_, cudaStream_t st_, long long key_, bool on_) : c(c_), st(st_), key(key_), on(on_) {}
+  // returns 1: replayed (skip the launches), 0: run the launches (captured if graphs are on), <0: error
+  int begin() {
+    if (!on) return 0;
+    auto it = c->graphs.find(key);
+    if (it != c->graphs.end()) {
+      if (cudaGraphLaunch(it->second.exec, st) != cudaSuccess) return fail(WE_ERR_CUDA, "cudaGraphLaunch failed");
+      c->launches += it->second.launches;
+      return 1;
+    }
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); on = false; return 0; }
+    capturing = true;
+    l0 = c->launches;
+    return 0;
+  }
+  int end() {
+    if (!capturing) return 0;
+    capturing = false;
+    cudaGraph_t g = nullptr;
+    if (cudaStreamEndCapture(st, &g) != cudaSuccess || !g) return fail(WE_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(cudaGetLastError()));
+    we_ctx::BatchGraph bg;
+    bg.launches = c->launches - l0;
+    const cudaError_t e = cudaGraphInstantiate(&bg.exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(WE_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    c->graphs[key] = bg;
+    if (cudaGraphLaunch(bg.exec, st) != cudaSuccess) return fail(WE_ERR_CUDA, "cudaGraphLaunch failed");
+    return 0;
+  }
+};
 
 // the slot chunk_counter % WE_NBUF holds the oldest batch in flight
 static int finish_lazy_all(we_ctx* c) {
@@ -742,12 +805,18 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     CK(cudaEventRecord(c->ev_in_ready[buf], c->s_copy));
     cudaStream_t st = c->s_comp, cov_st = c->s_comp;
     CK(cudaStreamWaitEvent(st, c->ev_in_ready[buf], 0));
-    CK(cudaMemsetAsync(c->d_zero, 0, c->zero_ints * sizeof(int), st));  // cells, state, queues, counters, flags
-    CK(cudaMemsetAsync(c->d_rec_count[buf], 0, (size_t)n * sizeof(int), st));
     const WeBox* bx = c->d_boxes[buf];
     const long long* fids = c->d_fids[buf];
     const bool interfacial = (c->recipe == WE_RECIPE_INTERFACIAL);
     dim3 gH((H + 255) / 256, n);
+    const bool graphs_on = !on_device && c->use_graphs && !c->prof && !c->opt.keep_debug;
+    const long long gkey = ((long long)buf * 4096 + n) * 2;
+    GraphRegion g1(c, st, gkey, graphs_on), g2(c, st, gkey + 1, graphs_on);
+    int replay = g1.begin();
+    if (replay < 0) return replay;
+    if (!replay) {
+    CK(cudaMemsetAsync(c->d_zero, 0, c->zero_ints * sizeof(int), st));  // cells, state, queues, counters, flags
+    CK(cudaMemsetAsync(c->d_rec_count[buf], 0, (size_t)n * sizeof(int), st));
     { ProfScope ps(c, WE_K_BIN, st);
       k_bin<<<gH, 256, 0, st>>>(c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_rank_of, c->d_tmp4, c->ncap);
       ps.stop(st); }
@@ -758,6 +827,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       k_scatter<<<gH, 256, 0, st>>>(H, bx, c->d_cell_count, c->d_cell_of, c->d_rank_of, c->d_tmp4, c->d_sorted4, c->ncap);
       ps.stop(st); }
     c->launches += 3;
+    }
     // pass-0 centres: every heavy atom (debug), solute united atoms (interfacial), waters (bulk)
     WeWork w0;
     w0.count = nullptr; w0.stride = 0;
@@ -788,12 +858,18 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       ps.stop(st);
       c->launches++;
     };
-    if (w0.static_count > 0) {
-      { ProfScope ps(c, WE_K_LIST2, st);
-        k_seed<<<dim3((w0.static_count + 255) / 256, n), 256, 0, st>>>(w0.static_count, w0.list, H, c->d_state);
-        ps.stop(st); }
+    if (w0.static_count > 0 && !replay) {
+      ProfScope ps(c, WE_K_LIST2, st);
+      k_seed<<<dim3((w0.static_count + 255) / 256, n), 256, 0, st>>>(w0.static_count, w0.list, H, c->d_state);
+      ps.stop(st);
       c->launches++;
-      CK(cudaEventRecord(c->ev_p0[buf], st));
+    }
+    if ((rc = g1.end())) return rc;
+    CK(cudaEventRecord(c->ev_p0[buf], st));
+    replay = g2.begin();
+    if (replay < 0) return replay;
+    if (!replay) {
+    if (w0.static_count > 0) {
       if (!c->opt.keep_debug) {
         rad(WE_K_RAD, w0, (long long)w0.static_count * n, interfacial ? c->d_state : nullptr, m0);
       } else {
@@ -845,6 +921,13 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
             c->opt.keep_shells ? c->h_shell[buf] : nullptr, wlab, n, c->d_diag);
         ps.stop(st); }
       c->launches += 1;
+    }
+    CK(cudaMemcpyAsync(c->h_diag, c->d_diag, sizeof(WeDiag), cudaMemcpyDeviceToHost, st));  // table load mirror
+    // per-frame record counts -> pinned staging (the records themselves are already in mapped memory)
+    CK(cudaMemcpyAsync(c->h_rec_count[buf], c->d_rec_count[buf], (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    if ((rc = g2.end())) return rc;
+    if (C > 0) {
       if (!c->lazy) {
         // zero-copy forces: the kernel waits on PCIe reads, so it runs beside the next batch's kernels
         cov_st = (frc_zero_copy && c->cov_stream) ? c->s_cov : st;
@@ -853,7 +936,10 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
           CK(cudaStreamWaitEvent(cov_st, c->ev_label[buf], 0));
         }
         ProfScope ps(c, WE_K_COV, cov_st);
-        k_cov<<<dim3((C + 511) / 512, n), 128, 0, cov_st>>>(
+        // zero-copy: the kernel is bound by PCIe read latency, not by SM throughput; about two blocks per
+        // SM keep as many reads in flight as the link takes and leave the SMs to the next batch
+        const int cov_bx = (cov_st != st) ? std::max(1, std::min((C + 511) / 512, (2 * c->n_sm + n - 1) / n)) : (C + 511) / 512;
+        k_cov<<<dim3(cov_bx, n), 128, 0, cov_st>>>(
             c->T, dp, df, c->d_rec_count[buf], c->d_rec[buf], c->d_centre_of_slot, c->d_cov_sum,
             c->d_cov_cnt, c->d_ft, nullptr, nullptr, 0, n);
         ps.stop(cov_st);
@@ -861,9 +947,6 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       }
     }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(c->h_diag, c->d_diag, sizeof(WeDiag), cudaMemcpyDeviceToHost, st));  // table load mirror
-    // per-frame record counts -> pinned staging (the records themselves are already in mapped memory)
-    CK(cudaMemcpyAsync(c->h_rec_count[buf], c->d_rec_count[buf], (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
     c->pending_n[buf] = n;
     c->frames_done += (unsigned long long)n;
     if (c->lazy && C > 0) {
@@ -933,14 +1016,15 @@ extern "C" int we_sync(we_ctx* c) {
     int rc0;
     if ((rc0 = finish_lazy_all(c))) return rc0;
   }
+  // drain in submission order; each slot waits for its own batch only, so the host sorts the lists of
+  // batch k while the device still runs the batches after it
+  int rc;
+  for (int i = 0; i < WE_NBUF; ++i)
+    if ((rc = drain(c, (int)((c->chunk_counter + i) % WE_NBUF)))) return rc;
   CK(cudaStreamSynchronize(c->s_copy));
   CK(cudaStreamSynchronize(c->s_comp));
   CK(cudaStreamSynchronize(c->s_cov));
   prof_resolve(c);
-  // drain in submission order
-  int rc;
-  for (int i = 0; i < WE_NBUF; ++i)
-    if ((rc = drain(c, (int)((c->chunk_counter + i) % WE_NBUF)))) return rc;
   WeDiag d;
   if ((rc = read_diag(c, &d))) return rc;
   switch (d.err_code) {
