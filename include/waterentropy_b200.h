@@ -87,6 +87,12 @@ typedef struct we_options {
                                 the recorded waters' forces straight from pinned host memory */
 } we_options;
 
+/* Tuning knobs read from the environment by we_create (defaults are the measured optimum on B200):
+ *   WE_COPY_GATE=0   uploads of a batch start as soon as its slot is free (default 1: when the previous
+ *                    batch's first neighbour pass starts)
+ *   WE_COV_STREAM=0  zero-copy k_cov on the compute stream (default 1: own low-priority stream)
+ *   WE_GRAPHS=0      launch every kernel individually (default 1: two CUDA graphs per batch for
+ *                    host-buffer submissions)                                                          */
 typedef struct we_ctx we_ctx;
 
 typedef struct we_diag {
