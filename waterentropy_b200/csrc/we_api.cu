@@ -430,8 +430,7 @@ extern "C" int we_reset(we_ctx* c) {
   c->debug.clear();
   c->frames_done = 0;
   c->recorded = 0;
-  c->out_pending[0] = c->out_pending[1] = false;
-  c->lazy_pending[0] = c->lazy_pending[1] = false;
+  for (int i = 0; i < WE_NBUF; ++i) { c->out_pending[i] = false; c->lazy_pending[i] = false; }
   c->seen_entries = 0;
   c->max_new = 0;
   if (c->h_diag) memset(c->h_diag, 0, sizeof(WeDiag));
