@@ -1,7 +1,7 @@
 // C ABI + host runtime of waterentropy_b200 (see include/waterentropy_b200.h).
 //
 // Host side of the hot path: topology upload, per-frame box / cell-grid set-up,
-// double-buffered H2D staging on a copy stream, kernel batches on a compute
+// H2D staging through a ring of four slots on a copy stream, kernel batches on a compute
 // stream, asynchronous D2H of the per-frame recorded-water lists.  There is no
 // CPU implementation of any kernel in this library: without a CUDA device every
 // entry point fails with WE_ERR_CUDA.
@@ -94,7 +94,7 @@ struct we_ctx {
   int *d_shell_n = nullptr, *d_shell_idx = nullptr, *d_nn = nullptr, *d_flags = nullptr, *d_acceptor = nullptr;
   unsigned char* d_interf = nullptr;
   int *d_state = nullptr, *d_wl1 = nullptr, *d_wl2 = nullptr, *d_n1 = nullptr, *d_n2 = nullptr;
-  int *d_hbq = nullptr, *d_wlh = nullptr, *d_nh = nullptr;
+  int *d_hbq = nullptr /* mark bytes: HB centres, then pass-2 shells */, *d_wlh = nullptr, *d_nh = nullptr;
   int* d_zero = nullptr;
   size_t zero_ints = 0;
   int hb_blocks = 0, label_blocks = 0;

@@ -6,7 +6,7 @@
 //   K2  k_rad        persistent, one warp per centre of a work list: flattened warp-dense
 //                    cell scan -> float32 prefilter -> exact fp64 distances -> exact top-25
 //                    -> RAD blocking test with the reference's float32 cosine
-//       k_seed / k_flag / k_mark / k_mark_bulk   the work lists: solute atoms -> interfacial
+//       marks in k_rad + k_seed / k_list1 / k_list2   the work lists: solute atoms -> interfacial
 //                    waters -> their shell members (the closure the reference memoises lazily)
 //   K3  k_hb         persistent over the centres whose HBs are needed: 8 lanes per donor
 //                    hydrogen, acceptor = argmin over the donor's RAD shell
@@ -251,8 +251,8 @@ struct WeRadSmem {
 // reference memoises shells lazily (analysis/RAD.py:86); the device computes
 // exactly the same closure in three dependent passes:
 //   pass 0  solute united atoms (interfacial) / every water centre (bulk)
-//   pass 1  interfacial waters found from pass 0 (k_flag)
-//   pass 2  shell members of the interfacial waters not yet computed (k_mark)
+//   pass 1  interfacial waters marked by pass 0 (k_list1)
+//   pass 2  shell members of the interfacial waters not yet computed (k_list2)
 // ---------------------------------------------------------------------------
 struct WeWork {
   const int* list;   // heavy slots; frame f starts at list + f * stride
@@ -545,7 +545,7 @@ __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __re
   __syncwarp();
   // ---- solute atoms without a water among their 20 nearest candidates need no RAD shell
   // (recipes/interfacial_solvent.py:50-56).  Their state goes back to "not computed", so
-  // that k_mark queues them again should an interfacial water hold them in its shell.
+  // that k_list2 queues them again should an interfacial water hold them in its shell.
   if (gate_only_state) {
     bool wat0 = false;
     if (lane < min(n25, WE_GATE_NBR)) wat0 = T.is_water[si[S.top[w][lane]]] != 0;
@@ -703,7 +703,7 @@ k_rad(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxe
 //   maths/trig.py:71-100 (candidates = heavy atoms of X's shell within 10 A of D,
 //   sorted by distance).  Sequential "rc < current and angle > 90" scan ==
 //   argmin over qualifying candidates of (rc, d, index); default = closest.
-// Only donors of centres whose HBs the recipe touches (need_hb) are evaluated.
+// Only donors of centres whose HBs the recipe touches (the HB work list) are evaluated.
 // ============================================================================
 __device__ __forceinline__ bool we_lex_less(double a0, double a1, int a2, double b0, double b1, int b2) {
   if (a0 < b0) return true;
