@@ -536,7 +536,8 @@ static int ensure_workspace(we_ctx* c, const float* dims0, bool need_input_buffe
   }
   if (c->opt.keep_debug) { AL(d_nbr_idx, F * H * WE_MAX_NBR) AL(d_nbr_dist, F * H * WE_MAX_NBR) AL(d_ft, F * std::max(1, c->C) * 6) }
 #undef AL
-  CK(cudaFuncSetAttribute(k_rad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WeRadSmem)));
+  CK(cudaFuncSetAttribute(k_rad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WeRadSmem)));
+  CK(cudaFuncSetAttribute(k_rad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WeRadSmem)));
   {
     std::vector<int> all(H);
     for (int i = 0; i < H; ++i) all[i] = i;
@@ -544,7 +545,7 @@ static int ensure_workspace(we_ctx* c, const float* dims0, bool need_input_buffe
     if ((rc = dev_upload(c, &p, all))) return rc;
     c->d_all_slots = (int*)p;
     int per_sm = 0, sms = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rad, WE_RAD_WARPS * 32, sizeof(WeRadSmem)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rad<false>, WE_RAD_WARPS * 32, sizeof(WeRadSmem)));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
     c->n_sm = std::max(1, sms);
     c->rad_blocks = std::max(1, per_sm) * std::max(1, sms);
@@ -851,9 +852,14 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
                                    : WeMarks{nullptr, mark_hb, nullptr, nullptr, 1};
     auto rad = [&](int id, const WeWork& wk, long long items, int* gate_state, const WeMarks& mk) {
       ProfScope ps(c, id, st);
-      k_rad<<<rad_grid(items), WE_RAD_WARPS * 32, sizeof(WeRadSmem), st>>>(
-          c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->d_tmp4, c->ncap, c->cell_target, wk, n, ro,
-          gate_state, mk, c->d_diag);
+      if (gate_state)
+        k_rad<true><<<rad_grid(items), WE_RAD_WARPS * 32, sizeof(WeRadSmem), st>>>(
+            c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->d_tmp4, c->ncap, c->cell_target, wk, n, ro,
+            gate_state, mk, c->d_diag);
+      else
+        k_rad<false><<<rad_grid(items), WE_RAD_WARPS * 32, sizeof(WeRadSmem), st>>>(
+            c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->d_tmp4, c->ncap, c->cell_target, wk, n, ro,
+            nullptr, mk, c->d_diag);
       ps.stop(st);
       c->launches++;
     };

@@ -239,7 +239,8 @@ struct WeRadSmem {
   int top[WE_RAD_WARPS][32];
   int stage[WE_RAD_WARPS][64];
   WeRowInfo rows[WE_RAD_WARPS];
-  float4 p4[WE_RAD_WARPS][32];  // ranked candidate k: position, separation e_k from the centre (float32)
+  float4 p4[WE_RAD_WARPS][32];  // ranked candidate k: position, separation e_k from the centre (float32);
+                                // before the ranking: float32 d^2 of the prefilter survivors (gated pass)
   float4 q4[WE_RAD_WARPS][32];  // float32 e_k^2, 1 / r_k^2, 2 e_k
   double q[WE_RAD_WARPS][32];   // r_k, the exact fp64 distance of ranked candidate k
   double log2tab[32];
@@ -303,12 +304,13 @@ __device__ __forceinline__ int we_flush(const WeBox& b, const float4* __restrict
 //   Survivors are warp-compacted into a 64-entry ring in shared memory.
 // Phase B (we_flush): every 32 staged survivors get the exact fp64 treatment, all lanes busy.
 // Returns the number kept (may exceed WE_CAND_CAP -> caller retries).
+template <bool defer>
 __device__ __forceinline__ int we_collect(const WeBox& b, const int* __restrict__ cstart,
                                           const float4* __restrict__ sorted, int c0, int c1, int c2,
                                           int wx, int wy, int wz, double r, float mx, float my,
                                           float mz, int my_atom, const int* ex, double* sd, float* sf,
                                           int* si, int* ss, int* stage, WeRowInfo* rows, int lane,
-                                          bool& dup) {
+                                          bool& dup, float* sg) {
   int n = 0, head = 0, cnt = 0;
   const int n0 = b.nc[0], n1 = b.nc[1], n2 = b.nc[2];
   const bool all_z = (2 * wz + 1 > n2), all_y = (2 * wy + 1 > n1), all_x = (2 * wx + 1 > n0);
@@ -373,7 +375,7 @@ __device__ __forceinline__ int we_collect(const WeBox& b, const int* __restrict_
     // ---- dense walk over the candidates of these rows ---------------------------------------
     // Row of dense index q = base + lane: rows that start at or before `base` are counted by one
     // ballot, rows that start inside the 32-wide window set bit (start - base) of a warp-wide OR.
-    auto probe = [&](int base, int& qi) -> bool {
+    auto probe = [&](int base, int& qi, float& d2) -> bool {
       const int rel = coff - base;
       const unsigned starts = __reduce_or_sync(0xffffffffu, (rel > 0 && rel < 32) ? (1u << rel) : 0u);
       const int r0 = __popc(__ballot_sync(0xffffffffu, rel <= 0)) - 1;
@@ -389,14 +391,16 @@ __device__ __forceinline__ int we_collect(const WeBox& b, const int* __restrict_
       if (simple) {
         const float ux = c.x - (second ? rp.w : rp.x);
         const float uy = c.y - rp.y, uz = c.z - rp.z;
-        return __fmaf_rn(ux, ux, __fmaf_rn(uy, uy, uz * uz)) <= rf2;
+        d2 = __fmaf_rn(ux, ux, __fmaf_rn(uy, uy, uz * uz));
+        return d2 <= rf2;
       }
       const float ux = c.x - mx, uy = c.y - my, uz = c.z - mz;
       if (mode == 0) {
         const float fx = __fmaf_rn(-b.box[0], rintf(ux * b.inv[0]), ux);
         const float fy = __fmaf_rn(-b.box[1], rintf(uy * b.inv[1]), uy);
         const float fz = __fmaf_rn(-b.box[2], rintf(uz * b.inv[2]), uz);
-        return __fmaf_rn(fx, fx, __fmaf_rn(fy, fy, fz * fz)) <= rf2;
+        d2 = __fmaf_rn(fx, fx, __fmaf_rn(fy, fy, fz * fz));
+        return d2 <= rf2;
       }
       if (mode == 1) {
         float s0 = ux * b.hinvf[0] + uy * b.hinvf[3] + uz * b.hinvf[6];
@@ -406,12 +410,20 @@ __device__ __forceinline__ int we_collect(const WeBox& b, const int* __restrict_
         const float fx = s0 * b.m[0] + s1 * b.m[3] + s2 * b.m[6];
         const float fy = s1 * b.m[4] + s2 * b.m[7];
         const float fz = s2 * b.m[8];
-        return (fx * fx + fy * fy + fz * fz) <= rf2;
+        d2 = fx * fx + fy * fy + fz * fz;
+        return d2 <= rf2;
       }
+      d2 = -1.0f;  // no float32 estimate for this box: the caller must not use the deferred mode
       return true;
     };
-    auto push = [&](bool pass, int qi) {
+    auto push = [&](bool pass, int qi, float d2) {
       const unsigned m = __ballot_sync(0xffffffffu, pass);
+      if (defer) {  // survivors are only listed (index into the cell-sorted array, float32 d^2)
+        const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+        if (pass && pos < WE_CAND_CAP) { ss[pos] = qi; sg[pos] = d2; }
+        cnt += __popc(m);
+        return;
+      }
       if (pass) stage[(head + cnt + __popc(m & ((1u << lane) - 1u))) & 63] = qi;
       cnt += __popc(m);
       if (cnt >= 32) {
@@ -424,13 +436,54 @@ __device__ __forceinline__ int we_collect(const WeBox& b, const int* __restrict_
     };
     for (int base = 0; base < total; base += 32) {
       int qa = 0;
-      const bool pa = probe(base, qa);
-      push(pa, qa);
+      float da = 0.f;
+      const bool pa = probe(base, qa, da);
+      push(pa, qa, da);
     }
   }
+  if (defer) { __syncwarp(); return cnt; }
   if (cnt > 0) {
     __syncwarp();
     n = we_flush(b, sorted, stage, head, cnt, r, mx, my, mz, my_atom, ex, sd, sf, si, ss, n, lane, dup);
+  }
+  dup = __any_sync(0xffffffffu, dup);
+  return n;
+}
+
+// Exact phase over the survivors listed by a deferred we_collect (ss[0..cnt) = indices into the
+// cell-sorted array).  In place: chunk i reads ss[32 i + lane] before anything is written, and the
+// compacted outputs land at indices <= the ones read.
+__device__ __forceinline__ int we_exact_list(const WeBox& b, const float4* __restrict__ sorted, int cnt,
+                                             double r, float mx, float my, float mz, int my_atom,
+                                             const int* ex, double* sd, float* sf, int* si, int* ss,
+                                             int lane, bool& dup) {
+  int n = 0;
+  for (int i0 = 0; i0 < cnt; i0 += 32) {
+    const int take = min(32, cnt - i0);
+    bool keep = false;
+    double dd = 0.0;
+    int ai = -1, qi = -1;
+    if (lane < take) {
+      qi = ss[i0 + lane];
+      const float4 c = sorted[qi];
+      ai = __float_as_int(c.w);
+      bool skip = (ai == my_atom);
+#pragma unroll
+      for (int e = 0; e < WE_MAX_EXCL; ++e) skip |= (ex[e] == ai);
+      if (!skip) {
+        if (c.x == mx && c.y == my && c.z == mz) dup = true;
+        dd = we_dist_fast(mx, my, mz, c.x, c.y, c.z, b);
+        keep = (dd <= r);
+      }
+    }
+    __syncwarp();
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const int p = n + __popc(m & ((1u << lane) - 1u));
+      sd[p] = dd; sf[p] = (float)dd; si[p] = ai; ss[p] = qi;
+    }
+    n += __popc(m);
+    __syncwarp();
   }
   dup = __any_sync(0xffffffffu, dup);
   return n;
@@ -452,7 +505,9 @@ struct WeMarks {
   int bulk;
 };
 
-// One centre (heavy slot h of frame f) on one warp.
+// One centre (heavy slot h of frame f) on one warp.  GATED: the gating pass of the interfacial recipe
+// (gate_only_state != nullptr) - a separate instantiation, so the other passes do not carry its code.
+template <bool GATED>
 __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __restrict__ fpos,
                                            const WeBox& b, const int* __restrict__ cstart,
                                            const int* __restrict__ cell_of_f,
@@ -471,6 +526,8 @@ __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __re
   for (int e = 0; e < WE_MAX_EXCL; ++e) ex[e] = T.excl[(size_t)h * WE_MAX_EXCL + e];
   const int cell = cell_of_f[h];
   const int c0 = cell & 1023, c1 = (cell >> 10) & 1023, c2 = cell >> 20;
+  static_assert(sizeof(float4) * 32 >= sizeof(float) * WE_CAND_CAP, "p4 doubles as the float32 d^2 list");
+  float* sg = reinterpret_cast<float*>(S.p4[w]);
   double* sd = S.d[w];
   float* sf = S.f[w];
   int* si = S.idx[w];
@@ -485,8 +542,60 @@ __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __re
   bool wide = false;
   for (int iter = 0; iter < 64; ++iter) {
     dup = false;
-    if (!wide) n = we_collect(b, cstart, sorted, c0, c1, c2, b.sw[0], b.sw[1], b.sw[2], r, mq[0], mq[1], mq[2], my_atom, ex, sd, sf, si, ss, S.stage[w], &S.rows[w], lane, dup);
-    else n = we_collect(b, cstart, sorted, c0, c1, c2, b.wide[0], b.wide[1], b.wide[2], r, mq[0], mq[1], mq[2], my_atom, ex, sd, sf, si, ss, S.stage[w], &S.rows[w], lane, dup);
+    if (GATED && !wide && iter == 0 && (!b.triclinic || b.pre_ok)) {
+      // Solute atom of the gating pass (recipes/interfacial_solvent.py:50-56): most are buried.  List the
+      // float32 survivors first; if at least 20 non-excluded solute atoms are closer (by a safe margin)
+      // than the nearest water in range and than the search radius, no water can be among the 20
+      // nearest candidates and the exact distances, the ranking and the RAD test are never needed.
+      const int nf = we_collect<true>(b, cstart, sorted, c0, c1, c2, b.sw[0], b.sw[1], b.sw[2], r, mq[0], mq[1], mq[2], my_atom, ex, sd, sf, si, ss, S.stage[w], &S.rows[w], lane, dup, sg);
+      if (nf > WE_CAND_CAP) {
+        n = nf;  // overflow: the shrink / retry logic below takes over with the interleaved mode
+      } else {
+        bool buried = false;
+        if (r <= r_cover) {  // everything closer than r has been seen
+          float wmin = (float)(r * r);
+          bool zero = false;
+          int solute_d2_bits[WE_CAND_CAP / 32];
+#pragma unroll
+          for (int k = 0; k < WE_CAND_CAP / 32; ++k) {
+            const int i = k * 32 + lane;
+            solute_d2_bits[k] = 0x7f7fffff;  // FLT_MAX: not a solute candidate
+            if (i < nf) {
+              const int ai = __float_as_int(sorted[ss[i]].w);
+              bool skip = (ai == my_atom);
+#pragma unroll
+              for (int e = 0; e < WE_MAX_EXCL; ++e) skip |= (ex[e] == ai);
+              if (!skip) {
+                const float d2 = sg[i];
+                zero |= !(d2 > 0.f);  // identical coordinates (or NaN): the exact path must see this centre
+                if (T.is_water[ai]) wmin = fminf(wmin, d2);
+                else solute_d2_bits[k] = __float_as_int(d2);
+              }
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) wmin = fminf(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
+          // strictly inside the radius and closer than the nearest water by 1e-3 relative in d^2
+          // (the float32 image shift of a triclinic row is good to ~1e-4 relative in d^2)
+          const float lim = wmin * (1.0f - 1.0e-3f);
+          int closer = 0;
+#pragma unroll
+          for (int k = 0; k < WE_CAND_CAP / 32; ++k)
+            closer += __popc(__ballot_sync(0xffffffffu, __int_as_float(solute_d2_bits[k]) < lim));
+          buried = (closer >= WE_GATE_NBR) && !__any_sync(0xffffffffu, zero);
+        }
+        if (buried) {
+          const size_t hob = (size_t)f * T.n_heavy + h;
+          if (lane == 0) { O.shell_n[hob] = 0; O.nn[hob] = -1; O.flags[hob] = 0; gate_only_state[hob] = 0; }
+          __syncwarp();
+          return;
+        }
+        dup = false;
+        n = we_exact_list(b, sorted, nf, r, mq[0], mq[1], mq[2], my_atom, ex, sd, sf, si, ss, lane, dup);
+      }
+    }
+    else if (!wide) n = we_collect<false>(b, cstart, sorted, c0, c1, c2, b.sw[0], b.sw[1], b.sw[2], r, mq[0], mq[1], mq[2], my_atom, ex, sd, sf, si, ss, S.stage[w], &S.rows[w], lane, dup, sg);
+    else n = we_collect<false>(b, cstart, sorted, c0, c1, c2, b.wide[0], b.wide[1], b.wide[2], r, mq[0], mq[1], mq[2], my_atom, ex, sd, sf, si, ss, S.stage[w], &S.rows[w], lane, dup, sg);
     if (n > WE_CAND_CAP) {
       if (n >= WE_MAX_NBR && r > 0.5) { r *= 0.85; if (lane == 0) atomicAdd(&diag->shrink_retries, 1ULL); continue; }
       status = WE_ST_OVERFLOW; break;
@@ -670,6 +779,7 @@ __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __re
 // Persistent kernel: gridDim.x blocks of WE_RAD_WARPS warps walk the work list of
 // every frame of the batch with a grid-stride loop (no empty blocks when the list
 // is short, natural load balance when per-centre cost varies).
+template <bool GATED>
 __global__ void __launch_bounds__(WE_RAD_WARPS * 32, WE_RAD_MINBLOCKS)
 k_rad(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes,
       const int* __restrict__ cell_start, const int* __restrict__ cell_of,
@@ -693,7 +803,7 @@ k_rad(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxe
     const int* cof = cell_of + (size_t)f * T.n_heavy;
     const float4* t4 = tmp4 + (size_t)f * T.n_heavy;
     for (int i = blockIdx.x * WE_RAD_WARPS + w; i < cnt; i += stride)
-      we_rad_one(T, fpos, b, cstart, cof, sorted, t4, search_radius, f, list[i], O, gate_only_state, M, diag, S, PT, lane, w);
+      we_rad_one<GATED>(T, fpos, b, cstart, cof, sorted, t4, search_radius, f, list[i], O, GATED ? gate_only_state : nullptr, M, diag, S, PT, lane, w);
   }
 }
 
