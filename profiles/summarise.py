@@ -30,7 +30,8 @@ KEEP = [
 
 
 def short(name):
-    return re.split(r"[(<]", name)[0].strip()
+    name = re.split(r"[(<]", name)[0].strip()
+    return name[5:] if name.startswith("void ") else name  # templated kernels print their return type
 
 
 def launches(path, out, command):
