@@ -765,8 +765,17 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       if ((rc = dev_alloc(c, &c->d_frc[i], (size_t)c->chunk * N * 3))) return rc;
     }
   }
-  for (int f0 = 0; f0 < n_frames; f0 += c->chunk) {
-    const int n = std::min(c->chunk, n_frames - f0);
+  // Host buffers: a call that fits in one or two batches would upload everything before computing
+  // anything, so (auto batch size only) it is cut into at least three batches of >= ~1 M centres each and
+  // the uploads of the later ones hide behind the kernels of the earlier ones.
+  int step = c->chunk;
+  if (!on_device && c->opt.chunk_frames <= 0 && n_frames < 3 * c->chunk) {
+    const int floor_frames = std::max(1, (int)(1000000LL / std::max(1, H)));
+    step = std::min(c->chunk, std::max((n_frames + 2) / 3, floor_frames));
+    if (step >= 8) step &= ~7;
+  }
+  for (int f0 = 0; f0 < n_frames; f0 += step) {
+    const int n = std::min(step, n_frames - f0);
     const int buf = (int)(c->chunk_counter % WE_NBUF);
     c->chunk_counter++;
     // staging buffers of this slot were last used WE_NBUF chunks ago
