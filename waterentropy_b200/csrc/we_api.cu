@@ -124,7 +124,7 @@ struct we_ctx {
   int pending_n[WE_NBUF] = {};
   cudaStream_t s_copy = nullptr, s_comp = nullptr, s_cov = nullptr;
   cudaEvent_t ev_in_ready[WE_NBUF]{}, ev_in_free[WE_NBUF]{}, ev_out_ready[WE_NBUF]{}, ev_p0[WE_NBUF]{};
-  int copy_gate = 1, cov_stream = 1, use_graphs = 1, n_sm = 148;
+  int copy_gate = 1, cov_stream = 1, use_graphs = 1, n_sm = 148, rad_blocks_gated = 0;
   // CUDA graphs of the two kernel runs of a batch (before / after the pass-0 event), per ring slot and
   // frame count; host-buffer submissions only (the device pointers of a slot are fixed)
   struct BatchGraph { cudaGraphExec_t exec = nullptr; unsigned long long launches = 0; };
@@ -549,6 +549,8 @@ static int ensure_workspace(we_ctx* c, const float* dims0, bool need_input_buffe
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
     c->n_sm = std::max(1, sms);
     c->rad_blocks = std::max(1, per_sm) * std::max(1, sms);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rad<true>, WE_RAD_WARPS * 32, sizeof(WeRadSmem)));
+    c->rad_blocks_gated = std::max(1, per_sm) * std::max(1, sms);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hb, 256, 0));
     c->hb_blocks = std::max(1, per_sm) * std::max(1, sms);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_label, 256, 0));
@@ -862,7 +864,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     auto rad = [&](int id, const WeWork& wk, long long items, int* gate_state, const WeMarks& mk) {
       ProfScope ps(c, id, st);
       if (gate_state)
-        k_rad<true><<<rad_grid(items), WE_RAD_WARPS * 32, sizeof(WeRadSmem), st>>>(
+        k_rad<true><<<(int)std::max<long long>(1, std::min<long long>((items + WE_RAD_WARPS - 1) / WE_RAD_WARPS, c->rad_blocks_gated)), WE_RAD_WARPS * 32, sizeof(WeRadSmem), st>>>(
             c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->d_tmp4, c->ncap, c->cell_target, wk, n, ro,
             gate_state, mk, c->d_diag);
       else

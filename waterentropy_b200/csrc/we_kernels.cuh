@@ -31,6 +31,9 @@
 #ifndef WE_RAD_MINBLOCKS
 #define WE_RAD_MINBLOCKS 3
 #endif
+#ifndef WE_RAD_MINBLOCKS_GATED
+#define WE_RAD_MINBLOCKS_GATED 4
+#endif
 #ifndef WE_HB_MINBLOCKS
 #define WE_HB_MINBLOCKS 3
 #endif
@@ -780,7 +783,7 @@ __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __re
 // every frame of the batch with a grid-stride loop (no empty blocks when the list
 // is short, natural load balance when per-centre cost varies).
 template <bool GATED>
-__global__ void __launch_bounds__(WE_RAD_WARPS * 32, WE_RAD_MINBLOCKS)
+__global__ void __launch_bounds__(WE_RAD_WARPS * 32, GATED ? WE_RAD_MINBLOCKS_GATED : WE_RAD_MINBLOCKS)
 k_rad(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes,
       const int* __restrict__ cell_start, const int* __restrict__ cell_of,
       const float4* __restrict__ sorted4, const float4* __restrict__ tmp4, int ncap,
