@@ -14,7 +14,7 @@
  * text.  One context per GPU; a context is not thread-safe.  All host arrays
  * are owned by the caller; the library copies what it needs during the call
  * (frame buffers passed to `we_submit` must stay valid until the next
- * `we_sync` / `we_finalize`).
+ * `we_sync`, or until `we_frames_retired` reports their batch as finished).
  */
 #ifndef WATERENTROPY_B200_H
 #define WATERENTROPY_B200_H
@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define WE_VERSION 100
+#define WE_VERSION 200
 
 /* recipes */
 #define WE_RECIPE_INTERFACIAL 0 /* recipes/interfacial_solvent.py:273-345 (_entropy_per_step) */
@@ -75,7 +75,8 @@ typedef struct we_topology {
 typedef struct we_options {
     int32_t device;          /* CUDA device ordinal */
     int32_t chunk_frames;    /* frames per kernel batch (0 = auto) */
-    int32_t table_log2;      /* log2 capacity of the label count table (0 = 16) */
+    int32_t table_log2;      /* log2 of the initial capacity of the label count table (0 = 17); it grows by
+                                device rehash when half full */
     int32_t keep_records;    /* 1: keep per-frame recorded-water lists (frame_solvent_indices) */
     int32_t keep_debug;      /* 1: keep all-centre shells / neighbours / acceptors / F,T of every frame */
     float search_radius;     /* first-pass candidate radius in A (0 = 6.6) */
@@ -85,7 +86,15 @@ typedef struct we_options {
                                 when the buffer is pinned, else whole frames), 1 whole frames, 2 recorded
                                 waters only, gathered by the host one batch later, 3 zero-copy: k_cov reads
                                 the recorded waters' forces straight from pinned host memory */
+    int32_t eig_flavour;     /* which OpenBLAS kernel family the principal-axis step replays (WE_EIG_*): the
+                                reference's eigenvector signs are whatever numpy.linalg.eig returns on the
+                                host it runs on (maths/transformations.py:121-124) */
 } we_options;
+
+/* numpy.linalg.eig = LAPACK dgeev on OpenBLAS; its level-1/2 kernels round differently per CPU family,
+ * which flips the eigenvector signs of ~1 molecule in 10^4 (csrc/we_eig3.cuh). */
+#define WE_EIG_OPENBLAS_AVX512 0 /* "SkylakeX" kernels: Intel AVX-512 hosts (where the golden vectors were made) */
+#define WE_EIG_OPENBLAS_AVX2 1   /* "Haswell" kernels: AVX2 hosts, AMD Zen */
 
 /* Tuning knobs read from the environment by we_create (defaults are the measured optimum on B200):
  *   WE_COPY_GATE=0   uploads of a batch start as soon as its slot is free (default 1: when the previous
@@ -104,6 +113,8 @@ typedef struct we_diag {
     uint64_t recorded;        /* recorded (water, frame) pairs so far */
     uint64_t fast_path_mismatches; /* keep_debug contexts replay every float32 fast-path decision of the RAD
                                       test exactly and count contradictions: must stay 0 */
+    uint64_t eig_fallbacks;   /* molecules whose inertia tensor took a LAPACK path that is not restated (exact
+                                 zeros / equal moments; never a water): Jacobi axes with a fixed sign rule */
 } we_diag;
 
 const char *we_last_error(void);
@@ -242,6 +253,9 @@ int we_test_angle_cos(int32_t device, const float *abc /*[n][9]*/, const float *
 int we_test_powf2(int32_t device, const float *x, int32_t n, float *out);
 int we_test_pow2(int32_t device, const double *x, int32_t n, double *out);
 int we_test_distance(int32_t device, const float *pairs /*[n][6]*/, const float *dims6, int32_t n, double *out);
+/* numpy.linalg.eig / MDAnalysis principal_axes of symmetric 3x3 tensors (maths/transformations.py:113-133):
+ * out [n][25] = wr(3), vr(9: eigenvector k at [3k..3k+2]), principal axes (9, rows), MOI_axis(3), status. */
+int we_test_eig3(int32_t device, const double *tensors /*[n][9]*/, int32_t n, int32_t flavour, double *out);
 
 #ifdef __cplusplus
 }

@@ -33,3 +33,33 @@ int h_angle_gt_90(float c) { return we_angle_gt_90(c) ? 1 : 0; }
 extern "C" void h_pow2(const double* x, int n, double* out) {
   for (int i = 0; i < n; ++i) out[i] = we_pow2(x[i]);
 }
+
+// ---- we_eig3.cuh: LAPACK dgeev replay for symmetric 3x3 tensors -----------------------------
+#include "../waterentropy_b200/csrc/we_eig3.cuh"
+extern "C" {
+// out [n][25] = wr(3), vr(9), principal axes(9), MOI_axis(3), status -- same layout as we_test_eig3
+void h_eig3(const double* t, int n, int flavour, double* out) {
+  for (int i = 0; i < n; ++i) {
+    double wr[3], vr[9], ax[3][3], moi[3];
+    const int st = we_dgeev3(t + 9 * i, wr, vr, flavour);
+    we_principal_axes(t + 9 * i, ax, moi, flavour);
+    double* o = out + 25 * i;
+    for (int k = 0; k < 3; ++k) o[k] = wr[k];
+    for (int k = 0; k < 9; ++k) o[3 + k] = vr[k];
+    for (int k = 0; k < 9; ++k) o[12 + k] = ax[k / 3][k % 3];
+    for (int k = 0; k < 3; ++k) o[21 + k] = moi[k];
+    o[24] = (double)st;
+  }
+}
+// x87 dnrm2 emulation (integer soft-float) and the same sum on the host's real x87 unit
+void h_x87_nrm2(const double* x, int n, int len, double* out) {
+  for (int i = 0; i < n; ++i) out[i] = we_x87_nrm2(x + (size_t)len * i, len);
+}
+void h_long_double_nrm2(const double* x, int n, int len, double* out) {
+  for (int i = 0; i < n; ++i) {
+    long double acc = 0.0L;
+    for (int k = 0; k < len; ++k) acc = acc + (long double)x[(size_t)len * i + k] * (long double)x[(size_t)len * i + k];
+    out[i] = (double)__builtin_sqrtl(acc);
+  }
+}
+}

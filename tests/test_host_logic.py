@@ -159,7 +159,7 @@ def test_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert set(_lib.EXPORTS) <= declared
-    assert _lib.load().we_version() == 100
+    assert _lib.load().we_version() == _lib.WE_VERSION == int(re.search(r"#define WE_VERSION (\d+)", header).group(1))
 
 
 def test_no_cpu_fallback_without_gpu():
@@ -318,3 +318,113 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 2
     assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+# ------------------------------------------------------- LAPACK dgeev replay (we_eig3.cuh)
+def _water_tensors(n, seed):
+    """Inertia tensors of rigid TIP3P waters in random orientations, built like MDAnalysis
+    `moment_of_inertia` from float32 coordinates (the oracle's arithmetic)."""
+    rng = np.random.default_rng(seed)
+    q = rng.standard_normal((n, 4))
+    q /= np.linalg.norm(q, axis=1)[:, None]
+    a, b, c, d = q.T
+    R = np.stack([np.stack([1 - 2 * (c * c + d * d), 2 * (b * c - a * d), 2 * (b * d + a * c)], -1),
+                  np.stack([2 * (b * c + a * d), 1 - 2 * (b * b + d * d), 2 * (c * d - a * b)], -1),
+                  np.stack([2 * (b * d - a * c), 2 * (c * d + a * b), 1 - 2 * (b * b + c * c)], -1)], 1)
+    half, r = np.deg2rad(104.52) / 2, 0.9572
+    loc = np.array([[0, 0, 0], [r * np.sin(half), 0, r * np.cos(half)], [-r * np.sin(half), 0, r * np.cos(half)]])
+    pos = (np.einsum("nij,aj->nai", R, loc) + rng.uniform(0, 100, (n, 1, 3)) + rng.normal(0, 0.02, (n, 3, 3))).astype(np.float32)
+    m = np.array([16.0, 1.008, 1.008])
+    com = (pos.astype(np.float64) * m[None, :, None]).sum(axis=1) / m.sum()
+    p = pos - com[:, None, :]
+    x, y, z = p[..., 0], p[..., 1], p[..., 2]
+    t = np.zeros((n, 3, 3))
+    t[:, 0, 0] = (m * (y ** 2 + z ** 2)).sum(axis=1)
+    t[:, 1, 1] = (m * (x ** 2 + z ** 2)).sum(axis=1)
+    t[:, 2, 2] = (m * (x ** 2 + y ** 2)).sum(axis=1)
+    t[:, 0, 1] = t[:, 1, 0] = -(m * x * y).sum(axis=1)
+    t[:, 0, 2] = t[:, 2, 0] = -(m * x * z).sum(axis=1)
+    t[:, 1, 2] = t[:, 2, 1] = -(m * y * z).sum(axis=1)
+    return t
+
+
+def _numpy_axes(t):
+    """MDAnalysis principal_axes + transformations.py:131-133 on a batch, via numpy.linalg.eig."""
+    w, v = np.linalg.eig(t)
+    w, v = w.real, v.real
+    order = np.argsort(w, axis=1)[:, ::-1]
+    ax = np.take_along_axis(v, order[:, None, :], axis=2).transpose(0, 2, 1)
+    hand = np.einsum("ni,ni->n", np.cross(ax[:, 0], ax[:, 1]), ax[:, 2])
+    ax = np.where((hand < 0)[:, None, None], -ax, ax)
+    moi = np.take_along_axis(w, np.argsort(np.abs(w), axis=1)[:, ::-1], axis=1)
+    return w, v, ax, moi
+
+
+def test_x87_nrm2_soft_float_is_the_hosts_x87(hostlib):
+    """OpenBLAS dnrm2 on x86-64 is x87 code (64-bit mantissa sums, fsqrt, one rounding to double); the
+    device has no such unit, so we_x87_nrm2 emulates it with integers.  Checked against the host's
+    real x87 unit (long double) and against NumPy's own BLAS through np.linalg.norm-free dgeev below."""
+    rng = np.random.default_rng(3)
+    for length in (1, 2, 3):
+        x = np.concatenate([rng.standard_normal((200_000, length)) * 10.0 ** rng.uniform(-8, 8, (200_000, 1)),
+                            rng.standard_normal((20_000, length)) * 10.0 ** rng.uniform(-150, 150, (20_000, 1)),
+                            np.array([[1.0, 0.0, 0.0][:length], [0.0] * length, [3.0, 4.0, 0.0][:length]])])
+        x = np.ascontiguousarray(x)
+        a, b = np.empty(len(x)), np.empty(len(x))
+        hostlib.h_x87_nrm2(_p(x), len(x), length, _p(a))
+        hostlib.h_long_double_nrm2(_p(x), len(x), length, _p(b))
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), length
+
+
+def test_eig3_replays_numpy_linalg_eig(hostlib):
+    """we_dgeev3 / we_principal_axes (host build of the source k_cov compiles) against numpy.linalg.eig:
+    bit-identical eigenvalues and eigenvectors - hence identical signs - when NumPy runs on an OpenBLAS
+    kernel family that is restated (AVX-512 "SkylakeX" here, AVX2 "Haswell")."""
+    flavour, source, pinned = _lib.host_eig_flavour()
+    t = _water_tensors(300_000, 17)
+    out = np.empty((len(t), 25))
+    hostlib.h_eig3(_p(np.ascontiguousarray(t)), len(t), flavour, _p(out))
+    assert (out[:, 24] == 0).all()
+    w, v, ax, moi = _numpy_axes(t)
+    mine_v = out[:, 3:12].reshape(-1, 3, 3).transpose(0, 2, 1)  # [n, component, eigenvector]
+    if pinned:
+        assert np.array_equal(out[:, 0:3].view(np.uint64), w.view(np.uint64)), source
+        assert np.array_equal(mine_v, v), source
+        assert np.array_equal(out[:, 12:21].reshape(-1, 3, 3), ax)
+        assert np.array_equal(out[:, 21:24], moi)
+    else:  # unknown BLAS: the algorithm is the same, a few molecules in 10^4 may still flip
+        same = np.all(np.abs(out[:, 12:21].reshape(-1, 3, 3) - ax) < 1e-12, axis=(1, 2))
+        assert same.mean() > 0.999, (source, same.mean())
+    # the two restated families differ from each other in about one molecule in 10^4: the flavour matters
+    other = np.empty_like(out)
+    hostlib.h_eig3(_p(np.ascontiguousarray(t)), len(t), 1 - flavour, _p(other))
+    flips = np.any(np.abs(other[:, 12:21] - out[:, 12:21]) > 1e-9, axis=1).mean()
+    assert 1e-6 < flips < 1e-3, flips
+
+
+def test_eig3_fixture_waters_match_reference_axes(hostlib):
+    """Principal axes and MOI of every water of the arginine fixture, frame 0, against the oracle
+    (numpy.linalg.eig, which reproduces the reference's off-diagonal goldens)."""
+    inp = gio.load_inputs("arginine")
+    top = gio.oracle_topology(inp)
+    waters = [int(a) for a in top.water_centres]
+    o = wo.forces_torques(top, inp["positions"][0], inp["forces"][0], waters)
+    idx = np.array([top.fragment_members[top.fragment_id[w]] for w in waters])
+    pos = inp["positions"][0][idx]
+    m = top.masses[idx]
+    com = (pos.astype(np.float64) * m[:, :, None]).sum(axis=1) / m.sum(axis=1)[:, None]
+    p = pos - com[:, None, :]
+    x, y, z = p[..., 0], p[..., 1], p[..., 2]
+    t = np.zeros((len(waters), 3, 3))
+    t[:, 0, 0] = (m * (y ** 2 + z ** 2)).sum(axis=1)
+    t[:, 1, 1] = (m * (x ** 2 + z ** 2)).sum(axis=1)
+    t[:, 2, 2] = (m * (x ** 2 + y ** 2)).sum(axis=1)
+    t[:, 0, 1] = t[:, 1, 0] = -(m * x * y).sum(axis=1)
+    t[:, 0, 2] = t[:, 2, 0] = -(m * x * z).sum(axis=1)
+    t[:, 1, 2] = t[:, 2, 1] = -(m * y * z).sum(axis=1)
+    flavour, source, pinned = _lib.host_eig_flavour()
+    out = np.empty((len(t), 25))
+    hostlib.h_eig3(_p(np.ascontiguousarray(t)), len(t), flavour, _p(out))
+    agree = np.all(np.abs(out[:, 12:21].reshape(-1, 3, 3) - o["axes"]) < 1e-12, axis=(1, 2))
+    assert agree.all() if pinned else agree.mean() > 0.99
+    assert np.allclose(out[:, 21:24], o["moi"], rtol=1e-13)

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(CSRC, "libwaterentropy_b200.so")
 SOURCES = ["we_api.cu"]
-HEADERS = ["we_kernels.cuh", "we_numerics.cuh", "we_pow64_tables.h", os.path.join("..", "..", "include", "waterentropy_b200.h")]
+HEADERS = ["we_kernels.cuh", "we_numerics.cuh", "we_eig3.cuh", "we_pow64_tables.h", os.path.join("..", "..", "include", "waterentropy_b200.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

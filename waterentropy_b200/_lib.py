@@ -11,6 +11,7 @@ import os
 from . import _build
 
 c_int32_p = C.POINTER(C.c_int32)
+WE_VERSION = 200  # include/waterentropy_b200.h; a stale build is refused
 
 
 class we_topology(C.Structure):
@@ -33,14 +34,14 @@ class we_options(C.Structure):
         ("device", C.c_int32), ("chunk_frames", C.c_int32), ("table_log2", C.c_int32),
         ("keep_records", C.c_int32), ("keep_debug", C.c_int32),
         ("search_radius", C.c_float), ("max_box", C.c_float), ("keep_shells", C.c_int32),
-        ("force_upload", C.c_int32),
+        ("force_upload", C.c_int32), ("eig_flavour", C.c_int32),
     ]
 
 
 class we_diag(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "wide_searches", "shrink_retries", "table_entries",
-        "kernel_launches", "frames_done", "recorded", "fast_path_mismatches")]
+        "kernel_launches", "frames_done", "recorded", "fast_path_mismatches", "eig_fallbacks")]
 
 
 EXPORTS = [
@@ -51,11 +52,73 @@ EXPORTS = [
     "we_debug_copy", "we_reset", "we_test_angle_cos", "we_test_powf2", "we_test_pow2", "we_test_distance",
     "we_profile", "we_kernel_times", "we_span_start", "we_span_stop",
     "we_label_entries_device", "we_merge_label_entries", "we_snapshot_cov", "we_wait_cov",
-    "we_copy_frame_shells",
+    "we_copy_frame_shells", "we_test_eig3",
 ]
 
 WE_ERR_DUPLICATE_COORD = -1
 WE_ERR_NO_NEIGHBOURS = -2
+
+# we_options.eig_flavour: which OpenBLAS kernel family the principal-axis step replays
+EIG_OPENBLAS_AVX512 = 0
+EIG_OPENBLAS_AVX2 = 1
+_EIG_NAMES = {"avx512": EIG_OPENBLAS_AVX512, "skylakex": EIG_OPENBLAS_AVX512, "0": EIG_OPENBLAS_AVX512,
+              "avx2": EIG_OPENBLAS_AVX2, "haswell": EIG_OPENBLAS_AVX2, "zen": EIG_OPENBLAS_AVX2, "1": EIG_OPENBLAS_AVX2}
+_AVX512_CORES = ("SKYLAKEX", "COOPERLAKE", "SAPPHIRERAPIDS")
+_AVX2_CORES = ("HASWELL", "ZEN", "BROADWELL", "EXCAVATOR")
+_host_flavour = None
+
+
+def numpy_openblas_core():
+    """Name of the kernel set NumPy's bundled OpenBLAS dispatched to on this host
+    (`openblas_get_corename`), or None when NumPy is not running on an OpenBLAS we can query."""
+    import numpy as np
+
+    np.linalg.eig(np.eye(2))  # make sure the LAPACK library is mapped
+    paths = []
+    try:
+        with open("/proc/self/maps") as fh:
+            for line in fh:
+                path = line.rsplit(" ", 1)[-1].strip()
+                if "openblas" in os.path.basename(path).lower() and path not in paths:
+                    paths.append(path)
+    except OSError:
+        return None
+    for path in paths:
+        try:
+            lib = C.CDLL(path)
+        except OSError:
+            continue
+        for sym in ("scipy_openblas_get_corename64_", "scipy_openblas_get_corename", "openblas_get_corename64_",
+                    "openblas_get_corename"):
+            fn = getattr(lib, sym, None)
+            if fn is not None:
+                fn.restype = C.c_char_p
+                name = fn()
+                return name.decode() if name else None
+    return None
+
+
+def host_eig_flavour():
+    """(flavour, source, pinned): the OpenBLAS kernel family `numpy.linalg.eig` runs on THIS host, which
+    is what the reference's eigenvector signs follow (maths/transformations.py:121-124).  `WE_EIG_FLAVOUR`
+    (avx512 | avx2) overrides.  `pinned` is False when the host's BLAS could not be identified; the
+    AVX-512 kernels (the ones the golden vectors were made with) are replayed then."""
+    global _host_flavour
+    env = os.environ.get("WE_EIG_FLAVOUR", "").strip().lower()
+    if env:
+        if env not in _EIG_NAMES:
+            raise ValueError(f"WE_EIG_FLAVOUR must be one of {sorted(_EIG_NAMES)}, got {env!r}")
+        return _EIG_NAMES[env], f"WE_EIG_FLAVOUR={env}", True
+    if _host_flavour is None:
+        core = numpy_openblas_core()
+        up = (core or "").upper()
+        if any(k in up for k in _AVX512_CORES):
+            _host_flavour = (EIG_OPENBLAS_AVX512, f"numpy OpenBLAS core {core}", True)
+        elif any(k in up for k in _AVX2_CORES):
+            _host_flavour = (EIG_OPENBLAS_AVX2, f"numpy OpenBLAS core {core}", True)
+        else:
+            _host_flavour = (EIG_OPENBLAS_AVX512, f"numpy BLAS core {core!r} not restated", False)
+    return _host_flavour
 
 _lib = None
 
@@ -79,6 +142,9 @@ def load():
     V, I, I64 = C.c_void_p, C.c_int32, C.c_int64
     L.we_last_error.restype = C.c_char_p
     L.we_version.restype = I
+    if L.we_version() != WE_VERSION:
+        raise ImportError(f"{path} is ABI version {L.we_version()}, this package needs {WE_VERSION}: rebuild it "
+                          "(__graft_entry__.build())")
     L.we_create.restype = I
     L.we_create.argtypes = [C.POINTER(we_topology), C.POINTER(we_options), C.POINTER(V)]
     L.we_destroy.restype = None
@@ -143,6 +209,8 @@ def load():
     L.we_test_pow2.argtypes = [I, V, I, V]
     L.we_test_distance.restype = I
     L.we_test_distance.argtypes = [I, V, V, I, V]
+    L.we_test_eig3.restype = I
+    L.we_test_eig3.argtypes = [I, V, I, I, V]
     _lib = L
     return L
 

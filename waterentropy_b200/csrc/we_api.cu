@@ -377,6 +377,7 @@ extern "C" int we_create(const we_topology* t, const we_options* opt, we_ctx** o
   if ((rc = dev_upload(c, &cos_p, centre_of_slot))) { we_destroy(c); return rc; }
   c->d_centre_of_slot = (int*)cos_p;
   // accumulators
+  if (c->opt.eig_flavour != WE_EIG_OPENBLAS_AVX512 && c->opt.eig_flavour != WE_EIG_OPENBLAS_AVX2) { delete c; return fail(WE_ERR_INVALID, "eig_flavour must be WE_EIG_OPENBLAS_AVX512 (0) or WE_EIG_OPENBLAS_AVX2 (1)"); }
   const int tl = c->opt.table_log2 > 0 ? c->opt.table_log2 : 17;
   if (tl < 4 || tl > 24) { we_destroy(c); return fail(WE_ERR_INVALID, "table_log2 must be in [4,24]"); }
   c->table_mask = (1u << tl) - 1u;
@@ -674,7 +675,7 @@ static int finish_lazy(we_ctx* c, int buf) {
   {
     ProfScope ps(c, WE_K_COV, st);
     k_cov<<<dim3((c->C + 511) / 512, n), 128, 0, st>>>(c->T, c->pend_dp[buf], nullptr, c->d_rec_count[buf], c->d_rec[buf], c->d_centre_of_slot,
-                                       c->d_cov_sum, c->d_cov_cnt, nullptr, c->d_fcomp[buf], c->d_fbase[buf], mf, n);
+                                       c->d_cov_sum, c->d_cov_cnt, nullptr, c->d_fcomp[buf], c->d_fbase[buf], mf, n, c->opt.eig_flavour, c->d_diag);
     ps.stop(st);
     c->launches += 1;
   }
@@ -957,7 +958,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
         const int cov_bx = (cov_st != st) ? std::max(1, std::min((C + 511) / 512, (2 * c->n_sm + n - 1) / n)) : (C + 511) / 512;
         k_cov<<<dim3(cov_bx, n), 128, 0, cov_st>>>(
             c->T, dp, df, c->d_rec_count[buf], c->d_rec[buf], c->d_centre_of_slot, c->d_cov_sum,
-            c->d_cov_cnt, c->d_ft, nullptr, nullptr, 0, n);
+            c->d_cov_cnt, c->d_ft, nullptr, nullptr, 0, n, c->opt.eig_flavour, c->d_diag);
         ps.stop(cov_st);
         c->launches += 1;
       }
@@ -1075,6 +1076,7 @@ extern "C" int we_get_diag(we_ctx* c, we_diag* out) {
   out->frames_done = c->frames_done;
   out->recorded = c->recorded;
   out->fast_path_mismatches = d.fast_path_mismatches;
+  out->eig_fallbacks = d.eig_fallbacks;
   return WE_OK;
 }
 
@@ -1383,6 +1385,20 @@ __global__ void k_test_dist(const float* pairs, WeBox b, int n, double* out) {
   }
 }
 
+__global__ void k_test_eig3(const double* t, int n, int flavour, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double wr[3], vr[9], ax[3][3], moi[3];
+  const int st = we_dgeev3(t + (size_t)i * 9, wr, vr, flavour);
+  we_principal_axes(t + (size_t)i * 9, ax, moi, flavour);
+  double* o = out + (size_t)i * 25;
+  for (int k = 0; k < 3; ++k) o[k] = wr[k];
+  for (int k = 0; k < 9; ++k) o[3 + k] = vr[k];
+  for (int k = 0; k < 9; ++k) o[12 + k] = ax[k / 3][k % 3];
+  for (int k = 0; k < 3; ++k) o[21 + k] = moi[k];
+  o[24] = (double)st;
+}
+
 template <typename Fn>
 static int run_test(int device, const void* in, size_t in_bytes, void* out, size_t out_bytes, Fn launch) {
   int ndev = 0;
@@ -1424,5 +1440,10 @@ extern "C" int we_test_distance(int32_t device, const float* pairs, const float*
   if (make_box(dims6, 7.0f, 1 << 20, &b)) return fail(WE_ERR_INVALID, "invalid box");
   return run_test(device, pairs, (size_t)n * 24, out, (size_t)n * 8, [&](void* di, void* dout) {
     k_test_dist<<<(n + 127) / 128, 128>>>((const float*)di, b, n, (double*)dout);
+  });
+}
+extern "C" int we_test_eig3(int32_t device, const double* tensors, int32_t n, int32_t flavour, double* out) {
+  return run_test(device, tensors, (size_t)n * 72, out, (size_t)n * 25 * 8, [&](void* di, void* dout) {
+    k_test_eig3<<<(n + 127) / 128, 128>>>((const double*)di, n, flavour, (double*)dout);
   });
 }

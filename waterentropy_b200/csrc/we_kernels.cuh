@@ -19,6 +19,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "we_numerics.cuh"
+#include "we_eig3.cuh"
 
 #define WE_MAX_NBR 25
 #define WE_GATE_NBR 20
@@ -82,6 +83,7 @@ struct WeDiag {
   unsigned long long shrink_retries;
   unsigned long long table_entries;
   unsigned long long fast_path_mismatches;  // debug contexts: float32 fast-path decisions the exact replay contradicts
+  unsigned long long eig_fallbacks;         // molecules whose inertia tensor took a LAPACK path that is not restated
   int err_code, err_frame, err_atom, pad;
 };
 
@@ -1279,9 +1281,11 @@ k_label(WeTopoDev T, const int* __restrict__ shell_n, const int* __restrict__ sh
 // K5 + K6: force / torque covariance of each recorded water.
 //   recipes/forces_torques.py:28-55, maths/transformations.py:12-79,104-135,
 //   entropy/convariances.py:21-84 (sums here; means are taken on the host).
-// Principal axes come from a cyclic Jacobi diagonalisation (the reference's
-// LAPACK dgeev eigenvector *signs* are not reproducible; diagonals are
-// sign-invariant).
+// Principal axes and moments replay numpy.linalg.eig (LAPACK dgeev as OpenBLAS executes it)
+// operation by operation (we_eig3.cuh), so every eigenvector carries the sign the reference
+// gets and the off-diagonal covariance elements match too.  Degenerate tensors whose LAPACK
+// path is not restated (exact zeros, equal moments: never a water) fall back to a cyclic
+// Jacobi diagonalisation with a fixed sign convention and are counted in we_diag.eig_fallbacks.
 // ============================================================================
 __device__ __forceinline__ void we_jacobi3(double a[3][3], double v[3][3], double ev[3]) {
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) v[i][j] = (i == j) ? 1.0 : 0.0;
@@ -1316,6 +1320,33 @@ __device__ __forceinline__ void we_jacobi3(double a[3][3], double v[3][3], doubl
   ev[0] = a[0][0]; ev[1] = a[1][1]; ev[2] = a[2][2];
 }
 
+// Fallback for tensors whose dgeev path is not restated: axes = rows by descending eigenvalue,
+// largest component of axes 0 and 1 positive, axis 2 = axis 0 x axis 1; am = moments by
+// descending magnitude (transformations.py:131-133).
+__device__ __noinline__ void we_axes_jacobi(double I[3][3], double ax[3][3], double am[3]) {
+  double V[3][3], ev[3];
+  we_jacobi3(I, V, ev);
+  int o0 = 0, o1 = 1, o2 = 2;
+  if (ev[o0] < ev[o1]) { int t = o0; o0 = o1; o1 = t; }
+  if (ev[o1] < ev[o2]) { int t = o1; o1 = o2; o2 = t; }
+  if (ev[o0] < ev[o1]) { int t = o0; o0 = o1; o1 = t; }
+  const int ord[3] = {o0, o1, o2};
+  for (int i = 0; i < 3; ++i) for (int k = 0; k < 3; ++k) ax[i][k] = V[k][ord[i]];
+  for (int i = 0; i < 2; ++i) {
+    int big = 0;
+    if (fabs(ax[i][1]) > fabs(ax[i][big])) big = 1;
+    if (fabs(ax[i][2]) > fabs(ax[i][big])) big = 2;
+    if (ax[i][big] < 0.0) { ax[i][0] = -ax[i][0]; ax[i][1] = -ax[i][1]; ax[i][2] = -ax[i][2]; }
+  }
+  ax[2][0] = ax[0][1] * ax[1][2] - ax[0][2] * ax[1][1];
+  ax[2][1] = ax[0][2] * ax[1][0] - ax[0][0] * ax[1][2];
+  ax[2][2] = ax[0][0] * ax[1][1] - ax[0][1] * ax[1][0];
+  am[0] = ev[0]; am[1] = ev[1]; am[2] = ev[2];
+  if (fabs(am[0]) < fabs(am[1])) { double t = am[0]; am[0] = am[1]; am[1] = t; }
+  if (fabs(am[1]) < fabs(am[2])) { double t = am[1]; am[1] = am[2]; am[2] = t; }
+  if (fabs(am[0]) < fabs(am[1])) { double t = am[0]; am[0] = am[1]; am[1] = t; }
+}
+
 // grid = (blocks per frame, frames); the blocks of a frame walk its recorded waters with a
 // grid-stride loop (about four warp-iterations each when every water is recorded).
 // K6: per-block shared-memory staging of the covariance sums (16 bin slots), flushed with one
@@ -1326,7 +1357,8 @@ k_cov(WeTopoDev T, const float* __restrict__ pos, const float* __restrict__ frc,
       const int* __restrict__ rec_count, const WeRecord* __restrict__ rec,
       const int* __restrict__ centre_of_slot, double* __restrict__ cov_sum,
       unsigned long long* __restrict__ cov_cnt, double* __restrict__ ft_out,
-      const float* __restrict__ fcomp, const int* __restrict__ fbase, int maxfrag, int n_frames) {
+      const float* __restrict__ fcomp, const int* __restrict__ fbase, int maxfrag, int n_frames,
+      int eig_flavour, WeDiag* diag) {
   __shared__ int s_bin[WE_COV_SLOTS];
   __shared__ double s_sum[WE_COV_SLOTS][18];
   __shared__ unsigned long long s_cnt[WE_COV_SLOTS];
@@ -1375,32 +1407,14 @@ k_cov(WeTopoDev T, const float* __restrict__ pos, const float* __restrict__ frc,
       I[1][2] -= m * y * z;
     }
     I[1][0] = I[0][1]; I[2][0] = I[0][2]; I[2][1] = I[1][2];
-    double V[3][3], ev[3];
-    we_jacobi3(I, V, ev);
-    // axes: rows = eigenvectors by descending eigenvalue (MDAnalysis principal_axes)
-    int o0 = 0, o1 = 1, o2 = 2;
-    if (ev[o0] < ev[o1]) { int t = o0; o0 = o1; o1 = t; }
-    if (ev[o1] < ev[o2]) { int t = o1; o1 = o2; o2 = t; }
-    if (ev[o0] < ev[o1]) { int t = o0; o0 = o1; o1 = t; }
-    const int ord[3] = {o0, o1, o2};
-    double ax[3][3];
-    for (int i = 0; i < 3; ++i) for (int k = 0; k < 3; ++k) ax[i][k] = V[k][ord[i]];
-    // deterministic sign convention: largest |component| of axes 0 and 1 positive,
-    // axis 2 = axis 0 x axis 1 (right-handed, like the reference's global flip)
-    for (int i = 0; i < 2; ++i) {
-      int big = 0;
-      if (fabs(ax[i][1]) > fabs(ax[i][big])) big = 1;
-      if (fabs(ax[i][2]) > fabs(ax[i][big])) big = 2;
-      if (ax[i][big] < 0.0) { ax[i][0] = -ax[i][0]; ax[i][1] = -ax[i][1]; ax[i][2] = -ax[i][2]; }
+    double ax[3][3], am[3];
+    {
+      const double tens[9] = {I[0][0], I[0][1], I[0][2], I[1][0], I[1][1], I[1][2], I[2][0], I[2][1], I[2][2]};
+      if (we_principal_axes(tens, ax, am, eig_flavour) != WE_EIG3_OK) {
+        atomicAdd(&diag->eig_fallbacks, 1ULL);
+        we_axes_jacobi(I, ax, am);
+      }
     }
-    ax[2][0] = ax[0][1] * ax[1][2] - ax[0][2] * ax[1][1];
-    ax[2][1] = ax[0][2] * ax[1][0] - ax[0][0] * ax[1][2];
-    ax[2][2] = ax[0][0] * ax[1][1] - ax[0][1] * ax[1][0];
-    // MOI_axis: eigenvalues by descending magnitude (transformations.py:131-133)
-    double am[3] = {ev[0], ev[1], ev[2]};
-    if (fabs(am[0]) < fabs(am[1])) { double t = am[0]; am[0] = am[1]; am[1] = t; }
-    if (fabs(am[1]) < fabs(am[2])) { double t = am[1]; am[1] = am[2]; am[2] = t; }
-    if (fabs(am[0]) < fabs(am[1])) { double t = am[0]; am[0] = am[1]; am[1] = t; }
     const double sq[3] = {sqrt(am[0]), sqrt(am[1]), sqrt(am[2])};
     double tq[3] = {0, 0, 0};
     float fsx = 0.f, fsy = 0.f, fsz = 0.f;

@@ -81,15 +81,24 @@ def decode_label_entries(top, recipe, entries) -> HBLabelCollection:
 class WaterEntropyEngine:
     def __init__(self, system, recipe="interfacial", device=0, chunk_frames=0, table_log2=0,
                  keep_records=True, keep_debug=False, search_radius=0.0, max_box=0.0, force_upload=0,
-                 keep_shells=False):
+                 keep_shells=False, eig_flavour=None):
+        """`eig_flavour`: "avx512" / "avx2" / None.  The reference's principal axes carry the eigenvector
+        signs `numpy.linalg.eig` returns on the host it runs on; None replays the OpenBLAS kernel family
+        of THIS host's NumPy (`_lib.host_eig_flavour`), so the off-diagonal covariance elements are the
+        ones the reference would produce here."""
         self.lib = _lib.load()
         self.top = SystemTopology.from_universe(system)
         self.recipe = RECIPE_BULK if recipe in ("bulk", RECIPE_BULK) else RECIPE_INTERFACIAL
         t, self._keep = self.top.c_struct(self.recipe)
+        if eig_flavour is None:
+            self.eig_flavour, self.eig_source, self.eig_pinned = _lib.host_eig_flavour()
+        else:
+            self.eig_flavour = _lib._EIG_NAMES[str(eig_flavour).lower()]
+            self.eig_source, self.eig_pinned = f"eig_flavour={eig_flavour}", True
         o = _lib.we_options(device=device, chunk_frames=chunk_frames, table_log2=table_log2,
                             keep_records=int(keep_records), keep_debug=int(keep_debug),
                             search_radius=search_radius, max_box=max_box, force_upload=force_upload,
-                            keep_shells=int(keep_shells))
+                            keep_shells=int(keep_shells), eig_flavour=self.eig_flavour)
         self._ctx = C.c_void_p()
         _lib.check(self.lib.we_create(C.byref(t), C.byref(o), C.byref(self._ctx)))
         self.device = device
