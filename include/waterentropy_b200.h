@@ -86,6 +86,9 @@ typedef struct we_options {
                                 when the buffer is pinned, else whole frames), 1 whole frames, 2 recorded
                                 waters only, gathered by the host one batch later, 3 zero-copy: k_cov reads
                                 the recorded waters' forces straight from pinned host memory */
+    int32_t shells_only;     /* 1: stop after the RAD shells of the interfacial waters (needs keep_shells, interfacial
+                                recipe): what get_interfacial_shells evaluates (recipes/interfacial_solvent.py:104-146)
+                                - no HBs, no labels, no neighbours' shells, no forces (frc may be NULL) */
     int32_t eig_flavour;     /* which OpenBLAS kernel family the principal-axis step replays (WE_EIG_*): the
                                 reference's eigenvector signs are whatever numpy.linalg.eig returns on the
                                 host it runs on (maths/transformations.py:121-124) */
@@ -126,6 +129,10 @@ int we_version(void);
 int we_create(const we_topology *topo, const we_options *opt, we_ctx **out);
 void we_destroy(we_ctx *ctx);
 
+/* Frames per kernel batch this context uses (we_options.chunk_frames, or the automatic size): a reader
+ * that hands over whole batches keeps the device busiest. */
+int we_batch_frames(we_ctx *ctx);
+
 /* Analyse `n_frames` frames held in HOST memory (pinned or pageable):
  *   pos, frc  float32 [n_frames][n_atoms][3]   (ts.positions / ts.forces)
  *   dims      float32 [n_frames][6]            (ts.dimensions)
@@ -142,13 +149,23 @@ int we_submit(we_ctx *ctx, const float *pos, const float *frc, const float *dims
 int we_submit_device(we_ctx *ctx, const float *d_pos, const float *d_frc, const float *dims,
                      const int64_t *frame_ids, int32_t n_frames);
 
+/* Input-buffer retirement: how many of the frames submitted so far no longer need their caller-owned
+ * buffers (uploads done, and for zero-copy forces the covariance kernel has read them).  Lets a reader
+ * recycle a small ring of pinned staging buffers instead of holding the trajectory until `we_sync`
+ * (the reference holds one frame at a time, recipes/interfacial_solvent.py:285).  `we_frames_retired`
+ * polls; `we_wait_frames_retired` blocks until at least `n_frames` are retired. */
+int64_t we_frames_retired(we_ctx *ctx);
+int we_wait_frames_retired(we_ctx *ctx, int64_t n_frames);
+
 /* Wait for all submitted work; surfaces the reference's per-frame exceptions
  * as WE_ERR_DUPLICATE_COORD / WE_ERR_NO_NEIGHBOURS. */
 int we_sync(we_ctx *ctx);
 int we_get_diag(we_ctx *ctx, we_diag *out);
 int we_error_location(we_ctx *ctx, int64_t *frame_id, int32_t *atom);
 
-/* ---- results (after we_sync) ------------------------------------------------ */
+/* ---- results ------------------------------------------------------------------
+ * The read-out calls below wait for every batch submitted so far (they synchronise the context's own
+ * streams), so they never return partially accumulated tables; per-frame errors are reported by we_sync. */
 
 /* Dense covariance table: sums over recorded waters of the two 3x3 outer
  * products (force, torque; recipes/forces_torques.py:50-53) and the counts
@@ -241,6 +258,14 @@ int we_kernel_times(we_ctx *ctx, double *ms /*[WE_N_KERNELS]*/, uint64_t *launch
 /* Device-time span on the compute stream (CUDA events, not wall clock). */
 int we_span_start(we_ctx *ctx);
 int we_span_stop(we_ctx *ctx, double *ms);
+
+/* recipes/forces_torques.py:14-55 (`get_forces_torques`, single-united-atom branch) for `n_mol` molecules
+ * given as compact arrays: pos / frc float32 [n_atoms_total][3], masses float64 [n_atoms_total], mol_ptr
+ * int32 [n_mol + 1] (CSR).  out float64 [n_mol][24] = rotated mass-weighted force (3), inertia-weighted torque
+ * (3), force covariance matrix (9), torque covariance matrix (9) (maths/transformations.py:67-79, halve = 0.5).
+ * Stateless; returns the number of molecules that needed the Jacobi fallback (>= 0) or an error. */
+int we_molecule_force_torque(int32_t device, const float *pos, const float *frc, const double *masses,
+                             const int32_t *mol_ptr, int32_t n_mol, int32_t eig_flavour, double *out);
 
 /* Clear the accumulators (start a new analysis with the same topology). */
 int we_reset(we_ctx *ctx);

@@ -191,10 +191,19 @@ int we_oracle_rad(int n_atoms, const float *pos, const float *dims,
         for (int i = 0; i < n_atoms; ++i) wrap_triclinic(pos + 3 * i, b.m, wrapped + 3 * i);
         P = wrapped;
     }
+    /* centres are independent (the reference maps frames over cores; within a frame its per-centre
+     * work is a pure function of the frame): OpenMP over centres, OMP_NUM_THREADS=1 for a serial run */
+    int failed = 0;
+#pragma omp parallel
+    {
     cand_t *cand = (cand_t *)malloc((size_t)n_heavy * sizeof(cand_t));
-    if (!cand) { free(wrapped); return -1; }
-
+    if (!cand) {
+#pragma omp atomic write
+        failed = 1;
+    }
+#pragma omp for schedule(dynamic, 4)
     for (int c = 0; c < n_centres; ++c) {
+        if (!cand) continue;
         int hs = centres ? centres[c] : c;
         int i = heavy_idx[hs];
         const float *pi = pos + 3 * i;   /* raw coordinates for angles / duplicate test */
@@ -246,8 +255,9 @@ int we_oracle_rad(int n_atoms, const float *pos, const float *dims,
         shell_n[c] = ns;
     }
     free(cand);
+    }
     free(wrapped);
-    return 0;
+    return failed ? -1 : 0;
 }
 
 /*

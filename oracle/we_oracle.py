@@ -56,7 +56,7 @@ def build(force: bool = False) -> str:
         os.makedirs(_BUILD, exist_ok=True)
         subprocess.check_call(
             [
-                "gcc", "-O2", "-fno-builtin", "-ffp-contract=off", "-fPIC",
+                "gcc", "-O2", "-fno-builtin", "-ffp-contract=off", "-fopenmp", "-fPIC",
                 "-shared", "-o", _SO, _SRC, "-lm",
             ]
         )
@@ -416,6 +416,114 @@ class FrameState:
         return out
 
 
+class LazyFrameState:
+    """Memoised per-centre RAD + HB state: shells and acceptors are computed on demand and cached, which is
+    exactly what the reference does per frame (`ShellCollection.find_shell`, analysis/RAD.py:86;
+    `HBCollection`, analysis/HB.py:142-169).  Same interface as `FrameState`; `n_evaluated` counts the
+    distinct centres whose neighbour search + RAD test ran - the reference's real per-frame work."""
+
+    def __init__(self, top: OracleTopology, pos, dims):
+        self.top = top
+        self.pos = np.ascontiguousarray(pos, dtype=np.float32)
+        self.dims = np.ascontiguousarray(dims, dtype=np.float32)
+        H = len(top.heavy_idx)
+        self.known = np.zeros(H, dtype=bool)
+        self.rad = dict(
+            nbr_total=np.zeros(H, dtype=np.int32), nbr_idx=-np.ones((H, MAX_NBR), dtype=np.int32),
+            nbr_dist=np.zeros((H, MAX_NBR), dtype=np.float64), shell_n=np.zeros(H, dtype=np.int32),
+            shell_idx=-np.ones((H, MAX_NBR), dtype=np.int32), gate=np.zeros(H, dtype=np.uint8),
+            status=np.zeros(H, dtype=np.int32))
+        self.don_of = {}
+        self.n_evaluated = 0
+        self.n_hb_centres = 0
+
+    def ensure(self, atoms):
+        """RAD state of the heavy atoms `atoms` (one batched call for those not yet known)."""
+        slots = np.unique(self.top.heavy_slot[np.asarray(list(atoms), dtype=np.int64)])
+        slots = slots[~self.known[slots]]
+        if len(slots) == 0:
+            return
+        r = rad_frame(self.top, self.pos, self.dims, centres=self.top.heavy_idx[slots])
+        for k in ("nbr_total", "nbr_idx", "nbr_dist", "shell_n", "shell_idx", "gate", "status"):
+            self.rad[k][slots] = r[k]
+        self.known[slots] = True
+        self.n_evaluated += len(slots)
+
+    def ensure_hb(self, atoms):
+        """Acceptors of the donor hydrogens of `atoms` (needs their shells)."""
+        todo = [int(a) for a in atoms if int(a) not in self.don_of]
+        if not todo:
+            return
+        self.ensure(todo)
+        don_x, don_h = [], []
+        for x in todo:
+            self.don_of[x] = []
+            for h in self.top.donors[x]:
+                don_x.append(x)
+                don_h.append(h)
+        self.n_hb_centres += len(todo)
+        if not don_x:
+            return
+        don_x = np.array(don_x, dtype=np.int32)
+        don_h = np.array(don_h, dtype=np.int32)
+        slots = self.top.heavy_slot[don_x]
+        acc, st = hb_frame(self.top, self.pos, self.dims, don_x, don_h, self.rad["shell_n"][slots],
+                           self.rad["shell_idx"][slots])
+        # a donor whose centre has no valid shell inherits the centre's failure
+        for x, h, a, s, rs in zip(don_x, don_h, acc, st, self.rad["status"][slots]):
+            self.don_of[int(x)].append((int(h), int(a), int(rs) if rs else int(s)))
+
+    def _slot(self, atom):
+        self.ensure([atom])
+        s = self.top.heavy_slot[atom]
+        st = int(self.rad["status"][s])
+        if st == 1:
+            raise ValueError(f"Atom coordinates of {atom} in neighbour list")
+        if st == 2:
+            raise ValueError("not enough values to unpack (no neighbours in cut-off)")
+        return s
+
+    def shell(self, atom):
+        s = self._slot(atom)
+        return [int(v) for v in self.rad["shell_idx"][s, : int(self.rad["shell_n"][s])]]
+
+    def neighbours(self, atom):
+        return self._slot(atom)
+
+    def donations(self, atom):
+        self.ensure_hb([atom])
+        out = []
+        for d, a, st in self.don_of.get(int(atom), []):
+            if st == 1:
+                raise ValueError("Atom coordinates in neighbour list (HB donor)")
+            if st == 2:
+                raise ValueError("not enough values to unpack (HB donor)")
+            out.append((d, a))
+        return out
+
+    def prefetch_interfacial(self):
+        """Batch the closure of the interfacial recipe (solute united atoms -> interfacial waters -> their
+        shell members -> donors of both) so the C routine sees large centre lists; the result is what the
+        one-at-a-time memoisation would hold."""
+        top = self.top
+        self.ensure(top.solute_UAs)
+        slots = top.heavy_slot[np.asarray(top.solute_UAs, dtype=np.int64)]
+        ok = (self.rad["status"][slots] == 0) & (self.rad["gate"][slots] == 1)
+        members = self.rad["shell_idx"][slots[ok]]
+        valid = np.arange(MAX_NBR)[None, :] < self.rad["shell_n"][slots[ok]][:, None]
+        cand = np.unique(members[valid])
+        inter = cand[top.is_water[cand] == 1]
+        self.ensure(inter)
+        s2 = top.heavy_slot[inter]
+        good = self.rad["status"][s2] == 0
+        m2 = self.rad["shell_idx"][s2[good]]
+        v2 = np.arange(MAX_NBR)[None, :] < self.rad["shell_n"][s2[good]][:, None]
+        mem = np.unique(m2[v2]) if len(m2) else np.zeros(0, dtype=np.int64)
+        self.ensure(mem)
+        self.ensure_hb(np.unique(np.concatenate([inter, mem])) if len(mem) else inter)
+        return inter
+
+
 def _nearest_nonlike(top, centre, shell):
     """analysis/shell_labels.py:90-105"""
     for n in shell:
@@ -543,10 +651,15 @@ def find_interfacial_solvent(top: OracleTopology, fs: FrameState, solute_UAs=Non
     return sorted(found)
 
 
-def interfacial_frame(top: OracleTopology, pos, frc, dims, frame_id):
+def interfacial_frame(top: OracleTopology, pos, frc, dims, frame_id, lazy=False):
     """recipes/interfacial_solvent.py:273-345 (`_entropy_per_step`).
-    Returns (frame_solvent_indices, CovMeans, LabelCounts, 1, detail)."""
-    fs = FrameState(top, pos, dims)
+    Returns (frame_solvent_indices, CovMeans, LabelCounts, 1, detail).  `lazy`: evaluate only the
+    centres the reference's memoisation touches (needed at full size; identical results)."""
+    if lazy:
+        fs = LazyFrameState(top, pos, dims)
+        fs.prefetch_interfacial()
+    else:
+        fs = FrameState(top, pos, dims)
     fsi = nested_dict()
     cov = CovMeans()
     lab = LabelCounts()
@@ -581,6 +694,7 @@ def interfacial_frame(top: OracleTopology, pos, frc, dims, frame_id):
         key = (f"{top.resnames[nn]}_{int(top.resids[nn])}", top.resnames[X])
         cov.add(key, ft["Fcov"][k], ft["Tcov"][k])
     detail["ft"] = ft
+    detail["n_rad_centres"] = int(getattr(fs, "n_evaluated", len(top.heavy_idx)))
     return fsi, cov, lab, 1, detail
 
 

@@ -760,3 +760,285 @@ def test_degenerate_systems():
     assert eng.cov_tables()[1].sum() == 0 and len(eng.label_entries()) == 0
     assert (eng.debug(0, "shell_n") >= 0).all()
     eng.close()
+
+
+# ------------------------------------------------------------ boundary: the remaining callables
+def test_get_forces_torques_matches_oracle():
+    """`recipes.forces_torques.get_forces_torques(covariances, molecule, nearest, system)`
+    (reference recipes/forces_torques.py:14-55): one water at a time through the device, folded into
+    the caller's CovarianceCollection like upstream's running mean - full 3x3 matrices vs the oracle."""
+    from waterentropy_b200.entropy.convariances import CovarianceCollection
+    from waterentropy_b200.io import Universe
+    from waterentropy_b200.recipes.forces_torques import get_forces_torques, molecule_force_torque
+
+    inp = gio.load_inputs("arginine")
+    top = gio.oracle_topology(inp)
+    u = Universe.from_arrays(inp["names"], inp["types"], inp["resnames"], inp["resids"], inp["masses"],
+                             inp["charges"], inp["bonds"], inp["positions"], inp["forces"], inp["dimensions"])
+    u.trajectory[2]
+    waters = [int(a) for a in top.water_centres[:40]]
+    o = wo.forces_torques(top, inp["positions"][2], inp["forces"][2], waters)
+    cov = CovarianceCollection()
+    ref = wo.CovMeans()
+    for k, w in enumerate(waters):
+        mol = top.fragment_members[top.fragment_id[w]]
+        get_forces_torques(cov, list(mol), "ARG_2", u)
+        ref.add(("ARG_2", "WAT"), o["Fcov"][k], o["Tcov"][k])
+    key = ("ARG_2", "WAT")
+    assert cov.counts[key] == 40 == ref.counts[key]
+    if _live_oracle_pinned():
+        assert _close_matrix(cov.forces[key], ref.forces[key]) and _close_matrix(cov.torques[key], ref.torques[key])
+    assert np.allclose(np.diag(cov.forces[key]), np.diag(ref.forces[key]), rtol=RTOL)
+    assert np.allclose(np.diag(cov.torques[key]), np.diag(ref.torques[key]), rtol=RTOL)
+    # batched form: all 900 waters in one launch, signed vectors
+    allw = [int(a) for a in top.water_centres]
+    idx = np.array([top.fragment_members[top.fragment_id[w]] for w in allw])
+    r = molecule_force_torque(inp["positions"][2][idx].reshape(-1, 3), inp["forces"][2][idx].reshape(-1, 3),
+                              top.masses[idx].reshape(-1), mol_ptr=np.arange(0, 3 * len(allw) + 1, 3))
+    oa = wo.forces_torques(top, inp["positions"][2], inp["forces"][2], allw)
+    if _live_oracle_pinned():
+        assert np.allclose(r["F"], oa["F"], rtol=RTOL, atol=1e-9 * np.abs(oa["F"]).max())
+        assert np.allclose(r["T"], oa["T"], rtol=RTOL, atol=1e-9 * np.abs(oa["T"]).max())
+        assert np.allclose(r["Fcov"], oa["Fcov"], rtol=RTOL, atol=1e-9 * np.abs(oa["Fcov"]).max())
+    # a multi-united-atom molecule is outside this path, like upstream's "not applicable to water" branch
+    with pytest.raises(NotImplementedError):
+        get_forces_torques(cov, list(range(0, 12)), "X", u)
+
+
+def test_find_interfacial_solvent_reference_indices():
+    """Product `find_interfacial_solvent` against the 31 indices of the reference's own test
+    (/root/reference/tests/analysis/test_RAD.py:96-130: arginine fixture, frame 0, all solutes)."""
+    from waterentropy_b200.io import Universe
+    from waterentropy_b200.recipes.interfacial_solvent import find_interfacial_solvent
+    from waterentropy_b200.system import SystemTopology
+
+    inp = gio.load_inputs("arginine")
+    u = Universe.from_arrays(inp["names"], inp["types"], inp["resnames"], inp["resids"], inp["masses"],
+                             inp["charges"], inp["bonds"], inp["positions"], inp["forces"], inp["dimensions"])
+    u.trajectory[0]
+    top = SystemTopology.from_universe(u)
+    solutes = [int(a) for a in range(top.n_atoms) if not top.is_water[a]]
+    got = find_interfacial_solvent(solutes, u)
+    assert sorted(got) == sorted([1024, 1282, 2056, 265, 2314, 1165, 274, 2077, 1057, 931, 55, 1855, 2497, 1474,
+                                  2245, 205, 2260, 85, 2005, 1753, 862, 1246, 481, 121, 1507, 1639, 235, 2413,
+                                  244, 1912, 505])
+    # tests/utils/test_selections.py:70-105 counts 34 waters over the same call with frame 2's coordinates
+    ref = gio.load_reference("arginine")
+    u.trajectory[2]
+    top_o = gio.oracle_topology(inp)
+    fs = wo.FrameState(top_o, inp["positions"][2], inp["dimensions"][2])
+    assert sorted(find_interfacial_solvent(solutes, u)) == sorted(wo.find_interfacial_solvent(top_o, fs))
+
+
+def test_waterShells_cli_prints_reference_lines(monkeypatch, capsys):
+    """`waterShells` (cli/run_find_Nc.py): one line per interfacial water with a non-like neighbour,
+    `frame atom_idx [shell] n` (recipes/interfacial_solvent.py:169-178)."""
+    from waterentropy_b200.cli import run_find_Nc as cli
+    from waterentropy_b200.io import Universe
+
+    inp = gio.load_inputs("arginine")
+    ref = gio.load_reference("arginine")
+    u = Universe.from_arrays(inp["names"], inp["types"], inp["resnames"], inp["resids"], inp["masses"],
+                             inp["charges"], inp["bonds"], inp["positions"], None, inp["dimensions"])  # no forces
+    monkeypatch.setattr(cli, "load_universe", lambda top, crd: u)
+    cli.main(["-top", "system.prmtop", "-crd", "system.nc", "-s", "0", "-e", "4", "-dt", "2"])
+    out = capsys.readouterr().out.splitlines()
+    assert "0 1024 [415, 931, 1318, 1618, 25, 1474, 1282] 7" in out   # tests/recipes/test_interfacial_solvent.py:51-54
+    assert "2 1024 [1318, 460, 580, 25, 1714, 19, 2497] 7" in out
+    want = ref["shells_api"]["0:4:2"]
+    lines = [ln for ln in out if ln[:2] in ("0 ", "2 ") and "[" in ln]
+    assert len(lines) == sum(len(v) for v in want.values()) == 32 + 36
+    for frame, by_atom in want.items():
+        for atom, shell in by_atom.items():
+            assert f"{frame} {atom} {shell} {len(shell)}" in out
+
+
+def test_shells_only_stops_where_the_reference_stops():
+    """get_interfacial_shells (recipes/interfacial_solvent.py:104-146) evaluates the interfacial waters' own
+    RAD shells and nothing downstream.  A duplicated coordinate at a far-away pair of waters makes the full
+    recipe raise only if one of them is needed; a shell MEMBER that coincides with another atom makes the
+    entropy recipe raise (its shell is needed for the labels) but not the shells recipe."""
+    from waterentropy_b200.engine import WaterEntropyEngine
+
+    inp = gio.load_inputs("synth_ortho")
+    top = gio.oracle_topology(inp)
+    P = inp["positions"][:1].copy()
+    fs = wo.FrameState(top, P[0], inp["dimensions"][0])
+    interfacial = set(wo.find_interfacial_solvent(top, fs))
+    waters = [int(a) for a in top.water_centres]
+    # a member M of an interfacial water's shell that is itself a non-interfacial water ...
+    pick = None
+    for w in sorted(interfacial):
+        for m in fs.shell(w):
+            if top.is_water[m] and m not in interfacial:
+                pick = (w, m)
+                break
+        if pick:
+            break
+    assert pick, "fixture has no such pair"
+    w, m = pick
+    # ... and a far-away non-interfacial water whose oxygen is moved onto M's oxygen
+    used = set(interfacial) | {m}
+    for s in interfacial:
+        used.update(fs.shell(s))
+    far = [a for a in waters if a not in used and np.linalg.norm(P[0, a] - P[0, m]) > 12.0]
+    P[0, far[0]] = P[0, m]
+    sys_ = _sys(inp)
+    full = WaterEntropyEngine(sys_, "interfacial", device=0)
+    full.submit(P, inp["forces"][:1], inp["dimensions"][:1], [0])
+    with pytest.raises(ValueError, match="neighbour list"):
+        full.sync()
+    full.close()
+    so = WaterEntropyEngine(sys_, "interfacial", device=0, keep_shells=True, shells_only=True)
+    so.submit(P, None, inp["dimensions"][:1], [0])       # no forces needed either
+    so.sync()
+    fs2 = wo.FrameState(top, P[0], inp["dimensions"][0])
+    got = so.frame_shells(0)
+    want = {}
+    for a in sorted(wo.find_interfacial_solvent(top, fs2)):
+        sh = fs2.shell(a)
+        if wo._nearest_nonlike(top, a, sh) is not None:
+            want[a] = sh
+    assert got == want and len(got) > 5
+    so.close()
+
+
+def test_submit_rejects_wrong_layouts():
+    """float64 / strided / wrong-device tensors must raise, not produce silent garbage."""
+    import torch
+
+    inp = gio.load_inputs("synth_sparse")
+    eng = _engine(inp)
+    P, Fr, D = inp["positions"][:2], inp["forces"][:2], inp["dimensions"][:2]
+    with pytest.raises(ValueError, match="float32"):
+        eng.submit(torch.from_numpy(P.astype(np.float64)), torch.from_numpy(Fr), D, [0, 1])
+    with pytest.raises(ValueError, match="contiguous"):
+        eng.submit(torch.from_numpy(P), torch.from_numpy(np.ascontiguousarray(Fr.transpose(0, 2, 1))).transpose(1, 2), D, [0, 1])
+    with pytest.raises(ValueError, match="submit_device"):
+        eng.submit(torch.from_numpy(P).cuda(), torch.from_numpy(Fr), D, [0, 1])
+    with pytest.raises(ValueError, match="CUDA tensor"):
+        eng.submit_device(P, Fr, D, [0, 1])
+    with pytest.raises(ValueError, match="shape"):
+        eng.submit(P[:, :-1], Fr[:, :-1], D, [0, 1])
+    with pytest.raises(ValueError, match="forces are required"):
+        eng.submit(P, None, D, [0, 1])
+    eng.submit(P, Fr, D, [0, 1])   # and the context is still usable
+    eng.sync()
+    eng.close()
+
+
+def test_pinned_ring_is_recycled_and_results_do_not_change():
+    """The recipe streams whole kernel batches through a ring of six pinned buffers that is refilled as the
+    engine retires batches (we_frames_retired): 40 one-frame batches wrap the ring six times and must give
+    the tables of a single big submission; read-outs without an explicit sync wait for the streams."""
+    from waterentropy_b200 import frames
+    from waterentropy_b200.io import Universe
+
+    inp = gio.load_inputs("synth_tric")
+    F = inp["positions"].shape[0]
+    reps = 40 // F + 1
+    Pm, Fm, Dm = (np.concatenate([inp[k]] * reps)[:40] for k in ("positions", "forces", "dimensions"))
+    u = Universe.from_arrays(inp["names"], inp["types"], inp["resnames"], inp["resids"], inp["masses"],
+                             inp["charges"], inp["bonds"], Pm, Fm, Dm)
+    one = _engine(inp)
+    one.submit(Pm, Fm, Dm, list(range(40)))
+    s1, c1 = one.cov_tables()                        # no sync(): the read-out itself waits
+    e1 = one.label_entries()
+    one.sync()
+    eng = _engine(inp, chunk_frames=1)
+    seen = set()
+    for P, Fr, D, ids in frames.iter_batches(u, range(40), 1, engine=eng):
+        seen.add(P.data_ptr() if hasattr(P, "data_ptr") else P.ctypes.data)
+        eng.submit(P, Fr, D, ids)
+        assert len(eng._inflight) <= frames.RING_SLOTS
+    assert len(seen) == frames.RING_SLOTS            # six buffers served forty batches
+    s2, c2 = eng.cov_tables()
+    e2 = eng.label_entries()
+    assert int(eng.lib.we_frames_retired(eng._ctx)) == 40
+    assert np.array_equal(c1, c2) and np.allclose(s1, s2, rtol=1e-12, atol=0)
+    e1, e2 = e1[np.lexsort((e1["hash2"], e1["hash"]))], e2[np.lexsort((e2["hash2"], e2["hash"]))]
+    for field in ("hash", "hash2", "shell_count", "donates", "accepts", "n_w", "first_seen_inv"):
+        assert np.array_equal(e1[field], e2[field]), field
+    assert [one.frame_records(k).tolist() for k in range(40)] == [eng.frame_records(k).tolist() for k in range(40)]
+    # frames already in page-locked memory are submitted in place (no staging copy)
+    u.pin()
+    eng.reset()
+    n_views = 0
+    for P, Fr, D, ids in frames.iter_batches(u, range(40), 8, engine=eng):
+        n_views += int(hasattr(P, "is_pinned") and P.is_pinned())
+        eng.submit(P, Fr, D, ids)
+    eng.sync()
+    assert n_views == 5
+    s3, c3 = eng.cov_tables()
+    assert np.array_equal(c1, c3) and np.allclose(s1, s3, rtol=1e-12, atol=0)
+    for e in (one, eng):
+        e.close()
+
+
+# ------------------------------------ full size: the PRODUCTION path against the oracle's closure
+@pytest.mark.parametrize("name,n_sampled", [("C3", 3), ("C4", 2), ("C5", 2)])
+def test_full_size_production_path_vs_oracle_closure(name, n_sampled):
+    """BASELINE.json configurations at full size through the production path (work lists, zero-copy
+    forces, CUDA graphs) over MORE than two kernel batches - batch boundaries, ring wrap, a ragged last
+    batch and label-table growth at size - against the oracle evaluated on the closure the reference's
+    lazy memoisation touches (solute united atoms -> interfacial waters -> their shell members -> donors;
+    `LazyFrameState`).  Per sampled frame: the recorded-water list with each water's nearest non-like atom
+    (bit-exact).  Over the sampled frames: label count tables (exact; they hold every water's labels, N_w,
+    donate / accept counts in aggregate), covariance counts and full 3x3 matrices per (residue, water) bin
+    (rtol 1e-9) - about one bin per recorded water at these sizes."""
+    import torch
+
+    from waterentropy_b200 import synthetic
+    from waterentropy_b200.engine import WaterEntropyEngine
+
+    s = synthetic.make_config(name)
+    top = wo.OracleTopology(s.masses, s.charges, s.resids, s.resnames, s.types, s.bonds)
+    probe = WaterEntropyEngine(s, "interfacial", device=0)
+    B = probe.batch_frames
+    probe.close()
+    n = 2 * B + 3
+    P = torch.empty((n, s.n_atoms, 3), dtype=torch.float32).pin_memory()
+    Fr = torch.empty((n, s.n_atoms, 3), dtype=torch.float32).pin_memory()
+    D = np.empty((n, 6), dtype=np.float32)
+    for k in range(n):
+        p, f, D[k] = s.frame(k)
+        P[k] = torch.from_numpy(p)
+        Fr[k] = torch.from_numpy(f)
+    big = WaterEntropyEngine(s, "interfacial", device=0, chunk_frames=B, table_log2=8)   # 256 slots: must grow
+    big.submit(P, Fr, D, list(range(n)))
+    big.sync()
+    assert big.diag()["frames_done"] == n and big.diag()["eig_fallbacks"] == 0
+    sampled = [5 % B, B + 1, 2 * B + 1][:n_sampled] if n_sampled == 3 else [B - 1, 2 * B + 2]
+    fsi_o, cov_o, lab_o = wo.nested_dict(), wo.CovMeans(), wo.LabelCounts()
+    closure = []
+    for f in sampled:
+        fsi, cov, lab, _, det = wo.interfacial_frame(top, P[f].numpy(), Fr[f].numpy(), D[f], f, lazy=True)
+        closure.append(det["n_rad_centres"])
+        want = sorted(zip(det["recorded"], det["nearest"]))
+        assert big.frame_records(f).tolist() == [list(t) for t in want], (name, f)
+        assert len(want) > 100
+        fsi_o.update(fsi)
+        cov_o.merge(cov)
+        lab_o.merge(lab)
+    small = WaterEntropyEngine(s, "interfacial", device=0, chunk_frames=1)
+    idx = torch.tensor(sampled)
+    small.submit(P[idx].contiguous(), Fr[idx].contiguous(), D[sampled], sampled)
+    small.sync()
+    got = small.hb_labels()
+    assert gio.plain(got.resid_labelled_shell_counts) == gio.plain(lab_o.resid_labelled_shell_counts)
+    assert gio.plain(got.labelled_shell_counts) == gio.plain(lab_o.labelled_shell_counts)
+    assert gio.plain(small.frame_solvent_indices()) == gio.plain(fsi_o)
+    _cmp_cov(small.covariances(), cov_o, full=_live_oracle_pinned())
+    # the multi-batch run: every recorded water is counted once in the label table and once in a bin,
+    # the sampled frames' keys are all there, and growing the table from 256 slots lost nothing
+    eb, es = big.label_entries(), small.label_entries()
+    n_rec = sum(len(big.frame_records(k)) for k in range(n))
+    assert int(eb["shell_count"].sum()) == n_rec == int(big.cov_tables()[1].sum()) == big.diag()["recorded"]
+    assert len(eb) > 256
+    keys_big = {(int(a), int(b)): int(c) for a, b, c in zip(eb["hash"], eb["hash2"], eb["shell_count"])}
+    for a, b, c in zip(es["hash"], es["hash2"], es["shell_count"]):
+        assert keys_big.get((int(a), int(b)), 0) >= int(c)
+    print(f"\\n{name}: {n} frames in batches of {B}; oracle closure {closure} of {len(top.heavy_idx)} heavy-atom centres; "
+          f"{n_rec} recorded waters, {len(eb)} label keys")
+    for e in (big, small):
+        e.close()

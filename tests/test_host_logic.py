@@ -428,3 +428,23 @@ def test_eig3_fixture_waters_match_reference_axes(hostlib):
     agree = np.all(np.abs(out[:, 12:21].reshape(-1, 3, 3) - o["axes"]) < 1e-12, axis=(1, 2))
     assert agree.all() if pinned else agree.mean() > 0.99
     assert np.allclose(out[:, 21:24], o["moi"], rtol=1e-13)
+
+
+def test_console_scripts_are_declared_like_upstream():
+    """pyproject.toml declares the reference's two console scripts (pyproject.toml:58-60 upstream) and
+    both entry points import and parse their flags without a GPU."""
+    import importlib
+    import tomllib
+
+    with open(os.path.join(REPO, "pyproject.toml"), "rb") as fh:
+        scripts = tomllib.load(fh)["project"]["scripts"]
+    assert set(scripts) == {"waterEntropy", "waterShells"}
+    for target in scripts.values():
+        mod, fn = target.split(":")
+        assert callable(getattr(importlib.import_module(mod), fn))
+    from waterentropy_b200.cli import run_find_Nc, runWaterEntropy
+
+    a = run_find_Nc.build_parser().parse_args(["-top", "t.prmtop", "-crd", "x.nc", "-s", "1", "-e", "9", "-dt", "2"])
+    assert (a.file_topology, a.file_coords, a.start, a.end, a.step) == ("t.prmtop", "x.nc", 1, 9, 2)
+    b = runWaterEntropy.build_parser().parse_args(["-top", "t", "-crd", "x", "-temp", "300", "-p"])
+    assert b.temperature == 300 and b.parallel

@@ -34,7 +34,7 @@ class we_options(C.Structure):
         ("device", C.c_int32), ("chunk_frames", C.c_int32), ("table_log2", C.c_int32),
         ("keep_records", C.c_int32), ("keep_debug", C.c_int32),
         ("search_radius", C.c_float), ("max_box", C.c_float), ("keep_shells", C.c_int32),
-        ("force_upload", C.c_int32), ("eig_flavour", C.c_int32),
+        ("force_upload", C.c_int32), ("shells_only", C.c_int32), ("eig_flavour", C.c_int32),
     ]
 
 
@@ -52,7 +52,8 @@ EXPORTS = [
     "we_debug_copy", "we_reset", "we_test_angle_cos", "we_test_powf2", "we_test_pow2", "we_test_distance",
     "we_profile", "we_kernel_times", "we_span_start", "we_span_stop",
     "we_label_entries_device", "we_merge_label_entries", "we_snapshot_cov", "we_wait_cov",
-    "we_copy_frame_shells", "we_test_eig3",
+    "we_copy_frame_shells", "we_test_eig3", "we_frames_retired", "we_wait_frames_retired",
+    "we_molecule_force_torque", "we_batch_frames",
 ]
 
 WE_ERR_DUPLICATE_COORD = -1
@@ -161,7 +162,7 @@ def load():
     L.we_get_diag.argtypes = [V, C.POINTER(we_diag)]
     L.we_error_location.restype = I
     L.we_error_location.argtypes = [V, C.POINTER(I64), C.POINTER(I)]
-    for name in ("we_n_bins", "we_n_label_entries", "we_n_heavy", "we_n_donors"):
+    for name in ("we_n_bins", "we_n_label_entries", "we_n_heavy", "we_n_donors", "we_batch_frames"):
         fn = getattr(L, name)
         fn.restype = I
         fn.argtypes = [V]
@@ -209,6 +210,12 @@ def load():
     L.we_test_pow2.argtypes = [I, V, I, V]
     L.we_test_distance.restype = I
     L.we_test_distance.argtypes = [I, V, V, I, V]
+    L.we_frames_retired.restype = I64
+    L.we_frames_retired.argtypes = [V]
+    L.we_wait_frames_retired.restype = I
+    L.we_wait_frames_retired.argtypes = [V, I64]
+    L.we_molecule_force_torque.restype = I
+    L.we_molecule_force_torque.argtypes = [I, V, V, V, V, I, I, V]
     L.we_test_eig3.restype = I
     L.we_test_eig3.argtypes = [I, V, I, I, V]
     _lib = L

@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <string>
 #include <map>
 #include <vector>
@@ -136,6 +137,10 @@ struct we_ctx {
   std::vector<FrameDebug> debug;
   unsigned long long launches = 0, frames_done = 0, recorded = 0;
   long long chunk_counter = 0;
+  // batches whose input buffers (the caller's host frames / device tensors) may still be read
+  struct InFlight { unsigned long long frames_end; int buf; };
+  std::deque<InFlight> inflight;
+  unsigned long long frames_retired = 0;
   // optional per-kernel CUDA-event timing (we_profile)
   bool prof = false;
   struct ProfRec { int id; cudaEvent_t a, b; };
@@ -378,6 +383,10 @@ extern "C" int we_create(const we_topology* t, const we_options* opt, we_ctx** o
   c->d_centre_of_slot = (int*)cos_p;
   // accumulators
   if (c->opt.eig_flavour != WE_EIG_OPENBLAS_AVX512 && c->opt.eig_flavour != WE_EIG_OPENBLAS_AVX2) { delete c; return fail(WE_ERR_INVALID, "eig_flavour must be WE_EIG_OPENBLAS_AVX512 (0) or WE_EIG_OPENBLAS_AVX2 (1)"); }
+  if (c->opt.shells_only && (t->recipe != WE_RECIPE_INTERFACIAL || !c->opt.keep_shells || c->opt.keep_debug)) {
+    delete c;
+    return fail(WE_ERR_INVALID, "shells_only needs the interfacial recipe with keep_shells and without keep_debug");
+  }
   const int tl = c->opt.table_log2 > 0 ? c->opt.table_log2 : 17;
   if (tl < 4 || tl > 24) { we_destroy(c); return fail(WE_ERR_INVALID, "table_log2 must be in [4,24]"); }
   c->table_mask = (1u << tl) - 1u;
@@ -431,6 +440,8 @@ extern "C" int we_reset(we_ctx* c) {
   c->debug.clear();
   c->frames_done = 0;
   c->recorded = 0;
+  c->inflight.clear();
+  c->frames_retired = 0;
   for (int i = 0; i < WE_NBUF; ++i) { c->out_pending[i] = false; c->lazy_pending[i] = false; }
   c->seen_entries = 0;
   c->max_new = 0;
@@ -464,18 +475,25 @@ extern "C" void we_destroy(we_ctx* c) {
   delete c;
 }
 
-static int ensure_workspace(we_ctx* c, const float* dims0, bool need_input_buffers) {
-  if (c->ws_ready) return 0;
-  const int H = c->H, N = c->N;
+// frames per kernel batch
+static int batch_frames(const we_ctx* c) {
   int chunk = c->opt.chunk_frames;
   if (chunk <= 0) {
     // ~3.2 M heavy-atom centres per batch: on C4 the per-batch fixed cost (a dozen launches, the tails of
     // the persistent kernels) is ~0.14 ms, 16 % of an 8-frame batch and 5 % of a 24-frame one
-    long long t = 3200000LL / std::max(1, H);
+    long long t = 3200000LL / std::max(1, c->H);
     if (c->opt.keep_shells) t /= 4;  // shells of the recorded waters are staged in pinned memory
     chunk = (int)std::max(1LL, std::min(128LL, t));
     if (chunk >= 8) chunk &= ~7;
   }
+  return chunk;
+}
+extern "C" int we_batch_frames(we_ctx* c) { return c ? batch_frames(c) : fail(WE_ERR_INVALID, "null context"); }
+
+static int ensure_workspace(we_ctx* c, const float* dims0, bool need_input_buffers) {
+  if (c->ws_ready) return 0;
+  const int H = c->H, N = c->N;
+  const int chunk = batch_frames(c);
   c->chunk = chunk;
   c->cell_target = c->opt.search_radius > 0.f ? c->opt.search_radius : 6.6f;
   // cell capacity from the largest box expected
@@ -496,7 +514,7 @@ static int ensure_workspace(we_ctx* c, const float* dims0, bool need_input_buffe
   // measured on this pool it is within 5 % of the whole-frame upload and much more sensitive to
   // a busy host, so whole frames (copy engine only, no CPU touch) are the default.
   c->lazy = need_input_buffers && !c->opt.keep_debug && c->maxfrag > 0 && c->maxfrag <= 8 &&
-            c->opt.force_upload == 2;
+            c->opt.force_upload == 2 && !c->opt.shells_only;
   if (need_input_buffers) {
     for (int i = 0; i < WE_NBUF; ++i) { AL(d_pos[i], F * N * 3) }  // d_frc: allocated on first whole-frame upload
   }
@@ -741,7 +759,8 @@ static int finish_lazy_all(we_ctx* c) {
 
 static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_device, const float* dims,
                        const int64_t* frame_ids, int n_frames) {
-  if (!c || !pos || !frc || !dims || !frame_ids) return fail(WE_ERR_INVALID, "null argument");
+  if (!c || !pos || !dims || !frame_ids) return fail(WE_ERR_INVALID, "null argument");
+  if (!frc && !c->opt.shells_only) return fail(WE_ERR_INVALID, "null force buffer (only a shells_only context runs without forces)");
   if (n_frames <= 0) return WE_OK;
   CK(cudaSetDevice(c->device));
   int rc = ensure_workspace(c, dims, !on_device);
@@ -753,7 +772,8 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
   // recipe).  If the caller's force buffer is pinned (UVA-mapped) the kernel reads exactly those
   // atoms straight from host memory over PCIe and the whole-frame upload is skipped.
   const float* frc_zero_copy = nullptr;
-  if (!on_device && !c->lazy && !c->opt.keep_debug &&
+  const bool no_forces = c->opt.shells_only != 0;  // nothing downstream of the shells reads forces
+  if (!no_forces && !on_device && !c->lazy && !c->opt.keep_debug &&
       (c->opt.force_upload == 3 || (c->opt.force_upload == 0 && c->recipe == WE_RECIPE_INTERFACIAL))) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, frc) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
@@ -763,16 +783,17 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     if (!frc_zero_copy && c->opt.force_upload == 3)
       return fail(WE_ERR_INVALID, "force_upload = 3 needs the force buffer in pinned (page-locked) host memory");
   }
-  if (!on_device && !c->lazy && !frc_zero_copy && !c->d_frc[0]) {
+  if (!no_forces && !on_device && !c->lazy && !frc_zero_copy && !c->d_frc[0]) {
     for (int i = 0; i < WE_NBUF; ++i) {
       if ((rc = dev_alloc(c, &c->d_frc[i], (size_t)c->chunk * N * 3))) return rc;
     }
   }
   // Host buffers: a call that fits in one or two batches would upload everything before computing
-  // anything, so (auto batch size only) it is cut into at least three batches of >= ~1 M centres each and
-  // the uploads of the later ones hide behind the kernels of the earlier ones.
+  // anything, so (auto batch size only, and only when the pipeline is empty: a caller that streams
+  // batch after batch already overlaps) it is cut into at least three batches of >= ~1 M centres each
+  // and the uploads of the later ones hide behind the kernels of the earlier ones.
   int step = c->chunk;
-  if (!on_device && c->opt.chunk_frames <= 0 && n_frames < 3 * c->chunk) {
+  if (!on_device && c->opt.chunk_frames <= 0 && n_frames < 3 * c->chunk && c->inflight.empty()) {
     const int floor_frames = std::max(1, (int)(1000000LL / std::max(1, H)));
     step = std::min(c->chunk, std::max((n_frames + 2) / 3, floor_frames));
     if (step >= 8) step &= ~7;
@@ -785,6 +806,10 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     if ((rc = finish_lazy(c, buf))) return rc;
     if ((rc = drain(c, buf))) return rc;
     CK(cudaEventSynchronize(c->ev_in_free[buf]));
+    while (!c->inflight.empty() && c->inflight.front().buf == buf) {  // the slot's previous batch is over
+      c->frames_retired = c->inflight.front().frames_end;
+      c->inflight.pop_front();
+    }
     if ((rc = maybe_grow_table(c))) return rc;
     for (int f = 0; f < n; ++f) {
       if (make_box(dims + (size_t)(f0 + f) * 6, c->cell_target, c->ncap, &c->h_boxes[buf][f]))
@@ -801,7 +826,9 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       if (c->copy_gate) CK(cudaStreamWaitEvent(c->s_copy, c->ev_p0[(buf + WE_NBUF - 1) % WE_NBUF], 0));
       CK(cudaMemcpyAsync(c->d_pos[buf], pos + (size_t)f0 * frame_floats, (size_t)n * frame_floats * sizeof(float), cudaMemcpyHostToDevice, c->s_copy));
       dp = c->d_pos[buf];
-      if (frc_zero_copy) {
+      if (no_forces) {
+        df = nullptr;
+      } else if (frc_zero_copy) {
         df = frc_zero_copy + (size_t)f0 * frame_floats;
       } else {
         if (!c->lazy)
@@ -810,7 +837,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       }
     } else {
       dp = pos + (size_t)f0 * frame_floats;
-      df = frc + (size_t)f0 * frame_floats;
+      df = no_forces ? nullptr : frc + (size_t)f0 * frame_floats;
     }
     CK(cudaMemcpyAsync(c->d_boxes[buf], c->h_boxes[buf], (size_t)n * sizeof(WeBox), cudaMemcpyHostToDevice, c->s_copy));
     CK(cudaMemcpyAsync(c->d_fids[buf], c->h_fids[buf], (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, c->s_copy));
@@ -820,6 +847,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     const WeBox* bx = c->d_boxes[buf];
     const long long* fids = c->d_fids[buf];
     const bool interfacial = (c->recipe == WE_RECIPE_INTERFACIAL);
+    const bool shells_only = c->opt.shells_only != 0;
     dim3 gH((H + 255) / 256, n);
     const bool graphs_on = !on_device && c->use_graphs && !c->prof && !c->opt.keep_debug;
     const long long gkey = ((long long)buf * 4096 + n) * 2;
@@ -901,6 +929,11 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
         k_list1<<<dim3((C + 255) / 256, n), 256, 0, st>>>(c->T, c->d_interf, c->d_state, c->d_wl1, c->d_n1);
         ps.stop(st); }
       WeWork w1{c->d_wl1, c->d_n1, C, 0};
+      if (shells_only) {
+        // get_interfacial_shells stops here: shells of the interfacial waters, nothing downstream
+        rad(WE_K_RAD1, w1, (long long)C * n, nullptr, no_marks);
+        c->launches += 1;
+      } else {
       rad(WE_K_RAD1, w1, (long long)C * n, nullptr, WeMarks{nullptr, mark_hb, mark_shell, nullptr, 0});
       { ProfScope ps(c, WE_K_LIST2, st);
         k_list2<<<gH, 256, 0, st>>>(c->T, mark_shell, mark_hb, c->d_state, c->d_wl2, c->d_n2, c->d_wlh, c->d_nh);
@@ -908,13 +941,14 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       WeWork w2{c->d_wl2, c->d_n2, H, 0};
       rad(WE_K_RAD2, w2, (long long)H * n, nullptr, no_marks);
       c->launches += 2;
+      }
     } else if (!interfacial && C > 0) {
       ProfScope ps(c, WE_K_LIST2, st);
       k_list2<<<gH, 256, 0, st>>>(c->T, nullptr, mark_hb, c->d_state, c->d_wl2, c->d_n2, c->d_wlh, c->d_nh);
       ps.stop(st);
       c->launches++;
     }
-    if (ND > 0) {
+    if (ND > 0 && !shells_only) {
       // HB work list: every heavy atom (debug) or the centres marked by the passes (k_list2)
       WeWork wh;
       if (c->opt.keep_debug) wh = WeWork{c->d_all_slots, nullptr, 0, H};
@@ -935,7 +969,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
             c->T, c->d_shell_n, c->d_shell_idx, c->d_nn, c->d_flags, c->d_acceptor, c->d_interf, fids,
             c->d_table, c->table_mask, c->d_rec_count[buf], c->d_rec[buf],
             (c->opt.keep_records || c->lazy || c->opt.keep_shells) ? c->h_rec[buf] : nullptr,
-            c->opt.keep_shells ? c->h_shell[buf] : nullptr, wlab, n, c->d_diag);
+            c->opt.keep_shells ? c->h_shell[buf] : nullptr, wlab, n, c->d_diag, shells_only ? 1 : 0);
         ps.stop(st); }
       c->launches += 1;
     }
@@ -944,7 +978,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     CK(cudaMemcpyAsync(c->h_rec_count[buf], c->d_rec_count[buf], (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
     }
     if ((rc = g2.end())) return rc;
-    if (C > 0) {
+    if (C > 0 && !shells_only) {
       if (!c->lazy) {
         // zero-copy forces: the kernel waits on PCIe reads, so it runs beside the next batch's kernels
         cov_st = (frc_zero_copy && c->cov_stream) ? c->s_cov : st;
@@ -966,7 +1000,8 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     CK(cudaGetLastError());
     c->pending_n[buf] = n;
     c->frames_done += (unsigned long long)n;
-    if (c->lazy && C > 0) {
+    c->inflight.push_back({c->frames_done, buf});
+    if (c->lazy && C > 0 && !shells_only) {
       // the covariance kernel of this batch runs one batch later, after the host has gathered
       // the forces of the recorded waters (finish_lazy); until then its inputs stay alive
       CK(cudaEventRecord(c->ev_label[buf], st));
@@ -1021,9 +1056,50 @@ extern "C" int we_submit_device(we_ctx* c, const float* d_pos, const float* d_fr
   return submit_impl(c, d_pos, d_frc, true, dims, frame_ids, n_frames);
 }
 
+// Everything submitted so far has updated the accumulators: the engine's streams are non-blocking, so
+// the blocking copies of the read-out calls (legacy default stream) do not order behind them by themselves.
+static int quiesce(we_ctx* c) {
+  CK(cudaSetDevice(c->device));
+  const int rc = finish_lazy_all(c);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(c->s_comp));
+  CK(cudaStreamSynchronize(c->s_cov));
+  return 0;
+}
+
 static int read_diag(we_ctx* c, WeDiag* d) {
   CK(cudaMemcpy(d, c->d_diag, sizeof(WeDiag), cudaMemcpyDeviceToHost));
   return 0;
+}
+
+// ---- input-buffer retirement ------------------------------------------------------------------
+extern "C" int64_t we_frames_retired(we_ctx* c) {
+  if (!c) return fail(WE_ERR_INVALID, "null context");
+  cudaSetDevice(c->device);
+  while (!c->inflight.empty()) {
+    const we_ctx::InFlight& b = c->inflight.front();
+    if (c->lazy_pending[b.buf]) break;  // its forces are still to be gathered from the caller's buffer
+    if (cudaEventQuery(c->ev_in_free[b.buf]) != cudaSuccess) { cudaGetLastError(); break; }
+    c->frames_retired = b.frames_end;
+    c->inflight.pop_front();
+  }
+  return (int64_t)c->frames_retired;
+}
+
+extern "C" int we_wait_frames_retired(we_ctx* c, int64_t n_frames) {
+  if (!c) return fail(WE_ERR_INVALID, "null context");
+  CK(cudaSetDevice(c->device));
+  if ((unsigned long long)std::max<int64_t>(0, n_frames) > c->frames_done)
+    return fail(WE_ERR_INVALID, "only %llu frames were submitted", c->frames_done);
+  while (!c->inflight.empty() && c->frames_retired < (unsigned long long)n_frames) {
+    const we_ctx::InFlight b = c->inflight.front();
+    int rc = finish_lazy(c, b.buf);
+    if (rc) return rc;
+    CK(cudaEventSynchronize(c->ev_in_free[b.buf]));
+    c->frames_retired = b.frames_end;
+    c->inflight.pop_front();
+  }
+  return WE_OK;
 }
 
 extern "C" int we_sync(we_ctx* c) {
@@ -1041,6 +1117,8 @@ extern "C" int we_sync(we_ctx* c) {
   CK(cudaStreamSynchronize(c->s_copy));
   CK(cudaStreamSynchronize(c->s_comp));
   CK(cudaStreamSynchronize(c->s_cov));
+  c->inflight.clear();
+  c->frames_retired = c->frames_done;
   prof_resolve(c);
   WeDiag d;
   if ((rc = read_diag(c, &d))) return rc;
@@ -1129,7 +1207,7 @@ extern "C" int we_copy_donors(we_ctx* c, int32_t* dx, int32_t* dh) {
 
 extern "C" int we_copy_cov(we_ctx* c, double* cov_sum, uint64_t* cov_cnt) {
   if (!c || !cov_sum || !cov_cnt) return fail(WE_ERR_INVALID, "null argument");
-  CK(cudaSetDevice(c->device));
+  { const int rc = quiesce(c); if (rc) return rc; }
   CK(cudaMemcpy(cov_sum, c->d_cov_sum, (size_t)c->B * 18 * sizeof(double), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(cov_cnt, c->d_cov_cnt, (size_t)c->B * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return WE_OK;
@@ -1170,6 +1248,7 @@ extern "C" int we_wait_cov(we_ctx* c, int32_t ticket, double* cov_sum, uint64_t*
 
 extern "C" int we_device_tables(we_ctx* c, void** s, void** n) {
   if (!c) return fail(WE_ERR_INVALID, "null context");
+  { const int rc = quiesce(c); if (rc) return rc; }  // the caller hands these to NCCL on its own stream
   if (s) *s = c->d_cov_sum;
   if (n) *n = c->d_cov_cnt;
   return WE_OK;
@@ -1189,6 +1268,7 @@ __global__ void k_compact(const WeLabelEntry* __restrict__ table, unsigned int n
 
 extern "C" int we_n_label_entries(we_ctx* c) {
   if (!c) return fail(WE_ERR_INVALID, "null context");
+  { const int rc = quiesce(c); if (rc) return rc; }
   WeDiag d;
   int rc = read_diag(c, &d);
   if (rc) return rc;
@@ -1446,4 +1526,42 @@ extern "C" int we_test_eig3(int32_t device, const double* tensors, int32_t n, in
   return run_test(device, tensors, (size_t)n * 72, out, (size_t)n * 25 * 8, [&](void* di, void* dout) {
     k_test_eig3<<<(n + 127) / 128, 128>>>((const double*)di, n, flavour, (double*)dout);
   });
+}
+
+// recipes/forces_torques.py:14-55 for molecules handed over as compact arrays (one launch, thread per
+// molecule): the same device function k_cov uses.
+extern "C" int we_molecule_force_torque(int32_t device, const float* pos, const float* frc, const double* masses,
+                                        const int32_t* mol_ptr, int32_t n_mol, int32_t eig_flavour, double* out) {
+  if (!pos || !frc || !masses || !mol_ptr || !out || n_mol < 0) return fail(WE_ERR_INVALID, "null argument");
+  if (eig_flavour != WE_EIG_OPENBLAS_AVX512 && eig_flavour != WE_EIG_OPENBLAS_AVX2) return fail(WE_ERR_INVALID, "bad eig_flavour");
+  if (n_mol == 0) return 0;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(WE_ERR_CUDA, "no CUDA device available; waterentropy_b200 has no CPU path");
+  CK(cudaSetDevice(device));
+  const size_t na = (size_t)mol_ptr[n_mol];
+  for (int i = 0; i < n_mol; ++i) if (mol_ptr[i + 1] <= mol_ptr[i]) return fail(WE_ERR_INVALID, "molecule %d has no atoms", i);
+  float *d_pos = nullptr, *d_frc = nullptr;
+  double *d_m = nullptr, *d_out = nullptr;
+  int* d_ptr = nullptr;
+  WeDiag* d_diag = nullptr;
+  cudaError_t e = cudaSuccess;
+  auto al = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes ? bytes : 1); };
+  al((void**)&d_pos, na * 12); al((void**)&d_frc, na * 12); al((void**)&d_m, na * 8);
+  al((void**)&d_ptr, ((size_t)n_mol + 1) * 4); al((void**)&d_out, (size_t)n_mol * 24 * 8); al((void**)&d_diag, sizeof(WeDiag));
+  WeDiag hd;
+  memset(&hd, 0, sizeof(hd));
+  if (e == cudaSuccess) e = cudaMemcpy(d_pos, pos, na * 12, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_frc, frc, na * 12, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_m, masses, na * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_ptr, mol_ptr, ((size_t)n_mol + 1) * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(d_diag, 0, sizeof(WeDiag));
+  if (e == cudaSuccess) {
+    k_force_torque<<<(n_mol + 127) / 128, 128>>>(d_pos, d_frc, d_m, d_ptr, n_mol, eig_flavour, d_diag, d_out);
+    e = cudaDeviceSynchronize();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out, d_out, (size_t)n_mol * 24 * 8, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(&hd, d_diag, sizeof(WeDiag), cudaMemcpyDeviceToHost);
+  cudaFree(d_pos); cudaFree(d_frc); cudaFree(d_m); cudaFree(d_ptr); cudaFree(d_out); cudaFree(d_diag);
+  if (e != cudaSuccess) return fail(WE_ERR_CUDA, "we_molecule_force_torque failed: %s", cudaGetErrorString(e));
+  return (int)hd.eig_fallbacks;
 }

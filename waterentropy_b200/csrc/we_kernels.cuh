@@ -1057,7 +1057,7 @@ __device__ __forceinline__ void we_label_one(const WeTopoDev& T, int f, int xs,
         const long long* __restrict__ frame_ids, WeLabelEntry* __restrict__ table,
         unsigned int table_mask, int* __restrict__ rec_count, WeRecord* __restrict__ rec,
         int2* __restrict__ rec_host, int* __restrict__ shell_host, WeLabelStage* stage,
-        WeDiag* diag, int lane) {
+        WeDiag* diag, int lane, int shells_only) {
   const size_t fo = (size_t)f * T.n_heavy;
   const size_t ho = fo + xs;
   const bool bulk = (T.recipe == 1);
@@ -1071,6 +1071,26 @@ __device__ __forceinline__ void we_label_one(const WeTopoDev& T, int f, int xs,
   int A = -1, as = -1;
   if (act) { A = shell_idx[ho * WE_MAX_NBR + lane]; as = T.heavy_slot[A]; }
   const int my_res = T.resname_id[X];
+  if (shells_only) {
+    // get_interfacial_shells (recipes/interfacial_solvent.py:131-146): the RAD shell of every interfacial
+    // water that has a non-like member; no HBs, no labels, no neighbours' shells are evaluated there
+    const int nn0 = nn_arr[ho];
+    if (nn0 < 0) return;
+    int r0 = 0;
+    if (lane == 0) {
+      r0 = atomicAdd(&rec_count[f], 1);
+      WeRecord rr; rr.atom = X; rr.nearest = nn0; rr.bin = -1; rr.pad = 0;
+      rec[(size_t)f * T.n_centres + r0] = rr;
+      if (rec_host) rec_host[(size_t)f * T.n_centres + r0] = make_int2(X, nn0);
+    }
+    if (shell_host) {
+      r0 = __shfl_sync(0xffffffffu, r0, 0);
+      int* o = shell_host + ((size_t)f * T.n_centres + r0) * (WE_MAX_NBR + 1);
+      if (lane == 0) o[0] = ns;
+      if (act) o[1 + lane] = A;
+    }
+    return;
+  }
   if (bulk) {
     // recipes/bulk_water.py:49-51: only shells made purely of the centre's resname
     const bool other = act && (T.resname_id[A] != my_res);
@@ -1247,7 +1267,8 @@ k_label(WeTopoDev T, const int* __restrict__ shell_n, const int* __restrict__ sh
         const int* __restrict__ acceptor, const unsigned char* __restrict__ interfacial,
         const long long* __restrict__ frame_ids, WeLabelEntry* __restrict__ table,
         unsigned int table_mask, int* __restrict__ rec_count, WeRecord* __restrict__ rec,
-        int2* __restrict__ rec_host, int* __restrict__ shell_host, WeWork work, int n_frames, WeDiag* diag) {
+        int2* __restrict__ rec_host, int* __restrict__ shell_host, WeWork work, int n_frames, WeDiag* diag,
+        int shells_only) {
   __shared__ WeLabelStage stage;
   for (int t = threadIdx.x; t < (int)(sizeof(WeLabelStage) / 4); t += blockDim.x) reinterpret_cast<unsigned int*>(&stage)[t] = 0u;
   __syncthreads();
@@ -1258,7 +1279,7 @@ k_label(WeTopoDev T, const int* __restrict__ shell_n, const int* __restrict__ sh
     const int* list = work.list + (size_t)f * work.stride;
     for (int i = blockIdx.x * (blockDim.x >> 5) + w; i < cnt; i += stride)
       we_label_one(T, f, list[i], shell_n, shell_idx, nn_arr, flags, acceptor, interfacial, frame_ids, table,
-                   table_mask, rec_count, rec, rec_host, shell_host, &stage, diag, lane);
+                   table_mask, rec_count, rec, rec_host, shell_host, &stage, diag, lane, shells_only);
   }
   // ---- fold the staged keys into the global table ----------------------------------------------
   __syncthreads();
@@ -1347,6 +1368,82 @@ __device__ __noinline__ void we_axes_jacobi(double I[3][3], double ax[3][3], dou
   if (fabs(am[0]) < fabs(am[1])) { double t = am[0]; am[0] = am[1]; am[1] = t; }
 }
 
+// One molecule: rotated mass-weighted force F and inertia-weighted torque tq in its principal-axis
+// frame (recipes/forces_torques.py:38-47, maths/transformations.py:12-64,104-135).  pos(k, i) /
+// frc(k, i): float32 component i of atom k, mass(k): fp64.
+template <class PosF, class FrcF, class MassF>
+__device__ __forceinline__ void we_force_torque(int na, PosF pos, FrcF frc, MassF mass, int eig_flavour,
+                                                WeDiag* diag, double F[3], double tq[3]) {
+  // centre of mass (mass-weighted, fp64, no unwrapping: forces_torques.py:40)
+  double mtot = 0.0, cx = 0.0, cy = 0.0, cz = 0.0;
+  for (int k = 0; k < na; ++k) {
+    const double m = mass(k);
+    cx += (double)pos(k, 0) * m; cy += (double)pos(k, 1) * m; cz += (double)pos(k, 2) * m;
+    mtot += m;
+  }
+  cx /= mtot; cy /= mtot; cz /= mtot;
+  double I[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int k = 0; k < na; ++k) {
+    const double m = mass(k);
+    const double x = (double)pos(k, 0) - cx, y = (double)pos(k, 1) - cy, z = (double)pos(k, 2) - cz;
+    I[0][0] += m * (y * y + z * z);
+    I[1][1] += m * (x * x + z * z);
+    I[2][2] += m * (x * x + y * y);
+    I[0][1] -= m * x * y;
+    I[0][2] -= m * x * z;
+    I[1][2] -= m * y * z;
+  }
+  I[1][0] = I[0][1]; I[2][0] = I[0][2]; I[2][1] = I[1][2];
+  double ax[3][3], am[3];
+  {
+    const double tens[9] = {I[0][0], I[0][1], I[0][2], I[1][0], I[1][1], I[1][2], I[2][0], I[2][1], I[2][2]};
+    if (we_principal_axes(tens, ax, am, eig_flavour) != WE_EIG3_OK) {
+      atomicAdd(&diag->eig_fallbacks, 1ULL);
+      we_axes_jacobi(I, ax, am);
+    }
+  }
+  const double sq[3] = {sqrt(am[0]), sqrt(am[1]), sqrt(am[2])};
+  tq[0] = tq[1] = tq[2] = 0.0;
+  float fsx = 0.f, fsy = 0.f, fsz = 0.f;
+  for (int k = 0; k < na; ++k) {
+    const double p[3] = {(double)pos(k, 0) - cx, (double)pos(k, 1) - cy, (double)pos(k, 2) - cz};
+    const float g0 = frc(k, 0), g1 = frc(k, 1), g2 = frc(k, 2);
+    const double g[3] = {(double)g0, (double)g1, (double)g2};
+    double rp[3], rg[3];
+    for (int i = 0; i < 3; ++i) {
+      rp[i] = ax[i][0] * p[0] + ax[i][1] * p[1] + ax[i][2] * p[2];
+      rg[i] = ax[i][0] * g[0] + ax[i][1] * g[1] + ax[i][2] * g[2];
+    }
+    tq[0] += (rp[1] * rg[2] - rp[2] * rg[1]) / sq[0];
+    tq[1] += (rp[2] * rg[0] - rp[0] * rg[2]) / sq[1];
+    tq[2] += (rp[0] * rg[1] - rp[1] * rg[0]) / sq[2];
+    if (k == 0) { fsx = g0; fsy = g1; fsz = g2; }
+    else { fsx = we_fadd(fsx, g0); fsy = we_fadd(fsy, g1); fsz = we_fadd(fsz, g2); }  // float32 sum (transformations.py:48)
+  }
+  const double msq = sqrt(mtot);
+  for (int i = 0; i < 3; ++i) F[i] = (ax[i][0] * (double)fsx + ax[i][1] * (double)fsy + ax[i][2] * (double)fsz) / msq;
+}
+
+// Stand-alone form of the above for `recipes.forces_torques.get_forces_torques`: molecules given as
+// compact arrays (CSR over atoms); out [n][24] = F(3), tq(3), F outer F / 4 (9), tq outer tq / 4 (9).
+__global__ void k_force_torque(const float* __restrict__ pos, const float* __restrict__ frc,
+                               const double* __restrict__ masses, const int* __restrict__ mol_ptr, int n_mol,
+                               int eig_flavour, WeDiag* diag, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_mol) return;
+  const int a0 = mol_ptr[i], a1 = mol_ptr[i + 1];
+  double F[3], tq[3];
+  we_force_torque(a1 - a0, [&](int k, int c) { return pos[3 * (a0 + k) + c]; },
+                  [&](int k, int c) { return frc[3 * (a0 + k) + c]; }, [&](int k) { return masses[a0 + k]; },
+                  eig_flavour, diag, F, tq);
+  double* o = out + (size_t)i * 24;
+  for (int c = 0; c < 3; ++c) { o[c] = F[c]; o[3 + c] = tq[c]; }
+  for (int c = 0; c < 3; ++c) for (int d = 0; d < 3; ++d) {
+    o[6 + 3 * c + d] = F[c] * F[d] * 0.25;       // get_covariance_matrix(ft, 0.5): outer * 0.5 ** 2
+    o[15 + 3 * c + d] = tq[c] * tq[d] * 0.25;
+  }
+}
+
 // grid = (blocks per frame, frames); the blocks of a frame walk its recorded waters with a
 // grid-stride loop (about four warp-iterations each when every water is recorded).
 // K6: per-block shared-memory staging of the covariance sums (16 bin slots), flushed with one
@@ -1385,58 +1482,11 @@ k_cov(WeTopoDev T, const float* __restrict__ pos, const float* __restrict__ frc,
     // forces: the whole frame (eager upload) or only the recorded molecules, gathered by the
     // host in record order (lazy upload: fcomp[(fbase[f] + r) * maxfrag + k][3])
     const float* ff = fcomp ? fcomp + ((size_t)(fbase[f] + r) * maxfrag) * 3 : frc + (size_t)f * T.n_atoms * 3;
-    // centre of mass (mass-weighted, fp64, no unwrapping: forces_torques.py:40)
-    double mtot = 0.0, cx = 0.0, cy = 0.0, cz = 0.0;
-    for (int k = a0; k < a1; ++k) {
-      const int at = T.frag_atoms[k];
-      const double m = T.masses[at];
-      cx += (double)fp[3 * at] * m; cy += (double)fp[3 * at + 1] * m; cz += (double)fp[3 * at + 2] * m;
-      mtot += m;
-    }
-    cx /= mtot; cy /= mtot; cz /= mtot;
-    double I[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    for (int k = a0; k < a1; ++k) {
-      const int at = T.frag_atoms[k];
-      const double m = T.masses[at];
-      const double x = (double)fp[3 * at] - cx, y = (double)fp[3 * at + 1] - cy, z = (double)fp[3 * at + 2] - cz;
-      I[0][0] += m * (y * y + z * z);
-      I[1][1] += m * (x * x + z * z);
-      I[2][2] += m * (x * x + y * y);
-      I[0][1] -= m * x * y;
-      I[0][2] -= m * x * z;
-      I[1][2] -= m * y * z;
-    }
-    I[1][0] = I[0][1]; I[2][0] = I[0][2]; I[2][1] = I[1][2];
-    double ax[3][3], am[3];
-    {
-      const double tens[9] = {I[0][0], I[0][1], I[0][2], I[1][0], I[1][1], I[1][2], I[2][0], I[2][1], I[2][2]};
-      if (we_principal_axes(tens, ax, am, eig_flavour) != WE_EIG3_OK) {
-        atomicAdd(&diag->eig_fallbacks, 1ULL);
-        we_axes_jacobi(I, ax, am);
-      }
-    }
-    const double sq[3] = {sqrt(am[0]), sqrt(am[1]), sqrt(am[2])};
-    double tq[3] = {0, 0, 0};
-    float fsx = 0.f, fsy = 0.f, fsz = 0.f;
-    for (int k = a0; k < a1; ++k) {
-      const int at = T.frag_atoms[k];
-      const double p[3] = {(double)fp[3 * at] - cx, (double)fp[3 * at + 1] - cy, (double)fp[3 * at + 2] - cz};
-      const int fa = fcomp ? (k - a0) : at;
-      const double g[3] = {(double)ff[3 * fa], (double)ff[3 * fa + 1], (double)ff[3 * fa + 2]};
-      double rp[3], rg[3];
-      for (int i = 0; i < 3; ++i) {
-        rp[i] = ax[i][0] * p[0] + ax[i][1] * p[1] + ax[i][2] * p[2];
-        rg[i] = ax[i][0] * g[0] + ax[i][1] * g[1] + ax[i][2] * g[2];
-      }
-      tq[0] += (rp[1] * rg[2] - rp[2] * rg[1]) / sq[0];
-      tq[1] += (rp[2] * rg[0] - rp[0] * rg[2]) / sq[1];
-      tq[2] += (rp[0] * rg[1] - rp[1] * rg[0]) / sq[2];
-      if (k == a0) { fsx = ff[3 * fa]; fsy = ff[3 * fa + 1]; fsz = ff[3 * fa + 2]; }
-      else { fsx = we_fadd(fsx, ff[3 * fa]); fsy = we_fadd(fsy, ff[3 * fa + 1]); fsz = we_fadd(fsz, ff[3 * fa + 2]); }  // float32 sum (transformations.py:48)
-    }
-    const double msq = sqrt(mtot);
-    double F[3];
-    for (int i = 0; i < 3; ++i) F[i] = (ax[i][0] * (double)fsx + ax[i][1] * (double)fsy + ax[i][2] * (double)fsz) / msq;
+    double F[3], tq[3];
+    we_force_torque(a1 - a0,
+                    [&](int k, int i) { return fp[3 * T.frag_atoms[a0 + k] + i]; },
+                    [&](int k, int i) { return ff[3 * (fcomp ? k : T.frag_atoms[a0 + k]) + i]; },
+                    [&](int k) { return T.masses[T.frag_atoms[a0 + k]]; }, eig_flavour, diag, F, tq);
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
       val[i * 3 + j] = F[i] * F[j] * 0.25;
       val[9 + i * 3 + j] = tq[i] * tq[j] * 0.25;

@@ -81,7 +81,7 @@ def decode_label_entries(top, recipe, entries) -> HBLabelCollection:
 class WaterEntropyEngine:
     def __init__(self, system, recipe="interfacial", device=0, chunk_frames=0, table_log2=0,
                  keep_records=True, keep_debug=False, search_radius=0.0, max_box=0.0, force_upload=0,
-                 keep_shells=False, eig_flavour=None):
+                 keep_shells=False, eig_flavour=None, shells_only=False):
         """`eig_flavour`: "avx512" / "avx2" / None.  The reference's principal axes carry the eigenvector
         signs `numpy.linalg.eig` returns on the host it runs on; None replays the OpenBLAS kernel family
         of THIS host's NumPy (`_lib.host_eig_flavour`), so the off-diagonal covariance elements are the
@@ -98,14 +98,21 @@ class WaterEntropyEngine:
         o = _lib.we_options(device=device, chunk_frames=chunk_frames, table_log2=table_log2,
                             keep_records=int(keep_records), keep_debug=int(keep_debug),
                             search_radius=search_radius, max_box=max_box, force_upload=force_upload,
-                            keep_shells=int(keep_shells), eig_flavour=self.eig_flavour)
+                            keep_shells=int(keep_shells), eig_flavour=self.eig_flavour,
+                            shells_only=int(shells_only))
         self._ctx = C.c_void_p()
         _lib.check(self.lib.we_create(C.byref(t), C.byref(o), C.byref(self._ctx)))
         self.device = device
         self.keep_records = keep_records
         self.keep_debug = keep_debug
+        self.shells_only = bool(shells_only)
         self.frame_ids = []
-        self._inflight = []  # keep host buffers alive until sync
+        self._inflight = []  # (frames submitted up to and including this call, buffers): kept alive until retired
+
+    @property
+    def batch_frames(self):
+        """Frames per kernel batch; a reader that submits whole batches keeps the device busiest."""
+        return _lib.check(self.lib.we_batch_frames(self._ctx))
 
     # ------------------------------------------------------------------
     def close(self):
@@ -125,9 +132,39 @@ class WaterEntropyEngine:
         self._inflight = []
 
     # ------------------------------------------------------------------
+    @staticmethod
+    def _check_frames(a, name, shape, cuda_device=None):
+        """Layout the kernels assume: float32, C-contiguous, the right shape (and device)."""
+        if hasattr(a, "data_ptr"):  # torch tensor
+            import torch
+
+            if a.dtype != torch.float32 or not a.is_contiguous():
+                raise ValueError(f"{name} must be a contiguous float32 tensor, got {a.dtype}, contiguous={a.is_contiguous()}")
+            if cuda_device is None and a.device.type != "cpu":
+                raise ValueError(f"{name} is on {a.device}; submit() takes host memory (use submit_device)")
+            if cuda_device is not None and (a.device.type != "cuda" or a.device.index != cuda_device):
+                raise ValueError(f"{name} is on {a.device}; this engine runs on cuda:{cuda_device}")
+        elif cuda_device is not None:
+            raise ValueError(f"{name} must be a CUDA tensor")
+        if tuple(a.shape) != tuple(shape):
+            raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(a.shape)}")
+
+    def _retire(self):
+        """Drop references to host buffers the device no longer reads (we_frames_retired)."""
+        if self._inflight:
+            done = int(self.lib.we_frames_retired(self._ctx))
+            while self._inflight and self._inflight[0][0] <= done:
+                self._inflight.pop(0)
+
+    def wait_retired(self, n_frames):
+        """Block until the first `n_frames` submitted frames no longer need their input buffers."""
+        _lib.check(self.lib.we_wait_frames_retired(self._ctx, int(n_frames)))
+        self._retire()
+
     def submit(self, positions, forces, dimensions, frame_ids):
         """Queue frames held in host memory (numpy arrays or CPU/pinned torch tensors).
-        positions/forces float32 [F,N,3], dimensions float32 [F,6], frame_ids int [F]."""
+        positions/forces float32 [F,N,3], dimensions float32 [F,6], frame_ids int [F].
+        `forces` may be None for a shells_only engine."""
         n = len(frame_ids)
         if n == 0:
             return
@@ -136,24 +173,38 @@ class WaterEntropyEngine:
             dimensions = np.ascontiguousarray(dimensions, dtype=np.float32)
         if not hasattr(positions, "data_ptr"):
             positions = np.ascontiguousarray(positions, dtype=np.float32)
+        if forces is not None and not hasattr(forces, "data_ptr"):
             forces = np.ascontiguousarray(forces, dtype=np.float32)
-        shape = tuple(positions.shape)
-        if shape != (n, self.top.n_atoms, 3) or tuple(forces.shape) != shape:
-            raise ValueError(f"positions/forces must have shape {(n, self.top.n_atoms, 3)}, got {shape}")
-        self._inflight.append((positions, forces, dimensions, fid))
-        _lib.check(self.lib.we_submit(self._ctx, _host_ptr(positions), _host_ptr(forces),
+        shape = (n, self.top.n_atoms, 3)
+        self._check_frames(positions, "positions", shape)
+        self._check_frames(dimensions, "dimensions", (n, 6))
+        if forces is None:
+            if not self.shells_only:
+                raise ValueError("forces are required (only a shells_only engine runs without them)")
+        else:
+            self._check_frames(forces, "forces", shape)
+        self._retire()
+        _lib.check(self.lib.we_submit(self._ctx, _host_ptr(positions), None if forces is None else _host_ptr(forces),
                                       _host_ptr(dimensions), fid.ctypes.data, n))
         self.frame_ids.extend(int(x) for x in fid)
+        self._inflight.append((len(self.frame_ids), (positions, forces, dimensions, fid)))
 
     def submit_device(self, d_positions, d_forces, dimensions, frame_ids):
         """Queue frames whose positions / forces are CUDA tensors on this engine's device."""
         n = len(frame_ids)
+        if n == 0:
+            return
         fid = np.ascontiguousarray(frame_ids, dtype=np.int64)
         dims = np.ascontiguousarray(dimensions, dtype=np.float32)
-        self._inflight.append((d_positions, d_forces, dims, fid))
+        shape = (n, self.top.n_atoms, 3)
+        self._check_frames(d_positions, "positions", shape, self.device)
+        self._check_frames(d_forces, "forces", shape, self.device)
+        self._check_frames(dims, "dimensions", (n, 6))
+        self._retire()
         _lib.check(self.lib.we_submit_device(self._ctx, d_positions.data_ptr(), d_forces.data_ptr(),
                                              dims.ctypes.data, fid.ctypes.data, n))
         self.frame_ids.extend(int(x) for x in fid)
+        self._inflight.append((len(self.frame_ids), (d_positions, d_forces, dims, fid)))
 
     def sync(self):
         try:

@@ -53,6 +53,9 @@ class _Trajectory:
     def __len__(self):
         return self.n_frames
 
+    def __repr__(self):  # what `print(u.trajectory)` shows (cli/run_find_Nc.py:36)
+        return f"<{type(self._u._source).__name__} with {self.n_frames} frames of {self._u.n_atoms} atoms>"
+
     @property
     def ts(self):
         return _Timestep(self._u._frame)
@@ -73,21 +76,50 @@ class _Trajectory:
 
 
 class _ArraySource:
-    """Frames held in memory."""
+    """Frames held in memory (forces optional: the shells path does not read them)."""
 
     def __init__(self, positions, forces, dimensions):
         self.P = np.ascontiguousarray(positions, dtype=np.float32)
-        self.F = np.ascontiguousarray(forces, dtype=np.float32)
+        self.F = None if forces is None else np.ascontiguousarray(forces, dtype=np.float32)
         self.dimensions = np.ascontiguousarray(dimensions, dtype=np.float32)
         self.n_frames = self.P.shape[0]
+        self.n_atoms = self.P.shape[1]
+        self.has_forces = self.F is not None
+        self._keep = None  # pinned torch tensors backing P / F after pin()
 
     def read(self, indices, out_pos=None, out_frc=None):
         idx = np.asarray(list(indices), dtype=np.int64)
         if out_pos is not None:
             out_pos[: len(idx)] = self.P[idx]
-            out_frc[: len(idx)] = self.F[idx]
-            return out_pos[: len(idx)], out_frc[: len(idx)], self.dimensions[idx]
-        return self.P[idx], self.F[idx], self.dimensions[idx]
+            if out_frc is not None:
+                if self.F is None:
+                    raise ValueError("the trajectory holds no forces; the covariance path needs them")
+                out_frc[: len(idx)] = self.F[idx]
+            return out_pos[: len(idx)], None if out_frc is None else out_frc[: len(idx)], self.dimensions[idx]
+        return self.P[idx], None if self.F is None else self.F[idx], self.dimensions[idx]
+
+    def pin(self):
+        """Move the frames into page-locked memory so that batches can be handed to the engine in place."""
+        import torch
+
+        if self._keep is None and torch.cuda.is_available():
+            tp = torch.from_numpy(self.P).pin_memory()
+            tf = None if self.F is None else torch.from_numpy(self.F).pin_memory()
+            self._keep = (tp, tf)
+            self.P = tp.numpy()
+            self.F = None if tf is None else tf.numpy()
+
+    def views(self, indices, forces=True):
+        """(positions, forces, dimensions) views of a contiguous run of frames in pinned memory, or None."""
+        if self._keep is None or not len(indices):
+            return None
+        i0, n = int(indices[0]), len(indices)
+        if list(indices) != list(range(i0, i0 + n)):
+            return None
+        tp, tf = self._keep
+        if forces and tf is None:
+            raise ValueError("the trajectory holds no forces; the covariance path needs them")
+        return tp[i0:i0 + n], (tf[i0:i0 + n] if forces else None), self.dimensions[i0:i0 + n]
 
 
 class Universe:
@@ -114,8 +146,6 @@ class Universe:
             raise NotImplementedError(
                 f"no reader for topology {ext_t!r} + coordinates {ext_c!r} "
                 "(supported: AMBER prmtop + NetCDF, prmtop + GROMACS TRR)")
-        if not x.has_forces:
-            raise ValueError("the trajectory holds no forces; the covariance path needs them")
         if x.n_atoms != t.n_atoms:
             raise ValueError(f"trajectory has {x.n_atoms} atoms, topology {t.n_atoms}")
         self._set_topology(t.names, t.types, t.resnames, t.resids, t.masses, t.charges, t.bonds)
@@ -124,8 +154,6 @@ class Universe:
     @classmethod
     def from_arrays(cls, names, types, resnames, resids, masses, charges, bonds, positions, forces, dimensions):
         u = cls()
-        if forces is None:
-            raise ValueError("the trajectory holds no forces; the covariance path needs them")
         u._set_topology(names, types, resnames, resids, masses, charges, bonds)
         u._source = _ArraySource(positions, forces, dimensions)
         return u
@@ -152,6 +180,21 @@ class Universe:
     def dimensions(self):
         return self._source.dimensions[self._frame]
 
+    @property
+    def has_forces(self):
+        return bool(getattr(self._source, "has_forces", True))
+
     # fast path used by waterentropy_b200.frames: a batch of frames straight into (pinned) buffers
     def frame_arrays(self, indices, out_pos=None, out_frc=None):
         return self._source.read(indices, out_pos, out_frc)
+
+    def pin(self):
+        """In-memory trajectories: page-lock the frames once; the recipes then submit them in place
+        (no staging copy, zero-copy force reads)."""
+        if hasattr(self._source, "pin"):
+            self._source.pin()
+        return self
+
+    def frame_views(self, indices, forces=True):
+        fn = getattr(self._source, "views", None)
+        return fn(indices, forces) if fn else None

@@ -29,18 +29,25 @@ def _device():
     return 0
 
 
-def _run(system, indices, recipe, keep_debug=False, keep_records=True, keep_shells=False):
+def _run(system, indices, recipe, keep_debug=False, keep_records=True, keep_shells=False, shells_only=False):
     if recipe == "interfacial" and len(SystemTopology.from_universe(system).solute_ua) == 0:
         # upstream ends in MDAnalysis' SelectionError here: `select_atoms("resid ")` with an empty
         # residue list (utils/selections.py:19-20); use the bulk recipe for solute-free systems
         raise ValueError("no solute molecules in the system: the interfacial recipe needs a solute "
                          "(use get_bulk_water_orient_entropy for pure water)")
+    if not shells_only and getattr(system, "has_forces", True) is False:
+        raise ValueError("the trajectory holds no forces; the covariance path needs them")
     eng = WaterEntropyEngine(system, recipe, device=_device(), keep_records=keep_records,
-                             keep_debug=keep_debug, keep_shells=keep_shells)
-    batch = max(1, min(64, 400_000 // max(1, len(eng.top.heavy_idx))))
-    for P, F, D, ids in iter_batches(system, indices, batch):
-        eng.submit(P, F, D, ids)
-    eng.sync()
+                             keep_debug=keep_debug, keep_shells=keep_shells, shells_only=shells_only)
+    # whole kernel batches from a recycled ring of pinned buffers: reading batch k + 1 overlaps the
+    # kernels of batch k, host memory stays O(ring)
+    try:
+        for P, F, D, ids in iter_batches(system, indices, eng.batch_frames, engine=eng, forces=not shells_only):
+            eng.submit(P, F, D, ids)
+        eng.sync()
+    except Exception:
+        eng.close()
+        raise
     return eng
 
 
@@ -84,7 +91,9 @@ def get_interfacial_shells(system, start: int, end: int, step: int):
     """Reference: `recipes/interfacial_solvent.py:104-146` -- RAD shells of the interfacial
     waters that have a non-like neighbour: `{frame: {water_idx: [shell idx ...]}}`."""
     indices = list(range(start, end, step))
-    eng = _run(system, indices, "interfacial", keep_shells=True)
+    # upstream stops at the interfacial waters' own shells here (no HBs, labels or neighbours' shells,
+    # no forces), so failures that only those later steps can raise must not surface: shells_only
+    eng = _run(system, indices, "interfacial", keep_shells=True, shells_only=True)
     out = nested_dict()
     for k, frame in enumerate(eng.frame_ids):
         for atom, shell in eng.frame_shells(k).items():
