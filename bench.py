@@ -113,88 +113,207 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arm
-_W = {}
-
-
-def _cpu_init(cfg_name, scale, seed):
+def _oracle(threads):
+    """The CPU restatement (oracle/), OpenMP over the centres of a frame with `threads` threads."""
+    os.environ["OMP_NUM_THREADS"] = str(max(1, int(threads)))  # read when libgomp starts: before the first call
     sys.path.insert(0, os.path.join(REPO, "oracle"))
     import we_oracle as wo
 
-    s = synthetic.make_config(cfg_name, scale=scale)
-    _W["wo"] = wo
-    _W["sys"] = s
-    _W["top"] = wo.OracleTopology(s.masses, s.charges, s.resids, s.resnames, s.types, s.bonds)
-    _W["seed"] = seed
+    return wo
 
 
-def _cpu_task(args):
-    """Full per-centre cost of the reference algorithm for a random sample of heavy-atom centres
-    of one frame: brute-force neighbour list + stable sort + RAD shell + HB acceptors."""
-    frame, m = args
-    wo, s, top = _W["wo"], _W["sys"], _W["top"]
-    P, F, D = s.frame(frame)
-    rng = np.random.default_rng([_W["seed"], frame])
-    H = len(top.heavy_idx)
-    m = min(m, H)
-    centres = np.sort(rng.choice(top.heavy_idx, size=m, replace=False))
-    t0 = time.perf_counter()
-    r = wo.rad_frame(top, P, D, centres=centres)
-    dx, dh, rows = [], [], []
-    for k, a in enumerate(centres):
-        for h in top.donors[int(a)]:
-            dx.append(int(a))
-            dh.append(h)
-            rows.append(k)
-    if dx:
-        wo.hb_frame(top, P, D, dx, dh, r["shell_n"][rows], r["shell_idx"][rows])
-    waters = [int(a) for a in centres if top.is_water[a]][: max(1, m // 4)]
-    wo.forces_torques(top, P, F, waters)
-    return time.perf_counter() - t0, m, H
+class CpuArm:
+    """The reference's per-frame work on the host cores, with the C + NumPy port of its algorithm.
+
+    What is timed is what `_entropy_per_step` (recipes/interfacial_solvent.py:273-345) evaluates for a frame -
+    not every heavy atom: the reference memoises shells lazily, so only the solute united atoms, the
+    interfacial waters they gate in, those waters' shell members and the donors of both are ever searched
+    (`LazyFrameState`); for the bulk recipe every water is a centre (recipes/bulk_water.py:37-72).  Synthetic
+    frame generation stays outside the clock.  A step is ONE frame, complete, on all cores (the per-centre
+    work is independent, like the reference's frames); if complete frames would not fit the time budget the
+    timed steps evaluate a random sample of the centres of the measured closure and scale by its size."""
+
+    def __init__(self, cfg_name, scale, threads):
+        self.wo = _oracle(threads)
+        self.threads = threads
+        self.sys = synthetic.make_config(cfg_name, scale=scale)
+        s = self.sys
+        self.top = self.wo.OracleTopology(s.masses, s.charges, s.resids, s.resnames, s.types, s.bonds)
+        self.bulk = len(s.solute_atoms) == 0
+        self.H = len(self.top.heavy_idx)
+        self.closure = None  # heavy-atom centres the reference evaluates per frame (measured)
+
+    def full_frame(self, k):
+        """(seconds, centres evaluated, recorded waters) of one complete frame."""
+        wo, top = self.wo, self.top
+        P, F, D = self.sys.frame(k)                      # untimed
+        t0 = time.perf_counter()
+        if self.bulk:
+            det = wo.bulk_frame(top, P, F, D, wo.CovMeans(), wo.LabelCounts())
+            n_c = self.H
+        else:
+            det = wo.interfacial_frame(top, P, F, D, k, lazy=True)[4]
+            n_c = det["n_rad_centres"]
+        dt = time.perf_counter() - t0
+        self.closure = n_c
+        self._closure_frame = k
+        return dt, n_c, len(det["recorded"])
+
+    def sampled_frame(self, k, m, seed=7):
+        """Seconds one frame would take, from `m` random centres of the closure (full per-centre cost:
+        brute-force neighbour list + sort + RAD, the HBs of their donors, force/torque of the waters among
+        them at the recorded fraction), scaled by closure / m."""
+        wo, top = self.wo, self.top
+        P, F, D = self.sys.frame(k)                      # untimed
+        rng = np.random.default_rng([seed, k])
+        m = min(m, self.H)
+        centres = np.sort(rng.choice(top.heavy_idx, size=m, replace=False))
+        t0 = time.perf_counter()
+        r = wo.rad_frame(top, P, D, centres=centres)
+        dx, dh, rows = [], [], []
+        for i, a in enumerate(centres):
+            for h in top.donors[int(a)]:
+                dx.append(int(a)); dh.append(h); rows.append(i)
+        if dx:
+            wo.hb_frame(top, P, D, dx, dh, r["shell_n"][rows], r["shell_idx"][rows])
+        waters = [int(a) for a in centres if top.is_water[a]][: max(1, m // 8)]
+        wo.forces_torques(top, P, F, waters)
+        dt = time.perf_counter() - t0
+        return dt * self.closure / m
 
 
-def cpu_rate(cfg_name, scale, cores, sample_centres, steps, warmup, seed=7):
-    """water.frames/s of the oracle port with `cores` frame-parallel processes."""
-    import multiprocessing as mp
-
-    s = synthetic.make_config(cfg_name, scale=scale)
-    W = s.n_waters
-    ctx = mp.get_context("fork")
+def cpu_rate(cfg_name, scale, threads, steps, warmup, budget_s, sample_centres=2048):
+    """water.frames/s of the oracle port: `steps` timed frames after `warmup` (>= 1: the first frame is always
+    complete and measures the closure).  Returns (rate, seconds per frame, description dict)."""
+    arm = CpuArm(cfg_name, scale, threads)
+    W = arm.sys.n_waters
+    t_first, closure, recorded = arm.full_frame(0)
+    total = max(1, warmup) + steps
+    complete = t_first * (total - 1) <= budget_s
     times = []
-    with ctx.Pool(cores, initializer=_cpu_init, initargs=(cfg_name, scale, seed)) as pool:
-        for it in range(warmup + steps):
-            t0 = time.perf_counter()
-            res = pool.map(_cpu_task, [(it * cores + c, sample_centres) for c in range(cores)])
-            wall = time.perf_counter() - t0
-            if it >= warmup:
-                times.append((wall, res))
-    # every process handled m of H centres of one frame -> fraction m/H of a frame each
-    tot_wall = sum(w for w, _ in times)
-    frames_equiv = sum(sum(m / H for _, m, H in res) for _, res in times)
-    rate = W * frames_equiv / tot_wall
-    m, H = times[0][1][0][1], times[0][1][0][2]
-    return rate, tot_wall / len(times), W, f"{m} of {H} heavy-atom centres of 1 frame per core per step, " \
-        f"full per-centre cost (brute-force neighbours + sort + RAD + HB + F/T), extrapolated linearly in centres"
+    for k in range(1, total):
+        if complete:
+            dt = arm.full_frame(k)[0]
+        else:
+            dt = arm.sampled_frame(k, sample_centres)
+        if k >= max(1, warmup):
+            times.append(dt)
+    if not times:
+        times = [t_first]
+    per_frame = statistics.median(times)
+    rate = W / per_frame
+    what = ("every timed step is one complete frame" if complete else
+            f"timed steps: {sample_centres} random centres per frame at full per-centre cost, scaled to the closure "
+            f"measured on a complete frame ({t_first:.1f} s, {W / t_first:.0f} water.frames/s unscaled)")
+    info = {
+        "sample": f"{'bulk' if arm.bulk else 'interfacial'} recipe, 1 frame per step on {threads} threads (OpenMP over centres); "
+                  f"the reference's own per-frame work: {closure} of {arm.H} heavy-atom centres are searched "
+                  f"({'every water' if arm.bulk else 'solute united atoms + interfacial waters + their shell members'}), "
+                  f"{recorded} waters recorded; {what}; synthetic frame generation untimed",
+        "centres_evaluated_per_frame": int(closure), "heavy_atom_centres": int(arm.H),
+        "closure_fraction": closure / arm.H, "complete_frames": bool(complete),
+        "first_complete_frame_s": t_first, "frame_s": [round(t, 3) for t in times],
+        "all_centres_equivalent": rate * closure / arm.H,
+    }
+    return rate, per_frame, info
+
+
+def reference_python_fixture(max_frames=4):
+    """The UNMODIFIED reference (staged by oracle/stage_ref.py into oracle/_ref, running on oracle/mda_shim)
+    through its own public entry point on its own arginine fixture (2,737 atoms, 900 waters): the only
+    workload it finishes in seconds - its cost per centre grows with the atom count."""
+    ref_dir = os.path.join(REPO, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "waterEntropy")):
+        return {"unavailable": "oracle/_ref is not staged (python oracle/stage_ref.py in the build container)"}
+    code = (
+        "import sys, os, time, json\n"
+        f"REPO={REPO!r}\n"
+        "sys.path[:0]=[os.path.join(REPO,'oracle','mda_shim'), os.path.join(REPO,'oracle','_ref'), REPO, os.path.join(REPO,'tests')]\n"
+        "os.environ.setdefault('WE_SHIM_INLINE','1')\n"
+        "import MDAnalysis, golden_io as gio\n"
+        "import waterEntropy.recipes.interfacial_solvent as Inter\n"
+        "inp=gio.load_inputs('arginine')\n"
+        "u=MDAnalysis.Universe.from_arrays(inp['names'],inp['types'],inp['charges'],inp['masses'],inp['resids'],inp['resnames'],inp['bonds'],inp['positions'],inp['forces'],inp['dimensions'])\n"
+        f"n={int(max_frames)}\n"
+        "t0=time.perf_counter(); r=Inter.get_interfacial_water_orient_entropy(u,0,n,1); dt=time.perf_counter()-t0\n"
+        "print(json.dumps({'seconds':dt,'frames':r[4],'recorded':int(sum(r[1].counts.values())),'file':Inter.__file__}))\n")
+    try:
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+        d = json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as exc:  # pragma: no cover
+        return {"unavailable": f"reference run failed: {exc}"}
+    return {"value": 900 * d["frames"] / d["seconds"], "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": f"unmodified reference ({os.path.relpath(d['file'], REPO)}) on oracle/mda_shim, serial "
+                      f"get_interfacial_water_orient_entropy over {d['frames']} frames of its arginine fixture "
+                      f"(2,737 atoms, 900 waters, {d['recorded']} recorded); not comparable across workloads: "
+                      "its per-centre cost grows with the atom count",
+            "seconds": d["seconds"]}
+
+
+def workload_config(args, s=None, recipe=None, input_bytes=None):
+    """`config` of the JSON line: the same keys in both arms so the driver's same-config check holds."""
+    s = s or synthetic.make_config(args.config, scale=args.scale)
+    recipe = recipe or ("interfacial" if len(s.solute_atoms) else "bulk")
+    input_bytes = input_bytes if input_bytes is not None else 24 * s.n_atoms * args.frames_per_step
+    return {"workload": synthetic.CONFIGS[args.config]["label"], "scale": args.scale,
+            "n_atoms": s.n_atoms, "n_waters": s.n_waters, "frames_per_step_per_gpu": args.frames_per_step,
+            "recipe": recipe,
+            "l2": f"inputs {input_bytes / 1e6:.0f} MB per step per GPU "
+                  + ("> 126 MB L2 (no flush needed)" if input_bytes > 126e6 else "<= L2: reduce reliance, see DESIGN.md")}
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = args.cpu_cores or (os.cpu_count() or 1)
-    rate, step_s, W, sample = cpu_rate(args.config, args.scale, cores, args.cpu_sample, args.steps, args.warmup)
+    rate, frame_s, info = cpu_rate(args.config, args.scale, cores, args.steps, args.warmup, args.cpu_budget)
+    sample = info.pop("sample")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": frame_s * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": synthetic.CONFIGS[args.config]["label"], "scale": args.scale},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, **info,
+                         "reference_python": reference_python_fixture()},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference = pure Python on MDAnalysis (not installable offline); timed arm is oracle/ (C + NumPy "
-                "restatement of the same algorithm, pinned against the reference's goldens), one process per core",
+        "note": "reference = pure Python on MDAnalysis (not installable offline); the timed arm is oracle/ (C + NumPy "
+                "restatement of the same algorithm, pinned against the reference's goldens) doing the reference's "
+                "per-frame work on all host cores; cpu_baseline.reference_python is the unmodified reference itself "
+                "on its own fixture",
     }
     print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def time_recipe(s, recipe, hP, hF, D, Fps, W, repeats=3):
+    """Wall clock of the public recipe entry point - `get_interfacial_water_orient_entropy(u, 0, F, 1)` (or the
+    bulk recipe) - on an in-memory Universe holding the step's frames in page-locked memory: engine creation,
+    topology upload, batch staging, kernels, table read-out, rebuilding the reference's Python objects and the
+    entropy post-processing all inside the clock.  One warm-up call, then the median of `repeats`."""
+    from waterentropy_b200.io import Universe
+    from waterentropy_b200.recipes.bulk_water import get_bulk_water_orient_entropy
+    from waterentropy_b200.recipes.interfacial_solvent import get_interfacial_water_orient_entropy
+
+    u = Universe.from_arrays(s.names, s.types, s.resnames, s.resids, s.masses, s.charges, s.bonds,
+                             hP.numpy(), hF.numpy(), D)
+    u._source._keep = (hP, hF)   # the frames are already page-locked: hand them over in place
+    call = (lambda: get_interfacial_water_orient_entropy(u, 0, Fps, 1)) if recipe == "interfacial" else \
+           (lambda: get_bulk_water_orient_entropy(u, 0, Fps, 1))
+    call()
+    runs = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        out = call()
+        runs.append(time.perf_counter() - t0)
+    sec = statistics.median(runs)
+    return {"value": W * Fps / sec, "unit": UNIT, "seconds": sec, "runs_s": [round(t, 4) for t in runs], "frames": Fps,
+            "call": ("get_interfacial_water_orient_entropy(u, 0, %d, 1)" % Fps) if recipe == "interfacial" else
+                    ("get_bulk_water_orient_entropy(u, 0, %d, 1)" % Fps),
+            "counts_bins": len(out[1].counts),
+            "timed": "whole call, wall clock: engine + topology upload, staging in whole kernel batches, kernels, "
+                     "read-out, CovarianceCollection / HBLabelCollection rebuild, Orientations + Vibrations"}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -330,16 +449,19 @@ def run_ours(args, rank, world, local_rank):
     # measurements of the same build differ by up to 2x while the device-timed value does not.  The K-step
     # region is therefore timed `--e2e-repeats` times (default 3), each a complete job (K steps + combine +
     # label read, tables reset in between); the fastest is reported and all are listed in e2e["runs_ms"].
-    e2e_runs = []
+    e2e_runs, combine_runs = [], []
     for _ in range(max(1, args.e2e_repeats)):
         barrier()
         t0 = time.perf_counter()
         nrec = e2e_steps(args.steps)
+        t1 = time.perf_counter()
         entries = e2e_finalize()
+        t2 = time.perf_counter()
         barrier()
         e2e_runs.append(maxr(time.perf_counter() - t0))
+        combine_runs.append(maxr(t2 - t1))
         eng.reset()
-    e2e_s = min(e2e_runs)
+    e2e_s = statistics.median(e2e_runs)
     clk = clocks.stop()
     e2e_val = world * W * Fps * args.steps / e2e_s
     # bytes that cross PCIe per step: positions, boxes and frame ids are copied; the forces either are
@@ -358,13 +480,20 @@ def run_ours(args, rank, world, local_rank):
     final_bytes = int(entries.nbytes)
     eng.close()
 
+    # ---------------- the call a user makes: the recipe itself (N = 1) ----------------
+    e2e_recipe = None
+    if world == 1 and not args.no_recipe:
+        e2e_recipe = time_recipe(s, recipe, hP, hF, D, Fps, W)
+
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = args.cpu_cores or (os.cpu_count() or 1)
         try:
-            rate, _, _, sample = cpu_rate(args.config, args.scale, cores, args.cpu_sample, 2, 1)
-            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            rate, _, info = cpu_rate(args.config, args.scale, cores, 1, 1, 25.0)
+            sample = info.pop("sample")
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, **info,
+                   "reference_python": reference_python_fixture()}
         except Exception as exc:  # pragma: no cover
             cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"failed: {exc}"}
 
@@ -373,24 +502,25 @@ def run_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": synthetic.CONFIGS[args.config]["label"], "scale": args.scale,
-                       "n_atoms": N, "n_waters": W, "frames_per_step_per_gpu": Fps,
-                       "recipe": recipe, "recorded_waters_per_step": int(nrec),
-                       "l2": f"inputs {input_bytes / 1e6:.0f} MB per step per GPU "
-                             + ("> 126 MB L2 (no flush needed)" if input_bytes > 126e6 else "<= L2: reduce reliance, see DESIGN.md")},
+            "config": workload_config(args, s, recipe, input_bytes),
             "clocks": clk,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "host_input_bytes_per_step": int(input_bytes + Fps * 32), "force_path": force_path,
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s / args.steps * 1e3,
                     "runs_ms_per_step": [round(t / args.steps * 1e3, 3) for t in e2e_runs],
+                    "combine_ms": round(statistics.median(combine_runs) * 1e3, 3),
+                    "combine_runs_ms": [round(t * 1e3, 3) for t in combine_runs],
                     "d2h_bytes_at_end_of_job": final_bytes,
                     "timed": "K x (submit from pinned host memory; stream-ordered covariance snapshot + recorded-water "
-                             "lists read on the host, overlapping the next step) + end-of-job combine and label-table read; "
-                             "fastest of runs_ms_per_step (complete jobs)"},
+                             "lists read on the host, overlapping the next step) + end-of-job combine and label-table read "
+                             "(combine_ms: all-reduce + all-gather + device merge + label read, inside the timed region); "
+                             "MEDIAN of runs_ms_per_step (complete jobs)",
+                    "recipe": e2e_recipe},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "diag": {k: diag[k] for k in ("wide_searches", "shrink_retries", "table_entries")},
+            "diag": {**{k: diag[k] for k in ("wide_searches", "shrink_retries", "table_entries", "eig_fallbacks")},
+                     "recorded_waters_per_step": int(nrec)},
         }
         print(json.dumps(line), flush=True)
 
@@ -405,7 +535,9 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="scale waters/residues of the config (tests only)")
     ap.add_argument("--frames-per-step", type=int, default=96)
     ap.add_argument("--chunk", type=int, default=0)
-    ap.add_argument("--cpu-sample", type=int, default=512, help="centres per core per step of the CPU arm")
+    ap.add_argument("--cpu-sample", type=int, default=2048, help="CPU arm: centres per sampled step (only when complete frames exceed --cpu-budget)")
+    ap.add_argument("--cpu-budget", type=float, default=240.0, help="--impl reference: seconds the timed steps may take")
+    ap.add_argument("--no-recipe", action="store_true", help="skip the e2e.recipe measurement")
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-repeats", type=int, default=3, help="timed repetitions of the K-step e2e job; the fastest is reported")

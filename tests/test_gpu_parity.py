@@ -817,7 +817,7 @@ def test_find_interfacial_solvent_reference_indices():
                              inp["charges"], inp["bonds"], inp["positions"], inp["forces"], inp["dimensions"])
     u.trajectory[0]
     top = SystemTopology.from_universe(u)
-    solutes = [int(a) for a in range(top.n_atoms) if not top.is_water[a]]
+    solutes = [int(a) for a in range(top.n_atoms) if int(inp["resids"][a]) in (1, 2, 3)]   # test_RAD.py:14-17
     got = find_interfacial_solvent(solutes, u)
     assert sorted(got) == sorted([1024, 1282, 2056, 265, 2314, 1165, 274, 2077, 1057, 931, 55, 1855, 2497, 1474,
                                   2245, 205, 2260, 85, 2005, 1753, 862, 1246, 481, 121, 1507, 1639, 235, 2413,
@@ -827,7 +827,8 @@ def test_find_interfacial_solvent_reference_indices():
     u.trajectory[2]
     top_o = gio.oracle_topology(inp)
     fs = wo.FrameState(top_o, inp["positions"][2], inp["dimensions"][2])
-    assert sorted(find_interfacial_solvent(solutes, u)) == sorted(wo.find_interfacial_solvent(top_o, fs))
+    everything = [int(a) for a in range(top.n_atoms) if not top.is_water[a]]
+    assert sorted(find_interfacial_solvent(everything, u)) == sorted(wo.find_interfacial_solvent(top_o, fs))
 
 
 def test_waterShells_cli_prints_reference_lines(monkeypatch, capsys):

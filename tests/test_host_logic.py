@@ -309,13 +309,17 @@ def test_bench_reference_arm_prints_the_contract_line():
     import sys
 
     out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "1", "--config", "C2", "--cpu-sample", "8", "--cpu-cores", "2"],
+                          "--warmup", "1", "--config", "C2", "--scale", "0.05", "--cpu-cores", "2"],
                          capture_output=True, text=True, timeout=300, cwd=REPO)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "water.frames/s" and line["higher_is_better"] is True
     assert line["value"] > 0 and line["n_gpus"] == 1 and line["steps"] == 1 and line["warmup"] == 1
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 2
+    assert line["cpu_baseline"]["complete_frames"] is True and line["cpu_baseline"]["centres_evaluated_per_frame"] > 0
+    assert set(line["config"]) >= {"workload", "n_atoms", "n_waters", "frames_per_step_per_gpu", "recipe"}
+    ref = line["cpu_baseline"]["reference_python"]
+    assert ref.get("kind") == "reference" or "unavailable" in ref
     assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
 

@@ -78,7 +78,10 @@ struct we_ctx {
   cudaEvent_t ev_snap[4]{};
   cudaEvent_t ev_cov = nullptr;
   long long snap_counter = 0;
-  unsigned long long seen_entries = 0, max_new = 0;
+  // label-table sizing: a key is inserted per recorded water at most, so the recorded waters per frame seen
+  // so far bound the growth of a batch; until a first batch has been drained only n_centres per frame does
+  long long max_rec_frame = -1;           // most recorded waters in one drained frame (-1: none drained yet)
+  unsigned long long frames_drained = 0;  // frames whose batch has certainly finished (their keys are in h_diag)
   WeDiag* d_diag = nullptr;
   // workspace
   bool ws_ready = false;
@@ -443,8 +446,8 @@ extern "C" int we_reset(we_ctx* c) {
   c->inflight.clear();
   c->frames_retired = 0;
   for (int i = 0; i < WE_NBUF; ++i) { c->out_pending[i] = false; c->lazy_pending[i] = false; }
-  c->seen_entries = 0;
-  c->max_new = 0;
+  c->max_rec_frame = -1;
+  c->frames_drained = 0;
   if (c->h_diag) memset(c->h_diag, 0, sizeof(WeDiag));
   return WE_OK;
 }
@@ -584,9 +587,11 @@ static int drain(we_ctx* c, int buf) {
   if (!c->out_pending[buf]) return 0;
   CK(cudaEventSynchronize(c->ev_out_ready[buf]));
   const int n = c->pending_n[buf];
+  c->frames_drained += (unsigned long long)n;
   for (int f = 0; f < n; ++f) {
     const int cnt = c->h_rec_count[buf][f];
     c->recorded += (unsigned long long)cnt;
+    c->max_rec_frame = std::max(c->max_rec_frame, (long long)cnt);
     if ((c->opt.keep_records || c->opt.keep_shells)) {
       // ascending atom index (recipes/interfacial_solvent.py:66,303): sort (atom, position) packed in
       // 64-bit keys - this runs on the submitting thread, between two batch submissions
@@ -626,14 +631,22 @@ __global__ void k_rehash(const WeLabelEntry* __restrict__ old_t, unsigned int ol
   for (int k = 0; k < 32; ++k) dst[k] = src[k];
 }
 
-// Keep the open-addressing table below ~50 % load: called between batches with the entry count
-// mirrored after the previous batch plus the largest per-batch growth seen so far (x4 margin).
+// Keep the open-addressing table below ~50 % load.  The table cannot grow while a batch runs, so before a
+// batch of `n` frames is queued it must hold every key that batch - and the batches still in flight, whose
+// keys the pinned mirror h_diag does not show yet - can add.  A batch adds at most one key per recorded
+// water: 2 x (most recorded waters seen in one frame) per frame once a batch has been drained, n_centres per
+// frame before that (submit_impl keeps the very first batch short for this reason).
 static int grow_table_to(we_ctx* c, unsigned long long need);
-static int maybe_grow_table(we_ctx* c) {
+static unsigned long long keys_per_frame_bound(const we_ctx* c) {
+  // bulk recipe: a key is (water resname, shell size) - a few dozen in total, whatever the system
+  if (c->recipe == WE_RECIPE_BULK) return 64;
+  if (c->max_rec_frame < 0) return (unsigned long long)std::max(1, c->C);
+  return std::min<unsigned long long>((unsigned long long)std::max(1, c->C), 2ULL * (unsigned long long)c->max_rec_frame + 64);
+}
+static int maybe_grow_table(we_ctx* c, int n) {
   const unsigned long long entries = c->h_diag->table_entries;
-  if (entries > c->seen_entries) c->max_new = std::max(c->max_new, entries - c->seen_entries);
-  c->seen_entries = entries;
-  return grow_table_to(c, entries + 4 * c->max_new + 1024);
+  const unsigned long long open_frames = c->frames_done - c->frames_drained + (unsigned long long)n;
+  return grow_table_to(c, entries + keys_per_frame_bound(c) * open_frames + 1024);
 }
 static int grow_table_to(we_ctx* c, unsigned long long need) {
   unsigned long long cap = (unsigned long long)c->table_mask + 1;
@@ -798,8 +811,24 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     step = std::min(c->chunk, std::max((n_frames + 2) / 3, floor_frames));
     if (step >= 8) step &= ~7;
   }
-  for (int f0 = 0; f0 < n_frames; f0 += step) {
-    const int n = std::min(step, n_frames - f0);
+  for (int f0 = 0, n = 0; f0 < n_frames; f0 += n) {
+    n = std::min(step, n_frames - f0);
+    if (c->max_rec_frame < 0 && c->C > 0 && c->recipe == WE_RECIPE_INTERFACIAL && !c->opt.shells_only) {
+      // No batch has been drained yet: only n_centres bounds the keys a frame can add.  The first batch is
+      // as many frames as the table takes on that bound (at least one); it is waited for, and from its
+      // recorded-water counts on the real bound applies.  One short batch + one wait per analysis.
+      if (c->frames_done > c->frames_drained) {
+        for (int i = 0; i < WE_NBUF; ++i) {
+          const int b = (int)((c->chunk_counter + i) % WE_NBUF);
+          if ((rc = finish_lazy(c, b))) return rc;
+          if ((rc = drain(c, b))) return rc;
+        }
+      }
+      if (c->max_rec_frame < 0) {
+        const unsigned long long cap = (unsigned long long)c->table_mask + 1;
+        n = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((unsigned long long)n, (cap / 2) / (unsigned long long)c->C));
+      }
+    }
     const int buf = (int)(c->chunk_counter % WE_NBUF);
     c->chunk_counter++;
     // staging buffers of this slot were last used WE_NBUF chunks ago
@@ -810,7 +839,15 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       c->frames_retired = c->inflight.front().frames_end;
       c->inflight.pop_front();
     }
-    if ((rc = maybe_grow_table(c))) return rc;
+    // batches that have finished meanwhile: move their lists to the host now (keeps the bound below tight)
+    for (int i = 1; i < WE_NBUF; ++i) {
+      const int b = (buf + i) % WE_NBUF;
+      if (c->lazy_pending[b]) break;
+      if (!c->out_pending[b]) continue;
+      if (cudaEventQuery(c->ev_out_ready[b]) != cudaSuccess) { cudaGetLastError(); break; }
+      if ((rc = drain(c, b))) return rc;
+    }
+    if ((rc = maybe_grow_table(c, n))) return rc;
     for (int f = 0; f < n; ++f) {
       if (make_box(dims + (size_t)(f0 + f) * 6, c->cell_target, c->ncap, &c->h_boxes[buf][f]))
         return fail(WE_ERR_INVALID, "frame %lld: box dimensions must be positive and finite", (long long)frame_ids[f0 + f]);
