@@ -49,3 +49,20 @@ def plain(d):
 
 
 TAGS = ["arginine", "aspirin", "synth_ortho", "synth_tric", "synth_sparse"]
+
+
+def write_gro(path, names, resnames, resids, positions, dimensions, title="written by tests/golden_io.py"):
+    """GRO text (nm, %8.3f) of one or more frames: positions [F, N, 3] in Angstrom, dimensions [F, 6]."""
+    import numpy as np
+
+    positions = np.asarray(positions)
+    if positions.ndim == 2:
+        positions, dimensions = positions[None], np.asarray(dimensions)[None]
+    with open(path, "w") as fh:
+        for P, D in zip(positions, dimensions):
+            fh.write(f"{title}\n{len(names):5d}\n")
+            nm = np.asarray(P, dtype=np.float64) / 10.0
+            for k in range(len(names)):
+                fh.write(f"{int(resids[k]) % 100000:5d}{str(resnames[k]):<5s}{str(names[k]):>5s}{(k + 1) % 100000:5d}"
+                         f"{nm[k, 0]:8.3f}{nm[k, 1]:8.3f}{nm[k, 2]:8.3f}\n")
+            fh.write(f"{D[0] / 10:10.5f}{D[1] / 10:10.5f}{D[2] / 10:10.5f}\n")

@@ -1043,3 +1043,34 @@ def test_full_size_production_path_vs_oracle_closure(name, n_sampled):
           f"{n_rec} recorded waters, {len(eb)} label keys")
     for e in (big, small):
         e.close()
+
+
+def test_c1_lysozyme_waterShells_vs_oracle(tmp_path, capsys):
+    """BASELINE.json config C1: the reference's example input (lysozyme, 10,659 waters, one GRO frame without
+    forces) through the `waterShells` command - GRO reader, template topology, shells-only CUDA path - against
+    the oracle on the same arrays: every solute united atom gates, every interfacial water's shell."""
+    from waterentropy_b200.cli import run_find_Nc as cli
+    from waterentropy_b200.io import Universe
+
+    d = np.load(gio.GOLD + "/c1_lysozyme_inputs.npz")
+    path = str(tmp_path / "system.gro")
+    gio.write_gro(path, d["names"], d["resnames"], d["resids"], d["positions"], d["dimensions"])
+    cli.main(["-top", path, "-crd", path])
+    out = capsys.readouterr().out.splitlines()
+    u = Universe(path, path)
+    top = wo.OracleTopology(u.atoms.masses, u.atoms.charges, u.atoms.resids, list(u.atoms.resnames),
+                            list(u.atoms.types), u.bonds.indices)
+    P, D = u.atoms.positions, u.dimensions
+    fs = wo.LazyFrameState(top, P, D)
+    fs.prefetch_interfacial()
+    want = {}
+    for a in wo.find_interfacial_solvent(top, fs):
+        sh = fs.shell(a)
+        if wo._nearest_nonlike(top, a, sh) is not None:
+            want[a] = sh
+    lines = [ln for ln in out if ln.startswith("0 ") and "[" in ln]
+    assert len(lines) == len(want) > 500
+    for a, sh in want.items():
+        assert f"0 {a} {sh} {len(sh)}" in out
+    print(f"\nC1: {len(want)} interfacial waters with a non-like shell member of {len(top.water_centres)}; "
+          f"oracle evaluated {fs.n_evaluated} of {len(top.heavy_idx)} heavy-atom centres")

@@ -452,3 +452,112 @@ def test_console_scripts_are_declared_like_upstream():
     assert (a.file_topology, a.file_coords, a.start, a.end, a.step) == ("t.prmtop", "x.nc", 1, 9, 2)
     b = runWaterEntropy.build_parser().parse_args(["-top", "t", "-crd", "x", "-temp", "300", "-p"])
     assert b.temperature == 300 and b.parallel
+
+
+# ------------------------------------------------- S_orient straight from device label entries
+def _entries_from_golden(top, d, bulk, rng):
+    """Device-format label entries (engine.ENTRY_DTYPE) encoding a golden `resid_labelled_shell_counts`
+    dict: labels -> sorted codes, per-label counts at the first occurrence of the label."""
+    from waterentropy_b200.engine import ENTRY_DTYPE
+    from waterentropy_b200.system import PREFIX
+
+    names = {n: i for i, n in enumerate(top.resname_table)}
+
+    def code(label):
+        for p in (0, 2, 3, 4):
+            if label.startswith(PREFIX[p]):
+                return (p << 13) | names[label[len(PREFIX[p]):]]
+        return (1 << 13) | names[label]
+
+    rows = []
+    for resid, a in d["resid_labelled_shell_counts"].items():
+        for resname, b in a.items():
+            for key, e in b.items():
+                codes = sorted(code(x) for x in key)
+                r = np.zeros((), dtype=ENTRY_DTYPE)
+                r["hash"], r["hash2"] = rng.integers(1, 2**62, 2)
+                r["first_seen_inv"] = np.uint64(2**63) - np.uint64(len(rows))   # insertion order of the golden dict
+                r["shell_count"], r["n_w"], r["n_labels"] = e["shell_count"], e["N_w"], len(codes)
+                r["nearest_resid"] = -1 if bulk else int(resid)
+                r["nearest_resname_id"] = names[resname]
+                r["labels"][:] = 0xFFFF
+                r["labels"][: len(codes)] = codes
+                for field, dst in (("donates_to", "donates"), ("accepts_from", "accepts")):
+                    for lab, c in e.get(field, {}).items():
+                        r[dst][codes.index(code(lab))] += c
+                rows.append(r)
+    out = np.array(rows, dtype=ENTRY_DTYPE) if rows else np.zeros(0, dtype=ENTRY_DTYPE)
+    return out[rng.permutation(len(out))]     # the device table has no order
+
+
+@pytest.mark.parametrize("tag", gio.TAGS)
+def test_sorient_from_entries_is_bit_identical_to_the_classes(tag):
+    """`Orientations.add_entries` (array operations on the device label entries, what the recipes use) ==
+    `Orientations.add_data(decode_label_entries(...))` (the reference's dictionaries), value for value."""
+    from waterentropy_b200.engine import decode_label_entries
+    from waterentropy_b200.system import RECIPE_BULK, RECIPE_INTERFACIAL
+
+    inp = gio.load_inputs(tag)
+    ref = gio.load_reference(tag)
+    top = SystemTopology(inp["masses"], inp["charges"], inp["resids"], list(inp["resnames"]), list(inp["types"]), inp["bonds"])
+    rng = np.random.default_rng(5)
+    cases = [(False, next(iter(ref["api"].values()))["labels"])] if "labels" in next(iter(ref["api"].values())) else []
+    cases += [(False, step["labels"]) for step in list(ref["per_step"].values())[:3]]
+    cases += [(True, b["labels"]) for b in list(ref["bulk"].values())[:1] if "labels" in b]
+    assert cases
+    for bulk, d in cases:
+        entries = _entries_from_golden(top, d, bulk, rng)
+        a = Orientations()
+        a.add_data(decode_label_entries(top, RECIPE_BULK if bulk else RECIPE_INTERFACIAL, entries))
+        b = Orientations()
+        b.add_entries(top, bulk, entries)
+        assert gio.plain(a.resid_labelled_Sorient) == gio.plain(b.resid_labelled_Sorient)
+        assert gio.plain(a.resname_labelled_Sorient) == gio.plain(b.resname_labelled_Sorient)
+        # merged duplicates (same key split over two entries, as two ranks would hold it) fold identically
+        if len(entries) > 3:
+            dup = entries[:3].copy()
+            dup["first_seen_inv"] -= np.uint64(1000)
+            both = np.concatenate([entries, dup])
+            a2, b2 = Orientations(), Orientations()
+            a2.add_data(decode_label_entries(top, RECIPE_BULK if bulk else RECIPE_INTERFACIAL, both))
+            b2.add_entries(top, bulk, both)
+            assert gio.plain(a2.resid_labelled_Sorient) == gio.plain(b2.resid_labelled_Sorient)
+            assert gio.plain(a2.resname_labelled_Sorient) == gio.plain(b2.resname_labelled_Sorient)
+
+
+# ------------------------------------------------------------ config C1: GRO reader + template topology
+def test_gro_reader_and_template_topology(tmp_path):
+    """BASELINE.json config C1 (example_inputs/lysozyme_solution/system.gro; committed as arrays by
+    tools/make_c1_fixture.py): the GRO reader reproduces the arrays, and the template topology gives the
+    molecule structure the shells path needs - one 1,960-atom protein, 8 chloride ions, 10,659 waters."""
+    from waterentropy_b200.io import Universe
+
+    d = np.load(os.path.join(REPO, "tests", "golden", "c1_lysozyme_inputs.npz"))
+    path = str(tmp_path / "system.gro")
+    gio.write_gro(path, d["names"], d["resnames"], d["resids"], d["positions"], d["dimensions"])
+    u = Universe(path, path)
+    assert u.n_atoms == 33945 and len(u.trajectory) == 1 and not u.has_forces and not u.has_charges
+    assert np.array_equal(u.atoms.positions, d["positions"][0])          # %8.3f nm round trip is exact
+    assert np.allclose(u.dimensions, [70.1008, 70.1008, 70.1008, 90, 90, 90])
+    assert list(u.atoms.names[:3]) == ["N", "H1", "H2"] and u.atoms.resnames[-1] == "CL" and int(u.atoms.resids[-1]) == 10796
+    top = SystemTopology.from_universe(u)
+    assert len(top.centres) == 10659 and len(top.heavy_idx) == 11668
+    assert len(top.solute_resids) == 137 and len(top.solute_ua) == 1009  # 129 residues + 8 CL; 1,001 + 8 heavy atoms
+    nonw = np.nonzero(top.is_water == 0)[0]
+    sizes = np.bincount(np.bincount(top.fragment_id[nonw]))
+    assert sizes[1960] == 1 and sizes[1] == 8                              # the whole protein is one molecule
+    deg = np.bincount(top.bonds.reshape(-1), minlength=top.n_atoms)
+    light = top.masses < 1.1
+    assert (deg[nonw][light[nonw]] == 1).all() and deg[nonw][~light[nonw]].max() <= 4
+    assert (deg[top.centres] == 2).all()                                   # water O - H1, O - H2
+    # the entropy recipes refuse a topology without charges; the shells path does not need them
+    from waterentropy_b200.recipes.interfacial_solvent import get_interfacial_water_orient_entropy
+
+    with pytest.raises(ValueError, match="forces|charges"):
+        get_interfacial_water_orient_entropy(u, 0, 1, 1)
+    # the real file, when present (build container): identical arrays
+    real = "/root/reference/example_inputs/lysozyme_solution/system.gro"
+    if os.path.exists(real):
+        r = Universe(real, real)
+        assert np.array_equal(r.atoms.positions, u.atoms.positions) and list(r.atoms.names) == list(u.atoms.names)
+        assert np.array_equal(SystemTopology.from_universe(r).bonds, top.bonds)

@@ -101,6 +101,10 @@ struct we_ctx {
   int *d_hbq = nullptr /* mark bytes: HB centres, then pass-2 shells */, *d_wlh = nullptr, *d_nh = nullptr;
   int* d_zero = nullptr;
   size_t zero_ints = 0;
+  // gating pass by cell group (k_gate)
+  unsigned char* d_grp_flag = nullptr;
+  int *d_grp_list = nullptr, *d_grp_count = nullptr, *d_work_counter = nullptr;
+  int gate_blocks = 0, use_gate = 1;
   int hb_blocks = 0, label_blocks = 0;
   int *d_all_slots = nullptr;
   int rad_blocks = 0;
@@ -380,6 +384,11 @@ extern "C" int we_create(const we_topology* t, const we_options* opt, we_ctx** o
   UP(frag_atoms, frag_atoms)
   UP(bin_of_atom, std::vector<int>(t->bin_of_atom, t->bin_of_atom + N))
   UP(centre_class, std::vector<int>(t->centre_class, t->centre_class + N))
+  {
+    std::vector<unsigned char> is_solute(std::max(1, H), 0);
+    for (int hs : solute) is_solute[hs] = 1;
+    UP(is_solute, is_solute)
+  }
 #undef UP
   const int* cos_p = nullptr;
   if ((rc = dev_upload(c, &cos_p, centre_of_slot))) { we_destroy(c); return rc; }
@@ -424,6 +433,7 @@ extern "C" int we_create(const we_topology* t, const we_options* opt, we_ctx** o
   if (const char* g = getenv("WE_COPY_GATE")) c->copy_gate = atoi(g);
   if (const char* g = getenv("WE_COV_STREAM")) c->cov_stream = atoi(g);
   if (const char* g = getenv("WE_GRAPHS")) c->use_graphs = atoi(g);
+  if (const char* g = getenv("WE_GATE")) c->use_gate = atoi(g);
   rc = we_reset(c);
   if (rc) { we_destroy(c); return rc; }
   *out = c;
@@ -545,7 +555,7 @@ static int ensure_workspace(we_ctx* c, const float* dims0, bool need_input_buffe
   {
     // everything that must be zero at the start of a batch lives in one block: one memset per batch
     const size_t n_cells = F * ((size_t)c->ncap + 1), n_fh = F * (size_t)H;
-    c->zero_ints = n_cells + 2 * n_fh + 3 * F + (n_fh + 3) / 4;
+    c->zero_ints = n_cells + 2 * n_fh + 4 * F + 8 + (n_fh + 3) / 4 + (n_cells + 3) / 4;
     AL(d_zero, c->zero_ints)
     int* p = c->d_zero;
     c->d_cell_count = p; p += n_cells;
@@ -554,12 +564,17 @@ static int ensure_workspace(we_ctx* c, const float* dims0, bool need_input_buffe
     c->d_nh = p; p += F;
     c->d_n1 = p; p += F;
     c->d_n2 = p; p += F;
-    c->d_interf = reinterpret_cast<unsigned char*>(p);
+    c->d_grp_count = p; p += F;
+    c->d_work_counter = p; p += 8;
+    c->d_interf = reinterpret_cast<unsigned char*>(p); p += (n_fh + 3) / 4;
+    c->d_grp_flag = reinterpret_cast<unsigned char*>(p);
+    AL(d_grp_list, n_cells)
   }
   if (c->opt.keep_debug) { AL(d_nbr_idx, F * H * WE_MAX_NBR) AL(d_nbr_dist, F * H * WE_MAX_NBR) AL(d_ft, F * std::max(1, c->C) * 6) }
 #undef AL
   CK(cudaFuncSetAttribute(k_rad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WeRadSmem)));
   CK(cudaFuncSetAttribute(k_rad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WeRadSmem)));
+  CK(cudaFuncSetAttribute(k_gate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WeGateSmem)));
   {
     std::vector<int> all(H);
     for (int i = 0; i < H; ++i) all[i] = i;
@@ -573,6 +588,8 @@ static int ensure_workspace(we_ctx* c, const float* dims0, bool need_input_buffe
     c->rad_blocks = std::max(1, per_sm) * std::max(1, sms);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rad<true>, WE_RAD_WARPS * 32, sizeof(WeRadSmem)));
     c->rad_blocks_gated = std::max(1, per_sm) * std::max(1, sms);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gate, WE_RAD_WARPS * 32, sizeof(WeGateSmem)));
+    c->gate_blocks = std::max(1, per_sm) * std::max(1, sms);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hb, 256, 0));
     c->hb_blocks = std::max(1, per_sm) * std::max(1, sms);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_label, 256, 0));
@@ -886,8 +903,17 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     const bool interfacial = (c->recipe == WE_RECIPE_INTERFACIAL);
     const bool shells_only = c->opt.shells_only != 0;
     dim3 gH((H + 255) / 256, n);
+    // gating pass by cell group (k_gate): production interfacial contexts, every frame of the batch with at
+    // least 8 cells per axis (the group window of 6 cells has one definite periodic image), a +-2 cell first
+    // search and, for triclinic boxes, a valid float32 prefilter
+    bool gate = interfacial && c->use_gate && !c->opt.keep_debug && S > 0 && C > 0;
+    for (int f = 0; gate && f < n; ++f) {
+      const WeBox& hb = c->h_boxes[buf][f];
+      for (int i = 0; i < 3; ++i) gate = gate && hb.nc[i] >= 8 && hb.sw[i] <= 2;
+      gate = gate && (!hb.triclinic || hb.pre_ok);
+    }
     const bool graphs_on = !on_device && c->use_graphs && !c->prof && !c->opt.keep_debug;
-    const long long gkey = ((long long)buf * 4096 + n) * 2;
+    const long long gkey = (((long long)buf * 4096 + n) * 2 + (gate ? 1 : 0)) * 2;
     GraphRegion g1(c, st, gkey, graphs_on), g2(c, st, gkey + 1, graphs_on);
     int replay = g1.begin();
     if (replay < 0) return replay;
@@ -895,7 +921,8 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     CK(cudaMemsetAsync(c->d_zero, 0, c->zero_ints * sizeof(int), st));  // cells, state, queues, counters, flags
     CK(cudaMemsetAsync(c->d_rec_count[buf], 0, (size_t)n * sizeof(int), st));
     { ProfScope ps(c, WE_K_BIN, st);
-      k_bin<<<gH, 256, 0, st>>>(c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_rank_of, c->d_tmp4, c->ncap);
+      k_bin<<<gH, 256, 0, st>>>(c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_rank_of, c->d_tmp4, c->ncap,
+                                gate ? c->d_grp_flag : nullptr);
       ps.stop(st); }
     { ProfScope ps(c, WE_K_SCAN, st);
       k_scan<<<n, 1024, 0, st>>>(bx, c->d_cell_count, c->ncap);
@@ -904,6 +931,12 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       k_scatter<<<gH, 256, 0, st>>>(H, bx, c->d_cell_count, c->d_cell_of, c->d_rank_of, c->d_tmp4, c->d_sorted4, c->ncap);
       ps.stop(st); }
     c->launches += 3;
+    if (gate) {
+      ProfScope ps(c, WE_K_LIST1, st);
+      k_grplist<<<dim3((c->ncap + 1 + 255) / 256, n), 256, 0, st>>>(bx, c->d_grp_flag, c->ncap, c->d_grp_list, c->d_grp_count);
+      ps.stop(st);
+      c->launches++;
+    }
     }
     // pass-0 centres: every heavy atom (debug), solute united atoms (interfacial), waters (bulk)
     WeWork w0;
@@ -929,7 +962,11 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
                                    : WeMarks{nullptr, mark_hb, nullptr, nullptr, 1};
     auto rad = [&](int id, const WeWork& wk, long long items, int* gate_state, const WeMarks& mk) {
       ProfScope ps(c, id, st);
-      if (gate_state)
+      if (gate_state && gate)
+        k_gate<<<c->gate_blocks, WE_RAD_WARPS * 32, sizeof(WeGateSmem), st>>>(
+            c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->d_tmp4, c->ncap, c->cell_target,
+            c->d_grp_list, c->d_grp_count, n, ro, gate_state, mk, c->d_diag, c->d_work_counter);
+      else if (gate_state)
         k_rad<true><<<(int)std::max<long long>(1, std::min<long long>((items + WE_RAD_WARPS - 1) / WE_RAD_WARPS, c->rad_blocks_gated)), WE_RAD_WARPS * 32, sizeof(WeRadSmem), st>>>(
             c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->d_tmp4, c->ncap, c->cell_target, wk, n, ro,
             gate_state, mk, c->d_diag);

@@ -76,6 +76,7 @@ struct WeTopoDev {
   const int* frag_atoms;
   const int* bin_of_atom;         // [N] covariance pair-bin of the atom's (resname,resid)
   const int* centre_class;        // [N] class of the centre's resname or -1
+  const unsigned char* is_solute; // [H] heavy slot is a solute united atom (pass-0 centre of the interfacial recipe)
 };
 
 struct WeDiag {
@@ -114,9 +115,11 @@ __device__ __forceinline__ void we_set_error(WeDiag* diag, int code, int frame, 
 // K1: cell list.  Replaces `select_atoms("mass 2 to 999 ...")` + brute-force
 // `capped_distance` (maths/trig.py:59-67, 26-34) as the candidate generator.
 // ============================================================================
+#define WE_GRP 2  // cells per edge of a cell group (k_gate)
 __global__ void k_bin(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes,
                       int* __restrict__ cell_count, int* __restrict__ cell_of,
-                      int* __restrict__ rank_of, float4* __restrict__ tmp4, int ncap) {
+                      int* __restrict__ rank_of, float4* __restrict__ tmp4, int ncap,
+                      unsigned char* __restrict__ grp_flag) {
   int h = blockIdx.x * blockDim.x + threadIdx.x;
   int f = blockIdx.y;
   if (h >= T.n_heavy) return;
@@ -144,6 +147,10 @@ __global__ void k_bin(WeTopoDev T, const float* __restrict__ pos, const WeBox* _
   cell_of[o] = (c2 << 20) | (c1 << 10) | c0;  // packed coordinates (<= 1023 cells per axis)
   rank_of[o] = atomicAdd(&cell_count[(size_t)f * (ncap + 1) + cell], 1);
   tmp4[o] = make_float4(q[0], q[1], q[2], __int_as_float(atom));
+  if (grp_flag && T.is_solute[h]) {  // the WE_GRP^3 cell group of a solute united atom has gating work (k_gate)
+    const int g0 = (b.nc[0] + WE_GRP - 1) / WE_GRP, g1 = (b.nc[1] + WE_GRP - 1) / WE_GRP;
+    grp_flag[(size_t)f * (ncap + 1) + ((size_t)(c2 / WE_GRP) * g1 + c1 / WE_GRP) * g0 + c0 / WE_GRP] = 1;
+  }
 }
 
 // exclusive scan of the per-frame cell counts, in place; [ncell] receives the total.
@@ -510,6 +517,13 @@ struct WeMarks {
   int bulk;
 };
 
+struct WeRadSmem;
+__device__ __forceinline__ void we_rad_finish(const WeTopoDev& T, const float* __restrict__ fpos, const WeBox& b,
+                                              const float4* __restrict__ sorted, int f, int h, int my_atom,
+                                              float rx, float ry, float rz, int n, int status, bool dup,
+                                              const WeRadOut& O, int* gate_only_state, const WeMarks& M,
+                                              WeDiag* diag, WeRadSmem& S, const WePowTables& PT, int lane, int w);
+
 // One centre (heavy slot h of frame f) on one warp.  GATED: the gating pass of the interfacial recipe
 // (gate_only_state != nullptr) - a separate instantiation, so the other passes do not carry its code.
 template <bool GATED>
@@ -611,6 +625,21 @@ __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __re
     if (!wide) { wide = true; if (lane == 0) atomicAdd(&diag->wide_searches, 1ULL); }
     r = fmin(r * 1.3, WE_CUTOFF);
   }
+  we_rad_finish(T, fpos, b, sorted, f, h, my_atom, rx, ry, rz, n, status, dup, O, gate_only_state, M, diag, S, PT, lane, w);
+}
+
+// Second half of a centre: the candidates (d <= r, exact fp64 distances sd, atom indices si, positions in
+// the cell-sorted array ss) are listed in the warp's shared-memory scratch; rank them, run the RAD test,
+// write the outputs and the marks.
+__device__ __forceinline__ void we_rad_finish(const WeTopoDev& T, const float* __restrict__ fpos, const WeBox& b,
+                                              const float4* __restrict__ sorted, int f, int h, int my_atom,
+                                              float rx, float ry, float rz, int n, int status, bool dup,
+                                              const WeRadOut& O, int* gate_only_state, const WeMarks& M,
+                                              WeDiag* diag, WeRadSmem& S, const WePowTables& PT, int lane, int w) {
+  double* sd = S.d[w];
+  float* sf = S.f[w];
+  int* si = S.idx[w];
+  int* ss = S.src[w];
   __syncwarp();
   if (status == WE_ST_OK && n > WE_CAND_CAP) status = WE_ST_OVERFLOW;
   if (status == WE_ST_OK && dup) status = WE_ST_DUPLICATE;
@@ -797,9 +826,20 @@ k_rad(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxe
   if (tid < 32) { S.log2tab[tid] = ((const double*)we_d_log2tab)[tid]; S.exp2tab[tid] = we_d_exp2tab[tid]; }
   __syncthreads();
   const WePowTables PT{S.log2tab, S.exp2tab};
+  // The work lists of the frames of a batch form ONE item space (frame after frame) that the warps of the
+  // grid walk with a common stride: `off` = items of the earlier frames, so the first item of a frame goes
+  // to the warp after the one that took the last item of the frame before.  (Per-frame striding from warp 0
+  // left most of the grid idle whenever a frame's list is shorter than the grid - the interfacial-water
+  // pass has ~1,500 centres per frame for 3,552 warps.)
   const int stride = gridDim.x * WE_RAD_WARPS;
+  const int gw = blockIdx.x * WE_RAD_WARPS + w;
+  int off = 0;
   for (int f = 0; f < n_frames; ++f) {
     const int cnt = work.count ? work.count[f] : work.static_count;
+    int i = gw - off;
+    if (i < 0) i += stride;
+    off = (off + cnt) % stride;
+    if (i >= cnt) continue;
     const int* list = work.list + (size_t)f * work.stride;
     const WeBox& b = boxes[f];
     const int* cstart = cell_start + (size_t)f * (ncap + 1);
@@ -807,8 +847,282 @@ k_rad(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxe
     const float* fpos = pos + (size_t)f * T.n_atoms * 3;
     const int* cof = cell_of + (size_t)f * T.n_heavy;
     const float4* t4 = tmp4 + (size_t)f * T.n_heavy;
-    for (int i = blockIdx.x * WE_RAD_WARPS + w; i < cnt; i += stride)
+    for (; i < cnt; i += stride)
       we_rad_one<GATED>(T, fpos, b, cstart, cof, sorted, t4, search_radius, f, list[i], O, GATED ? gate_only_state : nullptr, M, diag, S, PT, lane, w);
+  }
+}
+
+// ============================================================================
+// K4a, gating pass of the interfacial recipe (recipes/interfacial_solvent.py:47-65) by CELL GROUP.
+//
+// Most solute united atoms are buried: at least 20 other solute atoms are closer than the nearest water, so
+// no water can be among their 20 nearest candidates and neither exact distances nor a ranking nor a RAD shell
+// are ever needed.  Deciding that per atom with the generic warp-per-centre search costs a full candidate
+// scan with dependent global loads (~1,500 warp-instructions).  Here one block takes a group of 2 x 2 x 2
+// cells that holds solute atoms, stages the group's whole candidate window (the group's cells +- 2 cells, every
+// candidate shifted into the group's periodic image, water flag in the sign bit of its index) into shared
+// memory ONCE, and every solute atom of the group is then classified against the staged window: two sweeps
+// of float32 distances from shared memory (nearest water; solute atoms closer than it).  Atoms that are not
+// buried compact their prefilter survivors from the same staged window and continue with the exact fp64
+// distances, the ranking and the RAD test of the generic path (we_exact_list, we_rad_finish).  Anything unusual
+// - window or centre list larger than the staging buffers, fewer than 25 candidates inside the first radius -
+// goes through the generic search (we_rad_one), so the results are those of k_rad<true> in every case.
+// ============================================================================
+#define WE_GATE_STAGE_CAP 640
+#define WE_GATE_CENTRE_CAP 64
+#define WE_GATE_ROWS ((WE_GRP + 4) * (WE_GRP + 4))
+#ifndef WE_GATE_MINBLOCKS
+#define WE_GATE_MINBLOCKS 3
+#endif
+
+__device__ __forceinline__ int we_append_block(bool want, int* counter, int* s_cnt);
+
+__global__ void __launch_bounds__(256)
+k_grplist(const WeBox* __restrict__ boxes, const unsigned char* __restrict__ grp_flag, int ncap,
+          int* __restrict__ grp_list, int* __restrict__ grp_count) {
+  __shared__ int s_cnt[8];
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = blockIdx.y;
+  const WeBox& b = boxes[f];
+  const int ng = ((b.nc[0] + WE_GRP - 1) / WE_GRP) * ((b.nc[1] + WE_GRP - 1) / WE_GRP) * ((b.nc[2] + WE_GRP - 1) / WE_GRP);
+  const bool want = g < ng && grp_flag[(size_t)f * (ncap + 1) + g];
+  const int slot = we_append_block(want, &grp_count[f], s_cnt);
+  if (want) grp_list[(size_t)f * (ncap + 1) + slot] = g;
+}
+
+struct WeGateRow {  // one row (fixed y, z cell) of the group's window: up to two runs contiguous in x
+  int beg0, len0, beg1, len1, off;
+  int gbeg, gend;          // cell-sorted positions of the row's members that lie in the group itself
+  float sx0, sx1, sy, sz;  // periodic image shift of run 0 / run 1 (x) and of the row (y, z)
+  float rx0, rx1, ry, rz;  // orthorhombic boxes: reference point of the run (nearest-image wrap of raw coordinates)
+};
+
+struct WeGateSmem {
+  WeRadSmem R;
+  float4 cand[WE_GATE_STAGE_CAP];
+  WeGateRow rows[WE_GATE_ROWS];
+  int centres[WE_GATE_CENTRE_CAP];
+  int pref[130];
+  int n_cand, n_centres, item;
+};
+
+__global__ void __launch_bounds__(WE_RAD_WARPS * 32, WE_GATE_MINBLOCKS)
+k_gate(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes,
+       const int* __restrict__ cell_start, const int* __restrict__ cell_of,
+       const float4* __restrict__ sorted4, const float4* __restrict__ tmp4, int ncap, float search_radius,
+       const int* __restrict__ grp_list, const int* __restrict__ grp_count, int n_frames, WeRadOut O,
+       int* state, WeMarks M, WeDiag* diag, int* work_counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WeGateSmem& G = *reinterpret_cast<WeGateSmem*>(smem_raw);
+  WeRadSmem& S = G.R;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid < 32) { S.log2tab[tid] = ((const double*)we_d_log2tab)[tid]; S.exp2tab[tid] = we_d_exp2tab[tid]; }
+  if (tid == 0) {
+    int acc = 0;
+    for (int f = 0; f < n_frames; ++f) { G.pref[f] = acc; acc += grp_count[f]; }
+    G.pref[n_frames] = acc;
+  }
+  __syncthreads();
+  const WePowTables PT{S.log2tab, S.exp2tab};
+  const int total = G.pref[n_frames];
+  for (;;) {
+    __syncthreads();  // the previous group's staging buffers are free
+    if (tid == 0) { G.item = atomicAdd(work_counter, 1); G.n_cand = 0; G.n_centres = 0; }
+    __syncthreads();
+    const int item = G.item;
+    if (item >= total) break;
+    int f = 0;
+    while (G.pref[f + 1] <= item) ++f;
+    const int g = grp_list[(size_t)f * (ncap + 1) + item - G.pref[f]];
+    const WeBox& b = boxes[f];
+    const int n0 = b.nc[0], n1 = b.nc[1], n2 = b.nc[2];
+    const int ng0 = (n0 + WE_GRP - 1) / WE_GRP, ng1 = (n1 + WE_GRP - 1) / WE_GRP;
+    const int gx = g % ng0, gy = (g / ng0) % ng1, gz = g / (ng0 * ng1);
+    const int* cstart = cell_start + (size_t)f * (ncap + 1);
+    const float4* sorted = sorted4 + (size_t)f * T.n_heavy;
+    const float* fpos = pos + (size_t)f * T.n_atoms * 3;
+    const size_t fo = (size_t)f * T.n_heavy;
+    constexpr int NW = WE_GRP + 4;  // window cells per axis
+    // ---- rows of the window: cell ranges, image shifts --------------------------------------------
+    if (tid < WE_GATE_ROWS) {
+      const int iy = tid % NW, iz = tid / NW;
+      int zc = gz * WE_GRP - 2 + iz, yc = gy * WE_GRP - 2 + iy;
+      const int kz = zc < 0 ? -1 : (zc >= n2 ? 1 : 0);
+      zc -= kz * n2;
+      const int ky = yc < 0 ? -1 : (yc >= n1 ? 1 : 0);
+      yc -= ky * n1;
+      const int rowbase = (zc * n1 + yc) * n0;
+      const int lo = gx * WE_GRP - 2, hi = gx * WE_GRP + WE_GRP + 1;
+      WeGateRow r;
+      r.beg1 = 0; r.len1 = 0; r.sx1 = 0.f; r.rx1 = 0.f;
+      // image shift of the row (lower-triangular cell: rows a, b, c)
+      r.sy = ky * b.m[4] + kz * b.m[7];
+      r.sz = kz * b.m[8];
+      const float sxr = ky * b.m[3] + kz * b.m[6];
+      r.sx0 = sxr;
+      const float cw0 = b.box[0] / n0;  // orthorhombic only: cell edges for the reference points
+      r.ry = (yc + 0.5f) * (b.box[1] / n1);
+      r.rz = (zc + 0.5f) * (b.box[2] / n2);
+      if (lo < 0) {
+        r.beg0 = cstart[rowbase]; r.len0 = cstart[rowbase + hi + 1] - r.beg0;
+        r.beg1 = cstart[rowbase + lo + n0]; r.len1 = cstart[rowbase + n0] - r.beg1;
+        r.sx1 = sxr - b.m[0];
+        r.rx0 = 0.5f * (hi + 1) * cw0; r.rx1 = (0.5f * (lo + n0 + n0)) * cw0;
+      } else if (hi >= n0) {
+        r.beg0 = cstart[rowbase + lo]; r.len0 = cstart[rowbase + n0] - r.beg0;
+        r.beg1 = cstart[rowbase]; r.len1 = cstart[rowbase + hi - n0 + 1] - r.beg1;
+        r.sx1 = sxr + b.m[0];
+        r.rx0 = 0.5f * (lo + n0) * cw0; r.rx1 = 0.5f * (hi - n0 + 1) * cw0;
+      } else {
+        r.beg0 = cstart[rowbase + lo]; r.len0 = cstart[rowbase + hi + 1] - r.beg0;
+        r.rx0 = 0.5f * (lo + hi + 1) * cw0;
+      }
+      // members of the group itself in this row (window rows 2 .. 2 + WE_GRP - 1, x cells of the group)
+      r.gbeg = 0; r.gend = 0;
+      if (iy >= 2 && iy < 2 + WE_GRP && iz >= 2 && iz < 2 + WE_GRP && ky == 0 && kz == 0) {
+        const int x0 = gx * WE_GRP, x1 = min(x0 + WE_GRP, n0);
+        r.gbeg = cstart[rowbase + x0]; r.gend = cstart[rowbase + x1];
+      }
+      r.off = r.len0 + r.len1;
+      G.rows[tid] = r;
+    }
+    __syncthreads();
+    if (w == 0) {  // exclusive scan of the row lengths (WE_GATE_ROWS <= 64: two per lane)
+      const int a = lane < WE_GATE_ROWS ? G.rows[lane].off : 0;
+      const int c2 = lane + 32 < WE_GATE_ROWS ? G.rows[lane + 32].off : 0;
+      int ia = a, ic = c2;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int ta = __shfl_up_sync(0xffffffffu, ia, o), tc = __shfl_up_sync(0xffffffffu, ic, o);
+        if (lane >= o) { ia += ta; ic += tc; }
+      }
+      const int tot_a = __shfl_sync(0xffffffffu, ia, 31);
+      if (lane < WE_GATE_ROWS) G.rows[lane].off = ia - a;
+      if (lane + 32 < WE_GATE_ROWS) G.rows[lane + 32].off = tot_a + ic - c2;
+      if (lane == 31) G.n_cand = tot_a + ic;
+    }
+    __syncthreads();
+    const int n_cand = G.n_cand;
+    const bool fits = n_cand <= WE_GATE_STAGE_CAP;
+    // ---- stage the window (warp per row) and collect the group's solute atoms --------------------
+    for (int r = w; r < WE_GATE_ROWS; r += WE_RAD_WARPS) {
+      const WeGateRow& R = G.rows[r];
+      const int len = R.len0 + R.len1;
+      for (int e = lane; e < len; e += 32) {
+        const bool second = e >= R.len0;
+        const int qi = second ? R.beg1 + (e - R.len0) : R.beg0 + e;
+        const float4 c = sorted[qi];
+        const int atom = __float_as_int(c.w);
+        float x = c.x, y = c.y, z = c.z;
+        if (!b.triclinic) {  // raw coordinates: nearest image to the run's reference point
+          x = __fmaf_rn(-b.box[0], rintf((x - (second ? R.rx1 : R.rx0)) * b.inv[0]), x);
+          y = __fmaf_rn(-b.box[1], rintf((y - R.ry) * b.inv[1]), y);
+          z = __fmaf_rn(-b.box[2], rintf((z - R.rz) * b.inv[2]), z);
+        }
+        x += second ? R.sx1 : R.sx0; y += R.sy; z += R.sz;
+        if (fits) G.cand[R.off + e] = make_float4(x, y, z, __int_as_float(qi | (T.is_water[atom] ? 0x80000000 : 0)));
+        if (qi >= R.gbeg && qi < R.gend && T.is_solute[T.heavy_slot[atom]]) {
+          const int p = atomicAdd(&G.n_centres, 1);
+          if (p < WE_GATE_CENTRE_CAP) G.centres[p] = fits ? (R.off + e) : qi;
+        }
+      }
+    }
+    __syncthreads();
+    const int n_centres = G.n_centres;
+    const bool fast = fits && n_centres <= WE_GATE_CENTRE_CAP;
+    if (!fast) {
+      // generic search for every solute atom of the group (rare: an unusually dense window)
+      for (int r = 0; r < WE_GATE_ROWS; ++r) {
+        const WeGateRow& R = G.rows[r];
+        for (int q0 = R.gbeg + w; q0 < R.gend; q0 += WE_RAD_WARPS) {
+          const int h = T.heavy_slot[__float_as_int(sorted[q0].w)];
+          if (T.is_solute[h])
+            we_rad_one<true>(T, fpos, b, cstart, cell_of + fo, sorted, tmp4 + fo, search_radius, f, h, O, state, M, diag, S, PT, lane, w);
+        }
+      }
+      continue;
+    }
+    // ---- every solute atom of the group against the staged window --------------------------------
+    const double r_cover = fmin((double)b.rc_eff, WE_CUTOFF);
+    const double r = fmin((double)search_radius, r_cover);
+    const float rf = (float)r + 0.02f, rf2 = rf * rf;
+    for (int ci = w; ci < n_centres; ci += WE_RAD_WARPS) {
+      const int self = G.centres[ci];
+      const float4 me = G.cand[self];
+      const int qme = __float_as_int(me.w) & 0x7fffffff;
+      const float4 me_raw = sorted[qme];
+      const int my_atom = __float_as_int(me_raw.w);
+      const int h = T.heavy_slot[my_atom];
+      const size_t ho = fo + h;
+      const int exl = lane < WE_MAX_EXCL ? T.excl[(size_t)h * WE_MAX_EXCL + lane] : -1;
+      const int n_bonded = __popc(__ballot_sync(0xffffffffu, exl >= 0));
+      // sweep A: nearest water (float32, squared)
+      float wmin = (float)(r * r);
+      for (int i = lane; i < n_cand; i += 32) {
+        const float4 c = G.cand[i];
+        const float ux = c.x - me.x, uy = c.y - me.y, uz = c.z - me.z;
+        const float d2 = __fmaf_rn(ux, ux, __fmaf_rn(uy, uy, uz * uz));
+        if (__float_as_int(c.w) < 0) wmin = fminf(wmin, d2);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) wmin = fminf(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
+      // sweep B: solute atoms closer than the nearest water by 1e-3 relative in d^2 (the float32 image
+      // shift is good to ~1e-4); bonded atoms are not candidates of the reference: they are assumed to be
+      // among the counted ones (conservative when they are not); coincident coordinates go to the exact path
+      const float lim = wmin * (1.0f - 1.0e-3f);
+      int closer = 0;
+      bool zero = false;
+      for (int i0 = 0; i0 < n_cand; i0 += 32) {
+        const int i = i0 + lane;
+        bool near = false;
+        if (i < n_cand && i != self) {
+          const float4 c = G.cand[i];
+          const float ux = c.x - me.x, uy = c.y - me.y, uz = c.z - me.z;
+          const float d2 = __fmaf_rn(ux, ux, __fmaf_rn(uy, uy, uz * uz));
+          zero |= !(d2 > 0.f);
+          near = __float_as_int(c.w) >= 0 && d2 < lim;
+        }
+        closer += __popc(__ballot_sync(0xffffffffu, near));
+      }
+      const bool buried = (closer - n_bonded >= WE_GATE_NBR) && !__any_sync(0xffffffffu, zero);
+      if (buried) {
+        if (lane == 0) { O.shell_n[ho] = 0; O.nn[ho] = -1; O.flags[ho] = 0; state[ho] = 0; }
+        continue;
+      }
+      // sweep C: prefilter survivors -> the warp's candidate list; exact distances; the generic second half
+      int* ss = S.src[w];
+      int nf = 0;
+      for (int i0 = 0; i0 < n_cand; i0 += 32) {
+        const int i = i0 + lane;
+        bool keep = false;
+        int qi = 0;
+        if (i < n_cand) {
+          const float4 c = G.cand[i];
+          const float ux = c.x - me.x, uy = c.y - me.y, uz = c.z - me.z;
+          keep = __fmaf_rn(ux, ux, __fmaf_rn(uy, uy, uz * uz)) <= rf2;
+          qi = __float_as_int(c.w) & 0x7fffffff;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        const int p = nf + __popc(m & ((1u << lane) - 1u));
+        if (keep && p < WE_CAND_CAP) ss[p] = qi;
+        nf += __popc(m);
+      }
+      __syncwarp();
+      int n = -1;
+      bool dup = false;
+      if (nf <= WE_CAND_CAP) {
+        int ex[WE_MAX_EXCL];
+#pragma unroll
+        for (int e = 0; e < WE_MAX_EXCL; ++e) ex[e] = __shfl_sync(0xffffffffu, exl, e);
+        n = we_exact_list(b, sorted, nf, r, me_raw.x, me_raw.y, me_raw.z, my_atom, ex, S.d[w], S.f[w], S.idx[w], ss, lane, dup);
+      }
+      if (n < 0 || (n < WE_MAX_NBR && r < WE_CUTOFF)) {
+        // too many survivors, or fewer than 25 candidates inside the first radius: the adaptive generic search
+        we_rad_one<true>(T, fpos, b, cstart, cell_of + fo, sorted, tmp4 + fo, search_radius, f, h, O, state, M, diag, S, PT, lane, w);
+        continue;
+      }
+      we_rad_finish(T, fpos, b, sorted, f, h, my_atom, fpos[3 * my_atom], fpos[3 * my_atom + 1], fpos[3 * my_atom + 2],
+                    n, WE_ST_OK, dup, O, state, M, diag, S, PT, lane, w);
+    }
   }
 }
 
@@ -842,16 +1156,22 @@ k_hb(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes
   __syncthreads();
   const WePowTables PT{s_log2tab, s_exp2tab};
   const int sub = lane & 7, grp = (lane >> 3) & 1, hw = lane >> 4;
+  // one item space over the frames of the batch (see k_rad); a worker is half a warp
   const int stride = gridDim.x * (blockDim.x >> 5) * 2;
+  const int worker = (blockIdx.x * (blockDim.x >> 5) + w) * 2 + hw;
+  int off = 0;
   for (int f = 0; f < n_frames; ++f) {
     const int cnt = work.count ? work.count[f] : work.static_count;
+    int i = worker - off;
+    if (i < 0) i += stride;
+    off = (off + cnt) % stride;
+    if (!__any_sync(0xffffffffu, i < cnt)) continue;
     const int* list = work.list + (size_t)f * work.stride;
     const WeBox& b = boxes[f];
     const float* fpos = pos + (size_t)f * T.n_atoms * 3;
     const size_t fo = (size_t)f * T.n_heavy;
     const float half[3] = {0.5f * b.box[0], 0.5f * b.box[1], 0.5f * b.box[2]};
-    for (int i0 = (blockIdx.x * (blockDim.x >> 5) + w) * 2; i0 < cnt; i0 += stride) {
-      const int i = i0 + hw;
+    for (; __any_sync(0xffffffffu, i < cnt); i += stride) {
       const bool valid = i < cnt;
       int xs = 0, X = 0, nd = 0, d0 = 0, ns = 0, st = WE_ST_OK;
       if (valid) {
@@ -1273,11 +1593,15 @@ k_label(WeTopoDev T, const int* __restrict__ shell_n, const int* __restrict__ sh
   for (int t = threadIdx.x; t < (int)(sizeof(WeLabelStage) / 4); t += blockDim.x) reinterpret_cast<unsigned int*>(&stage)[t] = 0u;
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int stride = gridDim.x * (blockDim.x >> 5);
+  const int stride = gridDim.x * (blockDim.x >> 5);  // one item space over the frames of the batch (see k_rad)
+  int off = 0;
   for (int f = 0; f < n_frames; ++f) {
     const int cnt = work.count ? work.count[f] : work.static_count;
     const int* list = work.list + (size_t)f * work.stride;
-    for (int i = blockIdx.x * (blockDim.x >> 5) + w; i < cnt; i += stride)
+    int i = blockIdx.x * (blockDim.x >> 5) + w - off;
+    if (i < 0) i += stride;
+    off = (off + cnt) % stride;
+    for (; i < cnt; i += stride)
       we_label_one(T, f, list[i], shell_n, shell_idx, nn_arr, flags, acceptor, interfacial, frame_ids, table,
                    table_mask, rec_count, rec, rec_host, shell_host, &stage, diag, lane, shells_only);
   }

@@ -155,6 +155,12 @@ def merge_labels_nccl(eng, root_only=False):
 
 def combine(eng):
     """(CovarianceCollection, HBLabelCollection, frame_solvent_indices) of the whole job."""
+    cov, entries, fsi = combine_raw(eng)
+    return cov, eng.hb_labels(entries), fsi
+
+
+def combine_raw(eng):
+    """(CovarianceCollection, merged label entries, frame_solvent_indices) of the whole job."""
     import torch.distributed as dist
 
     tables = allreduce_cov(eng)
@@ -173,4 +179,4 @@ def combine(eng):
             for resname, by_resid in by_name.items():
                 for resid, atoms in by_resid.items():
                     fsi[frame][resname][resid] = atoms
-    return eng.covariances(tables), eng.hb_labels(merged), fsi
+    return eng.covariances(tables), merged, fsi

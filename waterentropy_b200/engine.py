@@ -329,12 +329,18 @@ class WaterEntropyEngine:
         out = nested_dict()
         for k, frame in enumerate(self.frame_ids):
             rec = self.frame_records(k)
-            for atom, nearest in rec:
-                if nearest < 0:
-                    continue
-                resname = top.resname_table[top.resname_id[nearest]]
-                resid = int(top.resids[nearest])
-                if resid not in out[frame][resname]:
-                    out[frame][resname][resid] = []
-                out[frame][resname][resid].append(int(atom))
+            rec = rec[rec[:, 1] >= 0]
+            if len(rec) == 0:
+                continue
+            # records are ascending in the water index; a stable sort by (resname, resid) of the nearest
+            # solute atom keeps that order inside every residue's list, as upstream's appends do
+            rn = top.resname_id[rec[:, 1]]
+            rid = top.resids[rec[:, 1]]
+            order = np.lexsort((rid, rn))
+            rn, rid, atoms = rn[order], rid[order], rec[order, 0]
+            cut = np.nonzero((rn[1:] != rn[:-1]) | (rid[1:] != rid[:-1]))[0] + 1
+            starts = np.concatenate([[0], cut])
+            by_frame = out[frame]
+            for s0, chunk in zip(starts, np.split(atoms, cut)):
+                by_frame[top.resname_table[rn[s0]]][int(rid[s0])] = chunk.tolist()
         return out

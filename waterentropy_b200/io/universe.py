@@ -129,6 +129,7 @@ class Universe:
     def __init__(self, topology=None, coordinates=None):
         self._frame = 0
         self._cache = (-1, None, None)
+        self.has_charges = True
         if topology is None:
             return
         ext_t = os.path.splitext(str(topology))[1].lower()
@@ -138,6 +139,20 @@ class Universe:
 
             t = AmberTopology(topology)
             x = NetCDFTrajectory(coordinates)
+        elif ext_t == ".gro":
+            # positions + names only: a template topology (no charges), good for the shells path
+            from .gro import GroFile, GroTopology
+
+            g = GroFile(topology)
+            t = GroTopology(g.names, g.resnames, g.resids, g.positions[0], g.dimensions[0])
+            if ext_c == ".gro":
+                x = g if str(coordinates) == str(topology) else GroFile(coordinates)
+            elif ext_c == ".trr":
+                from .gromacs import TRRTrajectory
+
+                x = TRRTrajectory(coordinates)
+            else:
+                raise NotImplementedError(f"no reader for coordinates {ext_c!r} with a GRO topology")
         elif ext_c == ".trr":
             from .gromacs import open_gromacs
 
@@ -145,10 +160,11 @@ class Universe:
         else:
             raise NotImplementedError(
                 f"no reader for topology {ext_t!r} + coordinates {ext_c!r} "
-                "(supported: AMBER prmtop + NetCDF, prmtop + GROMACS TRR)")
+                "(supported: AMBER prmtop + NetCDF, prmtop + GROMACS TRR, GRO + GRO / TRR for the shells path)")
         if x.n_atoms != t.n_atoms:
             raise ValueError(f"trajectory has {x.n_atoms} atoms, topology {t.n_atoms}")
         self._set_topology(t.names, t.types, t.resnames, t.resids, t.masses, t.charges, t.bonds)
+        self.has_charges = bool(getattr(t, "has_charges", True))
         self._source = x
 
     @classmethod
@@ -173,7 +189,7 @@ class Universe:
     def _current(self):
         if self._cache[0] != self._frame:
             P, F, _ = self._source.read([self._frame])
-            self._cache = (self._frame, P[0], F[0])
+            self._cache = (self._frame, P[0], None if F is None else F[0])
         return self._cache[1], self._cache[2]
 
     @property

@@ -14,10 +14,10 @@ from waterentropy_b200.recipes.interfacial_solvent import _run
 def get_bulk_water_orient_entropy(system, start: int, end: int, step: int, temperature=298):
     """Returns `(Sorient_dict, covariances, vibrations)`."""
     eng = _run(system, list(range(start, end, step)), "bulk", keep_records=False)
-    covariances, hb_labels = eng.covariances(), eng.hb_labels()
+    covariances, entries, top = eng.covariances(), eng.label_entries(), eng.top
     eng.close()
     Sorients = Orientations()
-    Sorients.add_data(hb_labels)
+    Sorients.add_entries(top, True, entries)
     vibrations = Vibrations(temperature)
     vibrations.add_data(covariances, diagonalise=True)
     return Sorients.resid_labelled_Sorient, covariances, vibrations

@@ -37,6 +37,9 @@ def _run(system, indices, recipe, keep_debug=False, keep_records=True, keep_shel
                          "(use get_bulk_water_orient_entropy for pure water)")
     if not shells_only and getattr(system, "has_forces", True) is False:
         raise ValueError("the trajectory holds no forces; the covariance path needs them")
+    if not shells_only and getattr(system, "has_charges", True) is False:
+        raise ValueError("the topology holds no charges (GRO template): hydrogen bonds cannot be assigned; "
+                         "only the shells path (get_interfacial_shells / waterShells) runs on it")
     eng = WaterEntropyEngine(system, recipe, device=_device(), keep_records=keep_records,
                              keep_debug=keep_debug, keep_shells=keep_shells, shells_only=shells_only)
     # whole kernel batches from a recycled ring of pinned buffers: reading batch k + 1 overlaps the
@@ -65,13 +68,16 @@ def get_interfacial_water_orient_entropy(system, start: int, end: int, step: int
     mine = wdist.shard_frames(indices, *world)
     eng = _run(system, mine, "interfacial")
     if world[1] > 1:
-        covariances, hb_labels, frame_solvent_indices = wdist.combine(eng)
+        covariances, entries, frame_solvent_indices = wdist.combine_raw(eng)
     else:
-        covariances, hb_labels, frame_solvent_indices = eng.covariances(), eng.hb_labels(), eng.frame_solvent_indices()
+        covariances, entries, frame_solvent_indices = eng.covariances(), eng.label_entries(), eng.frame_solvent_indices()
+    top = eng.top
     eng.close()
     n_frames = len(indices)
+    # the orientational-entropy table straight from the device label entries: the same numbers, bit for
+    # bit, as Orientations().add_data(HBLabelCollection) without rebuilding tens of thousands of dict keys
     Sorients = Orientations()
-    Sorients.add_data(hb_labels)
+    Sorients.add_entries(top, False, entries)
     vibrations = Vibrations(temperature)
     vibrations.add_data(covariances, diagonalise=True)
     return Sorients.resid_labelled_Sorient, covariances, vibrations, frame_solvent_indices, n_frames
