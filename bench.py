@@ -323,6 +323,18 @@ def run_ours(args, rank, world, local_rank):
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
+    # one slice of the host cores per rank: the submitting thread, the pinned-memory reader and the driver's
+    # helper threads of a rank stay off the other ranks' cores (8 ranks share the box's 32 vCPUs)
+    affinity = None
+    if world > 1 and hasattr(os, "sched_setaffinity"):
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+            os.sched_setaffinity(0, mine)
+            affinity = [mine[0], mine[-1]]
+        except OSError:
+            affinity = None
     s = synthetic.make_config(args.config, scale=args.scale)
     N, W = s.n_atoms, s.n_waters
     recipe = "interfacial" if len(s.solute_atoms) else "bulk"  # solute-free configs (C2): bulk recipe
@@ -462,6 +474,19 @@ def run_ours(args, rank, world, local_rank):
         combine_runs.append(maxr(t2 - t1))
         eng.reset()
     e2e_s = statistics.median(e2e_runs)
+    # per rank: what the host fed this GPU and how busy its kernels were (the e2e limiter at N > 1 is the box's
+    # aggregate host->device feed, not a collective)
+    my_e2e_ms = e2e_s / args.steps * 1e3
+    my_h2d = (P.nbytes + Fps * 32) / (my_e2e_ms * 1e-3) / 1e9
+    my_busy = (dev_ms / args.steps) / my_e2e_ms
+    if world > 1:
+        t = torch.tensor([my_h2d, my_busy], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allr, t)
+        per_rank = {"h2d_gbs": [round(float(x[0]), 2) for x in allr], "kernel_busy_frac": [round(float(x[1]), 3) for x in allr]}
+    else:
+        per_rank = {"h2d_gbs": [round(my_h2d, 2)], "kernel_busy_frac": [round(my_busy, 3)]}
+    per_rank["cpu_affinity_of_rank0"] = affinity
     clk = clocks.stop()
     e2e_val = world * W * Fps * args.steps / e2e_s
     # bytes that cross PCIe per step: positions, boxes and frame ids are copied; the forces either are
@@ -515,7 +540,7 @@ def run_ours(args, rank, world, local_rank):
                              "lists read on the host, overlapping the next step) + end-of-job combine and label-table read "
                              "(combine_ms: all-reduce + all-gather + device merge + label read, inside the timed region); "
                              "MEDIAN of runs_ms_per_step (complete jobs)",
-                    "recipe": e2e_recipe},
+                    "recipe": e2e_recipe, "per_rank": per_rank},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,

@@ -184,6 +184,12 @@ int we_wait_cov(we_ctx *ctx, int32_t ticket, double *cov_sum, uint64_t *cov_cnt)
  * (replaces CovarianceCollection.merge, entropy/convariances.py:86-108) */
 int we_device_tables(we_ctx *ctx, void **d_cov_sum, void **d_cov_cnt);
 
+/* Vibrational entropy of every covariance bin, computed on the device from the (all-reduced) tables:
+ * entropy/vibrations.py:142-192 with diagonalise=True.  `conversion` = Vibrations.mda_conversion()
+ * (entropy/vibrations.py:117-128).  out float64 [n_bins][2][3] = translational (force) and rotational (torque)
+ * terms in J / (K mol); bins without samples give zeros. */
+int we_vib_entropy(we_ctx *ctx, double temperature, double conversion, double *out);
+
 /* Label count table (HBLabelCollection, analysis/HB_labels.py:15-156).
  * Each entry is 512 bytes, layout `we_label_entry`. */
 typedef struct we_label_entry {
@@ -250,7 +256,8 @@ int we_debug_copy(we_ctx *ctx, int64_t k, int32_t field, void *out, int64_t byte
 #define WE_K_RAD1 8   /* k_rad, pass 1: interfacial waters */
 #define WE_K_RAD2 9   /* k_rad, pass 2: their shell members */
 #define WE_K_LIST2 10 /* k_seed + k_list2 (pass-2 and HB lists) */
-#define WE_N_KERNELS 11
+#define WE_K_GATE 11  /* k_gate (+ k_grplist): burial pre-stage of the gating pass, by cell group */
+#define WE_N_KERNELS 12
 /* Record CUDA events around every kernel launch on the compute stream (the
  * reference only has wall-clock prints, cli/runWaterEntropy.py:28-29,54). */
 int we_profile(we_ctx *ctx, int32_t enable);

@@ -1074,3 +1074,24 @@ def test_c1_lysozyme_waterShells_vs_oracle(tmp_path, capsys):
         assert f"0 {a} {sh} {len(sh)}" in out
     print(f"\nC1: {len(want)} interfacial waters with a non-like shell member of {len(top.water_centres)}; "
           f"oracle evaluated {fs.n_evaluated} of {len(top.heavy_idx)} heavy-atom centres")
+
+
+def test_device_vibrational_entropy_matches_the_host_class():
+    """per-bin S_vib computed on the device from the covariance tables vs the host class
+    (entropy/vibrations.py:142-192): rtol 1e-9, every bin of the arginine run."""
+    from waterentropy_b200.entropy.vibrations import Vibrations
+
+    inp = gio.load_inputs("arginine")
+    F = inp["positions"].shape[0]
+    eng = _engine(inp)
+    eng.submit(inp["positions"], inp["forces"], inp["dimensions"], list(range(F)))
+    eng.sync()
+    dev = eng.vibrational_entropies(298)
+    cov = eng.covariances()
+    vib = Vibrations(298)
+    vib.add_data(cov, diagonalise=True)
+    assert set(dev) == set(cov.counts) and len(dev) == 4
+    for k in dev:
+        assert np.allclose(dev[k][0], vib.translational_S[k], rtol=RTOL, atol=0)
+        assert np.allclose(dev[k][1], vib.rotational_S[k], rtol=RTOL, atol=0)
+    eng.close()

@@ -297,8 +297,14 @@ def test_streaming_readers_reproduce_golden_inputs():
         assert sum(got, []) == list(range(0, n, 2))
         st = SystemTopology.from_universe(u)
         assert st.n_atoms == len(g["masses"]) and np.allclose(st.charges, g["charges"])
+    # a GRO file as topology: names / residues only -> template topology (no charges), same frames
+    u = Universe(os.path.join(REF_FILES, "gromacs/aspirin_solution/system.gro"),
+                 os.path.join(REF_FILES, "gromacs/aspirin_solution/system.trr"))
+    g = gio.load_inputs("aspirin")
+    assert not u.has_charges and u.has_forces and u.n_atoms == len(g["masses"])
+    assert np.array_equal(u.frame_arrays(range(2))[0], g["positions"][:2])
     with pytest.raises(NotImplementedError):
-        Universe(os.path.join(REF_FILES, "gromacs/aspirin_solution/system.gro"),
+        Universe(os.path.join(REF_FILES, "gromacs/aspirin_solution/system.tpr"),
                  os.path.join(REF_FILES, "gromacs/aspirin_solution/system.trr"))
 
 

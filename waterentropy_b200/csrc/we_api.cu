@@ -102,8 +102,8 @@ struct we_ctx {
   int* d_zero = nullptr;
   size_t zero_ints = 0;
   // gating pass by cell group (k_gate)
-  unsigned char* d_grp_flag = nullptr;
-  int *d_grp_list = nullptr, *d_grp_count = nullptr, *d_work_counter = nullptr;
+  unsigned char *d_grp_flag = nullptr, *d_sflag = nullptr;
+  int *d_grp_list = nullptr, *d_grp_count = nullptr, *d_work_counter = nullptr, *d_wl0 = nullptr, *d_n0 = nullptr;
   int gate_blocks = 0, use_gate = 1;
   int hb_blocks = 0, label_blocks = 0;
   int *d_all_slots = nullptr;
@@ -385,9 +385,15 @@ extern "C" int we_create(const we_topology* t, const we_options* opt, we_ctx** o
   UP(bin_of_atom, std::vector<int>(t->bin_of_atom, t->bin_of_atom + N))
   UP(centre_class, std::vector<int>(t->centre_class, t->centre_class + N))
   {
-    std::vector<unsigned char> is_solute(std::max(1, H), 0);
+    std::vector<unsigned char> is_solute(std::max(1, H), 0), slot_flag(std::max(1, H), 0);
     for (int hs : solute) is_solute[hs] = 1;
+    for (int hs = 0; hs < H; ++hs) {
+      int nb = 0;
+      for (int e = 0; e < WE_MAX_EXCL; ++e) nb += excl[(size_t)hs * WE_MAX_EXCL + e] >= 0;
+      slot_flag[hs] = (unsigned char)((t->is_water[c->heavy_idx[hs]] ? 1 : 0) | (is_solute[hs] << 1) | (nb << 2));
+    }
     UP(is_solute, is_solute)
+    UP(slot_flag, slot_flag)
   }
 #undef UP
   const int* cos_p = nullptr;
@@ -555,7 +561,7 @@ static int ensure_workspace(we_ctx* c, const float* dims0, bool need_input_buffe
   {
     // everything that must be zero at the start of a batch lives in one block: one memset per batch
     const size_t n_cells = F * ((size_t)c->ncap + 1), n_fh = F * (size_t)H;
-    c->zero_ints = n_cells + 2 * n_fh + 4 * F + 8 + (n_fh + 3) / 4 + (n_cells + 3) / 4;
+    c->zero_ints = n_cells + 2 * n_fh + 5 * F + 8 + (n_fh + 3) / 4 + (n_cells + 3) / 4;
     AL(d_zero, c->zero_ints)
     int* p = c->d_zero;
     c->d_cell_count = p; p += n_cells;
@@ -565,10 +571,13 @@ static int ensure_workspace(we_ctx* c, const float* dims0, bool need_input_buffe
     c->d_n1 = p; p += F;
     c->d_n2 = p; p += F;
     c->d_grp_count = p; p += F;
+    c->d_n0 = p; p += F;
     c->d_work_counter = p; p += 8;
     c->d_interf = reinterpret_cast<unsigned char*>(p); p += (n_fh + 3) / 4;
     c->d_grp_flag = reinterpret_cast<unsigned char*>(p);
     AL(d_grp_list, n_cells)
+    AL(d_sflag, n_fh)
+    AL(d_wl0, F * (size_t)std::max(1, c->S))
   }
   if (c->opt.keep_debug) { AL(d_nbr_idx, F * H * WE_MAX_NBR) AL(d_nbr_dist, F * H * WE_MAX_NBR) AL(d_ft, F * std::max(1, c->C) * 6) }
 #undef AL
@@ -588,7 +597,7 @@ static int ensure_workspace(we_ctx* c, const float* dims0, bool need_input_buffe
     c->rad_blocks = std::max(1, per_sm) * std::max(1, sms);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rad<true>, WE_RAD_WARPS * 32, sizeof(WeRadSmem)));
     c->rad_blocks_gated = std::max(1, per_sm) * std::max(1, sms);
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gate, WE_RAD_WARPS * 32, sizeof(WeGateSmem)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gate, WE_GATE_WARPS * 32, sizeof(WeGateSmem)));
     c->gate_blocks = std::max(1, per_sm) * std::max(1, sms);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hb, 256, 0));
     c->hb_blocks = std::max(1, per_sm) * std::max(1, sms);
@@ -903,9 +912,9 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     const bool interfacial = (c->recipe == WE_RECIPE_INTERFACIAL);
     const bool shells_only = c->opt.shells_only != 0;
     dim3 gH((H + 255) / 256, n);
-    // gating pass by cell group (k_gate): production interfacial contexts, every frame of the batch with at
-    // least 8 cells per axis (the group window of 6 cells has one definite periodic image), a +-2 cell first
-    // search and, for triclinic boxes, a valid float32 prefilter
+    // burial pre-stage of the gating pass (k_gate): production interfacial contexts, every frame of the batch
+    // with enough cells per axis for the group window (6 x 6 x 5 cells) to have one definite periodic image,
+    // a +-2 cell first search and, for triclinic boxes, a valid float32 prefilter
     bool gate = interfacial && c->use_gate && !c->opt.keep_debug && S > 0 && C > 0;
     for (int f = 0; gate && f < n; ++f) {
       const WeBox& hb = c->h_boxes[buf][f];
@@ -928,11 +937,12 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       k_scan<<<n, 1024, 0, st>>>(bx, c->d_cell_count, c->ncap);
       ps.stop(st); }
     { ProfScope ps(c, WE_K_SCATTER, st);
-      k_scatter<<<gH, 256, 0, st>>>(H, bx, c->d_cell_count, c->d_cell_of, c->d_rank_of, c->d_tmp4, c->d_sorted4, c->ncap);
+      k_scatter<<<gH, 256, 0, st>>>(H, bx, c->d_cell_count, c->d_cell_of, c->d_rank_of, c->d_tmp4, c->d_sorted4, c->ncap,
+                                    c->T.slot_flag, gate ? c->d_sflag : nullptr);
       ps.stop(st); }
     c->launches += 3;
     if (gate) {
-      ProfScope ps(c, WE_K_LIST1, st);
+      ProfScope ps(c, WE_K_GATE, st);
       k_grplist<<<dim3((c->ncap + 1 + 255) / 256, n), 256, 0, st>>>(bx, c->d_grp_flag, c->ncap, c->d_grp_list, c->d_grp_count);
       ps.stop(st);
       c->launches++;
@@ -961,12 +971,22 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     const WeMarks m0 = interfacial ? WeMarks{c->d_interf, nullptr, nullptr, fids, 0}
                                    : WeMarks{nullptr, mark_hb, nullptr, nullptr, 1};
     auto rad = [&](int id, const WeWork& wk, long long items, int* gate_state, const WeMarks& mk) {
+      if (gate_state && gate) {
+        // buried solute atoms are settled by cell group; the rest form the work list of the generic search
+        ProfScope pg(c, WE_K_GATE, st);
+        k_gate<<<c->gate_blocks, WE_GATE_WARPS * 32, sizeof(WeGateSmem), st>>>(
+            c->T, bx, c->d_cell_count, c->d_sorted4, c->d_sflag, c->ncap, c->cell_target, c->d_grp_list, c->d_grp_count,
+            n, ro, gate_state, c->d_wl0, c->d_n0, std::max(1, S), c->d_work_counter);
+        pg.stop(st);
+      }
       ProfScope ps(c, id, st);
-      if (gate_state && gate)
-        k_gate<<<c->gate_blocks, WE_RAD_WARPS * 32, sizeof(WeGateSmem), st>>>(
-            c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->d_tmp4, c->ncap, c->cell_target,
-            c->d_grp_list, c->d_grp_count, n, ro, gate_state, mk, c->d_diag, c->d_work_counter);
-      else if (gate_state)
+      if (gate_state && gate) {
+        const WeWork open{c->d_wl0, c->d_n0, std::max(1, S), 0};
+        k_rad<false><<<rad_grid(items), WE_RAD_WARPS * 32, sizeof(WeRadSmem), st>>>(
+            c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->d_tmp4, c->ncap, c->cell_target, open, n, ro,
+            gate_state, mk, c->d_diag);
+        c->launches++;
+      } else if (gate_state)
         k_rad<true><<<(int)std::max<long long>(1, std::min<long long>((items + WE_RAD_WARPS - 1) / WE_RAD_WARPS, c->rad_blocks_gated)), WE_RAD_WARPS * 32, sizeof(WeRadSmem), st>>>(
             c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->d_tmp4, c->ncap, c->cell_target, wk, n, ro,
             gate_state, mk, c->d_diag);
@@ -1000,7 +1020,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     }
     if (interfacial && S > 0 && C > 0) {
       { ProfScope ps(c, WE_K_LIST1, st);
-        k_list1<<<dim3((C + 255) / 256, n), 256, 0, st>>>(c->T, c->d_interf, c->d_state, c->d_wl1, c->d_n1);
+        k_list1<<<gH, 256, 0, st>>>(c->T, c->d_sorted4, c->d_interf, c->d_state, c->d_wl1, c->d_n1);
         ps.stop(st); }
       WeWork w1{c->d_wl1, c->d_n1, C, 0};
       if (shells_only) {
@@ -1010,7 +1030,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       } else {
       rad(WE_K_RAD1, w1, (long long)C * n, nullptr, WeMarks{nullptr, mark_hb, mark_shell, nullptr, 0});
       { ProfScope ps(c, WE_K_LIST2, st);
-        k_list2<<<gH, 256, 0, st>>>(c->T, mark_shell, mark_hb, c->d_state, c->d_wl2, c->d_n2, c->d_wlh, c->d_nh);
+        k_list2<<<gH, 256, 0, st>>>(c->T, c->d_sorted4, mark_shell, mark_hb, c->d_state, c->d_wl2, c->d_n2, c->d_wlh, c->d_nh);
         ps.stop(st); }
       WeWork w2{c->d_wl2, c->d_n2, H, 0};
       rad(WE_K_RAD2, w2, (long long)H * n, nullptr, no_marks);
@@ -1018,7 +1038,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       }
     } else if (!interfacial && C > 0) {
       ProfScope ps(c, WE_K_LIST2, st);
-      k_list2<<<gH, 256, 0, st>>>(c->T, nullptr, mark_hb, c->d_state, c->d_wl2, c->d_n2, c->d_wlh, c->d_nh);
+      k_list2<<<gH, 256, 0, st>>>(c->T, c->d_sorted4, nullptr, mark_hb, c->d_state, c->d_wl2, c->d_n2, c->d_wlh, c->d_nh);
       ps.stop(st);
       c->launches++;
     }
@@ -1144,6 +1164,42 @@ static int quiesce(we_ctx* c) {
 static int read_diag(we_ctx* c, WeDiag* d) {
   CK(cudaMemcpy(d, c->d_diag, sizeof(WeDiag), cudaMemcpyDeviceToHost));
   return 0;
+}
+
+// ---- f3: vibrational entropy of every covariance bin on the device ---------------------------------
+// entropy/vibrations.py:142-192 with diagonalise=True: lambda = diagonal of the mean matrix in SI units,
+// nu = sqrt(lambda / kT), a = hbar nu / kT, S = R (a / (e^a - 1) - ln(1 - e^-a)); zero where a is zero.
+__global__ void k_vib_entropy(const double* __restrict__ cov_sum, const unsigned long long* __restrict__ cov_cnt,
+                              int n_bins, double conversion, double kT, double hbar, double gas, double* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_bins * 6) return;
+  const int b = t / 6, m = (t % 6) / 3, i = t % 3;
+  const unsigned long long n = cov_cnt[b];
+  double s = 0.0;
+  if (n) {
+    double lam = (cov_sum[(size_t)b * 18 + m * 9 + i * 4] / (double)n) * conversion;
+    if (!(lam >= 0.0)) lam = 0.0;
+    const double a = (hbar * sqrt(lam / kT)) / kT;
+    if (a != 0.0) {
+      const double bb = exp(a) - 1.0, cc = log(1.0 - exp(-a));
+      if (bb != 0.0 && cc != 0.0) s = a / bb - cc;
+    }
+  }
+  out[t] = s * gas;
+}
+
+extern "C" int we_vib_entropy(we_ctx* c, double temperature, double conversion, double* out) {
+  if (!c || !out) return fail(WE_ERR_INVALID, "null argument");
+  { const int rc = quiesce(c); if (rc) return rc; }
+  double* d_out = nullptr;
+  CK(cudaMalloc((void**)&d_out, (size_t)c->B * 6 * sizeof(double)));
+  const double kB = 1.38064852e-23, hbar = 1.0545718e-34, gas = 8.314;  // entropy/vibrations.py:26-29
+  k_vib_entropy<<<(c->B * 6 + 127) / 128, 128>>>(c->d_cov_sum, c->d_cov_cnt, c->B, conversion, kB * temperature, hbar, gas, d_out);
+  c->launches++;
+  cudaError_t e = cudaMemcpy(out, d_out, (size_t)c->B * 6 * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return fail(WE_ERR_CUDA, "we_vib_entropy failed: %s", cudaGetErrorString(e));
+  return WE_OK;
 }
 
 // ---- input-buffer retirement ------------------------------------------------------------------

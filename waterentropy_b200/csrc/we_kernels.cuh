@@ -77,6 +77,7 @@ struct WeTopoDev {
   const int* bin_of_atom;         // [N] covariance pair-bin of the atom's (resname,resid)
   const int* centre_class;        // [N] class of the centre's resname or -1
   const unsigned char* is_solute; // [H] heavy slot is a solute united atom (pass-0 centre of the interfacial recipe)
+  const unsigned char* slot_flag; // [H] bit 0 water, bit 1 solute united atom, bits 2.. bonded heavy atoms
 };
 
 struct WeDiag {
@@ -115,7 +116,10 @@ __device__ __forceinline__ void we_set_error(WeDiag* diag, int code, int frame, 
 // K1: cell list.  Replaces `select_atoms("mass 2 to 999 ...")` + brute-force
 // `capped_distance` (maths/trig.py:59-67, 26-34) as the candidate generator.
 // ============================================================================
-#define WE_GRP 2  // cells per edge of a cell group (k_gate)
+// cells per edge of a cell group of the gating pre-stage (k_gate)
+#define WE_GRP_X 2
+#define WE_GRP_Y 2
+#define WE_GRP_Z 1
 __global__ void k_bin(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes,
                       int* __restrict__ cell_count, int* __restrict__ cell_of,
                       int* __restrict__ rank_of, float4* __restrict__ tmp4, int ncap,
@@ -148,8 +152,8 @@ __global__ void k_bin(WeTopoDev T, const float* __restrict__ pos, const WeBox* _
   rank_of[o] = atomicAdd(&cell_count[(size_t)f * (ncap + 1) + cell], 1);
   tmp4[o] = make_float4(q[0], q[1], q[2], __int_as_float(atom));
   if (grp_flag && T.is_solute[h]) {  // the WE_GRP^3 cell group of a solute united atom has gating work (k_gate)
-    const int g0 = (b.nc[0] + WE_GRP - 1) / WE_GRP, g1 = (b.nc[1] + WE_GRP - 1) / WE_GRP;
-    grp_flag[(size_t)f * (ncap + 1) + ((size_t)(c2 / WE_GRP) * g1 + c1 / WE_GRP) * g0 + c0 / WE_GRP] = 1;
+    const int g0 = (b.nc[0] + WE_GRP_X - 1) / WE_GRP_X, g1 = (b.nc[1] + WE_GRP_Y - 1) / WE_GRP_Y;
+    grp_flag[(size_t)f * (ncap + 1) + ((size_t)(c2 / WE_GRP_Z) * g1 + c1 / WE_GRP_Y) * g0 + c0 / WE_GRP_X] = 1;
   }
 }
 
@@ -217,9 +221,12 @@ __global__ void k_scan(const WeBox* __restrict__ boxes, int* __restrict__ cell_c
   }
 }
 
+// sflag (optional): per position of the cell-sorted array, bit 0 = water, bit 1 = solute united atom,
+// bits 2.. = number of bonded heavy atoms (what k_gate needs of a candidate without chasing its atom index)
 __global__ void k_scatter(int n_heavy, const WeBox* __restrict__ boxes, const int* __restrict__ cell_start,
                           const int* __restrict__ cell_of, const int* __restrict__ rank_of,
-                          const float4* __restrict__ tmp4, float4* __restrict__ sorted4, int ncap) {
+                          const float4* __restrict__ tmp4, float4* __restrict__ sorted4, int ncap,
+                          const unsigned char* __restrict__ slot_flag, unsigned char* __restrict__ sflag) {
   int h = blockIdx.x * blockDim.x + threadIdx.x;
   int f = blockIdx.y;
   if (h >= n_heavy) return;
@@ -228,6 +235,7 @@ __global__ void k_scatter(int n_heavy, const WeBox* __restrict__ boxes, const in
   const int cell = ((pc >> 20) * boxes[f].nc[1] + ((pc >> 10) & 1023)) * boxes[f].nc[0] + (pc & 1023);
   int dst = cell_start[(size_t)f * (ncap + 1) + cell] + rank_of[o];
   sorted4[(size_t)f * n_heavy + dst] = tmp4[o];
+  if (sflag) sflag[(size_t)f * n_heavy + dst] = slot_flag[h];
 }
 
 // ============================================================================
@@ -243,7 +251,26 @@ struct WeRowInfo {  // per-warp description of up to 32 non-empty cell rows, com
   float4 rp[32];    // centre minus image shift: x (first run), y, z, x (second run)
 };
 
+// Asynchronous global -> shared copies (LDGSTS): the candidate windows of the cell scan are staged one
+// window ahead of the arithmetic, so the scan no longer waits on every window's gather.
+__device__ __forceinline__ void we_cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void we_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void we_cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+#ifndef WE_PREFETCH
+#define WE_PREFETCH 0  // candidate-window prefetch of the cell scan: 0 none, 1 cp.async ring, 2 registers
+#endif
+
 struct WeRadSmem {
+#if WE_PREFETCH == 1
+  float4 pre[WE_RAD_WARPS][64];  // two candidate windows per warp, filled by cp.async one window ahead
+#else
+  float4 pre[WE_RAD_WARPS][1];
+#endif
   double d[WE_RAD_WARPS][WE_CAND_CAP];
   int idx[WE_RAD_WARPS][WE_CAND_CAP];
   int src[WE_RAD_WARPS][WE_CAND_CAP];
@@ -322,7 +349,7 @@ __device__ __forceinline__ int we_collect(const WeBox& b, const int* __restrict_
                                           int wx, int wy, int wz, double r, float mx, float my,
                                           float mz, int my_atom, const int* ex, double* sd, float* sf,
                                           int* si, int* ss, int* stage, WeRowInfo* rows, int lane,
-                                          bool& dup, float* sg) {
+                                          bool& dup, float* sg, float4* ring) {
   int n = 0, head = 0, cnt = 0;
   const int n0 = b.nc[0], n1 = b.nc[1], n2 = b.nc[2];
   const bool all_z = (2 * wz + 1 > n2), all_y = (2 * wy + 1 > n1), all_x = (2 * wx + 1 > n0);
@@ -387,7 +414,10 @@ __device__ __forceinline__ int we_collect(const WeBox& b, const int* __restrict_
     // ---- dense walk over the candidates of these rows ---------------------------------------
     // Row of dense index q = base + lane: rows that start at or before `base` are counted by one
     // ballot, rows that start inside the 32-wide window set bit (start - base) of a warp-wide OR.
-    auto probe = [&](int base, int& qi, float& d2) -> bool {
+    // locate: the candidate of dense index base + lane (position in the cell-sorted array, its row);
+    // test: float32 prefilter of its coordinates.  Split so that the gather of the NEXT window can be in
+    // flight (cp.async into the warp's shared-memory ring) while this window is tested and pushed.
+    auto locate = [&](int base, int& qi, int& rinfo) -> bool {
       const int rel = coff - base;
       const unsigned starts = __reduce_or_sync(0xffffffffu, (rel > 0 && rel < 32) ? (1u << rel) : 0u);
       const int r0 = __popc(__ballot_sync(0xffffffffu, rel <= 0)) - 1;
@@ -395,13 +425,16 @@ __device__ __forceinline__ int we_collect(const WeBox& b, const int* __restrict_
       if (q >= total) return false;
       const int ro = r0 + __popc(starts & (0xffffffffu >> (31 - lane)));
       const int4 ri = rows->ri[ro];
-      const float4 rp = rows->rp[ro];
       const int t = q - ri.w;
       const bool second = t >= ri.y;
       qi = second ? ri.z + (t - ri.y) : ri.x + t;
-      const float4 c = sorted[qi];
+      rinfo = ro | (second ? 0x40000000 : 0);
+      return true;
+    };
+    auto test = [&](const float4 c, int rinfo, float& d2) -> bool {
       if (simple) {
-        const float ux = c.x - (second ? rp.w : rp.x);
+        const float4 rp = rows->rp[rinfo & 0xffff];
+        const float ux = c.x - ((rinfo & 0x40000000) ? rp.w : rp.x);
         const float uy = c.y - rp.y, uz = c.z - rp.z;
         d2 = __fmaf_rn(ux, ux, __fmaf_rn(uy, uy, uz * uz));
         return d2 <= rf2;
@@ -446,12 +479,60 @@ __device__ __forceinline__ int we_collect(const WeBox& b, const int* __restrict_
         __syncwarp();
       }
     };
+#if WE_PREFETCH == 1
+    {
+      int qa = 0, ra = 0, buf = 0;
+      bool va = locate(0, qa, ra);
+      if (va) we_cp_async16(&ring[lane], &sorted[qa]);
+      we_cp_async_commit();
+      for (int base = 0; base < total; base += 32) {
+        int qn = 0, rn = 0;
+        bool vn = false;
+        if (base + 32 < total) {
+          vn = locate(base + 32, qn, rn);
+          if (vn) we_cp_async16(&ring[(buf ^ 1) * 32 + lane], &sorted[qn]);
+        }
+        we_cp_async_commit();
+        we_cp_async_wait<1>();  // this window has landed; a lane reads back only what it copied itself
+        float da = 0.f;
+        bool pa = false;
+        if (va) pa = test(ring[buf * 32 + lane], ra, da);
+        push(pa, qa, da);
+        qa = qn; ra = rn; va = vn; buf ^= 1;
+      }
+      we_cp_async_wait<0>();
+    }
+#elif WE_PREFETCH == 2
+    {
+      int qa = 0, ra = 0;
+      bool va = locate(0, qa, ra);
+      float4 ca = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (va) ca = sorted[qa];
+      for (int base = 0; base < total; base += 32) {
+        int qn = 0, rn = 0;
+        bool vn = false;
+        float4 cn = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (base + 32 < total) {
+          vn = locate(base + 32, qn, rn);
+          if (vn) cn = sorted[qn];  // in flight while this window is tested and pushed
+        }
+        float da = 0.f;
+        bool pa = false;
+        if (va) pa = test(ca, ra, da);
+        push(pa, qa, da);
+        qa = qn; ra = rn; va = vn; ca = cn;
+      }
+    }
+#else
+    (void)ring;
     for (int base = 0; base < total; base += 32) {
-      int qa = 0;
+      int qa = 0, ra = 0;
       float da = 0.f;
-      const bool pa = probe(base, qa, da);
+      bool pa = locate(base, qa, ra);
+      if (pa) pa = test(sorted[qa], ra, da);
       push(pa, qa, da);
     }
+#endif
   }
   if (defer) { __syncwarp(); return cnt; }
   if (cnt > 0) {
@@ -492,7 +573,7 @@ __device__ __forceinline__ int we_exact_list(const WeBox& b, const float4* __res
     const unsigned m = __ballot_sync(0xffffffffu, keep);
     if (keep) {
       const int p = n + __popc(m & ((1u << lane) - 1u));
-      sd[p] = dd; sf[p] = (float)dd; si[p] = ai; ss[p] = qi;
+      if (p < WE_CAND_CAP) { sd[p] = dd; sf[p] = (float)dd; si[p] = ai; ss[p] = qi; }  // p <= its source index < cap
     }
     n += __popc(m);
     __syncwarp();
@@ -566,7 +647,7 @@ __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __re
       // float32 survivors first; if at least 20 non-excluded solute atoms are closer (by a safe margin)
       // than the nearest water in range and than the search radius, no water can be among the 20
       // nearest candidates and the exact distances, the ranking and the RAD test are never needed.
-      const int nf = we_collect<true>(b, cstart, sorted, c0, c1, c2, b.sw[0], b.sw[1], b.sw[2], r, mq[0], mq[1], mq[2], my_atom, ex, sd, sf, si, ss, S.stage[w], &S.rows[w], lane, dup, sg);
+      const int nf = we_collect<true>(b, cstart, sorted, c0, c1, c2, b.sw[0], b.sw[1], b.sw[2], r, mq[0], mq[1], mq[2], my_atom, ex, sd, sf, si, ss, S.stage[w], &S.rows[w], lane, dup, sg, S.pre[w]);
       if (nf > WE_CAND_CAP) {
         n = nf;  // overflow: the shrink / retry logic below takes over with the interleaved mode
       } else {
@@ -613,8 +694,8 @@ __device__ __forceinline__ void we_rad_one(const WeTopoDev& T, const float* __re
         n = we_exact_list(b, sorted, nf, r, mq[0], mq[1], mq[2], my_atom, ex, sd, sf, si, ss, lane, dup);
       }
     }
-    else if (!wide) n = we_collect<false>(b, cstart, sorted, c0, c1, c2, b.sw[0], b.sw[1], b.sw[2], r, mq[0], mq[1], mq[2], my_atom, ex, sd, sf, si, ss, S.stage[w], &S.rows[w], lane, dup, sg);
-    else n = we_collect<false>(b, cstart, sorted, c0, c1, c2, b.wide[0], b.wide[1], b.wide[2], r, mq[0], mq[1], mq[2], my_atom, ex, sd, sf, si, ss, S.stage[w], &S.rows[w], lane, dup, sg);
+    else if (!wide) n = we_collect<false>(b, cstart, sorted, c0, c1, c2, b.sw[0], b.sw[1], b.sw[2], r, mq[0], mq[1], mq[2], my_atom, ex, sd, sf, si, ss, S.stage[w], &S.rows[w], lane, dup, sg, S.pre[w]);
+    else n = we_collect<false>(b, cstart, sorted, c0, c1, c2, b.wide[0], b.wide[1], b.wide[2], r, mq[0], mq[1], mq[2], my_atom, ex, sd, sf, si, ss, S.stage[w], &S.rows[w], lane, dup, sg, S.pre[w]);
     if (n > WE_CAND_CAP) {
       if (n >= WE_MAX_NBR && r > 0.5) { r *= 0.85; if (lane == 0) atomicAdd(&diag->shrink_retries, 1ULL); continue; }
       status = WE_ST_OVERFLOW; break;
@@ -848,32 +929,33 @@ k_rad(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxe
     const int* cof = cell_of + (size_t)f * T.n_heavy;
     const float4* t4 = tmp4 + (size_t)f * T.n_heavy;
     for (; i < cnt; i += stride)
-      we_rad_one<GATED>(T, fpos, b, cstart, cof, sorted, t4, search_radius, f, list[i], O, GATED ? gate_only_state : nullptr, M, diag, S, PT, lane, w);
+      we_rad_one<GATED>(T, fpos, b, cstart, cof, sorted, t4, search_radius, f, list[i], O, gate_only_state, M, diag, S, PT, lane, w);
   }
 }
 
 // ============================================================================
-// K4a, gating pass of the interfacial recipe (recipes/interfacial_solvent.py:47-65) by CELL GROUP.
+// K4a, first stage of the gating pass of the interfacial recipe (recipes/interfacial_solvent.py:47-65):
+// which solute united atoms are BURIED, decided per cell group.
 //
 // Most solute united atoms are buried: at least 20 other solute atoms are closer than the nearest water, so
 // no water can be among their 20 nearest candidates and neither exact distances nor a ranking nor a RAD shell
-// are ever needed.  Deciding that per atom with the generic warp-per-centre search costs a full candidate
-// scan with dependent global loads (~1,500 warp-instructions).  Here one block takes a group of 2 x 2 x 2
-// cells that holds solute atoms, stages the group's whole candidate window (the group's cells +- 2 cells, every
+// are ever needed.  Deciding that with the generic warp-per-centre search costs a full candidate scan with
+// dependent global loads per atom (~1,500 warp-instructions).  Here one WARP takes a group of 2 x 2 x 1 cells
+// that holds solute atoms, stages the group's whole candidate window (the group's cells +- 2 cells; every
 // candidate shifted into the group's periodic image, water flag in the sign bit of its index) into shared
-// memory ONCE, and every solute atom of the group is then classified against the staged window: two sweeps
-// of float32 distances from shared memory (nearest water; solute atoms closer than it).  Atoms that are not
-// buried compact their prefilter survivors from the same staged window and continue with the exact fp64
-// distances, the ranking and the RAD test of the generic path (we_exact_list, we_rad_finish).  Anything unusual
-// - window or centre list larger than the staging buffers, fewer than 25 candidates inside the first radius -
-// goes through the generic search (we_rad_one), so the results are those of k_rad<true> in every case.
+// memory ONCE, and classifies every solute atom of the group against the staged window with two sweeps of
+// float32 distances from shared memory: the nearest water, then the solute atoms closer than it.  Buried
+// atoms get their (empty) result here; the others are appended to the work list of the generic search
+// (k_rad), which evaluates them exactly as before.  The test is conservative (1e-3 relative margin in d^2,
+// bonded atoms subtracted whether or not they were counted, coincident coordinates never buried), and a
+// group whose window or atom list exceeds the staging buffers hands all its atoms to the generic search, so
+// the results are those of k_rad<true> in every case.
 // ============================================================================
-#define WE_GATE_STAGE_CAP 640
+#define WE_GATE_STAGE_CAP 576
 #define WE_GATE_CENTRE_CAP 64
-#define WE_GATE_ROWS ((WE_GRP + 4) * (WE_GRP + 4))
-#ifndef WE_GATE_MINBLOCKS
-#define WE_GATE_MINBLOCKS 3
-#endif
+#define WE_GATE_ROWS ((WE_GRP_Y + 4) * (WE_GRP_Z + 4))
+#define WE_GATE_WARPS 4
+static_assert(WE_GATE_ROWS <= 32, "one lane per window row");
 
 __device__ __forceinline__ int we_append_block(bool want, int* counter, int* s_cnt);
 
@@ -884,245 +966,213 @@ k_grplist(const WeBox* __restrict__ boxes, const unsigned char* __restrict__ grp
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   const int f = blockIdx.y;
   const WeBox& b = boxes[f];
-  const int ng = ((b.nc[0] + WE_GRP - 1) / WE_GRP) * ((b.nc[1] + WE_GRP - 1) / WE_GRP) * ((b.nc[2] + WE_GRP - 1) / WE_GRP);
+  const int ng = ((b.nc[0] + WE_GRP_X - 1) / WE_GRP_X) * ((b.nc[1] + WE_GRP_Y - 1) / WE_GRP_Y) * ((b.nc[2] + WE_GRP_Z - 1) / WE_GRP_Z);
   const bool want = g < ng && grp_flag[(size_t)f * (ncap + 1) + g];
   const int slot = we_append_block(want, &grp_count[f], s_cnt);
   if (want) grp_list[(size_t)f * (ncap + 1) + slot] = g;
 }
 
-struct WeGateRow {  // one row (fixed y, z cell) of the group's window: up to two runs contiguous in x
-  int beg0, len0, beg1, len1, off;
-  int gbeg, gend;          // cell-sorted positions of the row's members that lie in the group itself
-  float sx0, sx1, sy, sz;  // periodic image shift of run 0 / run 1 (x) and of the row (y, z)
-  float rx0, rx1, ry, rz;  // orthorhombic boxes: reference point of the run (nearest-image wrap of raw coordinates)
+struct WeGateWarp {
+  float4 cand[WE_GATE_STAGE_CAP];  // x, y, z in the group's image; w = position in the cell-sorted array | water << 31
+  int4 ri[32];                     // per window row: beg0, len0, beg1, len1
+  int4 rj[32];                     // first staged index, packed (ky, kz, yc, zc, x-wrap case), gbeg, gend
+  int centres[WE_GATE_CENTRE_CAP]; // staged indices of the group's solute united atoms
+  int open[WE_GATE_CENTRE_CAP];    // heavy slots of the ones that are not buried
+  int n_centres;
 };
-
 struct WeGateSmem {
-  WeRadSmem R;
-  float4 cand[WE_GATE_STAGE_CAP];
-  WeGateRow rows[WE_GATE_ROWS];
-  int centres[WE_GATE_CENTRE_CAP];
+  WeGateWarp w[WE_GATE_WARPS];
   int pref[130];
-  int n_cand, n_centres, item;
 };
 
-__global__ void __launch_bounds__(WE_RAD_WARPS * 32, WE_GATE_MINBLOCKS)
-k_gate(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes,
-       const int* __restrict__ cell_start, const int* __restrict__ cell_of,
-       const float4* __restrict__ sorted4, const float4* __restrict__ tmp4, int ncap, float search_radius,
+__global__ void __launch_bounds__(WE_GATE_WARPS * 32)
+k_gate(WeTopoDev T, const WeBox* __restrict__ boxes, const int* __restrict__ cell_start,
+       const float4* __restrict__ sorted4, const unsigned char* __restrict__ sflag, int ncap, float search_radius,
        const int* __restrict__ grp_list, const int* __restrict__ grp_count, int n_frames, WeRadOut O,
-       int* state, WeMarks M, WeDiag* diag, int* work_counter) {
+       int* __restrict__ state, int* __restrict__ wl0, int* __restrict__ n0, int wl0_stride, int* work_counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  WeGateSmem& G = *reinterpret_cast<WeGateSmem*>(smem_raw);
-  WeRadSmem& S = G.R;
+  WeGateSmem& GS = *reinterpret_cast<WeGateSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  if (tid < 32) { S.log2tab[tid] = ((const double*)we_d_log2tab)[tid]; S.exp2tab[tid] = we_d_exp2tab[tid]; }
+  WeGateWarp& G = GS.w[w];
   if (tid == 0) {
     int acc = 0;
-    for (int f = 0; f < n_frames; ++f) { G.pref[f] = acc; acc += grp_count[f]; }
-    G.pref[n_frames] = acc;
+    for (int f = 0; f < n_frames; ++f) { GS.pref[f] = acc; acc += grp_count[f]; }
+    GS.pref[n_frames] = acc;
   }
   __syncthreads();
-  const WePowTables PT{S.log2tab, S.exp2tab};
-  const int total = G.pref[n_frames];
+  const int total = GS.pref[n_frames];
+  constexpr int NWY = WE_GRP_Y + 4;
   for (;;) {
-    __syncthreads();  // the previous group's staging buffers are free
-    if (tid == 0) { G.item = atomicAdd(work_counter, 1); G.n_cand = 0; G.n_centres = 0; }
-    __syncthreads();
-    const int item = G.item;
+    int item = 0;
+    if (lane == 0) item = atomicAdd(work_counter, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= total) break;
     int f = 0;
-    while (G.pref[f + 1] <= item) ++f;
-    const int g = grp_list[(size_t)f * (ncap + 1) + item - G.pref[f]];
+    while (GS.pref[f + 1] <= item) ++f;
+    const int g = grp_list[(size_t)f * (ncap + 1) + item - GS.pref[f]];
     const WeBox& b = boxes[f];
-    const int n0 = b.nc[0], n1 = b.nc[1], n2 = b.nc[2];
-    const int ng0 = (n0 + WE_GRP - 1) / WE_GRP, ng1 = (n1 + WE_GRP - 1) / WE_GRP;
+    const int n0c = b.nc[0], n1c = b.nc[1], n2c = b.nc[2];
+    const int ng0 = (n0c + WE_GRP_X - 1) / WE_GRP_X, ng1 = (n1c + WE_GRP_Y - 1) / WE_GRP_Y;
     const int gx = g % ng0, gy = (g / ng0) % ng1, gz = g / (ng0 * ng1);
     const int* cstart = cell_start + (size_t)f * (ncap + 1);
     const float4* sorted = sorted4 + (size_t)f * T.n_heavy;
-    const float* fpos = pos + (size_t)f * T.n_atoms * 3;
+    const unsigned char* sfl = sflag + (size_t)f * T.n_heavy;
     const size_t fo = (size_t)f * T.n_heavy;
-    constexpr int NW = WE_GRP + 4;  // window cells per axis
-    // ---- rows of the window: cell ranges, image shifts --------------------------------------------
-    if (tid < WE_GATE_ROWS) {
-      const int iy = tid % NW, iz = tid / NW;
-      int zc = gz * WE_GRP - 2 + iz, yc = gy * WE_GRP - 2 + iy;
-      const int kz = zc < 0 ? -1 : (zc >= n2 ? 1 : 0);
-      zc -= kz * n2;
-      const int ky = yc < 0 ? -1 : (yc >= n1 ? 1 : 0);
-      yc -= ky * n1;
-      const int rowbase = (zc * n1 + yc) * n0;
-      const int lo = gx * WE_GRP - 2, hi = gx * WE_GRP + WE_GRP + 1;
-      WeGateRow r;
-      r.beg1 = 0; r.len1 = 0; r.sx1 = 0.f; r.rx1 = 0.f;
-      // image shift of the row (lower-triangular cell: rows a, b, c)
-      r.sy = ky * b.m[4] + kz * b.m[7];
-      r.sz = kz * b.m[8];
-      const float sxr = ky * b.m[3] + kz * b.m[6];
-      r.sx0 = sxr;
-      const float cw0 = b.box[0] / n0;  // orthorhombic only: cell edges for the reference points
-      r.ry = (yc + 0.5f) * (b.box[1] / n1);
-      r.rz = (zc + 0.5f) * (b.box[2] / n2);
-      if (lo < 0) {
-        r.beg0 = cstart[rowbase]; r.len0 = cstart[rowbase + hi + 1] - r.beg0;
-        r.beg1 = cstart[rowbase + lo + n0]; r.len1 = cstart[rowbase + n0] - r.beg1;
-        r.sx1 = sxr - b.m[0];
-        r.rx0 = 0.5f * (hi + 1) * cw0; r.rx1 = (0.5f * (lo + n0 + n0)) * cw0;
-      } else if (hi >= n0) {
-        r.beg0 = cstart[rowbase + lo]; r.len0 = cstart[rowbase + n0] - r.beg0;
-        r.beg1 = cstart[rowbase]; r.len1 = cstart[rowbase + hi - n0 + 1] - r.beg1;
-        r.sx1 = sxr + b.m[0];
-        r.rx0 = 0.5f * (lo + n0) * cw0; r.rx1 = 0.5f * (hi - n0 + 1) * cw0;
+    const int lo = gx * WE_GRP_X - 2, hi = gx * WE_GRP_X + WE_GRP_X + 1;
+    const int xcase = lo < 0 ? 1 : (hi >= n0c ? 2 : 0);
+    // ---- one lane per window row: cell ranges, image, the group's own members ---------------------
+    int len = 0;
+    if (lane < WE_GATE_ROWS) {
+      const int iy = lane % NWY, iz = lane / NWY;
+      int zc = gz * WE_GRP_Z - 2 + iz, yc = gy * WE_GRP_Y - 2 + iy;
+      const int kz = zc < 0 ? -1 : (zc >= n2c ? 1 : 0);
+      zc -= kz * n2c;
+      const int ky = yc < 0 ? -1 : (yc >= n1c ? 1 : 0);
+      yc -= ky * n1c;
+      const int rowbase = (zc * n1c + yc) * n0c;
+      int beg0, len0, beg1 = 0, len1 = 0;
+      if (xcase == 1) {
+        beg0 = cstart[rowbase]; len0 = cstart[rowbase + hi + 1] - beg0;
+        beg1 = cstart[rowbase + lo + n0c]; len1 = cstart[rowbase + n0c] - beg1;
+      } else if (xcase == 2) {
+        beg0 = cstart[rowbase + lo]; len0 = cstart[rowbase + n0c] - beg0;
+        beg1 = cstart[rowbase]; len1 = cstart[rowbase + hi - n0c + 1] - beg1;
       } else {
-        r.beg0 = cstart[rowbase + lo]; r.len0 = cstart[rowbase + hi + 1] - r.beg0;
-        r.rx0 = 0.5f * (lo + hi + 1) * cw0;
+        beg0 = cstart[rowbase + lo]; len0 = cstart[rowbase + hi + 1] - beg0;
       }
-      // members of the group itself in this row (window rows 2 .. 2 + WE_GRP - 1, x cells of the group)
-      r.gbeg = 0; r.gend = 0;
-      if (iy >= 2 && iy < 2 + WE_GRP && iz >= 2 && iz < 2 + WE_GRP && ky == 0 && kz == 0) {
-        const int x0 = gx * WE_GRP, x1 = min(x0 + WE_GRP, n0);
-        r.gbeg = cstart[rowbase + x0]; r.gend = cstart[rowbase + x1];
+      int gbeg = 0, gend = 0;
+      if (iy >= 2 && iy < 2 + WE_GRP_Y && iz >= 2 && iz < 2 + WE_GRP_Z && ky == 0 && kz == 0) {
+        const int x0 = gx * WE_GRP_X, x1 = min(x0 + WE_GRP_X, n0c);
+        gbeg = cstart[rowbase + x0]; gend = cstart[rowbase + x1];
       }
-      r.off = r.len0 + r.len1;
-      G.rows[tid] = r;
+      len = len0 + len1;
+      G.ri[lane] = make_int4(beg0, len0, beg1, len1);
+      G.rj[lane] = make_int4(0, (ky + 1) | ((kz + 1) << 2) | (yc << 4) | (zc << 14), gbeg, gend);
     }
-    __syncthreads();
-    if (w == 0) {  // exclusive scan of the row lengths (WE_GATE_ROWS <= 64: two per lane)
-      const int a = lane < WE_GATE_ROWS ? G.rows[lane].off : 0;
-      const int c2 = lane + 32 < WE_GATE_ROWS ? G.rows[lane + 32].off : 0;
-      int ia = a, ic = c2;
-      for (int o = 1; o < 32; o <<= 1) {
-        const int ta = __shfl_up_sync(0xffffffffu, ia, o), tc = __shfl_up_sync(0xffffffffu, ic, o);
-        if (lane >= o) { ia += ta; ic += tc; }
-      }
-      const int tot_a = __shfl_sync(0xffffffffu, ia, 31);
-      if (lane < WE_GATE_ROWS) G.rows[lane].off = ia - a;
-      if (lane + 32 < WE_GATE_ROWS) G.rows[lane + 32].off = tot_a + ic - c2;
-      if (lane == 31) G.n_cand = tot_a + ic;
+    int incl = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
     }
-    __syncthreads();
-    const int n_cand = G.n_cand;
+    const int n_cand = __shfl_sync(0xffffffffu, incl, 31);
+    if (lane < WE_GATE_ROWS) G.rj[lane].x = incl - len;
+    if (lane == 0) G.n_centres = 0;
+    __syncwarp();
     const bool fits = n_cand <= WE_GATE_STAGE_CAP;
-    // ---- stage the window (warp per row) and collect the group's solute atoms --------------------
-    for (int r = w; r < WE_GATE_ROWS; r += WE_RAD_WARPS) {
-      const WeGateRow& R = G.rows[r];
-      const int len = R.len0 + R.len1;
-      for (int e = lane; e < len; e += 32) {
-        const bool second = e >= R.len0;
-        const int qi = second ? R.beg1 + (e - R.len0) : R.beg0 + e;
+    // ---- stage the window, two rows per sweep (half a warp each) -----------------------------------
+    const float cw0 = b.box[0] / n0c, cw1 = b.box[1] / n1c, cw2 = b.box[2] / n2c;
+    const int hw = lane >> 4, sub = lane & 15;
+    for (int r0 = 0; r0 < WE_GATE_ROWS; r0 += 2) {
+      const int r = r0 + hw;
+      if (r >= WE_GATE_ROWS) continue;
+      const int4 ri = G.ri[r];
+      const int4 rj = G.rj[r];
+      const int ky = (rj.y & 3) - 1, kz = ((rj.y >> 2) & 3) - 1, yc = (rj.y >> 4) & 1023, zc = (rj.y >> 14) & 1023;
+      const float sy = ky * b.m[4] + kz * b.m[7], sz = kz * b.m[8], sxr = ky * b.m[3] + kz * b.m[6];
+      for (int e = sub; e < ri.y + ri.w; e += 16) {
+        const bool second = e >= ri.y;
+        const int qi = second ? ri.z + (e - ri.y) : ri.x + e;
         const float4 c = sorted[qi];
-        const int atom = __float_as_int(c.w);
+        const unsigned fl = sfl[qi];
         float x = c.x, y = c.y, z = c.z;
-        if (!b.triclinic) {  // raw coordinates: nearest image to the run's reference point
-          x = __fmaf_rn(-b.box[0], rintf((x - (second ? R.rx1 : R.rx0)) * b.inv[0]), x);
-          y = __fmaf_rn(-b.box[1], rintf((y - R.ry) * b.inv[1]), y);
-          z = __fmaf_rn(-b.box[2], rintf((z - R.rz) * b.inv[2]), z);
+        if (!b.triclinic) {  // raw coordinates: nearest image to the centre of the run / row
+          float refx;
+          if (xcase == 1) refx = second ? 0.5f * (lo + n0c + n0c) * cw0 : 0.5f * (hi + 1) * cw0;
+          else if (xcase == 2) refx = second ? 0.5f * (hi - n0c + 1) * cw0 : 0.5f * (lo + n0c) * cw0;
+          else refx = 0.5f * (lo + hi + 1) * cw0;
+          x = __fmaf_rn(-b.box[0], rintf((x - refx) * b.inv[0]), x);
+          y = __fmaf_rn(-b.box[1], rintf((y - (yc + 0.5f) * cw1) * b.inv[1]), y);
+          z = __fmaf_rn(-b.box[2], rintf((z - (zc + 0.5f) * cw2) * b.inv[2]), z);
         }
-        x += second ? R.sx1 : R.sx0; y += R.sy; z += R.sz;
-        if (fits) G.cand[R.off + e] = make_float4(x, y, z, __int_as_float(qi | (T.is_water[atom] ? 0x80000000 : 0)));
-        if (qi >= R.gbeg && qi < R.gend && T.is_solute[T.heavy_slot[atom]]) {
+        x += sxr + (second ? (xcase == 1 ? -b.m[0] : b.m[0]) : 0.f);
+        y += sy; z += sz;
+        if (fits) G.cand[rj.x + e] = make_float4(x, y, z, __int_as_float(qi | ((fl & 1u) ? 0x80000000 : 0)));
+        if ((fl & 2u) && qi >= rj.z && qi < rj.w) {
           const int p = atomicAdd(&G.n_centres, 1);
-          if (p < WE_GATE_CENTRE_CAP) G.centres[p] = fits ? (R.off + e) : qi;
+          if (p < WE_GATE_CENTRE_CAP) G.centres[p] = fits ? (rj.x + e) : qi;
         }
       }
     }
-    __syncthreads();
+    if (fits) {  // pad to a multiple of 32: far away, not water
+      const int pad = ((n_cand + 31) & ~31) - n_cand;
+      if (lane < pad) G.cand[n_cand + lane] = make_float4(1.0e18f, 1.0e18f, 1.0e18f, __int_as_float(0x7fffffff));
+    }
+    __syncwarp();
     const int n_centres = G.n_centres;
-    const bool fast = fits && n_centres <= WE_GATE_CENTRE_CAP;
-    if (!fast) {
-      // generic search for every solute atom of the group (rare: an unusually dense window)
+    int n_open = 0;
+    if (!fits || n_centres > WE_GATE_CENTRE_CAP) {
+      // an unusually dense window: every solute atom of the group goes to the generic search
       for (int r = 0; r < WE_GATE_ROWS; ++r) {
-        const WeGateRow& R = G.rows[r];
-        for (int q0 = R.gbeg + w; q0 < R.gend; q0 += WE_RAD_WARPS) {
-          const int h = T.heavy_slot[__float_as_int(sorted[q0].w)];
-          if (T.is_solute[h])
-            we_rad_one<true>(T, fpos, b, cstart, cell_of + fo, sorted, tmp4 + fo, search_radius, f, h, O, state, M, diag, S, PT, lane, w);
+        const int4 rj = G.rj[r];
+        for (int q0 = rj.z; q0 < rj.w; q0 += 32) {
+          const int q = q0 + lane;
+          const bool want = q < rj.w && (sfl[q] & 2u);
+          const unsigned m = __ballot_sync(0xffffffffu, want);
+          int base = 0;
+          if (lane == 0 && m) base = atomicAdd(&n0[f], __popc(m));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (want) wl0[(size_t)f * wl0_stride + base + __popc(m & ((1u << lane) - 1u))] = T.heavy_slot[__float_as_int(sorted[q].w)];
         }
       }
       continue;
     }
-    // ---- every solute atom of the group against the staged window --------------------------------
+    // ---- every solute atom of the group against the staged window ----------------------------------
     const double r_cover = fmin((double)b.rc_eff, WE_CUTOFF);
-    const double r = fmin((double)search_radius, r_cover);
-    const float rf = (float)r + 0.02f, rf2 = rf * rf;
-    for (int ci = w; ci < n_centres; ci += WE_RAD_WARPS) {
+    const double rr = fmin((double)search_radius, r_cover);
+    for (int ci = 0; ci < n_centres; ++ci) {
       const int self = G.centres[ci];
       const float4 me = G.cand[self];
       const int qme = __float_as_int(me.w) & 0x7fffffff;
-      const float4 me_raw = sorted[qme];
-      const int my_atom = __float_as_int(me_raw.w);
-      const int h = T.heavy_slot[my_atom];
-      const size_t ho = fo + h;
-      const int exl = lane < WE_MAX_EXCL ? T.excl[(size_t)h * WE_MAX_EXCL + lane] : -1;
-      const int n_bonded = __popc(__ballot_sync(0xffffffffu, exl >= 0));
-      // sweep A: nearest water (float32, squared)
-      float wmin = (float)(r * r);
-      for (int i = lane; i < n_cand; i += 32) {
-        const float4 c = G.cand[i];
-        const float ux = c.x - me.x, uy = c.y - me.y, uz = c.z - me.z;
-        const float d2 = __fmaf_rn(ux, ux, __fmaf_rn(uy, uy, uz * uz));
-        if (__float_as_int(c.w) < 0) wmin = fminf(wmin, d2);
+      const int n_bonded = sfl[qme] >> 2;
+      // sweep A: float32 squared distances of the staged window, kept in registers (this lane's candidates):
+      // the nearest water; solute candidates keep their d^2, waters become +inf.  The window is padded to a
+      // multiple of 32 with far-away dummies, so there is no bounds test; the atom itself is a solute
+      // candidate at distance zero: it is counted and taken off again, and any OTHER zero distance
+      // (coincident coordinates) sends the atom to the exact path.
+      float wmin = (float)(rr * rr);
+      float dsol[WE_GATE_STAGE_CAP / 32];
+      int nzero = 0;
+#pragma unroll
+      for (int k = 0; k < WE_GATE_STAGE_CAP / 32; ++k) {
+        dsol[k] = __int_as_float(0x7f800000);
+        if (k * 32 < n_cand) {  // warp-uniform
+          const float4 c = G.cand[k * 32 + lane];
+          const float ux = c.x - me.x, uy = c.y - me.y, uz = c.z - me.z;
+          const float d2 = __fmaf_rn(ux, ux, __fmaf_rn(uy, uy, uz * uz));
+          const bool wat = __float_as_int(c.w) < 0;
+          wmin = fminf(wmin, wat ? d2 : wmin);
+          dsol[k] = wat ? dsol[k] : d2;
+          nzero += d2 > 0.f ? 0 : 1;
+        }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) wmin = fminf(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
-      // sweep B: solute atoms closer than the nearest water by 1e-3 relative in d^2 (the float32 image
-      // shift is good to ~1e-4); bonded atoms are not candidates of the reference: they are assumed to be
-      // among the counted ones (conservative when they are not); coincident coordinates go to the exact path
+      // sweep B: solute atoms closer than the nearest water by 1e-3 relative in d^2 (the float32 image shift
+      // is good to ~1e-4): compares on the registers, one warp reduction
       const float lim = wmin * (1.0f - 1.0e-3f);
-      int closer = 0;
-      bool zero = false;
-      for (int i0 = 0; i0 < n_cand; i0 += 32) {
-        const int i = i0 + lane;
-        bool near = false;
-        if (i < n_cand && i != self) {
-          const float4 c = G.cand[i];
-          const float ux = c.x - me.x, uy = c.y - me.y, uz = c.z - me.z;
-          const float d2 = __fmaf_rn(ux, ux, __fmaf_rn(uy, uy, uz * uz));
-          zero |= !(d2 > 0.f);
-          near = __float_as_int(c.w) >= 0 && d2 < lim;
-        }
-        closer += __popc(__ballot_sync(0xffffffffu, near));
-      }
-      const bool buried = (closer - n_bonded >= WE_GATE_NBR) && !__any_sync(0xffffffffu, zero);
-      if (buried) {
-        if (lane == 0) { O.shell_n[ho] = 0; O.nn[ho] = -1; O.flags[ho] = 0; state[ho] = 0; }
-        continue;
-      }
-      // sweep C: prefilter survivors -> the warp's candidate list; exact distances; the generic second half
-      int* ss = S.src[w];
-      int nf = 0;
-      for (int i0 = 0; i0 < n_cand; i0 += 32) {
-        const int i = i0 + lane;
-        bool keep = false;
-        int qi = 0;
-        if (i < n_cand) {
-          const float4 c = G.cand[i];
-          const float ux = c.x - me.x, uy = c.y - me.y, uz = c.z - me.z;
-          keep = __fmaf_rn(ux, ux, __fmaf_rn(uy, uy, uz * uz)) <= rf2;
-          qi = __float_as_int(c.w) & 0x7fffffff;
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        const int p = nf + __popc(m & ((1u << lane) - 1u));
-        if (keep && p < WE_CAND_CAP) ss[p] = qi;
-        nf += __popc(m);
-      }
-      __syncwarp();
-      int n = -1;
-      bool dup = false;
-      if (nf <= WE_CAND_CAP) {
-        int ex[WE_MAX_EXCL];
+      int mine = 0;
 #pragma unroll
-        for (int e = 0; e < WE_MAX_EXCL; ++e) ex[e] = __shfl_sync(0xffffffffu, exl, e);
-        n = we_exact_list(b, sorted, nf, r, me_raw.x, me_raw.y, me_raw.z, my_atom, ex, S.d[w], S.f[w], S.idx[w], ss, lane, dup);
+      for (int k = 0; k < WE_GATE_STAGE_CAP / 32; ++k) mine += dsol[k] < lim ? 1 : 0;
+      const int both = __reduce_add_sync(0xffffffffu, mine | (nzero << 16));
+      const int closer = (both & 0xffff) - 1;  // without the atom itself
+      const bool zero = (both >> 16) != 1;     // a zero distance besides its own
+      const bool buried = (closer - n_bonded >= WE_GATE_NBR) && !zero;
+      if (lane == 0) {
+        const int h = T.heavy_slot[__float_as_int(sorted[qme].w)];
+        if (buried) { O.shell_n[fo + h] = 0; O.nn[fo + h] = -1; O.flags[fo + h] = 0; state[fo + h] = 0; }
+        else G.open[n_open] = h;
       }
-      if (n < 0 || (n < WE_MAX_NBR && r < WE_CUTOFF)) {
-        // too many survivors, or fewer than 25 candidates inside the first radius: the adaptive generic search
-        we_rad_one<true>(T, fpos, b, cstart, cell_of + fo, sorted, tmp4 + fo, search_radius, f, h, O, state, M, diag, S, PT, lane, w);
-        continue;
-      }
-      we_rad_finish(T, fpos, b, sorted, f, h, my_atom, fpos[3 * my_atom], fpos[3 * my_atom + 1], fpos[3 * my_atom + 2],
-                    n, WE_ST_OK, dup, O, state, M, diag, S, PT, lane, w);
+      n_open += buried ? 0 : 1;
     }
+    __syncwarp();
+    if (n_open) {  // one append per group
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&n0[f], n_open);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      for (int i = lane; i < n_open; i += 32) wl0[(size_t)f * wl0_stride + base + i] = G.open[i];
+    }
+    __syncwarp();
   }
 }
 
@@ -1309,16 +1359,18 @@ __device__ __forceinline__ int we_append_block(bool want, int* counter, int* s_c
   return want ? slot : -1;
 }
 
+// The lists are built by walking the CELL-SORTED array, so consecutive entries are neighbours in space:
+// the warps of a block then search overlapping windows and share their cache lines.
 // pass-1 list: the waters marked interfacial by pass 0 (state 2 = queued as interfacial water)
 __global__ void __launch_bounds__(256)
-k_list1(WeTopoDev T, const unsigned char* __restrict__ interfacial, int* __restrict__ state,
-        int* __restrict__ wl1, int* __restrict__ n1) {
+k_list1(WeTopoDev T, const float4* __restrict__ sorted4, const unsigned char* __restrict__ interfacial,
+        int* __restrict__ state, int* __restrict__ wl1, int* __restrict__ n1) {
   __shared__ int s_cnt[8];
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const int f = blockIdx.y;
   const size_t fo = (size_t)f * T.n_heavy;
-  const int h = (c < T.n_centres) ? T.centres[c] : 0;
-  const bool want = (c < T.n_centres) && interfacial[fo + h];
+  const int h = (q < T.n_heavy) ? T.heavy_slot[__float_as_int(sorted4[fo + q].w)] : 0;
+  const bool want = (q < T.n_heavy) && interfacial[fo + h];  // only water centres are ever marked
   const int slot = we_append_block(want, &n1[f], s_cnt);
   if (want) { wl1[(size_t)f * T.n_centres + slot] = h; state[fo + h] = 2; }
 }
@@ -1326,14 +1378,15 @@ k_list1(WeTopoDev T, const unsigned char* __restrict__ interfacial, int* __restr
 // pass-2 list (marked shell members whose shell is not computed yet) and the HB list (marked
 // centres that have donor hydrogens)
 __global__ void __launch_bounds__(256)
-k_list2(WeTopoDev T, const unsigned char* __restrict__ mark_shell,
+k_list2(WeTopoDev T, const float4* __restrict__ sorted4, const unsigned char* __restrict__ mark_shell,
         const unsigned char* __restrict__ mark_hb, int* __restrict__ state, int* __restrict__ wl2,
         int* __restrict__ n2, int* __restrict__ wlh, int* __restrict__ nh) {
   __shared__ int s_cnt[8];
-  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const int f = blockIdx.y;
   const size_t fo = (size_t)f * T.n_heavy;
-  const bool valid = h < T.n_heavy;
+  const bool valid = q < T.n_heavy;
+  const int h = valid ? T.heavy_slot[__float_as_int(sorted4[fo + q].w)] : 0;
   const bool w2 = valid && mark_shell && mark_shell[fo + h] && state[fo + h] == 0;
   const bool wh = valid && mark_hb[fo + h] && T.don_ptr[h + 1] != T.don_ptr[h];
   const int p2 = we_append_block(w2, &n2[f], s_cnt);

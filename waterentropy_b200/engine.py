@@ -219,7 +219,7 @@ class WaterEntropyEngine:
 
     # ---- measurement ---------------------------------------------------------
     KERNELS = ["k_bin", "k_scan", "k_scatter", "k_rad", "k_hb", "k_list1", "k_label", "k_cov",
-               "k_rad_pass1", "k_rad_pass2", "k_seed_list2"]
+               "k_rad_pass1", "k_rad_pass2", "k_seed_list2", "k_gate"]
 
     def profile(self, enable=True):
         _lib.check(self.lib.we_profile(self._ctx, int(enable)))
@@ -258,6 +258,20 @@ class WaterEntropyEngine:
         c = np.zeros(nb, dtype=np.uint64)
         _lib.check(self.lib.we_wait_cov(self._ctx, ticket, s.ctypes.data, c.ctypes.data))
         return s, c
+
+    def vibrational_entropies(self, temperature=298):
+        """{(nearest, water resname): (translational S [3], rotational S [3])} of every occupied bin, computed
+        on the device from the covariance tables (entropy/vibrations.py:142-192, diagonalise=True)."""
+        from .entropy.vibrations import Vibrations
+
+        nb = self.lib.we_n_bins(self._ctx)
+        out = np.zeros((nb, 2, 3), dtype=np.float64)
+        _lib.check(self.lib.we_vib_entropy(self._ctx, float(temperature), Vibrations(temperature).mda_conversion(),
+                                           out.ctypes.data))
+        _, cnt = self.cov_tables()
+        cov = decode_cov_tables(self.top, self.recipe, np.zeros((nb, 2, 3, 3)), cnt)
+        keys = list(cov.counts.keys())
+        return {k: (out[b, 0].copy(), out[b, 1].copy()) for k, b in zip(keys, np.nonzero(cnt)[0])}
 
     def device_table_ptrs(self):
         a, b = C.c_void_p(), C.c_void_p()
