@@ -1020,7 +1020,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     }
     if (interfacial && S > 0 && C > 0) {
       { ProfScope ps(c, WE_K_LIST1, st);
-        k_list1<<<gH, 256, 0, st>>>(c->T, c->d_sorted4, c->d_interf, c->d_state, c->d_wl1, c->d_n1);
+        k_list1<<<dim3((C + 255) / 256, n), 256, 0, st>>>(c->T, c->d_interf, c->d_state, c->d_wl1, c->d_n1);
         ps.stop(st); }
       WeWork w1{c->d_wl1, c->d_n1, C, 0};
       if (shells_only) {
@@ -1030,7 +1030,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       } else {
       rad(WE_K_RAD1, w1, (long long)C * n, nullptr, WeMarks{nullptr, mark_hb, mark_shell, nullptr, 0});
       { ProfScope ps(c, WE_K_LIST2, st);
-        k_list2<<<gH, 256, 0, st>>>(c->T, c->d_sorted4, mark_shell, mark_hb, c->d_state, c->d_wl2, c->d_n2, c->d_wlh, c->d_nh);
+        k_list2<<<gH, 256, 0, st>>>(c->T, mark_shell, mark_hb, c->d_state, c->d_wl2, c->d_n2, c->d_wlh, c->d_nh);
         ps.stop(st); }
       WeWork w2{c->d_wl2, c->d_n2, H, 0};
       rad(WE_K_RAD2, w2, (long long)H * n, nullptr, no_marks);
@@ -1038,7 +1038,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       }
     } else if (!interfacial && C > 0) {
       ProfScope ps(c, WE_K_LIST2, st);
-      k_list2<<<gH, 256, 0, st>>>(c->T, c->d_sorted4, nullptr, mark_hb, c->d_state, c->d_wl2, c->d_n2, c->d_wlh, c->d_nh);
+      k_list2<<<gH, 256, 0, st>>>(c->T, nullptr, mark_hb, c->d_state, c->d_wl2, c->d_n2, c->d_wlh, c->d_nh);
       ps.stop(st);
       c->launches++;
     }

@@ -1359,18 +1359,18 @@ __device__ __forceinline__ int we_append_block(bool want, int* counter, int* s_c
   return want ? slot : -1;
 }
 
-// The lists are built by walking the CELL-SORTED array, so consecutive entries are neighbours in space:
-// the warps of a block then search overlapping windows and share their cache lines.
 // pass-1 list: the waters marked interfacial by pass 0 (state 2 = queued as interfacial water)
+// (building the lists in cell order - neighbouring centres on neighbouring warps - was measured: the
+// search passes gain 1-3 %, the list kernels and k_hb lose as much)
 __global__ void __launch_bounds__(256)
-k_list1(WeTopoDev T, const float4* __restrict__ sorted4, const unsigned char* __restrict__ interfacial,
-        int* __restrict__ state, int* __restrict__ wl1, int* __restrict__ n1) {
+k_list1(WeTopoDev T, const unsigned char* __restrict__ interfacial, int* __restrict__ state,
+        int* __restrict__ wl1, int* __restrict__ n1) {
   __shared__ int s_cnt[8];
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int f = blockIdx.y;
   const size_t fo = (size_t)f * T.n_heavy;
-  const int h = (q < T.n_heavy) ? T.heavy_slot[__float_as_int(sorted4[fo + q].w)] : 0;
-  const bool want = (q < T.n_heavy) && interfacial[fo + h];  // only water centres are ever marked
+  const int h = (c < T.n_centres) ? T.centres[c] : 0;
+  const bool want = (c < T.n_centres) && interfacial[fo + h];
   const int slot = we_append_block(want, &n1[f], s_cnt);
   if (want) { wl1[(size_t)f * T.n_centres + slot] = h; state[fo + h] = 2; }
 }
@@ -1378,15 +1378,14 @@ k_list1(WeTopoDev T, const float4* __restrict__ sorted4, const unsigned char* __
 // pass-2 list (marked shell members whose shell is not computed yet) and the HB list (marked
 // centres that have donor hydrogens)
 __global__ void __launch_bounds__(256)
-k_list2(WeTopoDev T, const float4* __restrict__ sorted4, const unsigned char* __restrict__ mark_shell,
+k_list2(WeTopoDev T, const unsigned char* __restrict__ mark_shell,
         const unsigned char* __restrict__ mark_hb, int* __restrict__ state, int* __restrict__ wl2,
         int* __restrict__ n2, int* __restrict__ wlh, int* __restrict__ nh) {
   __shared__ int s_cnt[8];
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
   const int f = blockIdx.y;
   const size_t fo = (size_t)f * T.n_heavy;
-  const bool valid = q < T.n_heavy;
-  const int h = valid ? T.heavy_slot[__float_as_int(sorted4[fo + q].w)] : 0;
+  const bool valid = h < T.n_heavy;
   const bool w2 = valid && mark_shell && mark_shell[fo + h] && state[fo + h] == 0;
   const bool wh = valid && mark_hb[fo + h] && T.don_ptr[h + 1] != T.don_ptr[h];
   const int p2 = we_append_block(w2, &n2[f], s_cnt);

@@ -151,7 +151,9 @@ def _entry_rows(top, e):
     lut = _label_ranks(top, codes[valid]) if valid.any() else np.full(65536, -1, dtype=np.int64)
     rank = np.where(valid, lut[codes], 1 << 40)
     first = valid & np.concatenate([np.ones((E, 1), dtype=bool), codes[:, 1:] != codes[:, :-1]], axis=1)
-    mult = ((codes[:, :, None] == codes[:, None, :]) & valid[:, :, None] & valid[:, None, :]).sum(axis=2)
+    # multiplicity of every member's label: the codes of an entry are sorted, equal labels are one run
+    run = np.cumsum(first, axis=1) - 1 + np.arange(E)[:, None] * 25
+    mult = np.bincount(run[valid], minlength=E * 25)[run]
     don = np.where(first, e["donates"].astype(np.int64), 0)
     acc = np.where(first, e["accepts"].astype(np.int64), 0)
     perm = np.argsort(rank, axis=1, kind="stable")  # members in Python's label order; equal labels stay adjacent
@@ -191,7 +193,10 @@ def _merge_entries(e, group_cols, key):
     """Entries with the same (group, label key) become one: counts add, N_w of the first insert stays."""
     E = len(e)
     seen = np.argsort(np.argsort(~e["first_seen_inv"], kind="stable"), kind="stable")
-    order = np.lexsort([seen] + [key[:, j] for j in range(24, -1, -1)] + list(reversed(group_cols)))
+    # label tuples compare like Python tuples when the ranks (+1, 0 = past the end) are read as one
+    # big-endian byte string: a single sort key instead of 25
+    packed = np.ascontiguousarray((key + 1).astype(">u2")).view("S50").reshape(E)
+    order = np.lexsort([seen, packed] + list(reversed(group_cols)))
     cols = [c[order] for c in group_cols]
     k = key[order]
     new = np.ones(E, dtype=bool)
