@@ -424,7 +424,7 @@ def run_ours(args, rank, world, local_rank):
         nonlocal d2h
         tables = eng.wait_cov(ticket)
         # the bulk recipe returns no per-frame lists (recipes/bulk_water.py:86-90)
-        nrec = sum(len(eng.frame_records(k0 + k)) for k in range(Fps)) if recipe == "interfacial" else 0
+        nrec = len(eng.frame_records_range(k0, Fps)[1]) if recipe == "interfacial" else 0
         d2h = tables[0].nbytes + tables[1].nbytes + Fps * 4 + nrec * 8
         return nrec
 

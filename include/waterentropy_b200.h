@@ -220,6 +220,10 @@ int we_merge_label_entries(we_ctx *ctx, const void *d_entries, int32_t n);
  * out = int32 [count][2] = (water atom index, nearest non-like atom index or -1), ascending. */
 int we_frame_record_count(we_ctx *ctx, int64_t k);
 int we_copy_frame_records(we_ctx *ctx, int64_t k, int32_t *out, int32_t capacity);
+/* The same for `n_frames` consecutive frames in one call: counts int32 [n_frames] (pairs per frame), out
+ * int32 [capacity][2] receives the frames' pairs back to back; returns the total number of pairs. */
+int64_t we_copy_frame_records_range(we_ctx *ctx, int64_t k0, int32_t n_frames, int32_t *counts, int32_t *out,
+                                    int64_t capacity);
 /* RAD shells of the recorded waters of frame k, same order as we_copy_frame_records
  * (needs we_options.keep_shells): out = int32 [count][26] = (n, member 0 .. member 24). */
 int we_copy_frame_shells(we_ctx *ctx, int64_t k, int32_t *out, int32_t capacity);

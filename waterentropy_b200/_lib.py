@@ -54,6 +54,7 @@ EXPORTS = [
     "we_label_entries_device", "we_merge_label_entries", "we_snapshot_cov", "we_wait_cov",
     "we_copy_frame_shells", "we_test_eig3", "we_frames_retired", "we_wait_frames_retired",
     "we_molecule_force_torque", "we_batch_frames", "we_vib_entropy",
+    "we_copy_frame_records_range",
 ]
 
 WE_ERR_DUPLICATE_COORD = -1
@@ -184,6 +185,8 @@ def load():
     L.we_frame_record_count.argtypes = [V, I64]
     L.we_copy_frame_records.restype = I
     L.we_copy_frame_records.argtypes = [V, I64, V, I]
+    L.we_copy_frame_records_range.restype = I64
+    L.we_copy_frame_records_range.argtypes = [V, I64, I, V, V, I64]
     L.we_copy_frame_shells.restype = I
     L.we_copy_frame_shells.argtypes = [V, I64, V, I]
     L.we_copy_heavy_idx.restype = I

@@ -105,6 +105,7 @@ struct we_ctx {
   unsigned char *d_grp_flag = nullptr, *d_sflag = nullptr;
   int *d_grp_list = nullptr, *d_grp_count = nullptr, *d_work_counter = nullptr, *d_wl0 = nullptr, *d_n0 = nullptr;
   int gate_blocks = 0, use_gate = 1;
+  bool cov_on_own_stream = false;  // the last batch's k_cov ran on s_cov (zero-copy forces)
   int hb_blocks = 0, label_blocks = 0;
   int *d_all_slots = nullptr;
   int rad_blocks = 0;
@@ -1076,6 +1077,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       if (!c->lazy) {
         // zero-copy forces: the kernel waits on PCIe reads, so it runs beside the next batch's kernels
         cov_st = (frc_zero_copy && c->cov_stream) ? c->s_cov : st;
+        c->cov_on_own_stream = (cov_st != st);
         if (cov_st != st) {
           CK(cudaEventRecord(c->ev_label[buf], st));
           CK(cudaStreamWaitEvent(cov_st, c->ev_label[buf], 0));
@@ -1355,12 +1357,21 @@ extern "C" int we_snapshot_cov(we_ctx* c) {
     if ((rc = pin_alloc(c, &c->h_snap[slot], bs + bc))) return rc;
     CK(cudaEventCreateWithFlags(&c->ev_snap[slot], cudaEventDisableTiming));
   }
+  // The tables are written by k_cov only.  When it runs on its own stream (zero-copy forces) the snapshot is
+  // queued there, behind the last k_cov, and the compute stream - already busy with the next batches - is
+  // not held up; otherwise everything is on the compute stream.
+  cudaStream_t ss = c->cov_on_own_stream ? c->s_cov : c->s_comp;
   if (!c->ev_cov) CK(cudaEventCreateWithFlags(&c->ev_cov, cudaEventDisableTiming));
-  CK(cudaEventRecord(c->ev_cov, c->s_cov));
-  CK(cudaStreamWaitEvent(c->s_comp, c->ev_cov, 0));
-  CK(cudaMemcpyAsync(c->h_snap[slot], c->d_cov_sum, bs, cudaMemcpyDeviceToHost, c->s_comp));
-  CK(cudaMemcpyAsync(c->h_snap[slot] + bs, c->d_cov_cnt, bc, cudaMemcpyDeviceToHost, c->s_comp));
-  CK(cudaEventRecord(c->ev_snap[slot], c->s_comp));
+  if (c->cov_on_own_stream) {  // behind everything queued on the compute stream so far, without blocking it
+    CK(cudaEventRecord(c->ev_cov, c->s_comp));
+    CK(cudaStreamWaitEvent(c->s_cov, c->ev_cov, 0));
+  } else {
+    CK(cudaEventRecord(c->ev_cov, c->s_cov));
+    CK(cudaStreamWaitEvent(c->s_comp, c->ev_cov, 0));
+  }
+  CK(cudaMemcpyAsync(c->h_snap[slot], c->d_cov_sum, bs, cudaMemcpyDeviceToHost, ss));
+  CK(cudaMemcpyAsync(c->h_snap[slot] + bs, c->d_cov_cnt, bc, cudaMemcpyDeviceToHost, ss));
+  CK(cudaEventRecord(c->ev_snap[slot], ss));
   return (int)(c->snap_counter++ & 0x7fffffff);
 }
 
@@ -1405,6 +1416,7 @@ extern "C" int we_n_label_entries(we_ctx* c) {
   return (int)d.table_entries;
 }
 
+static int compact_entries(we_ctx* c, int n);
 extern "C" int we_copy_label_entries(we_ctx* c, we_label_entry* out, int32_t capacity) {
   if (!c || !out) return fail(WE_ERR_INVALID, "null argument");
   CK(cudaSetDevice(c->device));
@@ -1412,16 +1424,25 @@ extern "C" int we_copy_label_entries(we_ctx* c, we_label_entry* out, int32_t cap
   if (n < 0) return n;
   if (n > capacity) return fail(WE_ERR_INVALID, "capacity %d < %d entries", capacity, n);
   if (n == 0) return 0;
-  WeLabelEntry* tmp = nullptr;
-  CK(cudaMalloc((void**)&tmp, (size_t)n * sizeof(WeLabelEntry)));
-  CK(cudaMemset(c->d_compact_n, 0, sizeof(int)));
-  const unsigned int tn = c->table_mask + 1;
-  k_compact<<<(tn + 255) / 256, 256>>>(c->d_table, tn, tmp, c->d_compact_n);
-  c->launches++;
-  cudaError_t e = cudaMemcpy(out, tmp, (size_t)n * sizeof(WeLabelEntry), cudaMemcpyDeviceToHost);
-  cudaFree(tmp);
-  if (e != cudaSuccess) return fail(WE_ERR_CUDA, "copy of label entries failed: %s", cudaGetErrorString(e));
+  const int rc = compact_entries(c, n);
+  if (rc) return rc;
+  CK(cudaMemcpy(out, c->d_compact, (size_t)n * sizeof(WeLabelEntry), cudaMemcpyDeviceToHost));
   return n;
+}
+
+// the table's occupied entries, packed into the context's compact buffer (kept between calls)
+static int compact_entries(we_ctx* c, int n) {
+  if ((size_t)n > c->compact_cap) {
+    if (c->d_compact) cudaFree(c->d_compact);
+    c->d_compact = nullptr;
+    c->compact_cap = (size_t)n + (size_t)n / 4 + 1024;
+    CK(cudaMalloc((void**)&c->d_compact, c->compact_cap * sizeof(WeLabelEntry)));
+  }
+  CK(cudaMemsetAsync(c->d_compact_n, 0, sizeof(int), c->s_comp));
+  const unsigned int tn = c->table_mask + 1;
+  if (n) { k_compact<<<(tn + 255) / 256, 256, 0, c->s_comp>>>(c->d_table, tn, c->d_compact, c->d_compact_n); c->launches++; }
+  CK(cudaStreamSynchronize(c->s_comp));
+  return 0;
 }
 
 extern "C" int we_label_entries_device(we_ctx* c, void** d_entries) {
@@ -1429,16 +1450,8 @@ extern "C" int we_label_entries_device(we_ctx* c, void** d_entries) {
   CK(cudaSetDevice(c->device));
   const int n = we_n_label_entries(c);
   if (n < 0) return n;
-  if ((size_t)n > c->compact_cap) {
-    if (c->d_compact) cudaFree(c->d_compact);
-    c->d_compact = nullptr;
-    c->compact_cap = (size_t)n + 1024;
-    CK(cudaMalloc((void**)&c->d_compact, c->compact_cap * sizeof(WeLabelEntry)));
-  }
-  CK(cudaMemset(c->d_compact_n, 0, sizeof(int)));
-  const unsigned int tn = c->table_mask + 1;
-  if (n) { k_compact<<<(tn + 255) / 256, 256>>>(c->d_table, tn, c->d_compact, c->d_compact_n); c->launches++; }
-  CK(cudaDeviceSynchronize());
+  const int rc = compact_entries(c, n);
+  if (rc) return rc;
   *d_entries = c->d_compact;
   return n;
 }
@@ -1513,6 +1526,25 @@ extern "C" int we_copy_frame_records(we_ctx* c, int64_t k, int32_t* out, int32_t
   if (n > capacity) return fail(WE_ERR_INVALID, "capacity too small");
   memcpy(out, c->frame_records[(size_t)k].data(), (size_t)n * 2 * sizeof(int));
   return n;
+}
+
+// the recorded waters of `n_frames` consecutive submitted frames in one call: counts[f] pairs per frame,
+// concatenated in `out` (capacity in pairs); returns the total number of pairs
+extern "C" int64_t we_copy_frame_records_range(we_ctx* c, int64_t k0, int32_t n_frames, int32_t* counts, int32_t* out,
+                                               int64_t capacity) {
+  if (!c || !counts || (!out && capacity > 0) || n_frames < 0 || k0 < 0) return fail(WE_ERR_INVALID, "bad argument");
+  if (n_frames == 0) return 0;
+  if (c->opt.keep_records || c->opt.keep_shells) { const int rc = drain_until(c, c->frame_records.size(), k0 + n_frames - 1); if (rc) return rc; }
+  if (k0 + n_frames > (int64_t)c->frame_records.size()) return fail(WE_ERR_INVALID, "frame ordinal out of range (keep_records set?)");
+  int64_t total = 0;
+  for (int f = 0; f < n_frames; ++f) {
+    const std::vector<int>& r = c->frame_records[(size_t)(k0 + f)];
+    counts[f] = (int32_t)(r.size() / 2);
+    if (total + counts[f] > capacity) return fail(WE_ERR_INVALID, "capacity too small");
+    if (!r.empty()) memcpy(out + 2 * total, r.data(), r.size() * sizeof(int));
+    total += counts[f];
+  }
+  return total;
 }
 
 extern "C" int we_copy_frame_shells(we_ctx* c, int64_t k, int32_t* out, int32_t capacity) {

@@ -299,6 +299,17 @@ class WaterEntropyEngine:
         _lib.check(self.lib.we_copy_frame_records(self._ctx, k, out.ctypes.data, len(out)))
         return out[:n]
 
+    def frame_records_range(self, k0, n):
+        """(counts [n], pairs [total, 2]) of the submitted frames k0 .. k0 + n - 1 in one call."""
+        counts = np.zeros(max(n, 1), dtype=np.int32)
+        cap = max(1, n * max(1, len(self.top.centres)))
+        if not hasattr(self, "_rec_buf") or len(self._rec_buf) < cap:
+            self._rec_buf = np.empty((cap, 2), dtype=np.int32)
+        total = self.lib.we_copy_frame_records_range(self._ctx, k0, n, counts.ctypes.data, self._rec_buf.ctypes.data, cap)
+        if total < 0:
+            _lib.check(int(total))
+        return counts[:n], self._rec_buf[:total]
+
     def frame_shells(self, k):
         """{water atom: [shell atoms, distance order]} of the recorded waters of submitted frame k."""
         n = _lib.check(self.lib.we_frame_record_count(self._ctx, k))
@@ -341,20 +352,26 @@ class WaterEntropyEngine:
         """frame_solvent_indices[frame][resname][resid] = [water atom idx ...] (ascending)."""
         top = self.top
         out = nested_dict()
-        for k, frame in enumerate(self.frame_ids):
-            rec = self.frame_records(k)
-            rec = rec[rec[:, 1] >= 0]
-            if len(rec) == 0:
-                continue
-            # records are ascending in the water index; a stable sort by (resname, resid) of the nearest
-            # solute atom keeps that order inside every residue's list, as upstream's appends do
-            rn = top.resname_id[rec[:, 1]]
-            rid = top.resids[rec[:, 1]]
-            order = np.lexsort((rid, rn))
-            rn, rid, atoms = rn[order], rid[order], rec[order, 0]
-            cut = np.nonzero((rn[1:] != rn[:-1]) | (rid[1:] != rid[:-1]))[0] + 1
-            starts = np.concatenate([[0], cut])
-            by_frame = out[frame]
-            for s0, chunk in zip(starts, np.split(atoms, cut)):
-                by_frame[top.resname_table[rn[s0]]][int(rid[s0])] = chunk.tolist()
+        n = len(self.frame_ids)
+        if n == 0:
+            return out
+        counts, pairs = self.frame_records_range(0, n)
+        frame_of = np.repeat(np.arange(n), counts)
+        keep = pairs[:, 1] >= 0
+        frame_of, atoms, near = frame_of[keep], pairs[keep, 0], pairs[keep, 1]
+        if len(atoms) == 0:
+            return out
+        # records are ascending in the water index inside a frame; a stable sort by (frame, resname, resid) of
+        # the nearest solute atom keeps that order inside every residue's list, as upstream's appends do
+        rn, rid = top.resname_id[near], top.resids[near]
+        order = np.lexsort((rid, rn, frame_of))
+        frame_of, rn, rid, atoms = frame_of[order], rn[order], rid[order], atoms[order]
+        cut = np.nonzero((frame_of[1:] != frame_of[:-1]) | (rn[1:] != rn[:-1]) | (rid[1:] != rid[:-1]))[0] + 1
+        starts = np.concatenate([[0], cut])
+        ends = np.concatenate([cut, [len(atoms)]])
+        atoms_l = atoms.tolist()
+        names = top.resname_table
+        fids = self.frame_ids
+        for s0, e0, fk, a, b in zip(starts.tolist(), ends.tolist(), frame_of[starts].tolist(), rn[starts].tolist(), rid[starts].tolist()):
+            out[fids[fk]][names[a]][b] = atoms_l[s0:e0]
         return out
