@@ -1252,6 +1252,13 @@ extern "C" int we_sync(we_ctx* c) {
   c->inflight.clear();
   c->frames_retired = c->frames_done;
   prof_resolve(c);
+#ifdef WE_CHECKED
+  {
+    int line = 0;
+    CK(cudaMemcpyFromSymbol(&line, we_check_line, sizeof(int)));
+    if (line) return fail(WE_ERR_INVALID, "WE_CHECKED build: index bound violated at we_kernels.cuh:%d", line);
+  }
+#endif
   WeDiag d;
   if ((rc = read_diag(c, &d))) return rc;
   switch (d.err_code) {

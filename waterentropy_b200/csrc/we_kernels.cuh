@@ -105,6 +105,16 @@ struct WeLabelEntry {  // 512 bytes
 };
 static_assert(sizeof(WeLabelEntry) == 512, "label entry must be 512 bytes");
 
+// Bounds checks of our own (compute-sanitizer is closed on this pool): a -DWE_CHECKED build records the
+// source line of the first violated index bound and we_sync reports it; the parity suite is run once per
+// round against that build (profiles/).  The default build compiles the checks away.
+#ifdef WE_CHECKED
+__device__ int we_check_line = 0;
+#define WE_ASSERT(cond) do { if (!(cond)) atomicCAS(&we_check_line, 0, __LINE__); } while (0)
+#else
+#define WE_ASSERT(cond) ((void)0)
+#endif
+
 __device__ __forceinline__ void we_set_error(WeDiag* diag, int code, int frame, int atom) {
   if (atomicCAS(&diag->err_code, 0, code) == 0) {
     diag->err_frame = frame;
@@ -148,6 +158,7 @@ __global__ void k_bin(WeTopoDev T, const float* __restrict__ pos, const WeBox* _
   c0 = max(c0, 0); c1 = max(c1, 0); c2 = max(c2, 0);
   int cell = (c2 * b.nc[1] + c1) * b.nc[0] + c0;
   size_t o = (size_t)f * T.n_heavy + h;
+  WE_ASSERT(cell >= 0 && cell < ncap && b.nc[0] <= 1023 && b.nc[1] <= 1023 && b.nc[2] <= 1023);
   cell_of[o] = (c2 << 20) | (c1 << 10) | c0;  // packed coordinates (<= 1023 cells per axis)
   rank_of[o] = atomicAdd(&cell_count[(size_t)f * (ncap + 1) + cell], 1);
   tmp4[o] = make_float4(q[0], q[1], q[2], __int_as_float(atom));
@@ -234,6 +245,7 @@ __global__ void k_scatter(int n_heavy, const WeBox* __restrict__ boxes, const in
   const int pc = cell_of[o];
   const int cell = ((pc >> 20) * boxes[f].nc[1] + ((pc >> 10) & 1023)) * boxes[f].nc[0] + (pc & 1023);
   int dst = cell_start[(size_t)f * (ncap + 1) + cell] + rank_of[o];
+  WE_ASSERT(cell >= 0 && cell < ncap && dst >= 0 && dst < n_heavy);
   sorted4[(size_t)f * n_heavy + dst] = tmp4[o];
   if (sflag) sflag[(size_t)f * n_heavy + dst] = slot_flag[h];
 }
@@ -314,6 +326,7 @@ __device__ __forceinline__ int we_flush(const WeBox& b, const float4* __restrict
   int ai = -1, qi = -1;
   if (lane < take) {
     qi = stage[(head + lane) & 63];
+    WE_ASSERT(qi >= 0);
     const float4 c = sorted[qi];
     ai = __float_as_int(c.w);
     bool skip = (ai == my_atom);
@@ -428,6 +441,7 @@ __device__ __forceinline__ int we_collect(const WeBox& b, const int* __restrict_
       const int t = q - ri.w;
       const bool second = t >= ri.y;
       qi = second ? ri.z + (t - ri.y) : ri.x + t;
+      WE_ASSERT(ro >= 0 && ro < 32 && t >= 0 && qi >= 0);
       rinfo = ro | (second ? 0x40000000 : 0);
       return true;
     };
@@ -853,6 +867,7 @@ __device__ __forceinline__ void we_rad_finish(const WeTopoDev& T, const float* _
   const bool member = act && !blocked;
   const unsigned mm = __ballot_sync(0xffffffffu, member);
   const int ns = __popc(mm);
+  WE_ASSERT(ns <= WE_MAX_NBR && h >= 0 && h < T.n_heavy);
   if (member) O.shell_idx[ho * WE_MAX_NBR + __popc(mm & ((1u << lane) - 1u))] = cidx;
   bool nonlike = false, wat = false;
   if (act) {
@@ -1087,6 +1102,7 @@ k_gate(WeTopoDev T, const WeBox* __restrict__ boxes, const int* __restrict__ cel
         }
         x += sxr + (second ? (xcase == 1 ? -b.m[0] : b.m[0]) : 0.f);
         y += sy; z += sz;
+        WE_ASSERT(!fits || (rj.x + e >= 0 && rj.x + e < WE_GATE_STAGE_CAP && qi >= 0 && qi < T.n_heavy));
         if (fits) G.cand[rj.x + e] = make_float4(x, y, z, __int_as_float(qi | ((fl & 1u) ? 0x80000000 : 0)));
         if ((fl & 2u) && qi >= rj.z && qi < rj.w) {
           const int p = atomicAdd(&G.n_centres, 1);
@@ -1170,6 +1186,7 @@ k_gate(WeTopoDev T, const WeBox* __restrict__ boxes, const int* __restrict__ cel
       int base = 0;
       if (lane == 0) base = atomicAdd(&n0[f], n_open);
       base = __shfl_sync(0xffffffffu, base, 0);
+      WE_ASSERT(n_open <= WE_GATE_CENTRE_CAP && base + n_open <= wl0_stride);
       for (int i = lane; i < n_open; i += 32) wl0[(size_t)f * wl0_stride + base + i] = G.open[i];
     }
     __syncwarp();
@@ -1372,6 +1389,7 @@ k_list1(WeTopoDev T, const unsigned char* __restrict__ interfacial, int* __restr
   const int h = (c < T.n_centres) ? T.centres[c] : 0;
   const bool want = (c < T.n_centres) && interfacial[fo + h];
   const int slot = we_append_block(want, &n1[f], s_cnt);
+  WE_ASSERT(!want || (slot >= 0 && slot < T.n_centres));
   if (want) { wl1[(size_t)f * T.n_centres + slot] = h; state[fo + h] = 2; }
 }
 
@@ -1389,8 +1407,10 @@ k_list2(WeTopoDev T, const unsigned char* __restrict__ mark_shell,
   const bool w2 = valid && mark_shell && mark_shell[fo + h] && state[fo + h] == 0;
   const bool wh = valid && mark_hb[fo + h] && T.don_ptr[h + 1] != T.don_ptr[h];
   const int p2 = we_append_block(w2, &n2[f], s_cnt);
+  WE_ASSERT((!w2 || (p2 >= 0 && p2 < T.n_heavy)));
   if (w2) { wl2[fo + p2] = h; state[fo + h] = 1; }
   const int ph = we_append_block(wh, &nh[f], s_cnt);
+  WE_ASSERT(!wh || (ph >= 0 && ph < T.n_heavy));
   if (wh) wlh[fo + ph] = h;
 }
 
@@ -1611,6 +1631,7 @@ __device__ __forceinline__ void we_label_one(const WeTopoDev& T, int f, int xs,
   int r = 0;
   if (lane == 0) {
     r = atomicAdd(&rec_count[f], 1);
+    WE_ASSERT(r >= 0 && r < T.n_centres);
     WeRecord rr;
     rr.atom = X;
     rr.nearest = bulk ? -1 : nn;
@@ -1852,6 +1873,7 @@ k_cov(WeTopoDev T, const float* __restrict__ pos, const float* __restrict__ frc,
   if (act) {
     const WeRecord rr = rec[(size_t)f * T.n_centres + r];
     bin = rr.bin;
+    WE_ASSERT(bin >= 0 && bin < T.n_bins);
     const int c = centre_of_slot[T.heavy_slot[rr.atom]];
     const int a0 = T.frag_ptr[c], a1 = T.frag_ptr[c + 1];
     const float* fp = pos + (size_t)f * T.n_atoms * 3;
