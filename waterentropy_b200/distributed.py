@@ -135,22 +135,29 @@ def merge_labels_nccl(eng, root_only=False):
     ws, rank = dist.get_world_size(), dist.get_rank()
     dev = torch.device("cuda", eng.device)
     ptr, n = eng.label_entries_device()
-    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(ws)]
-    dist.all_gather(sizes, torch.tensor([n], dtype=torch.int64, device=dev))
-    sizes = [int(x.item()) for x in sizes]
+    sizes_t = torch.zeros(ws, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(sizes_t, torch.tensor([n], dtype=torch.int64, device=dev))
+    sizes = [int(x) for x in sizes_t.tolist()]
     cap = max(max(sizes), 1)
-    mine = torch.zeros(cap * 512, dtype=torch.uint8, device=dev)
+    mine = torch.empty(cap * 512, dtype=torch.uint8, device=dev)
     if n:
         mine[: n * 512].copy_(_device_tensor(ptr, n * 512, np.uint8, eng.device))
-    outs = [torch.empty_like(mine) for _ in range(ws)]
-    dist.all_gather(outs, mine)
-    torch.cuda.synchronize(dev)
-    if root_only and rank != 0:
-        return eng.label_entries()[:0]
+    if root_only:
+        # only rank 0 needs the other ranks' entries: one gather over NVLink instead of an all-gather
+        outs = [torch.empty_like(mine) for _ in range(ws)] if rank == 0 else None
+        dist.gather(mine, outs, dst=0)
+        torch.cuda.synchronize(dev)
+        if rank != 0:
+            return eng.label_entries(copy=False)[:0]
+    else:
+        flat = torch.empty(ws * cap * 512, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(flat, mine)
+        torch.cuda.synchronize(dev)
+        outs = [flat[r * cap * 512:(r + 1) * cap * 512] for r in range(ws)]
     for r in range(ws):
         if r != rank and sizes[r]:
             eng.merge_label_entries_device(outs[r].data_ptr(), sizes[r])
-    return eng.label_entries()
+    return eng.label_entries(copy=False)
 
 
 def combine(eng):

@@ -119,6 +119,7 @@ class WaterEntropyEngine:
         if getattr(self, "_ctx", None) and self._ctx.value:
             self.lib.we_destroy(self._ctx)
             self._ctx = C.c_void_p()
+        self._entry_buf = None
 
     def __del__(self):  # pragma: no cover
         try:
@@ -278,11 +279,29 @@ class WaterEntropyEngine:
         _lib.check(self.lib.we_device_tables(self._ctx, C.byref(a), C.byref(b)))
         return a.value, b.value, self.lib.we_n_bins(self._ctx)
 
-    def label_entries(self):
+    def label_entries(self, copy=True):
+        """The label table's occupied entries (structured array, ENTRY_DTYPE).  Read into page-locked memory
+        (tens of MB once several ranks' tables are merged).  `copy=False` returns a view of that staging
+        buffer, valid until the next call on this engine (what the recipes use: they consume it at once)."""
         n = _lib.check(self.lib.we_n_label_entries(self._ctx))
-        out = np.zeros(max(n, 1), dtype=ENTRY_DTYPE)
-        got = _lib.check(self.lib.we_copy_label_entries(self._ctx, out.ctypes.data, len(out)))
-        return out[:got]
+        if n == 0:
+            return np.zeros(0, dtype=ENTRY_DTYPE)
+        buf = getattr(self, "_entry_buf", None)
+        if buf is None or buf.numel() < n * ENTRY_DTYPE.itemsize:
+            try:
+                import torch
+
+                buf = torch.empty(int(n * 1.25 + 1024) * ENTRY_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
+            except Exception:  # pragma: no cover
+                buf = None
+            self._entry_buf = buf
+        if buf is None:  # pragma: no cover
+            out = np.zeros(n, dtype=ENTRY_DTYPE)
+            got = _lib.check(self.lib.we_copy_label_entries(self._ctx, out.ctypes.data, len(out)))
+            return out[:got]
+        view = buf.numpy().view(ENTRY_DTYPE)
+        got = _lib.check(self.lib.we_copy_label_entries(self._ctx, view.ctypes.data, len(view)))
+        return view[:got].copy() if copy else view[:got]
 
     def label_entries_device(self):
         """(device pointer, count) of this rank's compacted label entries (512 B each)."""
@@ -346,7 +365,7 @@ class WaterEntropyEngine:
         return decode_cov_tables(self.top, self.recipe, s, c)
 
     def hb_labels(self, entries=None) -> HBLabelCollection:
-        return decode_label_entries(self.top, self.recipe, self.label_entries() if entries is None else entries)
+        return decode_label_entries(self.top, self.recipe, self.label_entries(copy=False) if entries is None else entries)
 
     def frame_solvent_indices(self):
         """frame_solvent_indices[frame][resname][resid] = [water atom idx ...] (ascending)."""

@@ -14,7 +14,7 @@ from waterentropy_b200.recipes.interfacial_solvent import _run
 def get_bulk_water_orient_entropy(system, start: int, end: int, step: int, temperature=298):
     """Returns `(Sorient_dict, covariances, vibrations)`."""
     eng = _run(system, list(range(start, end, step)), "bulk", keep_records=False)
-    covariances, entries, top = eng.covariances(), eng.label_entries(), eng.top
+    covariances, entries, top = eng.covariances(), eng.label_entries(copy=False), eng.top
     eng.close()
     Sorients = Orientations()
     Sorients.add_entries(top, True, entries)

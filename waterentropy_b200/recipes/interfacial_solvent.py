@@ -70,7 +70,7 @@ def get_interfacial_water_orient_entropy(system, start: int, end: int, step: int
     if world[1] > 1:
         covariances, entries, frame_solvent_indices = wdist.combine_raw(eng)
     else:
-        covariances, entries, frame_solvent_indices = eng.covariances(), eng.label_entries(), eng.frame_solvent_indices()
+        covariances, entries, frame_solvent_indices = eng.covariances(), eng.label_entries(copy=False), eng.frame_solvent_indices()
     top = eng.top
     eng.close()
     n_frames = len(indices)
