@@ -499,9 +499,11 @@ extern "C" void we_destroy(we_ctx* c) {
 static int batch_frames(const we_ctx* c) {
   int chunk = c->opt.chunk_frames;
   if (chunk <= 0) {
-    // ~3.2 M heavy-atom centres per batch: on C4 the per-batch fixed cost (a dozen launches, the tails of
-    // the persistent kernels) is ~0.14 ms, 16 % of an 8-frame batch and 5 % of a 24-frame one
-    long long t = 3200000LL / std::max(1, c->H);
+    // ~3.5 M heavy-atom centres per batch (32 frames on C4): the per-batch fixed cost (a dozen launches, the
+    // tails of the persistent kernels) is ~0.14 ms on C4, 16 % of an 8-frame batch, 5 % of a 24-frame one;
+    // 32-frame batches measured +3.5 % device-resident over 24, end to end unchanged; 48 hurts the overlap
+    // of uploads and kernels (two batches per 96-frame submission)
+    long long t = 3500000LL / std::max(1, c->H);
     if (c->opt.keep_shells) t /= 4;  // shells of the recorded waters are staged in pinned memory
     chunk = (int)std::max(1LL, std::min(128LL, t));
     if (chunk >= 8) chunk &= ~7;

@@ -26,7 +26,9 @@
 #define WE_MAX_EXCL 8
 #define WE_CAND_CAP 128
 #define WE_CUTOFF 10.0
+#ifndef WE_RAD_WARPS
 #define WE_RAD_WARPS 8
+#endif
 #define WE_CELLS_PER_RADIUS 2  // cell edge = search radius / 2, searched +-2 cells
 // resident blocks per SM the register allocator must allow for (tuned on B200)
 #ifndef WE_RAD_MINBLOCKS
