@@ -529,6 +529,8 @@ def run_ours(args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, s, recipe, input_bytes),
+            "value_arm": "device-resident inputs, keep_records=False: the per-frame recorded-water lists "
+                         "(frame_solvent_indices) are produced and read back in the e2e arm only",
             "clocks": clk,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "host_input_bytes_per_step": int(input_bytes + Fps * 32), "force_path": force_path,
