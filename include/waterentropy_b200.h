@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define WE_VERSION 200
+#define WE_VERSION 201
 
 /* recipes */
 #define WE_RECIPE_INTERFACIAL 0 /* recipes/interfacial_solvent.py:273-345 (_entropy_per_step) */
@@ -277,6 +277,25 @@ int we_span_stop(we_ctx *ctx, double *ms);
  * Stateless; returns the number of molecules that needed the Jacobi fallback (>= 0) or an error. */
 int we_molecule_force_torque(int32_t device, const float *pos, const float *frc, const double *masses,
                              const int32_t *mol_ptr, int32_t n_mol, int32_t eig_flavour, double *out);
+
+/* recipes/forces_torques.py:14-93 for `multiple_UAs` molecules (more than one heavy atom in one residue;
+ * maths/transformations.py:82-353: united-atom inertia tensor, get_bonded_axes, get_custom_axes,
+ * get_custom_PI_MOI), `n_mol` molecules given as compact arrays over an atom POOL (the molecules' atoms plus
+ * every atom bonded to one of their united atoms): pos / frc float32 [n_pool][3], masses float64 [n_pool];
+ * mol_ptr / mol_atoms: CSR of pool indices per molecule, ascending atom index; ua_ptr [n_mol + 1]: first united
+ * atom of each molecule in ua_atom (pool indices of its heavy atoms, ascending); per united atom three CSR
+ * lists of pool indices, each ascending by atom index: hv = bonded heavy atoms (2 <= mass <= 999), lt = bonded
+ * light atoms (1 <= mass <= 1.1), hin = the light ones that belong to the molecule; box3 = dimensions[:3].
+ * out_mol float64 [n_mol][24]: whole-molecule force (3), torque (3), covariance matrices (9 + 9, no halving);
+ * out_ua float64 [n_ua][25]: the same in the united atom's bonded-axes frame, then 1.0 / 0.0 = has a frame
+ * (an atom bonded to exactly one other heavy atom and no hydrogen has none, forces_torques.py:66).
+ * Stateless; returns the number of Jacobi fallbacks (>= 0) or an error. */
+int we_molecule_force_torque_multi(int32_t device, const float *pos, const float *frc, const double *masses,
+                                   int32_t n_pool, const int32_t *mol_ptr, const int32_t *mol_atoms, int32_t n_mol,
+                                   const int32_t *ua_ptr, const int32_t *ua_atom, const int32_t *hv_ptr,
+                                   const int32_t *hv, const int32_t *lt_ptr, const int32_t *lt,
+                                   const int32_t *hin_ptr, const int32_t *hin, const float *box3,
+                                   int32_t eig_flavour, double *out_mol, double *out_ua);
 
 /* Clear the accumulators (start a new analysis with the same topology). */
 int we_reset(we_ctx *ctx);

@@ -209,6 +209,12 @@ class Atom:
             self._u, np.array(top.fragment_members[top.fragment_id[self.index]])
         )
 
+    def __add__(self, other):
+        # Atom + AtomGroup / Atom -> AtomGroup in the order written (maths/transformations.py:312)
+        if isinstance(other, Atom):
+            return AtomGroup(self._u, np.array([self.index, other.index]))
+        return AtomGroup(self._u, np.concatenate([[self.index], other._ix]))
+
     def __repr__(self):
         return f"<Atom {self.index}: {self.name} of {self.resname} {self.resid}>"
 

@@ -638,6 +638,158 @@ def forces_torques(top: OracleTopology, pos, frc, waters):
     return dict(F=Fv, T=Tv, Fcov=Fcov, Tcov=Tcov, axes=AX, moi=MOI)
 
 
+# --------------------------------------------------------------------------
+# `multiple_UAs` molecules (recipes/forces_torques.py:14-93 with maths/transformations.py:82-353):
+# whole-molecule matrices in the principal-axis frame + one pair of matrices per united atom in its
+# bonded-axes frame.  Plain loops; float32 / float64 placement follows NumPy's promotion of the
+# reference's expressions (positions, forces, box are float32; masses, centres of mass float64).
+# --------------------------------------------------------------------------
+def _get_vector(a, b, dims3):
+    """maths/trig.py:139-157.  Note the first test: EVERY negative component gets +box."""
+    delta = b - a
+    out = []
+    for delt, box in zip(delta, dims3):
+        if delt < 0 and delt < 0.5 * box:
+            delt = delt + box
+        if delt > 0 and delt > 0.5 * box:
+            delt = delt - box
+        out.append(delt)
+    return np.array(out)
+
+
+def _principal_axes_moi(pos32, masses):
+    """shim AtomGroup.principal_axes / moment_of_inertia + maths/transformations.py:113-133"""
+    com = (pos32.astype(np.float64) * masses[:, None]).sum(axis=0) / masses.sum()
+    p = pos32 - com
+    t = np.zeros((3, 3))
+    t[0][0] = (masses * (p[:, 1] ** 2 + p[:, 2] ** 2)).sum()
+    t[0][1] = t[1][0] = -(masses * p[:, 0] * p[:, 1]).sum()
+    t[0][2] = t[2][0] = -(masses * p[:, 0] * p[:, 2]).sum()
+    t[1][1] = (masses * (p[:, 0] ** 2 + p[:, 2] ** 2)).sum()
+    t[1][2] = t[2][1] = -(masses * p[:, 1] * p[:, 2]).sum()
+    t[2][2] = (masses * (p[:, 0] ** 2 + p[:, 1] ** 2)).sum()
+    e_val, e_vec = np.linalg.eig(t)
+    order = np.argsort(e_val)[::-1]
+    axes = e_vec[:, order].T
+    if np.dot(np.cross(axes[0], axes[1]), axes[2]) < 0:
+        axes = axes * -1
+    return com, t, axes
+
+
+def _moi_axis(tensor):
+    ev = np.linalg.eig(tensor)[0]
+    return ev[np.abs(ev).argsort()[::-1]]
+
+
+def _custom_axes(a, b_list, c, dims3):
+    """maths/transformations.py:166-228"""
+    axis1 = np.zeros(3)
+    for b in b_list:
+        ab = _get_vector(a, b, dims3)
+        axis1 += np.divide(ab, np.sqrt((ab**2).sum(axis=-1)))
+    ac = _get_vector(b_list[0], c, dims3) if len(b_list) > 2 else _get_vector(a, c, dims3)
+    ac_norm = np.divide(ac, np.sqrt((ac**2).sum(axis=-1)))
+    axis2 = np.cross(ac_norm, axis1) if len(b_list) > 2 else np.cross(axis1, ac_norm)
+    axis3 = np.cross(axis1, axis2)
+    return np.array((axis1, axis2, axis3))
+
+
+def _custom_PI_MOI(pos32, masses, custom_axes, centre32, dims3):
+    """maths/transformations.py:231-283 (incl. the column-wise division by the ROW norms of :239-240)"""
+    norm2 = np.sum(custom_axes**2, axis=1)
+    PI = custom_axes / norm2**0.5
+    RR = _get_vector(pos32[0], centre32, dims3)
+    for i in range(3):
+        if np.dot(PI[i], RR) < 0:
+            PI[i] = -PI[i]
+    translated = pos32 - centre32
+    mi = np.zeros(3)
+    for coord, mass in zip(translated, masses):
+        mi += np.sum(np.cross(PI, coord) ** 2 * mass, axis=1)
+    return PI, mi
+
+
+def _torque_force(pos32, frc32, masses, centre, axes, mi_axis):
+    """maths/transformations.py:12-64"""
+    rc = np.tensordot(pos32 - centre, axes.T, axes=1)
+    rf = np.tensordot(frc32, axes.T, axes=1)
+    torque = np.sum(np.divide(np.cross(rc, rf), np.sqrt(mi_axis)), axis=0)
+    fs = np.sum(frc32, axis=0)
+    force = np.tensordot(fs, axes.T, axes=1) / np.sum(masses) ** 0.5
+    return force, torque
+
+
+def bonded_axes(top: OracleTopology, pos, dims3, atom):
+    """maths/transformations.py:286-353 -> (axes, MI axis) or (None, position) as upstream."""
+    heavy = [j for j in sorted(top.adj[atom]) if 2.0 <= top.masses[j] <= 999.0]
+    light = [j for j in sorted(top.adj[atom]) if 1.0 <= top.masses[j] <= 1.1]
+    ua_all = [atom] + heavy + light
+    a = pos[atom]
+    custom = None
+    vec = a
+    if len(heavy) == 2:
+        custom = _custom_axes(a, [pos[heavy[0]]], pos[heavy[1]], dims3)
+    if len(heavy) == 1 and len(light) >= 1:
+        custom = _custom_axes(a, [pos[heavy[0]]], pos[light[0]], dims3)
+    if len(heavy) > 2:
+        custom = _custom_axes(a, pos[heavy], pos[heavy[1]], dims3)
+    if len(heavy) == 1 and len(light) == 1:
+        custom = _custom_axes(a, [pos[heavy[0]]], np.zeros(3), dims3)
+    if len(heavy) == 0:
+        _, tens, custom = _principal_axes_moi(pos[ua_all], top.masses[ua_all])
+        vec = _moi_axis(tens)
+    if custom is not None:
+        custom, vec = _custom_PI_MOI(pos[ua_all], top.masses[ua_all], custom, a, dims3)
+    return custom, vec
+
+
+def forces_torques_multi(top: OracleTopology, pos, frc, dims, indices):
+    """recipes/forces_torques.py:14-93 for ONE `multiple_UAs` molecule (atom indices ascending).
+    Returns dict(whole_F, whole_T [3,3]; ua_F, ua_T [k,3,3]; uas = the united atoms that got a frame)."""
+    idx = np.asarray(sorted(int(i) for i in indices), dtype=np.int64)
+    dims3 = np.asarray(dims, dtype=np.float32)[:3]
+    p32, f32, m = pos[idx], frc[idx], top.masses[idx]
+    uas = [int(i) for i in idx if 2.0 <= top.masses[i] <= 999.0]
+    inside = set(int(i) for i in idx)
+    # maths/transformations.py:82-101: united-atom masses (hydrogens bonded INSIDE the molecule)
+    ua_masses = []
+    for i in idx:
+        if top.masses[i] > 1.1:
+            mm = top.masses[i]
+            for h in sorted(top.adj[int(i)]):
+                if h in inside and 1.0 <= top.masses[h] <= 1.1:
+                    mm += top.masses[h]
+            ua_masses.append(mm)
+    com, _, axes = _principal_axes_moi(p32, m)
+    tens = np.zeros((3, 3))
+    for coord, mass in zip(pos[uas], ua_masses):  # maths/transformations.py:138-163
+        dx, dy, dz = coord[0] - com[0], coord[1] - com[1], coord[2] - com[2]
+        tens[0][0] += (abs(dy) ** 2 + abs(dz) ** 2) * mass
+        tens[0][1] -= dx * dy * mass
+        tens[1][0] -= dx * dy * mass
+        tens[1][1] += (abs(dx) ** 2 + abs(dz) ** 2) * mass
+        tens[0][2] -= dx * dz * mass
+        tens[2][0] -= dx * dz * mass
+        tens[2][2] += (abs(dx) ** 2 + abs(dy) ** 2) * mass
+        tens[1][2] -= dy * dz * mass
+        tens[2][1] -= dy * dz * mass
+    F, T = _torque_force(p32, f32, m, com, axes, _moi_axis(tens))
+    out = dict(whole_F=np.outer(F, F), whole_T=np.outer(T, T), uas=[], ua_F=[], ua_T=[])
+    for ua in uas:
+        custom, mi = bonded_axes(top, pos, dims3, ua)
+        if custom is None:
+            continue
+        F, T = _torque_force(p32, f32, m, pos[ua], custom, mi)
+        out["uas"].append(ua)
+        out["ua_F"].append(np.outer(F, F))
+        out["ua_T"].append(np.outer(T, T))
+    if not out["uas"]:
+        raise ValueError("need at least one array to concatenate")  # np.concatenate([]) upstream (:88-92)
+    out["ua_F"] = np.array(out["ua_F"])
+    out["ua_T"] = np.array(out["ua_T"])
+    return out
+
+
 def find_interfacial_solvent(top: OracleTopology, fs: FrameState, solute_UAs=None):
     """recipes/interfacial_solvent.py:25-66 -> sorted unique water atom indices"""
     uas = top.solute_UAs if solute_UAs is None else solute_UAs

@@ -63,3 +63,24 @@ void h_long_double_nrm2(const double* x, int n, int len, double* out) {
   }
 }
 }
+
+// ---- we_multi_ua.cuh: the `multiple_UAs` force / torque item function, host build -------------
+// Same argument list as the C ABI's we_molecule_force_torque_multi (minus the device ordinal), so the
+// CPU suite can drive the product's own host-side packing (recipes/forces_torques.py) through it.
+struct WeDiag { unsigned long long eig_fallbacks; };
+#include "../waterentropy_b200/csrc/we_multi_ua.cuh"
+extern "C" int h_molecule_force_torque_multi(int device, const float* pos, const float* frc, const double* masses,
+                                             int n_pool, const int* mol_ptr, const int* mol_atoms, int n_mol,
+                                             const int* ua_ptr, const int* ua_atom, const int* hv_ptr, const int* hv,
+                                             const int* lt_ptr, const int* lt, const int* hin_ptr, const int* hin,
+                                             const float* box3, int eig_flavour, double* out_mol, double* out_ua) {
+  (void)device; (void)n_pool;
+  WeMultiUA A;
+  A.pos = pos; A.frc = frc; A.mass = masses; A.mol_ptr = mol_ptr; A.mol_atoms = mol_atoms; A.ua_ptr = ua_ptr;
+  A.ua_atom = ua_atom; A.hv_ptr = hv_ptr; A.hv = hv; A.lt_ptr = lt_ptr; A.lt = lt; A.hin_ptr = hin_ptr; A.hin = hin;
+  A.box[0] = box3[0]; A.box[1] = box3[1]; A.box[2] = box3[2];
+  A.n_mol = n_mol; A.n_ua = ua_ptr[n_mol]; A.eig_flavour = eig_flavour;
+  WeDiag d = {0};
+  for (int item = 0; item < A.n_mol + A.n_ua; ++item) we_multi_ua_item(A, item, &d, out_mol, out_ua);
+  return (int)d.eig_fallbacks;
+}

@@ -800,9 +800,89 @@ def test_get_forces_torques_matches_oracle():
         assert np.allclose(r["F"], oa["F"], rtol=RTOL, atol=1e-9 * np.abs(oa["F"]).max())
         assert np.allclose(r["T"], oa["T"], rtol=RTOL, atol=1e-9 * np.abs(oa["T"]).max())
         assert np.allclose(r["Fcov"], oa["Fcov"], rtol=RTOL, atol=1e-9 * np.abs(oa["Fcov"]).max())
-    # a multi-united-atom molecule is outside this path, like upstream's "not applicable to water" branch
-    with pytest.raises(NotImplementedError):
-        get_forces_torques(cov, list(range(0, 12)), "X", u)
+
+
+def _universe(inp):
+    from waterentropy_b200.io import Universe
+
+    return Universe.from_arrays(inp["names"], inp["types"], inp["resnames"], inp["resids"], inp["masses"],
+                                inp["charges"], inp["bonds"], inp["positions"], inp["forces"], inp["dimensions"])
+
+
+class _Group:
+    """stand-in for an MDAnalysis AtomGroup handed to get_forces_torques (hashable, like upstream's)"""
+
+    def __init__(self, u, indices):
+        self.indices = np.asarray(indices, dtype=np.int64)
+        self.resnames = np.asarray(u.atoms.resnames)[self.indices]
+
+
+def test_get_forces_torques_multiple_UAs_matches_reference(golden_flavour):
+    """the `multiple_UAs` branch (recipes/forces_torques.py:58-93, maths/transformations.py:
+    82-353) on the device against outputs of the UNMODIFIED reference (tests/golden/multi_ua_reference.json.gz,
+    oracle/make_golden_multi_ua.py): whole-molecule matrices and the stacked bonded-axes matrices of every
+    united atom, all nine elements, rtol 1e-9 (relative to the matrix scale where elements cancel)."""
+    from waterentropy_b200.entropy.convariances import CovarianceCollection
+    from waterentropy_b200.recipes.forces_torques import get_forces_torques, multi_ua_force_torque
+
+    ref = gio.load_reference("multi_ua")
+    unis = {}
+    n_ua = 0
+    for c in ref["cases"]:
+        tag = c["fixture"]
+        if tag not in unis:
+            unis[tag] = _universe(gio.load_inputs(tag))
+        u = unis[tag]
+        u.trajectory[c["frame"]]
+        mol = _Group(u, c["indices"])
+        cov = CovarianceCollection()
+        get_forces_torques(cov, mol, "NEAR", u)
+        whole = ("NEAR", mol.resnames[0])
+        assert set(cov.forces.keys()) == {whole, (mol, mol)}
+        assert cov.counts[whole] == 1 and cov.counts[(mol, mol)] == 1
+        assert _close_matrix(cov.forces[whole], c["whole_F"]), (tag, c["frame"], c["indices"][0])
+        assert _close_matrix(cov.torques[whole], c["whole_T"]), (tag, c["frame"], c["indices"][0])
+        got_F, got_T = np.asarray(cov.forces[(mol, mol)]), np.asarray(cov.torques[(mol, mol)])
+        assert got_F.shape == np.asarray(c["ua_F"]).shape
+        for k in range(len(got_F)):
+            assert _close_matrix(got_F[k], c["ua_F"][k]), (tag, c["frame"], c["indices"][0], k)
+            assert _close_matrix(got_T[k], c["ua_T"][k]), (tag, c["frame"], c["indices"][0], k)
+        n_ua += len(got_F)
+    assert n_ua == 211
+    # "polymer" molecules (several residues): whole-molecule matrices only, not halved
+    for c in ref["polymers"]:
+        u = unis[c["fixture"]]
+        u.trajectory[c["frame"]]
+        mol = _Group(u, c["indices"])
+        cov = CovarianceCollection()
+        get_forces_torques(cov, mol, "NEAR", u)
+        assert len(cov.forces) == c["keys"] == 1
+        assert _close_matrix(cov.forces[("NEAR", mol.resnames[0])], c["whole_F"])
+        assert _close_matrix(cov.torques[("NEAR", mol.resnames[0])], c["whole_T"])
+    # batched form against the live oracle: every solute residue of the triclinic fixture in one launch
+    inp = gio.load_inputs("synth_tric")
+    top = gio.oracle_topology(inp)
+    u = unis.setdefault("synth_tric", _universe(inp))
+    u.trajectory[2]
+    mols = []
+    for rid in sorted(set(int(r) for r in inp["resids"][top.is_water == 0])):
+        idx = np.nonzero(inp["resids"] == rid)[0]
+        if int(top.is_heavy[idx].sum()) > 1:
+            mols.append(idx)
+    res = multi_ua_force_torque(u, mols)
+    assert len(res) == len(mols) > 5
+    for idx, r in zip(mols, res):
+        with np.errstate(all="ignore"):
+            o = wo.forces_torques_multi(top, inp["positions"][2], inp["forces"][2], inp["dimensions"][2], idx)
+        assert list(r["uas"]) == o["uas"]
+        if _live_oracle_pinned():
+            assert _close_matrix(r["Fcov"], o["whole_F"]) and _close_matrix(r["Tcov"], o["whole_T"])
+        for k in range(len(o["uas"])):  # bonded-axes frames involve no eigenvector sign
+            assert _close_matrix(r["ua_Fcov"][k], o["ua_F"][k]) and _close_matrix(r["ua_Tcov"][k], o["ua_T"][k])
+    # a molecule without any united atom has no length scale upstream either
+    light = [int(i) for i in np.nonzero(gio.load_inputs("arginine")["masses"] < 1.1)[0][:2]]
+    with pytest.raises(ValueError):
+        get_forces_torques(CovarianceCollection(), light, "X", unis["arginine"])
 
 
 def test_find_interfacial_solvent_reference_indices():

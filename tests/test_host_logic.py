@@ -308,6 +308,45 @@ def test_streaming_readers_reproduce_golden_inputs():
                  os.path.join(REF_FILES, "gromacs/aspirin_solution/system.trr"))
 
 
+def test_multiple_UAs_host_build_of_the_kernel_vs_reference(hostlib, monkeypatch):
+    """SURVEY 8 f.4 without a GPU: the item function of `k_force_torque_multi` (csrc/we_multi_ua.cuh) compiled
+    for the host, driven by the product's own packing code (`recipes.forces_torques.multi_ua_force_torque`:
+    atom pool, CSR bond lists), against outputs of the unmodified reference (recipes/forces_torques.py:14-93,
+    tests/golden/multi_ua_reference.json.gz).  The GPU suite runs the same comparison through the C ABI."""
+    from waterentropy_b200 import _lib
+    from waterentropy_b200.io import Universe
+    from waterentropy_b200.recipes import forces_torques as ft
+
+    I, V = ctypes.c_int, ctypes.c_void_p
+    hostlib.h_molecule_force_torque_multi.restype = I
+    hostlib.h_molecule_force_torque_multi.argtypes = [I, V, V, V, I, V, V, I, V, V, V, V, V, V, V, V, V, I, V, V]
+
+    class _Host:
+        we_molecule_force_torque_multi = hostlib.h_molecule_force_torque_multi
+
+    monkeypatch.setattr(_lib, "load", lambda: _Host())
+    ref = gio.load_reference("multi_ua")
+    unis, n_ua = {}, 0
+    for c in ref["cases"]:
+        tag = c["fixture"]
+        if tag not in unis:
+            inp = gio.load_inputs(tag)
+            unis[tag] = Universe.from_arrays(inp["names"], inp["types"], inp["resnames"], inp["resids"], inp["masses"],
+                                             inp["charges"], inp["bonds"], inp["positions"], inp["forces"],
+                                             inp["dimensions"])
+        u = unis[tag]
+        u.trajectory[c["frame"]]
+        r = ft.multi_ua_force_torque(u, [c["indices"]], eig_flavour="avx512", device=0)[0]
+        for key, got in (("whole_F", r["Fcov"]), ("whole_T", r["Tcov"]), ("ua_F", r["ua_Fcov"]), ("ua_T", r["ua_Tcov"])):
+            want = np.asarray(c[key])
+            got = np.asarray(got)
+            assert want.shape == got.shape
+            for a, b in zip(want.reshape(-1, 3, 3), got.reshape(-1, 3, 3)):
+                assert np.allclose(b, a, rtol=1e-9, atol=1e-9 * np.abs(a).max()), (tag, c["frame"], key)
+        n_ua += len(r["uas"])
+    assert n_ua == 211
+
+
 def test_bench_reference_arm_prints_the_contract_line():
     """`bench.py --impl reference` runs without a GPU (it times the oracle port on the host cores) and
     prints one JSON line with the keys the driver reads."""

@@ -11,7 +11,7 @@ import os
 from . import _build
 
 c_int32_p = C.POINTER(C.c_int32)
-WE_VERSION = 200  # include/waterentropy_b200.h; a stale build is refused
+WE_VERSION = 201  # include/waterentropy_b200.h; a stale build is refused
 
 
 class we_topology(C.Structure):
@@ -53,7 +53,7 @@ EXPORTS = [
     "we_profile", "we_kernel_times", "we_span_start", "we_span_stop",
     "we_label_entries_device", "we_merge_label_entries", "we_snapshot_cov", "we_wait_cov",
     "we_copy_frame_shells", "we_test_eig3", "we_frames_retired", "we_wait_frames_retired",
-    "we_molecule_force_torque", "we_batch_frames", "we_vib_entropy",
+    "we_molecule_force_torque", "we_molecule_force_torque_multi", "we_batch_frames", "we_vib_entropy",
     "we_copy_frame_records_range",
 ]
 
@@ -219,6 +219,8 @@ def load():
     L.we_wait_frames_retired.argtypes = [V, I64]
     L.we_molecule_force_torque.restype = I
     L.we_molecule_force_torque.argtypes = [I, V, V, V, V, I, I, V]
+    L.we_molecule_force_torque_multi.restype = I
+    L.we_molecule_force_torque_multi.argtypes = [I, V, V, V, I, V, V, I, V, V, V, V, V, V, V, V, V, I, V, V]
     L.we_vib_entropy.restype = I
     L.we_vib_entropy.argtypes = [V, C.c_double, C.c_double, V]
     L.we_test_eig3.restype = I

@@ -17,6 +17,7 @@
 
 #include "../../include/waterentropy_b200.h"
 #include "we_kernels.cuh"
+#include "we_multi_ua.cuh"
 
 static_assert(sizeof(we_label_entry) == sizeof(WeLabelEntry), "ABI entry layout");
 
@@ -1697,6 +1698,75 @@ extern "C" int we_test_eig3(int32_t device, const double* tensors, int32_t n, in
   return run_test(device, tensors, (size_t)n * 72, out, (size_t)n * 25 * 8, [&](void* di, void* dout) {
     k_test_eig3<<<(n + 127) / 128, 128>>>((const double*)di, n, flavour, (double*)dout);
   });
+}
+
+// recipes/forces_torques.py:14-93 for `multiple_UAs` molecules handed over as compact arrays: one launch,
+// one thread per molecule and per united atom (we_multi_ua.cuh).
+extern "C" int we_molecule_force_torque_multi(int32_t device, const float* pos, const float* frc, const double* masses,
+                                              int32_t n_pool, const int32_t* mol_ptr, const int32_t* mol_atoms, int32_t n_mol,
+                                              const int32_t* ua_ptr, const int32_t* ua_atom, const int32_t* hv_ptr,
+                                              const int32_t* hv, const int32_t* lt_ptr, const int32_t* lt,
+                                              const int32_t* hin_ptr, const int32_t* hin, const float* box3,
+                                              int32_t eig_flavour, double* out_mol, double* out_ua) {
+  if (!pos || !frc || !masses || !mol_ptr || !mol_atoms || !ua_ptr || !ua_atom || !hv_ptr || !hv || !lt_ptr || !lt ||
+      !hin_ptr || !hin || !box3 || !out_mol || !out_ua || n_mol < 0 || n_pool <= 0)
+    return fail(WE_ERR_INVALID, "null argument");
+  if (eig_flavour != WE_EIG_OPENBLAS_AVX512 && eig_flavour != WE_EIG_OPENBLAS_AVX2) return fail(WE_ERR_INVALID, "bad eig_flavour");
+  if (n_mol == 0) return 0;
+  const int n_ua = ua_ptr[n_mol];
+  auto in_pool = [&](const int32_t* a, int n) { for (int i = 0; i < n; ++i) if (a[i] < 0 || a[i] >= n_pool) return false; return true; };
+  auto csr_ok = [&](const int32_t* p, int n) { if (p[0] != 0) return false; for (int i = 0; i < n; ++i) if (p[i + 1] < p[i]) return false; return true; };
+  if (!csr_ok(mol_ptr, n_mol) || !csr_ok(ua_ptr, n_mol) || !csr_ok(hv_ptr, n_ua) || !csr_ok(lt_ptr, n_ua) || !csr_ok(hin_ptr, n_ua))
+    return fail(WE_ERR_INVALID, "malformed CSR offsets");
+  for (int i = 0; i < n_mol; ++i) if (mol_ptr[i + 1] == mol_ptr[i]) return fail(WE_ERR_INVALID, "molecule %d has no atoms", i);
+  if (!in_pool(mol_atoms, mol_ptr[n_mol]) || !in_pool(ua_atom, n_ua) || !in_pool(hv, hv_ptr[n_ua]) || !in_pool(lt, lt_ptr[n_ua]) ||
+      !in_pool(hin, hin_ptr[n_ua]))
+    return fail(WE_ERR_INVALID, "atom index outside the pool");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(WE_ERR_CUDA, "no CUDA device available; waterentropy_b200 has no CPU path");
+  CK(cudaSetDevice(device));
+  cudaError_t e = cudaSuccess;
+  std::vector<void*> owned;
+  auto up = [&](const void* src, size_t bytes) -> void* {
+    void* d = nullptr;
+    if (e == cudaSuccess) e = cudaMalloc(&d, bytes ? bytes : 4);
+    if (e == cudaSuccess) owned.push_back(d);
+    if (e == cudaSuccess && src && bytes) e = cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice);
+    return d;
+  };
+  WeMultiUA A;
+  A.pos = (const float*)up(pos, (size_t)n_pool * 12);
+  A.frc = (const float*)up(frc, (size_t)n_pool * 12);
+  A.mass = (const double*)up(masses, (size_t)n_pool * 8);
+  A.mol_ptr = (const int*)up(mol_ptr, ((size_t)n_mol + 1) * 4);
+  A.mol_atoms = (const int*)up(mol_atoms, (size_t)mol_ptr[n_mol] * 4);
+  A.ua_ptr = (const int*)up(ua_ptr, ((size_t)n_mol + 1) * 4);
+  A.ua_atom = (const int*)up(ua_atom, (size_t)n_ua * 4);
+  A.hv_ptr = (const int*)up(hv_ptr, ((size_t)n_ua + 1) * 4);
+  A.hv = (const int*)up(hv, (size_t)hv_ptr[n_ua] * 4);
+  A.lt_ptr = (const int*)up(lt_ptr, ((size_t)n_ua + 1) * 4);
+  A.lt = (const int*)up(lt, (size_t)lt_ptr[n_ua] * 4);
+  A.hin_ptr = (const int*)up(hin_ptr, ((size_t)n_ua + 1) * 4);
+  A.hin = (const int*)up(hin, (size_t)hin_ptr[n_ua] * 4);
+  A.box[0] = box3[0]; A.box[1] = box3[1]; A.box[2] = box3[2];
+  A.n_mol = n_mol; A.n_ua = n_ua; A.eig_flavour = eig_flavour;
+  double* d_mol = (double*)up(nullptr, (size_t)n_mol * 24 * 8);
+  double* d_ua = (double*)up(nullptr, (size_t)(n_ua ? n_ua : 1) * 25 * 8);
+  WeDiag* d_diag = (WeDiag*)up(nullptr, sizeof(WeDiag));
+  WeDiag hd;
+  memset(&hd, 0, sizeof(hd));
+  if (e == cudaSuccess) e = cudaMemset(d_diag, 0, sizeof(WeDiag));
+  if (e == cudaSuccess) {
+    const int items = n_mol + n_ua;
+    k_force_torque_multi<<<(items + 63) / 64, 64>>>(A, d_diag, d_mol, d_ua);
+    e = cudaDeviceSynchronize();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out_mol, d_mol, (size_t)n_mol * 24 * 8, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && n_ua) e = cudaMemcpy(out_ua, d_ua, (size_t)n_ua * 25 * 8, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(&hd, d_diag, sizeof(WeDiag), cudaMemcpyDeviceToHost);
+  for (void* d : owned) cudaFree(d);
+  if (e != cudaSuccess) return fail(WE_ERR_CUDA, "we_molecule_force_torque_multi failed: %s", cudaGetErrorString(e));
+  return (int)hd.eig_fallbacks;
 }
 
 // recipes/forces_torques.py:14-55 for molecules handed over as compact arrays (one launch, thread per

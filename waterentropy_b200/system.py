@@ -141,8 +141,9 @@ class SystemTopology:
         if len(centres) and (heavy_per_frag[cf] != 1).any():
             bad = centres[np.nonzero(heavy_per_frag[cf] != 1)[0][0]]
             raise NotImplementedError(
-                f"water atom {bad} belongs to a molecule with several united atoms; only single-UA "
-                "solvent is supported (recipes/forces_torques.py:58-93 is out of scope)"
+                f"water atom {bad} belongs to a molecule with several united atoms; the per-frame recipes record "
+                "single-UA solvent only (molecules with several united atoms go through "
+                "recipes.forces_torques.get_forces_torques, reference recipes/forces_torques.py:58-93)"
             )
         sizes = (ends - starts)[cf]
         self.frag_ptr = np.ascontiguousarray(np.concatenate([[0], np.cumsum(sizes)]), dtype=np.int32)
