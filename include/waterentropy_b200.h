@@ -270,6 +270,18 @@ int we_kernel_times(we_ctx *ctx, double *ms /*[WE_N_KERNELS]*/, uint64_t *launch
 int we_span_start(we_ctx *ctx);
 int we_span_stop(we_ctx *ctx, double *ms);
 
+/* entropy/orientations.py:298-370 (`Orientations.get_orientational_entropy_from_dict` over
+ * `WaterOrientCalculator`, :22-238) on the device, from this context's label table (after the cross-rank merge
+ * on rank 0): one row per group of label entries, the shell types of a group folded in Python's sorted order of
+ * their label tuples as upstream does.  label_rank uint16 [65536]: rank of every label code (prefix << 13 |
+ * resname id) in Python's string order of the label strings (topology only; unused codes: anything).
+ * by_resname = 0: groups are (nearest resid, nearest resname) = `resid_labelled_Sorient`; 1: groups are the
+ * nearest resname alone with the entries of all resids merged = `resname_labelled_Sorient` (and both tables of
+ * the bulk recipe).  out_keys int32 [max_groups][2] = resid, resname id of each group (unordered);
+ * out_rows float64 [max_groups][8] = Sor, count, N_c, N_w, Nc_eff, pbias, Sor_Nc, Sor_Nw (:361-370). */
+int we_orient_entropy(we_ctx *ctx, const uint16_t *label_rank, int32_t by_resname, int32_t max_groups,
+                      int32_t *out_keys, double *out_rows, int32_t *n_groups);
+
 /* recipes/forces_torques.py:14-55 (`get_forces_torques`, single-united-atom branch) for `n_mol` molecules
  * given as compact arrays: pos / frc float32 [n_atoms_total][3], masses float64 [n_atoms_total], mol_ptr
  * int32 [n_mol + 1] (CSR).  out float64 [n_mol][24] = rotated mass-weighted force (3), inertia-weighted torque

@@ -1175,3 +1175,57 @@ def test_device_vibrational_entropy_matches_the_host_class():
         assert np.allclose(dev[k][0], vib.translational_S[k], rtol=RTOL, atol=0)
         assert np.allclose(dev[k][1], vib.rotational_S[k], rtol=RTOL, atol=0)
     eng.close()
+
+
+def _cmp_sorient(dev, host):
+    dev, host = gio.plain(dev), gio.plain(host)
+    assert dev.keys() == host.keys()
+    n = 0
+    for k, v in host.items():
+        if isinstance(v, dict):
+            n += _cmp_sorient(dev[k], v)
+        else:
+            assert dev[k][1] == v[1] and isinstance(dev[k][1], int)       # counts are integers
+            assert dev[k] == pytest.approx(v, rel=RTOL, abs=1e-12), (k, dev[k], v)
+            n += 1
+    return n
+
+
+@pytest.mark.parametrize("case", ["arginine", "synth_ortho", "synth_tric", "arginine_bulk", "C3"])
+def test_device_orientational_entropy_matches_the_host_classes(case):
+    """`we_orient_entropy` (csrc/we_orient.cuh) - the label table sorted, merged across resids
+    and folded ON THE DEVICE in the reference's visiting order - against `sorient_from_entries`, which is
+    bit-identical to the reference's Orientations / WaterOrientCalculator classes (entropy/orientations.py:
+    22-370; tests/test_host_logic.py).  rtol 1e-9, both tables, integer counts exact; the C3 case has thousands
+    of label keys over ~140 residues, so the resname table merges the duplicates of many resids."""
+    from waterentropy_b200.entropy.orientations import Orientations, sorient_from_entries
+
+    bulk = case.endswith("_bulk")
+    if case == "C3":
+        from waterentropy_b200 import synthetic
+        from waterentropy_b200.engine import WaterEntropyEngine
+
+        s = synthetic.make_config("C3")
+        P, Fr, D = s.frames(0, 12)
+        eng = WaterEntropyEngine(s, "interfacial", device=0)
+        eng.submit(P, Fr, D, list(range(12)))
+    else:
+        inp = gio.load_inputs(case.replace("_bulk", ""))
+        F = inp["positions"].shape[0]
+        eng = _engine(inp, "bulk" if bulk else "interfacial")
+        eng.submit(inp["positions"], inp["forces"], inp["dimensions"], list(range(F)))
+    eng.sync()
+    entries = eng.label_entries()
+    host_resid, host_resname = sorient_from_entries(eng.top, bulk, entries)
+    o = Orientations()
+    o.add_device(eng)
+    assert _cmp_sorient(o.resid_labelled_Sorient, host_resid) >= 1
+    assert _cmp_sorient(o.resname_labelled_Sorient, host_resname) >= 1
+    if case == "C3":
+        assert len(entries) > 2000 and len(gio.plain(host_resid)) > 100
+    # the table is left as it was (the call only reads it): a second call and the entries agree
+    again = Orientations()
+    again.add_device(eng)
+    assert gio.plain(again.resid_labelled_Sorient) == gio.plain(o.resid_labelled_Sorient)
+    assert np.array_equal(np.sort(eng.label_entries()["hash"]), np.sort(entries["hash"]))
+    eng.close()

@@ -53,7 +53,7 @@ EXPORTS = [
     "we_profile", "we_kernel_times", "we_span_start", "we_span_stop",
     "we_label_entries_device", "we_merge_label_entries", "we_snapshot_cov", "we_wait_cov",
     "we_copy_frame_shells", "we_test_eig3", "we_frames_retired", "we_wait_frames_retired",
-    "we_molecule_force_torque", "we_molecule_force_torque_multi", "we_batch_frames", "we_vib_entropy",
+    "we_molecule_force_torque", "we_molecule_force_torque_multi", "we_batch_frames", "we_vib_entropy", "we_orient_entropy",
     "we_copy_frame_records_range",
 ]
 
@@ -223,6 +223,8 @@ def load():
     L.we_molecule_force_torque_multi.argtypes = [I, V, V, V, I, V, V, I, V, V, V, V, V, V, V, V, V, I, V, V]
     L.we_vib_entropy.restype = I
     L.we_vib_entropy.argtypes = [V, C.c_double, C.c_double, V]
+    L.we_orient_entropy.restype = I
+    L.we_orient_entropy.argtypes = [V, V, I, I, V, V, V]
     L.we_test_eig3.restype = I
     L.we_test_eig3.argtypes = [I, V, I, I, V]
     _lib = L

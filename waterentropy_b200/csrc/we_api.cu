@@ -18,6 +18,7 @@
 #include "../../include/waterentropy_b200.h"
 #include "we_kernels.cuh"
 #include "we_multi_ua.cuh"
+#include "we_orient.cuh"
 
 static_assert(sizeof(we_label_entry) == sizeof(WeLabelEntry), "ABI entry layout");
 
@@ -1204,6 +1205,59 @@ extern "C" int we_vib_entropy(we_ctx* c, double temperature, double conversion, 
   cudaError_t e = cudaMemcpy(out, d_out, (size_t)c->B * 6 * sizeof(double), cudaMemcpyDeviceToHost);
   cudaFree(d_out);
   if (e != cudaSuccess) return fail(WE_ERR_CUDA, "we_vib_entropy failed: %s", cudaGetErrorString(e));
+  return WE_OK;
+}
+
+// entropy/orientations.py:298-370 on the device: one row per group of label entries (we_orient.cuh).
+static int compact_entries(we_ctx* c, int n);
+extern "C" int we_orient_entropy(we_ctx* c, const uint16_t* label_rank, int32_t by_resname, int32_t max_groups,
+                                 int32_t* out_keys, double* out_rows, int32_t* n_groups) {
+  if (!c || !label_rank || !out_keys || !out_rows || !n_groups || max_groups < 0) return fail(WE_ERR_INVALID, "null argument");
+  { const int rc = quiesce(c); if (rc) return rc; }
+  const int n = we_n_label_entries(c);
+  if (n < 0) return n;
+  *n_groups = 0;
+  if (n == 0) return WE_OK;
+  { const int rc = compact_entries(c, n); if (rc) return rc; }
+  int n_pad = 1;
+  while (n_pad < n) n_pad <<= 1;
+  unsigned short* d_rank = nullptr;
+  WeOrientRec* d_rec = nullptr;
+  WeOrientRow* d_rows = nullptr;
+  double* d_out = nullptr;
+  int *d_keys = nullptr, *d_ng = nullptr;
+  cudaError_t e = cudaSuccess;
+  auto al = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes ? bytes : 8); };
+  al((void**)&d_rank, 65536 * sizeof(unsigned short));
+  al((void**)&d_rec, (size_t)n_pad * sizeof(WeOrientRec));
+  al((void**)&d_rows, (size_t)n * sizeof(WeOrientRow));
+  al((void**)&d_out, (size_t)max_groups * 8 * sizeof(double));
+  al((void**)&d_keys, (size_t)max_groups * 2 * sizeof(int));
+  al((void**)&d_ng, sizeof(int));
+  cudaStream_t st = c->s_comp;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_rank, label_rank, 65536 * sizeof(unsigned short), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_ng, 0, sizeof(int), st);
+  if (e == cudaSuccess) {
+    const WeLabelEntry* ent = c->d_compact;
+    k_orient_keys<<<(n_pad + 127) / 128, 128, 0, st>>>(ent, n, n_pad, d_rank, by_resname ? 1 : 0, d_rec);
+    c->launches++;
+    for (int k = 2; k <= n_pad; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) { k_orient_bitonic<<<(n_pad + 255) / 256, 256, 0, st>>>(d_rec, n_pad, j, k); c->launches++; }
+    k_orient_rows<<<(n + 127) / 128, 128, 0, st>>>(ent, d_rec, n, d_rank, d_rows);
+    k_orient_fold<<<(n + 127) / 128, 128, 0, st>>>(ent, d_rec, d_rows, n, max_groups, d_ng, d_out, d_keys);
+    c->launches += 2;
+    e = cudaStreamSynchronize(st);
+  }
+  int ng = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(&ng, d_ng, sizeof(int), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && ng <= max_groups && ng > 0) {
+    e = cudaMemcpy(out_rows, d_out, (size_t)ng * 8 * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(out_keys, d_keys, (size_t)ng * 2 * sizeof(int), cudaMemcpyDeviceToHost);
+  }
+  cudaFree(d_rank); cudaFree(d_rec); cudaFree(d_rows); cudaFree(d_out); cudaFree(d_keys); cudaFree(d_ng);
+  if (e != cudaSuccess) return fail(WE_ERR_CUDA, "we_orient_entropy failed: %s", cudaGetErrorString(e));
+  *n_groups = ng;
+  if (ng > max_groups) return fail(WE_ERR_INVALID, "max_groups %d < %d groups", max_groups, ng);
   return WE_OK;
 }
 

@@ -16,7 +16,7 @@ import numpy as np
 from . import _lib
 from .analysis.HB_labels import HBLabelCollection
 from .entropy.convariances import CovarianceCollection
-from .system import RECIPE_BULK, RECIPE_INTERFACIAL, SystemTopology
+from .system import PREFIX, RECIPE_BULK, RECIPE_INTERFACIAL, SystemTopology
 from .utils.helpers import nested_dict
 
 ENTRY_DTYPE = np.dtype(
@@ -273,6 +273,42 @@ class WaterEntropyEngine:
         cov = decode_cov_tables(self.top, self.recipe, np.zeros((nb, 2, 3, 3)), cnt)
         keys = list(cov.counts.keys())
         return {k: (out[b, 0].copy(), out[b, 1].copy()) for k, b in zip(keys, np.nonzero(cnt)[0])}
+
+    def orient_entropy(self, bulk=None):
+        """`(resid_labelled_Sorient, resname_labelled_Sorient)` computed on the device from this context's
+        label table (`we_orient_entropy`; reference `entropy/orientations.py:298-370`): the label entries
+        never come to the host.  Rows are `[Sor, count, N_c, N_w, Nc_eff, pbias, Sor_Nc, Sor_Nw]`."""
+        bulk = (self.recipe == RECIPE_BULK) if bulk is None else bool(bulk)
+        top = self.top
+        rank = getattr(top, "_we_label_rank", None)
+        if rank is None:  # Python's string order over the whole label alphabet (topology only)
+            nres = len(top.resname_table)
+            codes = np.array([(p << 13) | r for p in range(len(PREFIX)) for r in range(nres)], dtype=np.int64)
+            strings = [top.label_string(int(c)) for c in codes]
+            order = sorted(range(len(codes)), key=strings.__getitem__)
+            rank = np.zeros(65536, dtype=np.uint16)
+            rank[codes[order]] = np.arange(len(order), dtype=np.uint16)
+            top._we_label_rank = rank
+        n_entries = _lib.check(self.lib.we_n_label_entries(self._ctx))
+        tables = []
+        for by_resname in ((1, 1) if bulk else (0, 1)):
+            cap = max(1, n_entries)
+            keys = np.zeros((cap, 2), dtype=np.int32)
+            rows = np.zeros((cap, 8), dtype=np.float64)
+            ng = C.c_int32(0)
+            _lib.check(self.lib.we_orient_entropy(self._ctx, rank.ctypes.data, by_resname, cap, keys.ctypes.data,
+                                                  rows.ctypes.data, C.byref(ng)))
+            tables.append((keys[:ng.value], rows[:ng.value]))
+        by_resid, by_resname_t = nested_dict(), nested_dict()
+        for (keys, rows), table in zip(tables, (by_resid, by_resname_t)):
+            for (resid, rn), row in zip(keys.tolist(), rows.tolist()):
+                name = top.resname_table[rn]
+                row[1] = int(row[1])
+                if table is by_resname_t:
+                    table[name] = row
+                else:
+                    table[name if bulk else int(resid)][name] = row
+        return by_resid, by_resname_t
 
     def device_table_ptrs(self):
         a, b = C.c_void_p(), C.c_void_p()

@@ -97,6 +97,12 @@ class Orientations:
         """Fill both tables straight from the device label entries (no HBLabelCollection in between)."""
         self.resid_labelled_Sorient, self.resname_labelled_Sorient = sorient_from_entries(top, bulk, entries)
 
+    def add_device(self, engine, bulk=None):
+        """Fill both tables on the device (`we_orient_entropy`, csrc/we_orient.cuh): the label table is sorted,
+        merged and folded there in the reference's order and only one row per residue comes back.  Agrees with
+        `add_entries` / `add_data` to rounding (device `log` / `pow`; tested at rtol 1e-9)."""
+        self.resid_labelled_Sorient, self.resname_labelled_Sorient = engine.orient_entropy(bulk)
+
     def add_data(self, hb_labels):
         self.get_orientational_entropy_from_dict(
             hb_labels.labelled_shell_counts, self.resname_labelled_Sorient)

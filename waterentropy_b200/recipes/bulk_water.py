@@ -14,10 +14,10 @@ from waterentropy_b200.recipes.interfacial_solvent import _run
 def get_bulk_water_orient_entropy(system, start: int, end: int, step: int, temperature=298):
     """Returns `(Sorient_dict, covariances, vibrations)`."""
     eng = _run(system, list(range(start, end, step)), "bulk", keep_records=False)
-    covariances, entries, top = eng.covariances(), eng.label_entries(copy=False), eng.top
-    eng.close()
+    covariances = eng.covariances()
     Sorients = Orientations()
-    Sorients.add_entries(top, True, entries)
+    Sorients.add_device(eng, bulk=True)  # reduced on the device (we_orient_entropy)
+    eng.close()
     vibrations = Vibrations(temperature)
     vibrations.add_data(covariances, diagonalise=True)
     return Sorients.resid_labelled_Sorient, covariances, vibrations

@@ -67,17 +67,18 @@ def get_interfacial_water_orient_entropy(system, start: int, end: int, step: int
     world = wdist.world() if parallel else (0, 1)
     mine = wdist.shard_frames(indices, *world)
     eng = _run(system, mine, "interfacial")
+    Sorients = Orientations()
     if world[1] > 1:
+        # the orientational-entropy table from the merged label entries with array operations: the same
+        # numbers, bit for bit, as Orientations().add_data(HBLabelCollection)
         covariances, entries, frame_solvent_indices = wdist.combine_raw(eng)
+        Sorients.add_entries(eng.top, False, entries)
     else:
-        covariances, entries, frame_solvent_indices = eng.covariances(), eng.label_entries(copy=False), eng.frame_solvent_indices()
-    top = eng.top
+        # one GPU: the table is reduced on the device (we_orient_entropy), the label entries stay there
+        covariances, frame_solvent_indices = eng.covariances(), eng.frame_solvent_indices()
+        Sorients.add_device(eng)
     eng.close()
     n_frames = len(indices)
-    # the orientational-entropy table straight from the device label entries: the same numbers, bit for
-    # bit, as Orientations().add_data(HBLabelCollection) without rebuilding tens of thousands of dict keys
-    Sorients = Orientations()
-    Sorients.add_entries(top, False, entries)
     vibrations = Vibrations(temperature)
     vibrations.add_data(covariances, diagonalise=True)
     return Sorients.resid_labelled_Sorient, covariances, vibrations, frame_solvent_indices, n_frames
