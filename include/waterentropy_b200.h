@@ -100,8 +100,8 @@ typedef struct we_options {
 #define WE_EIG_OPENBLAS_AVX2 1   /* "Haswell" kernels: AVX2 hosts, AMD Zen */
 
 /* Tuning knobs read from the environment by we_create (defaults are the measured optimum on B200):
- *   WE_COPY_GATE=0   uploads of a batch start as soon as its slot is free (default 1: when the previous
- *                    batch's first neighbour pass starts)
+ *   WE_COPY_GATE=1   hold the upload of a batch back until the previous batch's first neighbour pass starts
+ *                    (default 0: uploads run back to back as soon as a slot is free)
  *   WE_COV_STREAM=0  zero-copy k_cov on the compute stream (default 1: own low-priority stream)
  *   WE_GRAPHS=0      launch every kernel individually (default 1: two CUDA graphs per batch for
  *                    host-buffer submissions)                                                          */

@@ -132,6 +132,25 @@ def test_device_distance_bit_exact(dims):
     assert np.array_equal(out, ref)
 
 
+@pytest.mark.parametrize("dims", [[165.3, 165.3, 165.3, 60, 60, 90], [33.0, 29.0, 41.0, 75.0, 80.0, 100.0],
+                                   [50.0, 50.0, 50.0, 70.53, 109.47, 70.53]])
+def test_device_triclinic_distance_is_the_true_minimum_image(dims):
+    """Size-independent property for the unpinned triclinic case (C4's box first): the device distance equals the
+    shortest of 343 periodic images computed independently in fp64, up to the float32 rounding of the wrap."""
+    from test_oracle_golden import _true_minimum_image
+    from waterentropy_b200 import _lib
+
+    L = _lib.load()
+    rng = np.random.default_rng(12)
+    n = 200_000
+    span = float(max(dims[:3]))
+    pairs = rng.uniform(-0.4 * span, 1.4 * span, (n, 6)).astype(np.float32)
+    d32 = np.array(dims, dtype=np.float32)
+    out = np.empty(n)
+    _lib.check(L.we_test_distance(0, _p(pairs), _p(d32), n, _p(out)))
+    assert np.max(np.abs(out - _true_minimum_image(pairs, d32))) < 2e-4 * max(1.0, span / 50.0)
+
+
 def test_device_eig3_replays_numpy_linalg_eig():
     """we_dgeev3 on the device vs numpy.linalg.eig on 10^6 random TIP3P orientations: bit-identical
     eigenvalues / eigenvectors (so identical signs) when the host's OpenBLAS family is restated; the sign

@@ -135,7 +135,7 @@ struct we_ctx {
   int pending_n[WE_NBUF] = {};
   cudaStream_t s_copy = nullptr, s_comp = nullptr, s_cov = nullptr;
   cudaEvent_t ev_in_ready[WE_NBUF]{}, ev_in_free[WE_NBUF]{}, ev_out_ready[WE_NBUF]{}, ev_p0[WE_NBUF]{};
-  int copy_gate = 1, cov_stream = 1, use_graphs = 1, n_sm = 148, rad_blocks_gated = 0;
+  int copy_gate = 0, cov_stream = 1, use_graphs = 1, n_sm = 148, rad_blocks_gated = 0;
   // CUDA graphs of the two kernel runs of a batch (before / after the pass-0 event), per ring slot and
   // frame count; host-buffer submissions only (the device pointers of a slot are fixed)
   struct BatchGraph { cudaGraphExec_t exec = nullptr; unsigned long long launches = 0; };
@@ -889,8 +889,11 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     if (!on_device) {
       // While a host->device DMA is in flight every kernel launch of the compute stream takes 20-40 us
       // longer (measured: the short kernels of a batch appear 2-3x slower, the 0.4 ms first neighbour
-      // pass +3 %).  So the upload of this batch starts when the first pass of the previous batch
-      // starts and is over before the run of short kernels that follows it (WE_COPY_GATE=0: ungated).
+      // pass +3 %).  WE_COPY_GATE=1 therefore holds the upload of this batch back until the first pass
+      // of the previous batch starts.  That paid while an upload was shorter than a batch's kernels; with
+      // 32-frame batches on C4 the upload (2.2 ms) is as long as the kernels (2.1 ms), the gate only
+      // idles the copy engine, and back-to-back uploads are faster (7.77 -> 7.40 ms per 96-frame step):
+      // the default is ungated.
       if (c->copy_gate) CK(cudaStreamWaitEvent(c->s_copy, c->ev_p0[(buf + WE_NBUF - 1) % WE_NBUF], 0));
       CK(cudaMemcpyAsync(c->d_pos[buf], pos + (size_t)f0 * frame_floats, (size_t)n * frame_floats * sizeof(float), cudaMemcpyHostToDevice, c->s_copy));
       dp = c->d_pos[buf];

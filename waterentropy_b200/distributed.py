@@ -124,7 +124,7 @@ def allgather_entries(entries):
     return [o.cpu().numpy().view(entries.dtype)[:k] for o, k in zip(outs, sizes)]
 
 
-def merge_labels_nccl(eng, root_only=False):
+def merge_labels_nccl(eng, root_only=False, download=True):
     """Job-wide label table, merged on the device: all-gather of the compacted entries over NCCL,
     then `we_merge_label_entries` folds the other ranks' entries into this rank's table.
     Returns the merged entries (host structured array); with `root_only` only rank 0 merges and
@@ -157,6 +157,8 @@ def merge_labels_nccl(eng, root_only=False):
     for r in range(ws):
         if r != rank and sizes[r]:
             eng.merge_label_entries_device(outs[r].data_ptr(), sizes[r])
+    if not download:  # the merged table stays on the device (Orientations.add_device reduces it there)
+        return None
     return eng.label_entries(copy=False)
 
 
@@ -166,13 +168,15 @@ def combine(eng):
     return cov, eng.hb_labels(entries), fsi
 
 
-def combine_raw(eng):
-    """(CovarianceCollection, merged label entries, frame_solvent_indices) of the whole job."""
+def combine_raw(eng, download_entries=True):
+    """(CovarianceCollection, merged label entries, frame_solvent_indices) of the whole job.  With NCCL the
+    label tables are merged on the device; `download_entries=False` then leaves the merged table there and
+    returns None in its place."""
     import torch.distributed as dist
 
     tables = allreduce_cov(eng)
     if dist.get_backend() == "nccl":
-        merged = merge_labels_nccl(eng)
+        merged = merge_labels_nccl(eng, download=download_entries)
     else:
         merged = merge_label_entries(allgather_entries(eng.label_entries()))
     fsi_local = {k: {a: dict(b) for a, b in v.items()} for k, v in eng.frame_solvent_indices().items()}

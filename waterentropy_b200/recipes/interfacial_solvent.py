@@ -69,10 +69,13 @@ def get_interfacial_water_orient_entropy(system, start: int, end: int, step: int
     eng = _run(system, mine, "interfacial")
     Sorients = Orientations()
     if world[1] > 1:
-        # the orientational-entropy table from the merged label entries with array operations: the same
-        # numbers, bit for bit, as Orientations().add_data(HBLabelCollection)
-        covariances, entries, frame_solvent_indices = wdist.combine_raw(eng)
-        Sorients.add_entries(eng.top, False, entries)
+        covariances, entries, frame_solvent_indices = wdist.combine_raw(eng, download_entries=False)
+        if entries is None:
+            Sorients.add_device(eng)  # NCCL: the tables were merged on the device and are reduced there
+        else:
+            # host combine (gloo): from the merged label entries with array operations, the same numbers,
+            # bit for bit, as Orientations().add_data(HBLabelCollection)
+            Sorients.add_entries(eng.top, False, entries)
     else:
         # one GPU: the table is reduced on the device (we_orient_entropy), the label entries stay there
         covariances, frame_solvent_indices = eng.covariances(), eng.frame_solvent_indices()
