@@ -1259,6 +1259,13 @@ extern "C" int we_orient_entropy(we_ctx* c, const uint16_t* label_rank, int32_t 
   }
   cudaFree(d_rank); cudaFree(d_rec); cudaFree(d_rows); cudaFree(d_out); cudaFree(d_keys); cudaFree(d_ng);
   if (e != cudaSuccess) return fail(WE_ERR_CUDA, "we_orient_entropy failed: %s", cudaGetErrorString(e));
+#ifdef WE_CHECKED
+  {
+    int line = 0;
+    CK(cudaMemcpyFromSymbol(&line, we_check_line, sizeof(int)));
+    if (line) return fail(WE_ERR_INVALID, "WE_CHECKED build: index bound violated at line %d of we_orient.cuh / we_kernels.cuh", line);
+  }
+#endif
   *n_groups = ng;
   if (ng > max_groups) return fail(WE_ERR_INVALID, "max_groups %d < %d groups", max_groups, ng);
   return WE_OK;

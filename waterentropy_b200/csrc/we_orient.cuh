@@ -107,6 +107,7 @@ __global__ void k_orient_rows(const WeLabelEntry* __restrict__ e, const WeOrient
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const WeOrientRec me = rec[i];
+  WE_ASSERT(me.src >= 0 && me.src < n && me.n <= 25);  // padding records sort behind the n real ones
   if (i > 0 && we_orient_same_type(rec[i - 1], me)) { rows[i].w = -1; return; }
   // ---- merge the run (analysis/HB_labels.py:158-296): counts add, N_w of the earliest insert ----
   const WeLabelEntry& first = e[me.src];
@@ -116,6 +117,7 @@ __global__ void k_orient_rows(const WeLabelEntry* __restrict__ e, const WeOrient
   unsigned long long w = first.shell_count, seen = first.first_seen_inv;
   int n_w = first.n_w;
   for (int j = i + 1; j < n && we_orient_same_type(me, rec[j]); ++j) {
+    WE_ASSERT(rec[j].src >= 0 && rec[j].src < n);
     const WeLabelEntry& x = e[rec[j].src];
     for (int k = 0; k < 25; ++k) { don[k] += x.donates[k]; acc[k] += x.accepts[k]; }
     w += x.shell_count;
@@ -194,6 +196,7 @@ __global__ void k_orient_fold(const WeLabelEntry* __restrict__ e, const WeOrient
   }
   const int g = atomicAdd(n_groups, 1);
   if (g >= max_groups) return;
+  WE_ASSERT(me.src >= 0 && me.src < n);
   double* o = out_rows + (size_t)g * 8;
   o[0] = s_hb; o[1] = (double)total; o[2] = n_c; o[3] = n_w; o[4] = n_eff; o[5] = bias; o[6] = s_nc; o[7] = s_nw;
   const WeLabelEntry& x = e[me.src];
