@@ -350,11 +350,11 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def maxr(x):
+    def maxr(x, op=None):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op or dist.ReduceOp.MAX)
         return float(t.item())
 
     # ---------------- device-resident arm (value) ----------------
@@ -463,7 +463,7 @@ def run_ours(args, rank, world, local_rank):
     # measurements of the same build differ by up to 2x while the device-timed value does not.  The K-step
     # region is therefore timed `--e2e-repeats` times (default 3), each a complete job (K steps + combine +
     # label read, tables reset in between); the fastest is reported and all are listed in e2e["runs_ms"].
-    e2e_runs, combine_runs, local_runs = [], [], []
+    e2e_runs, combine_runs, combine_wait_runs, local_runs = [], [], [], []
     for _ in range(max(1, args.e2e_repeats)):
         barrier()
         t0 = time.perf_counter()
@@ -474,7 +474,10 @@ def run_ours(args, rank, world, local_rank):
         local_runs.append(t1 - t0)  # this rank's own K steps, before the combine and the closing barrier
         barrier()
         e2e_runs.append(maxr(time.perf_counter() - t0))
-        combine_runs.append(maxr(t2 - t1))
+        # the exchange itself = what the LAST rank to arrive spends in it (MIN over ranks); ranks that finish
+        # their steps earlier (faster host feed) also wait in the collective for the others (MAX over ranks)
+        combine_runs.append(maxr(t2 - t1, dist.ReduceOp.MIN if world > 1 else None))
+        combine_wait_runs.append(maxr(t2 - t1))
         eng.reset()
     e2e_s = statistics.median(e2e_runs)
     # per rank: what the host fed this GPU and how busy its kernels were (the e2e limiter at N > 1 is the box's
@@ -540,10 +543,11 @@ def run_ours(args, rank, world, local_rank):
                     "runs_ms_per_step": [round(t / args.steps * 1e3, 3) for t in e2e_runs],
                     "combine_ms": round(statistics.median(combine_runs) * 1e3, 3),
                     "combine_runs_ms": [round(t * 1e3, 3) for t in combine_runs],
+                    "combine_incl_wait_for_slowest_rank_ms": round(statistics.median(combine_wait_runs) * 1e3, 3),
                     "d2h_bytes_at_end_of_job": final_bytes,
                     "timed": "K x (submit from pinned host memory; stream-ordered covariance snapshot + recorded-water "
                              "lists read on the host, overlapping the next step) + end-of-job combine and label-table read "
-                             "(combine_ms: all-reduce + all-gather + device merge + label read, inside the timed region); "
+                             "(combine_ms: all-reduce + gather + device merge + label read as the last rank to arrive sees it, inside the timed region); "
                              "MEDIAN of runs_ms_per_step (complete jobs)",
                     "recipe": e2e_recipe, "per_rank": per_rank},
             "gpu_launches": int(launches),
