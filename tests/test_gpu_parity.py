@@ -878,6 +878,28 @@ def test_get_forces_torques_multiple_UAs_matches_reference(golden_flavour):
         assert len(cov.forces) == c["keys"] == 1
         assert _close_matrix(cov.forces[("NEAR", mol.resnames[0])], c["whole_F"])
         assert _close_matrix(cov.torques[("NEAR", mol.resnames[0])], c["whole_T"])
+
+    # bonding cases no fixture molecule has (tests/golden/odd_ua_inputs.npz, outputs of the unmodified reference):
+    # united atoms without a heavy neighbour, four heavy neighbours, and a molecule none of whose united atoms
+    # gets a frame - upstream raises ValueError there AFTER it has stored the whole-molecule matrices
+    uo = _universe(gio.load_inputs("odd_ua"))
+    for c in ref["odd"]:
+        uo.trajectory[c["frame"]]
+        mol = _Group(uo, c["indices"])
+        cov = CovarianceCollection()
+        if "raises" in c:
+            with pytest.raises(ValueError):
+                get_forces_torques(cov, mol, "NEAR", uo)
+            assert set(cov.forces.keys()) == {("NEAR", mol.resnames[0])}
+            assert _close_matrix(cov.forces[("NEAR", mol.resnames[0])], c["whole_F"])
+            continue   # (a linear molecule: its torque is divided by the square root of a rounding-noise moment)
+        get_forces_torques(cov, mol, "NEAR", uo)
+        assert _close_matrix(cov.forces[("NEAR", mol.resnames[0])], c["whole_F"])
+        assert _close_matrix(cov.torques[("NEAR", mol.resnames[0])], c["whole_T"])
+        got_F, got_T = np.asarray(cov.forces[(mol, mol)]), np.asarray(cov.torques[(mol, mol)])
+        assert got_F.shape == np.asarray(c["ua_F"]).shape
+        for k in range(len(got_F)):
+            assert _close_matrix(got_F[k], c["ua_F"][k]) and _close_matrix(got_T[k], c["ua_T"][k])
     # batched form against the live oracle: every solute residue of the triclinic fixture in one launch
     inp = gio.load_inputs("synth_tric")
     top = gio.oracle_topology(inp)

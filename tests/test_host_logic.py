@@ -345,6 +345,27 @@ def test_multiple_UAs_host_build_of_the_kernel_vs_reference(hostlib, monkeypatch
                 assert np.allclose(b, a, rtol=1e-9, atol=1e-9 * np.abs(a).max()), (tag, c["frame"], key)
         n_ua += len(r["uas"])
     assert n_ua == 211
+    # the odd bonding cases (no heavy neighbour, four heavy neighbours, the origin as third point) and the
+    # molecule without any frame, where `get_forces_torques` raises like upstream's np.concatenate([])
+    from waterentropy_b200.entropy.convariances import CovarianceCollection
+
+    inp = gio.load_inputs("odd_ua")
+    uo = Universe.from_arrays(inp["names"], inp["types"], inp["resnames"], inp["resids"], inp["masses"], inp["charges"],
+                              inp["bonds"], inp["positions"], inp["forces"], inp["dimensions"])
+    monkeypatch.setenv("WE_EIG_FLAVOUR", "avx512")
+    for c in ref["odd"]:
+        uo.trajectory[c["frame"]]
+        cov = CovarianceCollection()
+        if "raises" in c:
+            with pytest.raises(ValueError):
+                ft.get_forces_torques(cov, c["indices"], "NEAR", uo)
+            assert len(cov.forces) == 1
+            continue
+        r = ft.multi_ua_force_torque(uo, [c["indices"]], eig_flavour="avx512", device=0)[0]
+        for key, got in (("whole_F", r["Fcov"]), ("whole_T", r["Tcov"]), ("ua_F", r["ua_Fcov"]), ("ua_T", r["ua_Tcov"])):
+            want = np.asarray(c[key])
+            for a, b in zip(want.reshape(-1, 3, 3), np.asarray(got).reshape(-1, 3, 3)):
+                assert np.allclose(b, a, rtol=1e-9, atol=1e-9 * np.abs(a).max()), (c["frame"], key)
 
 
 def test_bench_reference_arm_prints_the_contract_line():

@@ -163,4 +163,9 @@ def get_forces_torques(covariances, molecule, nearest: str, system):
     covariances.add_data(nearest, name, r["Fcov"], r["Tcov"])
     if len(r["uas"]) == 0:
         raise ValueError("need at least one array to concatenate")  # np.concatenate([]) upstream (:88-92)
-    covariances.add_data(molecule, molecule, r["ua_Fcov"], r["ua_Tcov"])
+    try:
+        hash(molecule)
+        key = molecule            # upstream keys this entry by the AtomGroup itself (:87-93)
+    except TypeError:
+        key = tuple(int(i) for i in idx)   # a bare index list / array was handed in
+    covariances.add_data(key, key, r["ua_Fcov"], r["ua_Tcov"])
