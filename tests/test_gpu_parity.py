@@ -1270,3 +1270,57 @@ def test_device_orientational_entropy_matches_the_host_classes(case):
     assert gio.plain(again.resid_labelled_Sorient) == gio.plain(o.resid_labelled_Sorient)
     assert np.array_equal(np.sort(eng.label_entries()["hash"]), np.sort(entries["hash"]))
     eng.close()
+
+
+def test_recipes_reuse_the_last_context_and_results_do_not_change(golden_flavour):
+    """The recipes keep the last context (device workspace, pinned buffers) and reuse it after `we_reset` when
+    the next call has the same topology object, recipe and options - the reference's unit of work is ONE frame
+    per `_entropy_per_step` call.  Reused contexts must give what fresh ones give, other options / systems must
+    not be served from the cache, and WE_ENGINE_CACHE=0 switches it off."""
+    import os
+
+    from waterentropy_b200.io import Universe
+    from waterentropy_b200.recipes import interfacial_solvent as rec
+    from waterentropy_b200.recipes.bulk_water import get_bulk_water_orient_entropy
+
+    inp = gio.load_inputs("arginine")
+    ref = gio.load_reference("arginine")
+    mk = lambda: Universe.from_arrays(inp["names"], inp["types"], inp["resnames"], inp["resids"], inp["masses"],  # noqa: E731
+                                      inp["charges"], inp["bonds"], inp["positions"], inp["forces"], inp["dimensions"])
+    u = mk()
+    rec.drop_cached_context()
+    c0, r0 = rec._CACHE["created"], rec._CACHE["reused"]
+    outs = [rec._entropy_per_step((i, u)) for i in (0, 1, 2, 0)]          # four calls, one context
+    assert rec._CACHE["created"] - c0 == 1 and rec._CACHE["reused"] - r0 == 3
+    for (fsi, cov, lab, n), i in zip(outs, (0, 1, 2, 0)):
+        want = ref["per_step"][i]
+        assert gio.plain(fsi) == want["frame_solvent_indices"]
+        assert gio.plain(lab.resid_labelled_shell_counts) == want["labels"]["resid_labelled_shell_counts"]
+        _cmp_cov(cov, want["cov"])
+    assert gio.plain(outs[0][2].labelled_shell_counts) == gio.plain(outs[3][2].labelled_shell_counts)
+    for k in outs[0][1].counts:
+        # same frame, reused context (fp64 atomics: the order of the additions is free, not the value)
+        assert np.allclose(outs[0][1].forces[k], outs[3][1].forces[k], rtol=1e-13, atol=0)
+    # a longer run after single frames, then other options and another recipe: new contexts, right answers
+    a = rec.get_interfacial_water_orient_entropy(u, 0, 10, 1)
+    assert rec._CACHE["reused"] - r0 == 4
+    shells = rec.get_interfacial_shells(u, 0, 4, 2)                          # shells-only context: not the cached one
+    assert gio.plain(shells) == ref["shells_api"]["0:4:2"]
+    b = rec.get_interfacial_water_orient_entropy(u, 0, 10, 1)
+    assert gio.plain(a[3]) == gio.plain(b[3]) == ref["api"]["0:10:1"]["frame_solvent_indices"]
+    for k in a[1].counts:
+        assert np.allclose(a[1].forces[k], b[1].forces[k], rtol=1e-13, atol=0) and a[1].counts[k] == b[1].counts[k]
+    assert _cmp_sorient(a[0], b[0]) >= 1
+    get_bulk_water_orient_entropy(u, 0, 2, 1)
+    u2 = mk()                                                                # equal topology, other object: no reuse
+    before = rec._CACHE["reused"]
+    rec._entropy_per_step((0, u2))
+    assert rec._CACHE["reused"] == before
+    os.environ["WE_ENGINE_CACHE"] = "0"
+    try:
+        before = rec._CACHE["created"]
+        rec._entropy_per_step((0, u2)); rec._entropy_per_step((0, u2))
+        assert rec._CACHE["created"] - before == 2 and rec._CACHE["eng"] is None
+    finally:
+        del os.environ["WE_ENGINE_CACHE"]
+    rec.drop_cached_context()

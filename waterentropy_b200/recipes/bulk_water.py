@@ -8,7 +8,7 @@ from __future__ import annotations
 
 from waterentropy_b200.entropy.orientations import Orientations
 from waterentropy_b200.entropy.vibrations import Vibrations
-from waterentropy_b200.recipes.interfacial_solvent import _run
+from waterentropy_b200.recipes.interfacial_solvent import _release, _run
 
 
 def get_bulk_water_orient_entropy(system, start: int, end: int, step: int, temperature=298):
@@ -17,7 +17,7 @@ def get_bulk_water_orient_entropy(system, start: int, end: int, step: int, tempe
     covariances = eng.covariances()
     Sorients = Orientations()
     Sorients.add_device(eng, bulk=True)  # reduced on the device (we_orient_entropy)
-    eng.close()
+    _release(eng)
     vibrations = Vibrations(temperature)
     vibrations.add_data(covariances, diagonalise=True)
     return Sorients.resid_labelled_Sorient, covariances, vibrations

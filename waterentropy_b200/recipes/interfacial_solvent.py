@@ -29,6 +29,69 @@ def _device():
     return 0
 
 
+# ---- context cache -----------------------------------------------------------------------------
+# Creating a context costs ~0.2 s on a C4-sized system (device workspace, pinned record buffers, the first
+# short batch that sizes the label table) - more than the kernels of a hundred frames.  The reference's unit
+# of work is `_entropy_per_step`, ONE frame per call (dask maps it over the frames), and users call the recipes
+# block after block; so the last context is kept and reused (after `we_reset`) by the next call with the same
+# topology object, recipe, device and options.  One context at most is kept; WE_ENGINE_CACHE=0 disables it.
+_CACHE = {"key": None, "eng": None, "created": 0, "reused": 0}
+_ENV_KEYS = ("WE_EIG_FLAVOUR", "WE_COPY_GATE", "WE_COV_STREAM", "WE_GRAPHS", "WE_GATE", "WE_LIB_PATH")
+
+
+def _cache_key(top, recipe, kw):
+    import os
+
+    return (id(top), recipe, _device(), tuple(sorted(kw.items())), tuple(os.environ.get(k) for k in _ENV_KEYS))
+
+
+def _acquire(system, recipe, **kw):
+    import os
+
+    top = SystemTopology.from_universe(system)
+    key = _cache_key(top, recipe, kw)
+    eng = None
+    if _CACHE["eng"] is not None:
+        eng, _CACHE["eng"] = _CACHE["eng"], None
+        if _CACHE["key"] == key and eng.top is top and os.environ.get("WE_ENGINE_CACHE", "1") != "0":
+            try:
+                eng.reset()
+                _CACHE["reused"] += 1
+                eng._cache_key = key
+                return eng
+            except Exception:  # a context left in an error state is not reused
+                pass
+        eng.close()
+    eng = WaterEntropyEngine(top, recipe, device=_device(), **kw)
+    _CACHE["created"] += 1
+    eng._cache_key = key
+    return eng
+
+
+def _release(eng):
+    """Hand a context back after a successful run (instead of `close`)."""
+    import os
+
+    if os.environ.get("WE_ENGINE_CACHE", "1") == "0" or getattr(eng, "_cache_key", None) is None:
+        eng.close()
+        return
+    if _CACHE["eng"] is not None:
+        _CACHE["eng"].close()
+    _CACHE["key"], _CACHE["eng"] = eng._cache_key, eng
+
+
+def drop_cached_context():
+    """Free the cached context (device workspace, pinned buffers) now."""
+    if _CACHE["eng"] is not None:
+        _CACHE["eng"].close()
+    _CACHE["key"], _CACHE["eng"] = None, None
+
+
+import atexit  # noqa: E402
+
+atexit.register(drop_cached_context)
+
+
 def _run(system, indices, recipe, keep_debug=False, keep_records=True, keep_shells=False, shells_only=False):
     if recipe == "interfacial" and len(SystemTopology.from_universe(system).solute_ua) == 0:
         # upstream ends in MDAnalysis' SelectionError here: `select_atoms("resid ")` with an empty
@@ -40,8 +103,8 @@ def _run(system, indices, recipe, keep_debug=False, keep_records=True, keep_shel
     if not shells_only and getattr(system, "has_charges", True) is False:
         raise ValueError("the topology holds no charges (GRO template): hydrogen bonds cannot be assigned; "
                          "only the shells path (get_interfacial_shells / waterShells) runs on it")
-    eng = WaterEntropyEngine(system, recipe, device=_device(), keep_records=keep_records,
-                             keep_debug=keep_debug, keep_shells=keep_shells, shells_only=shells_only)
+    eng = _acquire(system, recipe, keep_records=keep_records, keep_debug=keep_debug, keep_shells=keep_shells,
+                   shells_only=shells_only)
     # whole kernel batches from a recycled ring of pinned buffers: reading batch k + 1 overlaps the
     # kernels of batch k, host memory stays O(ring)
     try:
@@ -80,7 +143,7 @@ def get_interfacial_water_orient_entropy(system, start: int, end: int, step: int
         # one GPU: the table is reduced on the device (we_orient_entropy), the label entries stay there
         covariances, frame_solvent_indices = eng.covariances(), eng.frame_solvent_indices()
         Sorients.add_device(eng)
-    eng.close()
+    _release(eng)
     n_frames = len(indices)
     vibrations = Vibrations(temperature)
     vibrations.add_data(covariances, diagonalise=True)
@@ -93,7 +156,7 @@ def _entropy_per_step(args):
     index, system = args
     eng = _run(system, [index], "interfacial")
     out = (eng.frame_solvent_indices(), eng.covariances(), eng.hb_labels(), 1)
-    eng.close()
+    _release(eng)
     return out
 
 
@@ -108,7 +171,7 @@ def get_interfacial_shells(system, start: int, end: int, step: int):
     for k, frame in enumerate(eng.frame_ids):
         for atom, shell in eng.frame_shells(k).items():
             out[frame][atom] = shell
-    eng.close()
+    _release(eng)
     return out
 
 
@@ -130,7 +193,7 @@ def find_interfacial_solvent(solutes, system, shells=None):
         a = int(a)
         if int(top.fragment_id[a]) in frag and (flags[slot[a]] & 1):
             found.update(n for n in all_shells[a] if top.is_water[n])
-    eng.close()
+    _release(eng)
     return list(found)
 
 
