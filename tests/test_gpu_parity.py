@@ -1160,8 +1160,15 @@ def test_full_size_production_path_vs_oracle_closure(name, n_sampled):
     keys_big = {(int(a), int(b)): int(c) for a, b, c in zip(eb["hash"], eb["hash2"], eb["shell_count"])}
     for a, b, c in zip(es["hash"], es["hash2"], es["shell_count"]):
         assert keys_big.get((int(a), int(b)), 0) >= int(c)
+    # S_orient of the multi-batch table: reduced on the device == the host classes over the downloaded entries
+    from waterentropy_b200.entropy.orientations import Orientations, sorient_from_entries
+
+    host_resid, host_resname = sorient_from_entries(big.top, False, eb)
+    dev = Orientations()
+    dev.add_device(big)
+    n_rows = _cmp_sorient(dev.resid_labelled_Sorient, host_resid) + _cmp_sorient(dev.resname_labelled_Sorient, host_resname)
     print(f"\\n{name}: {n} frames in batches of {B}; oracle closure {closure} of {len(top.heavy_idx)} heavy-atom centres; "
-          f"{n_rec} recorded waters, {len(eb)} label keys")
+          f"{n_rec} recorded waters, {len(eb)} label keys, {n_rows} S_orient rows")
     for e in (big, small):
         e.close()
 
