@@ -370,7 +370,8 @@ def run_ours(args, rank, world, local_rank):
     # ---------------- device-resident arm (value) ----------------
     # every output of the path is produced in the timed region: covariance tables, label table and (interfacial
     # recipe) the per-frame recorded-water lists, which k_label writes to pinned host memory
-    eng = WaterEntropyEngine(s, recipe, device=local_rank, keep_records=(recipe == "interfacial"), chunk_frames=args.chunk)
+    eng = WaterEntropyEngine(s, recipe, device=local_rank, keep_records=(recipe == "interfacial"), chunk_frames=args.chunk,
+                             search_radius=args.search_radius)
     dP, dF = torch.from_numpy(P).cuda(), torch.from_numpy(Fr).cuda()
     for _ in range(args.warmup):
         eng.submit_device(dP, dF, D, ids)
@@ -427,7 +428,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---------------- end-to-end arm (host buffers through the public API) ----------------
     eng = WaterEntropyEngine(s, recipe, device=local_rank, keep_records=(recipe == "interfacial"), chunk_frames=args.chunk,
-                             force_upload=args.force_upload)
+                             force_upload=args.force_upload, search_radius=args.search_radius)
     hP, hF = torch.from_numpy(P).pin_memory(), torch.from_numpy(Fr).pin_memory()
     d2h = 0
 
@@ -581,6 +582,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=2048, help="CPU arm: centres per sampled step (only when complete frames exceed --cpu-budget)")
     ap.add_argument("--cpu-budget", type=float, default=240.0, help="--impl reference: seconds the timed steps may take")
+    ap.add_argument("--search-radius", type=float, default=0.0, help="first-pass candidate radius in A (0 = library default); tuning only, results do not depend on it")
     ap.add_argument("--no-recipe", action="store_true", help="skip the e2e.recipe measurement")
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")

@@ -89,6 +89,10 @@ struct we_ctx {
   bool ws_ready = false;
   int chunk = 0, ncap = 0;
   float cell_target = 7.0f;
+  // first candidate radius of a centre, per k_rad pass, as a fraction of cell_target (the cells always cover
+  // cell_target: a centre that finds fewer than 25 candidates inside the first radius rescans the same cells
+  // at the covered radius before it widens the search)
+  float r_first_frac[3] = {1.0f, 1.0f, 1.0f};
   float* d_pos[WE_NBUF] = {};
   float* d_frc[WE_NBUF] = {};
   WeBox* d_boxes[WE_NBUF] = {};
@@ -443,6 +447,14 @@ extern "C" int we_create(const we_topology* t, const we_options* opt, we_ctx** o
   if (const char* g = getenv("WE_COV_STREAM")) c->cov_stream = atoi(g);
   if (const char* g = getenv("WE_GRAPHS")) c->use_graphs = atoi(g);
   if (const char* g = getenv("WE_GATE")) c->use_gate = atoi(g);
+  if (const char* g = getenv("WE_R_FIRST")) {  // tuning: "f0,f1,f2" fractions of the cell radius per pass
+    float a = 1.f, b = 1.f, d = 1.f;
+    const int k = sscanf(g, "%f,%f,%f", &a, &b, &d);
+    if (k >= 1) c->r_first_frac[0] = a;
+    if (k >= 2) c->r_first_frac[1] = b;
+    if (k >= 3) c->r_first_frac[2] = d;
+    for (float& v : c->r_first_frac) v = std::min(1.0f, std::max(0.3f, v));
+  }
   rc = we_reset(c);
   if (rc) { we_destroy(c); return rc; }
   *out = c;
@@ -510,7 +522,7 @@ static int batch_frames(const we_ctx* c) {
     chunk = (int)std::max(1LL, std::min(128LL, t));
     if (chunk >= 8) chunk &= ~7;
   }
-  return chunk;
+  return std::min(chunk, 128);  // per-batch frame tables in shared memory (k_gate, k_rad) hold 128 frames
 }
 extern "C" int we_batch_frames(we_ctx* c) { return c ? batch_frames(c) : fail(WE_ERR_INVALID, "null context"); }
 
@@ -978,6 +990,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     // pass 0 of the recipe: solute united atoms mark interfacial waters / bulk waters mark their HB centres
     const WeMarks m0 = interfacial ? WeMarks{c->d_interf, nullptr, nullptr, fids, 0}
                                    : WeMarks{nullptr, mark_hb, nullptr, nullptr, 1};
+    int rad_launch = 0;  // every k_rad launch of a batch claims from its own counter (zeroed with the batch's zero block)
     auto rad = [&](int id, const WeWork& wk, long long items, int* gate_state, const WeMarks& mk) {
       if (gate_state && gate) {
         // buried solute atoms are settled by cell group; the rest form the work list of the generic search
@@ -988,20 +1001,21 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
         pg.stop(st);
       }
       ProfScope ps(c, id, st);
+      const float r_first = c->cell_target * c->r_first_frac[id == WE_K_RAD ? 0 : (id == WE_K_RAD1 ? 1 : 2)];
       if (gate_state && gate) {
         const WeWork open{c->d_wl0, c->d_n0, std::max(1, S), 0};
         k_rad<false><<<rad_grid(items), WE_RAD_WARPS * 32, sizeof(WeRadSmem), st>>>(
-            c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->d_tmp4, c->ncap, c->cell_target, open, n, ro,
-            gate_state, mk, c->d_diag);
+            c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->d_tmp4, c->ncap, r_first, open, n, ro,
+            gate_state, mk, c->d_diag, c->d_work_counter + 1 + (rad_launch++ % 7));
         c->launches++;
       } else if (gate_state)
         k_rad<true><<<(int)std::max<long long>(1, std::min<long long>((items + WE_RAD_WARPS - 1) / WE_RAD_WARPS, c->rad_blocks_gated)), WE_RAD_WARPS * 32, sizeof(WeRadSmem), st>>>(
-            c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->d_tmp4, c->ncap, c->cell_target, wk, n, ro,
-            gate_state, mk, c->d_diag);
+            c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->d_tmp4, c->ncap, r_first, wk, n, ro,
+            gate_state, mk, c->d_diag, c->d_work_counter + 1 + (rad_launch++ % 7));
       else
         k_rad<false><<<rad_grid(items), WE_RAD_WARPS * 32, sizeof(WeRadSmem), st>>>(
-            c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->d_tmp4, c->ncap, c->cell_target, wk, n, ro,
-            nullptr, mk, c->d_diag);
+            c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_sorted4, c->d_tmp4, c->ncap, r_first, wk, n, ro,
+            nullptr, mk, c->d_diag, c->d_work_counter + 1 + (rad_launch++ % 7));
       ps.stop(st);
       c->launches++;
     };
