@@ -276,6 +276,8 @@ static int make_box(const float* dims, float cell_target, int ncap, WeBox* b) {
     b->wide[i] = std::max(1, (int)std::ceil((WE_CUTOFF * (1.0 + 1e-5)) / cw));
   }
   b->rc_eff = (float)std::min(rc, 1e30);
+  b->cg[0] = (float)(by / b->nc[1]); b->cg[1] = (float)(cy / b->nc[2]); b->cg[2] = (float)(cz / b->nc[2]);
+  b->cg[3] = (float)(bx / b->nc[1]); b->cg[4] = (float)(cx / b->nc[2]); b->cg[5] = (float)(b->nc[0] / ax);
   // inverse of the lower-triangular cell matrix (row-vector convention r = s . M)
   double hi[9] = {1.0 / ax, 0, 0, -bx / (ax * by), 1.0 / by, 0, (bx * cy - by * cx) / (ax * by * cz), -cy / (by * cz), 1.0 / cz};
   for (int i = 0; i < 9; ++i) { b->hinv[i] = hi[i]; b->hinvf[i] = (float)hi[i]; }

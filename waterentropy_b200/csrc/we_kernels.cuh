@@ -278,6 +278,10 @@ __device__ __forceinline__ void we_cp_async_wait() { asm volatile("cp.async.wait
 #ifndef WE_RAD_DYNAMIC
 #define WE_RAD_DYNAMIC 1  // k_rad: 1 = warps claim centres from a counter, 0 = static common stride
 #endif
+#ifndef WE_CULL
+#define WE_CULL 1  // cell scan: skip the rows / x cells of the searched block that the search sphere cannot reach
+#endif
+#define WE_CULL_MARGIN 0.05f  // Angstrom; the float32 prefilter itself keeps r + 0.02
 #ifndef WE_PREFETCH
 #define WE_PREFETCH 0  // candidate-window prefetch of the cell scan: 0 none, 1 cp.async ring, 2 registers
 #endif
@@ -377,6 +381,21 @@ __device__ __forceinline__ int we_collect(const WeBox& b, const int* __restrict_
   const float rf = (float)r + 0.02f;  // float prefilter radius (exact test follows in fp64)
   const float rf2 = rf * rf;
   const bool simple = b.triclinic && !(all_x || all_y || all_z);
+#if WE_CULL
+  // row culling (below) needs one definite periodic image per visited cell on every axis
+  const bool cull = (2 * wx + 1 < n0) && (2 * wy + 1 < n1) && (2 * wz + 1 < n2);
+#else
+  const bool cull = false;
+#endif
+  const float cull_r = (float)r + WE_CULL_MARGIN;
+  const float cull_r2 = cull_r * cull_r;
+  // the centre inside the box (orthorhombic coordinates are stored raw; triclinic ones are wrapped already)
+  float cx_w = mx, cy_w = my, cz_w = mz;
+  if (cull && !b.triclinic) {
+    cx_w = mx - floorf(mx * b.inv[0]) * b.box[0];
+    cy_w = my - floorf(my * b.inv[1]) * b.box[1];
+    cz_w = mz - floorf(mz * b.inv[2]) * b.box[2];
+  }
   const int mode = !b.triclinic ? 0 : (b.pre_ok ? 1 : 2);
   for (int row0 = 0; row0 < nrows; row0 += 32) {
     // ---- one lane per row: cell ranges and image shift --------------------------------------
@@ -399,15 +418,40 @@ __device__ __forceinline__ int we_collect(const WeBox& b, const int* __restrict_
       px1 = px0;
       if (all_x) { beg0 = cstart[rowbase]; len0 = cstart[rowbase + n0] - beg0; }
       else {
-        const int lo = c0 - wx, hi = c0 + wx;
-        if (lo < 0) {
-          beg0 = cstart[rowbase]; len0 = cstart[rowbase + hi + 1] - beg0;
-          beg1 = cstart[rowbase + lo + n0]; len1 = cstart[rowbase + n0] - beg1; px1 = px0 + b.m[0];
-        } else if (hi >= n0) {
-          beg0 = cstart[rowbase + lo]; len0 = cstart[rowbase + n0] - beg0;
-          beg1 = cstart[rowbase]; len1 = cstart[rowbase + hi - n0 + 1] - beg1; px1 = px0 - b.m[0];
-        } else {
-          beg0 = cstart[rowbase + lo]; len0 = cstart[rowbase + hi + 1] - beg0;
+        int lo = c0 - wx, hi = c0 + wx;
+        if (cull) {
+          // The searched block of cells is a parallelepiped around a sphere (17 % of its volume in a
+          // 60/60/90 degree box): drop the rows the sphere does not reach and trim the others in x.
+          // Lower bound of the distance between the centre and the row's tube (infinite in x), from the
+          // bounding rectangle of the tube's cross-section in the y-z plane (lower-triangular cell: z depends
+          // on the c index only, y on b and c); what remains of the radius bounds |x - x_centre|, and the
+          // x cells follow after subtracting the range of the row's shear s1 m3 + s2 m6.  WE_CULL_MARGIN
+          // covers float rounding and atoms clamped into edge cells (k_bin); it exceeds the prefilter's own
+          // margin, so exactly the candidates the prefilter would reject are skipped.
+          const int yu = c1 + iy - wy, zu = c2 + iz - wz;  // unwrapped cell indices of the row
+          const float zl = zu * b.cg[2], yz0 = zu * b.cg[1], yl = yu * b.cg[0];
+          const float gz = fmaxf(0.f, fmaxf(zl - cz_w, cz_w - (zl + b.cg[2])));
+          const float gy = fmaxf(0.f, fmaxf(yl + fminf(yz0, yz0 + b.cg[1]) - cy_w, cy_w - (yl + b.cg[0] + fmaxf(yz0, yz0 + b.cg[1]))));
+          const float rem = cull_r2 - (gy * gy + gz * gz);
+          if (rem < 0.f) hi = lo - 1;
+          else {
+            const float hx = sqrtf(rem);
+            const float sa = yu * b.cg[3], sb = zu * b.cg[4];
+            const float shlo = fminf(sa, sa + b.cg[3]) + fminf(sb, sb + b.cg[4]);
+            const float shhi = fmaxf(sa, sa + b.cg[3]) + fmaxf(sb, sb + b.cg[4]);
+            lo = max(lo, (int)floorf((cx_w - hx - shhi) * b.cg[5]));
+            hi = min(hi, (int)floorf((cx_w + hx - shlo) * b.cg[5]));
+          }
+        }
+        if (lo <= hi) {
+          // the part of [lo, hi] inside the box, and the part in the neighbouring image (wrapped cells)
+          const int a0 = max(lo, 0), a1 = min(hi, n0 - 1);
+          if (a0 <= a1) { beg0 = cstart[rowbase + a0]; len0 = cstart[rowbase + a1 + 1] - beg0; }
+          if (lo < 0) {
+            beg1 = cstart[rowbase + lo + n0]; len1 = cstart[rowbase + min(hi, -1) + n0 + 1] - beg1; px1 = px0 + b.m[0];
+          } else if (hi >= n0) {
+            beg1 = cstart[rowbase + max(lo, n0) - n0]; len1 = cstart[rowbase + hi - n0 + 1] - beg1; px1 = px0 - b.m[0];
+          }
         }
       }
     }

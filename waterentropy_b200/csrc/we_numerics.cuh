@@ -383,6 +383,9 @@ struct WeBox {
   double wfac[3]; // slanted wrap bounds: {m3/m4, (m4*m6 - m3*m7)/(m4*m8), m7/m8}
   float rc_eff;   // radius guaranteed covered by the +-1 cell search
   int pre_ok;     // triclinic float prefilter valid (10 A < half the smallest cell width)
+  // cell geometry for the scan's row culling (k_rad): y extent of a cell row m4/n1, y shift per z cell m7/n2,
+  // z extent m8/n2, x shift per y cell m3/n1, x shift per z cell m6/n2, x cells per Angstrom n0/m0
+  float cg[6];
 };
 
 WE_HD double we_round_half_away(double s) {
