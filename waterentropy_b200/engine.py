@@ -11,6 +11,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+from collections import defaultdict
+
 import numpy as np
 
 from . import _lib
@@ -418,15 +420,25 @@ class WaterEntropyEngine:
             return out
         # records are ascending in the water index inside a frame; a stable sort by (frame, resname, resid) of
         # the nearest solute atom keeps that order inside every residue's list, as upstream's appends do
-        rn, rid = top.resname_id[near], top.resids[near]
-        order = np.lexsort((rid, rn, frame_of))
-        frame_of, rn, rid, atoms = frame_of[order], rn[order], rid[order], atoms[order]
-        cut = np.nonzero((frame_of[1:] != frame_of[:-1]) | (rn[1:] != rn[:-1]) | (rid[1:] != rid[:-1]))[0] + 1
+        rn, rid = top.resname_id[near].astype(np.int64), top.resids[near].astype(np.int64)
+        # one stable sort on a combined (frame, resname, resid) key instead of a three-key lexsort
+        rid0 = int(rid.min())
+        key = (frame_of.astype(np.int64) * (int(rn.max()) + 1) + rn) * (int(rid.max()) - rid0 + 1) + (rid - rid0)
+        order = np.argsort(key, kind="stable")
+        key, atoms = key[order], atoms[order]
+        cut = np.nonzero(key[1:] != key[:-1])[0] + 1
         starts = np.concatenate([[0], cut])
         ends = np.concatenate([cut, [len(atoms)]])
         atoms_l = atoms.tolist()
+        # the residue lists in one C-level pass, then one dict per (frame, resname)
+        lists = list(map(atoms_l.__getitem__, map(slice, starts.tolist(), ends.tolist())))
+        g_frame, g_rn, g_rid = frame_of[order][starts], rn[order][starts], rid[order][starts]
+        cut2 = np.nonzero((g_frame[1:] != g_frame[:-1]) | (g_rn[1:] != g_rn[:-1]))[0] + 1
+        s2 = np.concatenate([[0], cut2]).tolist()
+        e2 = np.concatenate([cut2, [len(starts)]]).tolist()
+        rid_l = g_rid.tolist()
         names = top.resname_table
         fids = self.frame_ids
-        for s0, e0, fk, a, b in zip(starts.tolist(), ends.tolist(), frame_of[starts].tolist(), rn[starts].tolist(), rid[starts].tolist()):
-            out[fids[fk]][names[a]][b] = atoms_l[s0:e0]
+        for s0, e0, fk, a in zip(s2, e2, g_frame[s2].tolist(), g_rn[s2].tolist()):
+            out[fids[fk]][names[a]] = defaultdict(nested_dict, zip(rid_l[s0:e0], lists[s0:e0]))
         return out
