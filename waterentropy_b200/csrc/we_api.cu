@@ -139,7 +139,7 @@ struct we_ctx {
   int pending_n[WE_NBUF] = {};
   cudaStream_t s_copy = nullptr, s_comp = nullptr, s_cov = nullptr;
   cudaEvent_t ev_in_ready[WE_NBUF]{}, ev_in_free[WE_NBUF]{}, ev_out_ready[WE_NBUF]{}, ev_p0[WE_NBUF]{};
-  int copy_gate = 0, cov_stream = 1, use_graphs = 1, n_sm = 148, rad_blocks_gated = 0;
+  int copy_gate = 0, cov_stream = 2, use_graphs = 1, n_sm = 148, rad_blocks_gated = 0;
   // CUDA graphs of the two kernel runs of a batch (before / after the pass-0 event), per ring slot and
   // frame count; host-buffer submissions only (the device pointers of a slot are fixed)
   struct BatchGraph { cudaGraphExec_t exec = nullptr; unsigned long long launches = 0; };
@@ -1099,7 +1099,9 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     if (C > 0 && !shells_only) {
       if (!c->lazy) {
         // zero-copy forces: the kernel waits on PCIe reads, so it runs beside the next batch's kernels
-        cov_st = (frc_zero_copy && c->cov_stream) ? c->s_cov : st;
+        // (WE_COV_STREAM=2: also with forces resident on the device - the kernel is one long dependent fp64
+        // chain per water, ~80 us whatever the count, and fits beside the next batch's cell-list kernels)
+        cov_st = ((frc_zero_copy && c->cov_stream) || c->cov_stream >= 2) ? c->s_cov : st;
         c->cov_on_own_stream = (cov_st != st);
         if (cov_st != st) {
           CK(cudaEventRecord(c->ev_label[buf], st));
