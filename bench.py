@@ -428,7 +428,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---------------- end-to-end arm (host buffers through the public API) ----------------
     eng = WaterEntropyEngine(s, recipe, device=local_rank, keep_records=(recipe == "interfacial"), chunk_frames=args.chunk,
-                             force_upload=args.force_upload, search_radius=args.search_radius)
+                             force_upload=args.force_upload, search_radius=args.search_radius, pos_upload=args.pos_upload)
     hP, hF = torch.from_numpy(P).pin_memory(), torch.from_numpy(Fr).pin_memory()
     d2h = 0
 
@@ -475,13 +475,18 @@ def run_ours(args, rank, world, local_rank):
     # region is therefore timed `--e2e-repeats` times (default 3), each a complete job (K steps + combine +
     # label read, tables reset in between); the fastest is reported and all are listed in e2e["runs_ms"].
     e2e_runs, combine_runs, combine_wait_runs, local_runs = [], [], [], []
+    dma_bytes, light_atoms, pack_ms = 0, 0, 0.0
     for _ in range(max(1, args.e2e_repeats)):
         barrier()
+        dma0, pack0 = eng.diag()["h2d_dma_bytes"], eng.diag()["host_pack_us"]
         t0 = time.perf_counter()
         nrec = e2e_steps(args.steps)
         t1 = time.perf_counter()
         entries = e2e_finalize()
         t2 = time.perf_counter()
+        dg = eng.diag()  # counted by the library: bytes the copy engine moved, light atoms read in place
+        dma_bytes, light_atoms = (dg["h2d_dma_bytes"] - dma0) / args.steps, dg["light_atoms_fetched"] / args.steps
+        pack_ms = (dg["host_pack_us"] - pack0) / args.steps / 1e3
         local_runs.append(t1 - t0)  # this rank's own K steps, before the combine and the closing barrier
         barrier()
         e2e_runs.append(maxr(time.perf_counter() - t0))
@@ -494,7 +499,7 @@ def run_ours(args, rank, world, local_rank):
     # per rank: what the host fed this GPU and how busy its kernels were (the e2e limiter at N > 1 is the box's
     # aggregate host->device feed, not a collective)
     my_e2e_ms = statistics.median(local_runs) / args.steps * 1e3
-    my_h2d = (P.nbytes + Fps * 32) / (my_e2e_ms * 1e-3) / 1e9
+    my_h2d = dma_bytes / (my_e2e_ms * 1e-3) / 1e9
     my_busy = (dev_ms / args.steps) / my_e2e_ms
     if world > 1:
         t = torch.tensor([my_h2d, my_busy], dtype=torch.float64, device="cuda")
@@ -510,14 +515,18 @@ def run_ours(args, rank, world, local_rank):
     # copied whole (force_upload 1 / bulk recipe) or stay in pinned host memory and k_cov reads the atoms
     # of the recorded waters in place (zero-copy, the default for the interfacial recipe)
     zero_copy = recipe == "interfacial" and args.force_upload in (0, 3)
+    packed = light_atoms > 0 or dma_bytes < 0.9 * P.nbytes
+    position_path = ("packed: host threads gather the heavy atoms into pinned staging, the copy engine moves those; "
+                     "the light atoms the path reads are read in place from the caller's pinned buffer"
+                     if packed else "whole position frames copied")
     if zero_copy:
-        h2d = P.nbytes + Fps * 32 + int(nrec) * 3 * 12
+        h2d = dma_bytes + int(nrec) * 3 * 12 + light_atoms * 12
         force_path = "zero-copy: recorded waters' atoms read in place from pinned host memory"
     elif args.force_upload == 2:
-        h2d = P.nbytes + Fps * 32 + int(nrec) * 3 * 12
+        h2d = dma_bytes + int(nrec) * 3 * 12 + light_atoms * 12
         force_path = "recorded waters' atoms gathered by the host, uploaded compactly"
     else:
-        h2d = input_bytes + Fps * 32
+        h2d = dma_bytes + light_atoms * 12
         force_path = "whole force frames copied"
     final_bytes = int(entries.nbytes)
     eng.close()
@@ -549,7 +558,9 @@ def run_ours(args, rank, world, local_rank):
                          "tables on the device, per-frame recorded-water lists written to pinned host memory)",
             "clocks": clk,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                    "host_input_bytes_per_step": int(input_bytes + Fps * 32), "force_path": force_path,
+                    "h2d_dma_bytes_per_step": int(dma_bytes), "h2d_zero_copy_atoms_per_step": int(light_atoms + (int(nrec) * 3 if zero_copy else 0)),
+                    "host_input_bytes_per_step": int(input_bytes + Fps * 32), "position_path": position_path, "host_pack_ms_per_step": round(pack_ms, 3),
+                    "force_path": force_path,
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s / args.steps * 1e3,
                     "runs_ms_per_step": [round(t / args.steps * 1e3, 3) for t in e2e_runs],
                     "combine_ms": round(statistics.median(combine_runs) * 1e3, 3),
@@ -587,6 +598,7 @@ def main():
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-repeats", type=int, default=3, help="timed repetitions of the K-step e2e job; the fastest is reported")
+    ap.add_argument("--pos-upload", type=int, default=0, help="e2e arm: 0 auto, 1 whole frames, 2 packed (heavy atoms by DMA, light atoms read in place)")
     ap.add_argument("--force-upload", type=int, default=0, help="e2e arm: 0 auto, 1 whole frames, 2 host gather, 3 zero-copy")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define WE_VERSION 201
+#define WE_VERSION 202
 
 /* recipes */
 #define WE_RECIPE_INTERFACIAL 0 /* recipes/interfacial_solvent.py:273-345 (_entropy_per_step) */
@@ -92,6 +92,14 @@ typedef struct we_options {
     int32_t eig_flavour;     /* which OpenBLAS kernel family the principal-axis step replays (WE_EIG_*): the
                                 reference's eigenvector signs are whatever numpy.linalg.eig returns on the
                                 host it runs on (maths/transformations.py:121-124) */
+    int32_t pos_upload;      /* we_submit, how positions reach the device: 0 / 1 whole frames (one DMA copy of
+                                [n][n_atoms][3]); 2 packed (interfacial recipe, PINNED buffers): host threads gather
+                                the heavy atoms (all the neighbour search reads: a third of a water box) into
+                                pinned staging, only those are copied, and the few light atoms the path reads
+                                (donor hydrogens of the centres whose hydrogen bonds are evaluated, atoms of the
+                                recorded waters) are read straight from the caller's buffer by the device.
+                                Same results; a third of the DMA bytes; measured SLOWER than whole frames on a
+                                full x16 link, so never chosen automatically */
 } we_options;
 
 /* numpy.linalg.eig = LAPACK dgeev on OpenBLAS; its level-1/2 kernels round differently per CPU family,
@@ -103,6 +111,8 @@ typedef struct we_options {
  *   WE_COPY_GATE=1   hold the upload of a batch back until the previous batch's first neighbour pass starts
  *                    (default 0: uploads run back to back as soon as a slot is free)
  *   WE_COV_STREAM=0  zero-copy k_cov on the compute stream (default 1: own low-priority stream)
+ *   WE_PACK_THREADS=n  host threads that gather the heavy atoms of packed uploads (default: the cores this
+ *                    process may run on, at most 16)
  *   WE_GRAPHS=0      launch every kernel individually (default 1: two CUDA graphs per batch for
  *                    host-buffer submissions)                                                          */
 typedef struct we_ctx we_ctx;
@@ -118,6 +128,10 @@ typedef struct we_diag {
                                       test exactly and count contradictions: must stay 0 */
     uint64_t eig_fallbacks;   /* molecules whose inertia tensor took a LAPACK path that is not restated (exact
                                  zeros / equal moments; never a water): Jacobi axes with a fixed sign rule */
+    uint64_t h2d_dma_bytes;   /* bytes the copy engine moved host -> device for frames (positions whole or packed,
+                                 forces when uploaded whole, boxes, frame ids) */
+    uint64_t light_atoms_fetched; /* packed uploads: light atoms the device read from the caller's pinned buffer */
+    uint64_t host_pack_us;    /* packed uploads: wall time the submitting thread spent in the host gather */
 } we_diag;
 
 const char *we_last_error(void);
@@ -261,7 +275,8 @@ int we_debug_copy(we_ctx *ctx, int64_t k, int32_t field, void *out, int64_t byte
 #define WE_K_RAD2 9   /* k_rad, pass 2: their shell members */
 #define WE_K_LIST2 10 /* k_seed + k_list2 (pass-2 and HB lists) */
 #define WE_K_GATE 11  /* k_gate (+ k_grplist): burial pre-stage of the gating pass, by cell group */
-#define WE_N_KERNELS 12
+#define WE_K_FETCH 12 /* k_fetch_light (packed uploads): light atoms read from the caller's pinned buffer */
+#define WE_N_KERNELS 13
 /* Record CUDA events around every kernel launch on the compute stream (the
  * reference only has wall-clock prints, cli/runWaterEntropy.py:28-29,54). */
 int we_profile(we_ctx *ctx, int32_t enable);

@@ -485,13 +485,28 @@ def test_chunking_and_device_resident_inputs_agree():
     inp = gio.load_inputs("synth_tric")
     F = inp["positions"].shape[0]
     outs = []
-    for mode in ("chunk1", "chunkall", "device", "lazy", "zerocopy"):
+    for mode in ("chunk1", "chunkall", "device", "lazy", "zerocopy", "packed", "packed_chunk3"):
         fu = {"lazy": 2, "zerocopy": 3}.get(mode, 1)
-        eng = _engine(inp, chunk_frames=1 if mode in ("chunk1", "lazy") else 8, force_upload=fu)
-        if mode == "zerocopy":
+        # zero-copy forces with whole-frame positions; packed positions (heavy atoms by DMA, the light atoms
+        # the path reads fetched from the pinned buffer) with whole-frame / zero-copy forces
+        pu = {"zerocopy": 1, "packed": 2, "packed_chunk3": 2}.get(mode, 0)
+        if mode == "packed_chunk3":
+            fu = 3
+        eng = _engine(inp, chunk_frames={"chunk1": 1, "lazy": 1, "packed_chunk3": 3}.get(mode, 8), force_upload=fu,
+                      pos_upload=pu)
+        if mode in ("zerocopy", "packed", "packed_chunk3"):
             hp = torch.from_numpy(inp["positions"]).pin_memory()
             hf = torch.from_numpy(inp["forces"]).pin_memory()
             eng.submit(hp, hf, inp["dimensions"], list(range(F)))
+            eng.sync()
+            d = eng.diag()
+            H = len(eng.top.heavy_idx)
+            if pu == 2:  # only the heavy atoms went through the copy engine
+                assert 0 < d["light_atoms_fetched"] < F * (inp["positions"].shape[1] - H)
+                extra = F * 4096 + (0 if fu == 3 else inp["forces"].nbytes)  # boxes, frame ids; whole-frame forces
+                assert F * H * 12 <= d["h2d_dma_bytes"] <= F * H * 12 + extra
+            else:
+                assert d["light_atoms_fetched"] == 0 and d["h2d_dma_bytes"] >= inp["positions"].nbytes
         elif mode == "device":
             dp = torch.from_numpy(inp["positions"]).cuda()
             df = torch.from_numpy(inp["forces"]).cuda()
@@ -511,6 +526,16 @@ def test_chunking_and_device_resident_inputs_agree():
         assert np.allclose(outs[0][5], o[5], rtol=1e-12)
         for a, b in zip(outs[0][6], o[6]):
             assert np.array_equal(a, b)
+
+
+def test_packed_upload_needs_pinned_positions():
+    inp = gio.load_inputs("synth_ortho")
+    eng = _engine(inp, pos_upload=2)
+    with pytest.raises(Exception, match="pinned"):
+        eng.submit(inp["positions"], inp["forces"], inp["dimensions"], list(range(inp["positions"].shape[0])))
+    eng.close()
+    with pytest.raises(Exception, match="pos_upload"):
+        _engine(inp, pos_upload=2, keep_debug=True)
 
 
 def test_records_of_frames_in_flight_are_readable_without_sync():

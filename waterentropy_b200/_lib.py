@@ -11,7 +11,7 @@ import os
 from . import _build
 
 c_int32_p = C.POINTER(C.c_int32)
-WE_VERSION = 201  # include/waterentropy_b200.h; a stale build is refused
+WE_VERSION = 202  # include/waterentropy_b200.h; a stale build is refused
 
 
 class we_topology(C.Structure):
@@ -35,13 +35,15 @@ class we_options(C.Structure):
         ("keep_records", C.c_int32), ("keep_debug", C.c_int32),
         ("search_radius", C.c_float), ("max_box", C.c_float), ("keep_shells", C.c_int32),
         ("force_upload", C.c_int32), ("shells_only", C.c_int32), ("eig_flavour", C.c_int32),
+        ("pos_upload", C.c_int32),
     ]
 
 
 class we_diag(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "wide_searches", "shrink_retries", "table_entries",
-        "kernel_launches", "frames_done", "recorded", "fast_path_mismatches", "eig_fallbacks")]
+        "kernel_launches", "frames_done", "recorded", "fast_path_mismatches", "eig_fallbacks",
+        "h2d_dma_bytes", "light_atoms_fetched", "host_pack_us")]
 
 
 EXPORTS = [

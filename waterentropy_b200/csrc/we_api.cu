@@ -6,6 +6,12 @@
 // CPU implementation of any kernel in this library: without a CUDA device every
 // entry point fails with WE_ERR_CUDA.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <sched.h>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -58,6 +64,84 @@ struct FrameDebug {
 #endif
 static const int WE_NBUF = WE_NBUF_SLOTS;
 
+// ---------------------------------------------------------------------------
+// Host threads of the packed upload (we_options.pos_upload): gather the heavy atoms of a batch of frames
+// out of the caller's [n][n_atoms][3] buffer into pinned staging, [n][n_heavy][3].  A persistent pool; the
+// calling thread works too.  (GPU-box host, 16 cores: 96 C4 frames in 4.3 ms = 85 GB/s of source swept.)
+// ---------------------------------------------------------------------------
+struct WePackPool {
+  std::vector<std::thread> th;
+  std::mutex m;
+  std::condition_variable cv, cv_done;
+  bool stop = false;
+  unsigned long long gen = 0;
+  int busy = 0;
+  const float* src = nullptr; float* dst = nullptr; const int* heavy = nullptr;
+  int H = 0, n_tasks = 0, slices = 1;
+  size_t n3 = 0;
+  std::atomic<int> next{0};
+  explicit WePackPool(int n_threads) {
+    for (int i = 1; i < n_threads; ++i) th.emplace_back([this] { loop(); });
+  }
+  ~WePackPool() {
+    { std::lock_guard<std::mutex> l(m); stop = true; }
+    cv.notify_all();
+    for (auto& t : th) t.join();
+  }
+  void work() {
+    for (;;) {
+      const int t = next.fetch_add(1);
+      if (t >= n_tasks) break;
+      const int f = t / slices, k = t % slices;
+      const int a = (int)((long long)H * k / slices), b = (int)((long long)H * (k + 1) / slices);
+      const float* s = src + (size_t)f * n3;
+      float* d = dst + (size_t)f * H * 3;
+      for (int i = a; i < b; ++i) {
+        const size_t j = 3 * (size_t)heavy[i];
+        d[3 * (size_t)i] = s[j]; d[3 * (size_t)i + 1] = s[j + 1]; d[3 * (size_t)i + 2] = s[j + 2];
+      }
+    }
+  }
+  // A worker spins for `spin_us` after its last task before it sleeps on the condition variable: batches
+  // follow each other within ~2 ms while a trajectory streams, and a sleeping thread of a virtual machine
+  // takes 100s of microseconds to come back.
+  long spin_us = 0;
+  std::atomic<unsigned long long> gen_a{0};
+  void loop() {
+    unsigned long long seen = 0;
+    for (;;) {
+      bool got = false;
+      if (spin_us > 0) {
+        const auto t0 = std::chrono::steady_clock::now();
+        for (;;) {
+          if (gen_a.load(std::memory_order_acquire) != seen) { got = true; break; }
+          for (int i = 0; i < 64; ++i) __builtin_ia32_pause();
+          if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(spin_us)) break;
+        }
+      }
+      {
+        std::unique_lock<std::mutex> l(m);
+        if (!got) cv.wait(l, [&] { return stop || gen != seen; });
+        if (stop) return;
+        seen = gen;
+      }
+      work();
+      { std::lock_guard<std::mutex> l(m); if (--busy == 0) cv_done.notify_one(); }
+    }
+  }
+  void run(const float* src_, float* dst_, const int* heavy_, int H_, size_t n3_, int n_frames) {
+    src = src_; dst = dst_; heavy = heavy_; H = H_; n3 = n3_;
+    slices = 8;
+    n_tasks = n_frames * slices;
+    next.store(0);
+    { std::lock_guard<std::mutex> l(m); busy = (int)th.size(); ++gen; gen_a.store(gen, std::memory_order_release); }
+    cv.notify_all();
+    work();
+    std::unique_lock<std::mutex> l(m);
+    cv_done.wait(l, [&] { return busy == 0; });
+  }
+};
+
 struct we_ctx {
   int device = 0;
   we_options opt{};
@@ -94,6 +178,16 @@ struct we_ctx {
   // at the covered radius before it widens the search)
   float r_first_frac[3] = {1.0f, 1.0f, 1.0f};
   float* d_pos[WE_NBUF] = {};
+  // packed uploads: pinned staging and device copy of the heavy atoms [chunk][H][3]; per ring slot the device
+  // alias of the caller's frame buffer (read by k_fetch_light through a pointer in device memory, so that the
+  // launch can live in the batch's CUDA graph)
+  float* h_pack[WE_NBUF] = {};
+  float* d_pack[WE_NBUF] = {};
+  const float** d_src[WE_NBUF] = {};
+  const float** h_src = nullptr;
+  WePackPool* pool = nullptr;
+  int pack_threads = 0;
+  unsigned long long h2d_bytes = 0, pack_us = 0;
   float* d_frc[WE_NBUF] = {};
   WeBox* d_boxes[WE_NBUF] = {};
   long long* d_fids[WE_NBUF] = {};
@@ -137,7 +231,8 @@ struct we_ctx {
   int* h_shell[WE_NBUF] = {};  // mapped pinned: RAD shells of recorded waters (keep_shells)
   std::vector<std::vector<int>> frame_shells;
   int pending_n[WE_NBUF] = {};
-  cudaStream_t s_copy = nullptr, s_comp = nullptr, s_cov = nullptr;
+  cudaStream_t s_copy = nullptr, s_comp = nullptr, s_cov = nullptr, s_aux = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_in_ready[WE_NBUF]{}, ev_in_free[WE_NBUF]{}, ev_out_ready[WE_NBUF]{}, ev_p0[WE_NBUF]{};
   int copy_gate = 0, cov_stream = 2, use_graphs = 1, n_sm = 148, rad_blocks_gated = 0;
   // CUDA graphs of the two kernel runs of a batch (before / after the pass-0 event), per ring slot and
@@ -434,6 +529,9 @@ extern "C" int we_create(const we_topology* t, const we_options* opt, we_ctx** o
     CK(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithPriority(&c->s_comp, cudaStreamNonBlocking, prio_hi));
     CK(cudaStreamCreateWithPriority(&c->s_cov, cudaStreamNonBlocking, prio_lo));
+    CK(cudaStreamCreateWithPriority(&c->s_aux, cudaStreamNonBlocking, prio_lo));
+    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   }
   for (int i = 0; i < WE_NBUF; ++i) {
     CK(cudaEventCreateWithFlags(&c->ev_in_ready[i], cudaEventDisableTiming));
@@ -445,6 +543,18 @@ extern "C" int we_create(const we_topology* t, const we_options* opt, we_ctx** o
   }
   if ((rc = pin_alloc(c, &c->h_diag, 1))) { we_destroy(c); return rc; }
   memset(c->h_diag, 0, sizeof(WeDiag));
+  if (c->opt.pos_upload < 0 || c->opt.pos_upload > 2) { we_destroy(c); return fail(WE_ERR_INVALID, "pos_upload must be 0 (auto), 1 (whole frames) or 2 (packed)"); }
+  if (c->opt.pos_upload == 2 && (t->recipe != WE_RECIPE_INTERFACIAL || c->opt.keep_debug || c->opt.force_upload == 2)) {
+    we_destroy(c);
+    return fail(WE_ERR_INVALID, "pos_upload = 2 (packed) needs the interfacial recipe, without keep_debug and without force_upload = 2");
+  }
+  {
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int avail = (sched_getaffinity(0, sizeof(set), &set) == 0) ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+    c->pack_threads = std::max(1, std::min(16, avail));
+    if (const char* g = getenv("WE_PACK_THREADS")) c->pack_threads = std::max(1, std::min(64, atoi(g)));
+  }
   if (const char* g = getenv("WE_COPY_GATE")) c->copy_gate = atoi(g);
   if (const char* g = getenv("WE_COV_STREAM")) c->cov_stream = atoi(g);
   if (const char* g = getenv("WE_GRAPHS")) c->use_graphs = atoi(g);
@@ -497,7 +607,12 @@ extern "C" void we_destroy(we_ctx* c) {
   drop_graphs(c);
   if (c->s_copy) cudaStreamDestroy(c->s_copy);
   if (c->s_comp) cudaStreamDestroy(c->s_comp);
+  delete c->pool;
+  c->pool = nullptr;
   if (c->s_cov) cudaStreamDestroy(c->s_cov);
+  if (c->s_aux) cudaStreamDestroy(c->s_aux);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->ev_cov) cudaEventDestroy(c->ev_cov);
   for (int i = 0; i < WE_NBUF; ++i) {
     if (c->ev_in_ready[i]) cudaEventDestroy(c->ev_in_ready[i]);
@@ -846,6 +961,42 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       if ((rc = dev_alloc(c, &c->d_frc[i], (size_t)c->chunk * N * 3))) return rc;
     }
   }
+  // Positions: the neighbour search reads heavy atoms only (a third of a water box), and of the light atoms
+  // the path reads only the donor hydrogens of the centres whose hydrogen bonds are evaluated and the atoms
+  // of the recorded waters (~5 % of the waters on C4).  PACKED uploads: host threads gather the heavy atoms
+  // into pinned staging, the copy engine moves those, k_bin scatters them into the device's full-layout
+  // positions and k_fetch_light reads the light atoms straight from the caller's buffer - which therefore
+  // has to be pinned.  A third of the PCIe bytes of a whole-frame copy; the end-to-end arm was upload-bound.
+  const float* pos_zero_copy = nullptr;
+  // MEASURED (C4, one B200, 16 host cores): 9.2-10.8 ms per 96-frame step against 7.4 ms for whole frames.  The
+  // copy engine moves a third of the bytes (124 MB instead of 362 MB per step), but the light atoms arrive as
+  // ~350,000 scattered 24-byte PCIe reads per batch (k_fetch_light: 0.5-1.0 ms beside a 0.45 ms search pass,
+  // k_hb waits for it), every kernel runs slower under that traffic, and the host gather (3.7-5.3 ms per step
+  // on all 16 cores) is as long as the DMA it replaces.  So packed uploads are what pos_upload = 2 asks for,
+  // never what auto (0) picks; the path stays as the tested starting point for hosts whose PCIe feed per GPU
+  // is far below one x16 link (eight ranks on one box get 21 GB/s each).
+  if (!on_device && c->opt.pos_upload == 2) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, pos) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+      pos_zero_copy = (const float*)at.devicePointer;
+    else
+      cudaGetLastError();
+    if (!pos_zero_copy && c->opt.pos_upload == 2)
+      return fail(WE_ERR_INVALID, "pos_upload = 2 needs the position buffer in pinned (page-locked) host memory");
+  }
+  const bool packed = pos_zero_copy != nullptr;
+  if (packed && !c->h_pack[0]) {
+    for (int i = 0; i < WE_NBUF; ++i) {
+      if ((rc = pin_alloc(c, &c->h_pack[i], (size_t)c->chunk * H * 3))) return rc;
+      if ((rc = dev_alloc(c, &c->d_pack[i], (size_t)c->chunk * H * 3))) return rc;
+      if ((rc = dev_alloc(c, &c->d_src[i], 1))) return rc;
+    }
+    if ((rc = pin_alloc(c, &c->h_src, WE_NBUF))) return rc;
+    if (!c->pool) {
+      c->pool = new WePackPool(c->pack_threads);
+      if (const char* g = getenv("WE_PACK_SPIN_US")) c->pool->spin_us = atol(g);
+    }
+  }
   // Host buffers: a call that fits in one or two batches would upload everything before computing
   // anything, so (auto batch size only, and only when the pipeline is empty: a caller that streams
   // batch after batch already overlaps) it is cut into at least three batches of >= ~1 M centres each
@@ -909,15 +1060,29 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       // idles the copy engine, and back-to-back uploads are faster (7.77 -> 7.40 ms per 96-frame step):
       // the default is ungated.
       if (c->copy_gate) CK(cudaStreamWaitEvent(c->s_copy, c->ev_p0[(buf + WE_NBUF - 1) % WE_NBUF], 0));
-      CK(cudaMemcpyAsync(c->d_pos[buf], pos + (size_t)f0 * frame_floats, (size_t)n * frame_floats * sizeof(float), cudaMemcpyHostToDevice, c->s_copy));
+      if (packed) {
+        // the slot's staging was last read by the DMA of the batch WE_NBUF batches ago (ev_in_free above)
+        const auto tp0 = std::chrono::steady_clock::now();
+        c->pool->run(pos + (size_t)f0 * frame_floats, c->h_pack[buf], c->heavy_idx.data(), H, frame_floats, n);
+        c->pack_us += (unsigned long long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - tp0).count();
+        CK(cudaMemcpyAsync(c->d_pack[buf], c->h_pack[buf], (size_t)n * H * 3 * sizeof(float), cudaMemcpyHostToDevice, c->s_copy));
+        c->h_src[buf] = pos_zero_copy + (size_t)f0 * frame_floats;
+        CK(cudaMemcpyAsync(c->d_src[buf], &c->h_src[buf], sizeof(float*), cudaMemcpyHostToDevice, c->s_copy));
+        c->h2d_bytes += (unsigned long long)n * H * 3 * sizeof(float) + sizeof(float*);
+      } else {
+        CK(cudaMemcpyAsync(c->d_pos[buf], pos + (size_t)f0 * frame_floats, (size_t)n * frame_floats * sizeof(float), cudaMemcpyHostToDevice, c->s_copy));
+        c->h2d_bytes += (unsigned long long)n * frame_floats * sizeof(float);
+      }
       dp = c->d_pos[buf];
       if (no_forces) {
         df = nullptr;
       } else if (frc_zero_copy) {
         df = frc_zero_copy + (size_t)f0 * frame_floats;
       } else {
-        if (!c->lazy)
+        if (!c->lazy) {
           CK(cudaMemcpyAsync(c->d_frc[buf], frc + (size_t)f0 * frame_floats, (size_t)n * frame_floats * sizeof(float), cudaMemcpyHostToDevice, c->s_copy));
+          c->h2d_bytes += (unsigned long long)n * frame_floats * sizeof(float);
+        }
         df = c->d_frc[buf];
       }
     } else {
@@ -926,6 +1091,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     }
     CK(cudaMemcpyAsync(c->d_boxes[buf], c->h_boxes[buf], (size_t)n * sizeof(WeBox), cudaMemcpyHostToDevice, c->s_copy));
     CK(cudaMemcpyAsync(c->d_fids[buf], c->h_fids[buf], (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, c->s_copy));
+    if (!on_device) c->h2d_bytes += (unsigned long long)n * (sizeof(WeBox) + sizeof(long long));
     CK(cudaEventRecord(c->ev_in_ready[buf], c->s_copy));
     cudaStream_t st = c->s_comp, cov_st = c->s_comp;
     CK(cudaStreamWaitEvent(st, c->ev_in_ready[buf], 0));
@@ -944,7 +1110,7 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       gate = gate && (!hb.triclinic || hb.pre_ok);
     }
     const bool graphs_on = !on_device && c->use_graphs && !c->prof && !c->opt.keep_debug;
-    const long long gkey = (((long long)buf * 4096 + n) * 2 + (gate ? 1 : 0)) * 2;
+    const long long gkey = ((((long long)buf * 4096 + n) * 2 + (gate ? 1 : 0)) * 2 + (packed ? 1 : 0)) * 2;
     GraphRegion g1(c, st, gkey, graphs_on), g2(c, st, gkey + 1, graphs_on);
     int replay = g1.begin();
     if (replay < 0) return replay;
@@ -953,7 +1119,8 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
     CK(cudaMemsetAsync(c->d_rec_count[buf], 0, (size_t)n * sizeof(int), st));
     { ProfScope ps(c, WE_K_BIN, st);
       k_bin<<<gH, 256, 0, st>>>(c->T, dp, bx, c->d_cell_count, c->d_cell_of, c->d_rank_of, c->d_tmp4, c->ncap,
-                                gate ? c->d_grp_flag : nullptr);
+                                gate ? c->d_grp_flag : nullptr, packed ? c->d_pack[buf] : nullptr,
+                                packed ? c->d_pos[buf] : nullptr);
       ps.stop(st); }
     { ProfScope ps(c, WE_K_SCAN, st);
       k_scan<<<n, 1024, 0, st>>>(bx, c->d_cell_count, c->ncap);
@@ -1056,8 +1223,22 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       { ProfScope ps(c, WE_K_LIST2, st);
         k_list2<<<gH, 256, 0, st>>>(c->T, mark_shell, mark_hb, c->d_state, c->d_wl2, c->d_n2, c->d_wlh, c->d_nh);
         ps.stop(st); }
+      if (packed) {
+        // light atoms of the centres on the HB list (k_hb: donor hydrogens; k_cov: the recorded waters' atoms),
+        // read over PCIe beside the last search pass: a fork / join through the auxiliary stream (also inside
+        // the captured graph)
+        CK(cudaEventRecord(c->ev_fork, st));
+        CK(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0));
+        { ProfScope ps(c, WE_K_FETCH, c->s_aux);
+          k_fetch_light<<<dim3(64, n), 128, 0, c->s_aux>>>(c->T, c->d_src[buf], c->d_pos[buf], WeWork{c->d_wlh, c->d_nh, H, 0},
+                                                           c->d_centre_of_slot, n, c->d_diag);
+          ps.stop(c->s_aux); }
+        CK(cudaEventRecord(c->ev_join, c->s_aux));
+        c->launches += 1;
+      }
       WeWork w2{c->d_wl2, c->d_n2, H, 0};
       rad(WE_K_RAD2, w2, (long long)H * n, nullptr, no_marks);
+      if (packed) CK(cudaStreamWaitEvent(st, c->ev_join, 0));
       c->launches += 2;
       }
     } else if (!interfacial && C > 0) {
@@ -1379,6 +1560,9 @@ extern "C" int we_get_diag(we_ctx* c, we_diag* out) {
   out->recorded = c->recorded;
   out->fast_path_mismatches = d.fast_path_mismatches;
   out->eig_fallbacks = d.eig_fallbacks;
+  out->h2d_dma_bytes = c->h2d_bytes;
+  out->light_atoms_fetched = d.light_fetched;
+  out->host_pack_us = c->pack_us;
   return WE_OK;
 }
 

@@ -88,6 +88,7 @@ struct WeDiag {
   unsigned long long table_entries;
   unsigned long long fast_path_mismatches;  // debug contexts: float32 fast-path decisions the exact replay contradicts
   unsigned long long eig_fallbacks;         // molecules whose inertia tensor took a LAPACK path that is not restated
+  unsigned long long light_fetched;         // packed uploads: light atoms read from the caller's pinned buffer
   int err_code, err_frame, err_atom, pad;
 };
 
@@ -132,16 +133,29 @@ __device__ __forceinline__ void we_set_error(WeDiag* diag, int code, int frame, 
 #define WE_GRP_X 2
 #define WE_GRP_Y 2
 #define WE_GRP_Z 1
+// `packed` (optional): the heavy atoms of the batch as the host packed them, [frame][heavy slot][3]; the
+// kernel then also writes them to their places in the full [frame][atom][3] layout `pos_out`, which is what
+// the later kernels read (the hydrogens they need follow through k_fetch_light).
 __global__ void k_bin(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxes,
                       int* __restrict__ cell_count, int* __restrict__ cell_of,
                       int* __restrict__ rank_of, float4* __restrict__ tmp4, int ncap,
-                      unsigned char* __restrict__ grp_flag) {
+                      unsigned char* __restrict__ grp_flag, const float* __restrict__ packed,
+                      float* __restrict__ pos_out) {
   int h = blockIdx.x * blockDim.x + threadIdx.x;
   int f = blockIdx.y;
   if (h >= T.n_heavy) return;
   const WeBox& b = boxes[f];
   int atom = T.heavy_idx[h];
-  const float* p = pos + ((size_t)f * T.n_atoms + atom) * 3;
+  float p[3];
+  if (packed) {
+    const float* s = packed + ((size_t)f * T.n_heavy + h) * 3;
+    float* d = pos_out + ((size_t)f * T.n_atoms + atom) * 3;
+    p[0] = s[0]; p[1] = s[1]; p[2] = s[2];
+    d[0] = p[0]; d[1] = p[1]; d[2] = p[2];
+  } else {
+    const float* s = pos + ((size_t)f * T.n_atoms + atom) * 3;
+    p[0] = s[0]; p[1] = s[1]; p[2] = s[2];
+  }
   float q[3] = {p[0], p[1], p[2]};
   if (b.triclinic) we_wrap_tric(p[0], p[1], p[2], b.m, b.wfac, q);
   double s[3];
@@ -1430,6 +1444,61 @@ __global__ void k_seed(int n, const int* __restrict__ list, int n_heavy, int* __
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int f = blockIdx.y;
   if (i < n) state[(size_t)f * n_heavy + list[i]] = 1;
+}
+
+// Packed uploads (we_options.pos_upload): only the heavy atoms of a frame cross PCIe by DMA.  The light atoms
+// the path reads - the donor hydrogens of the centres whose hydrogen bonds are evaluated (k_hb) and every atom
+// of a recorded water (k_cov); both sets are inside the HB work list - are copied here, straight from the
+// caller's pinned frame buffer (zero-copy reads, `*src_slot` = device alias of frame 0 of the batch) into
+// their places in the device's full-layout positions.  Eight lanes per listed centre, one float per lane:
+// the two hydrogens of a water are six consecutive floats, i.e. ONE load instruction and one or two 32-byte
+// PCIe reads per water (a thread per atom and component-wise loads made three requests per atom).
+// <= 32 registers: a block fits beside the persistent k_rad blocks of the pass it overlaps.
+__global__ void __launch_bounds__(128, 16)
+k_fetch_light(WeTopoDev T, const float* const* __restrict__ src_slot, float* __restrict__ pos_out, WeWork work,
+              const int* __restrict__ centre_of_slot, int n_frames, WeDiag* diag) {
+  const int f = blockIdx.y;
+  if (f >= n_frames) return;
+  const int cnt = work.count ? work.count[f] : work.static_count;
+  const float* src = *src_slot + (size_t)f * T.n_atoms * 3;
+  float* dst = pos_out + (size_t)f * T.n_atoms * 3;
+  const int* list = work.list + (size_t)f * work.stride;
+  const int sub = threadIdx.x & 7;
+  int fetched = 0;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; i < cnt; i += (gridDim.x * blockDim.x) >> 3) {
+    const int xs = list[i];
+    const int k = centre_of_slot[xs];
+    const int a0 = k >= 0 ? T.frag_ptr[k] : 0, a1 = k >= 0 ? T.frag_ptr[k + 1] : 0;
+    const int d0 = T.don_ptr[xs], d1 = T.don_ptr[xs + 1];
+    // j-th light atom of the entry: the light atoms of a water centre's molecule (k_cov takes the whole
+    // molecule), then the donor hydrogens (k_hb) that are not among them
+    auto nth = [&](int j) -> int {
+      for (int a = a0; a < a1; ++a) {
+        const int at = T.frag_atoms[a];
+        if (T.heavy_slot[at] >= 0) continue;
+        if (j == 0) return at;
+        --j;
+      }
+      for (int d = d0; d < d1; ++d) {
+        const int at = T.don_h[d];
+        bool in_frag = false;
+        for (int a = a0; a < a1; ++a) in_frag |= (T.frag_atoms[a] == at);
+        if (in_frag) continue;
+        if (j == 0) return at;
+        --j;
+      }
+      return -1;
+    };
+    for (int t = sub;; t += 8) {
+      const int at = nth(t / 3);
+      if (at < 0) break;
+      const int c = t % 3;
+      dst[3 * (size_t)at + c] = src[3 * (size_t)at + c];
+      fetched += (c == 0);
+    }
+  }
+  fetched = __reduce_add_sync(0xffffffffu, fetched);
+  if ((threadIdx.x & 31) == 0 && fetched) atomicAdd(&diag->light_fetched, (unsigned long long)fetched);
 }
 
 // Block-aggregated append for 256-thread blocks: the threads with `want` get consecutive slots of a

@@ -83,7 +83,7 @@ def decode_label_entries(top, recipe, entries) -> HBLabelCollection:
 class WaterEntropyEngine:
     def __init__(self, system, recipe="interfacial", device=0, chunk_frames=0, table_log2=0,
                  keep_records=True, keep_debug=False, search_radius=0.0, max_box=0.0, force_upload=0,
-                 keep_shells=False, eig_flavour=None, shells_only=False):
+                 keep_shells=False, eig_flavour=None, shells_only=False, pos_upload=0):
         """`eig_flavour`: "avx512" / "avx2" / None.  The reference's principal axes carry the eigenvector
         signs `numpy.linalg.eig` returns on the host it runs on; None replays the OpenBLAS kernel family
         of THIS host's NumPy (`_lib.host_eig_flavour`), so the off-diagonal covariance elements are the
@@ -101,7 +101,7 @@ class WaterEntropyEngine:
                             keep_records=int(keep_records), keep_debug=int(keep_debug),
                             search_radius=search_radius, max_box=max_box, force_upload=force_upload,
                             keep_shells=int(keep_shells), eig_flavour=self.eig_flavour,
-                            shells_only=int(shells_only))
+                            shells_only=int(shells_only), pos_upload=int(pos_upload))
         self._ctx = C.c_void_p()
         _lib.check(self.lib.we_create(C.byref(t), C.byref(o), C.byref(self._ctx)))
         self.device = device
@@ -222,7 +222,7 @@ class WaterEntropyEngine:
 
     # ---- measurement ---------------------------------------------------------
     KERNELS = ["k_bin", "k_scan", "k_scatter", "k_rad", "k_hb", "k_list1", "k_label", "k_cov",
-               "k_rad_pass1", "k_rad_pass2", "k_seed_list2", "k_gate"]
+               "k_rad_pass1", "k_rad_pass2", "k_seed_list2", "k_gate", "k_fetch_light"]
 
     def profile(self, enable=True):
         _lib.check(self.lib.we_profile(self._ctx, int(enable)))
