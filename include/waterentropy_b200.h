@@ -112,7 +112,8 @@ typedef struct we_options {
  *                    (default 0: uploads run back to back as soon as a slot is free)
  *   WE_COV_STREAM=0  zero-copy k_cov on the compute stream (default 1: own low-priority stream)
  *   WE_PACK_THREADS=n  host threads that gather the heavy atoms of packed uploads (default: the cores this
- *                    process may run on, at most 16)
+ *                    process may run on, at most 16); WE_PACK_SPIN_US=t lets them spin t microseconds for the
+ *                    next batch before they sleep
  *   WE_GRAPHS=0      launch every kernel individually (default 1: two CUDA graphs per batch for
  *                    host-buffer submissions)                                                          */
 typedef struct we_ctx we_ctx;

@@ -1123,8 +1123,8 @@ def test_pinned_ring_is_recycled_and_results_do_not_change():
 
 
 # ------------------------------------ full size: the PRODUCTION path against the oracle's closure
-@pytest.mark.parametrize("name,n_sampled", [("C3", 3), ("C4", 2), ("C5", 2)])
-def test_full_size_production_path_vs_oracle_closure(name, n_sampled):
+@pytest.mark.parametrize("name,n_sampled,pos_upload", [("C3", 3, 0), ("C4", 2, 0), ("C5", 2, 0), ("C3", 3, 2)])
+def test_full_size_production_path_vs_oracle_closure(name, n_sampled, pos_upload):
     """BASELINE.json configurations at full size through the production path (work lists, zero-copy
     forces, CUDA graphs) over MORE than two kernel batches - batch boundaries, ring wrap, a ragged last
     batch and label-table growth at size - against the oracle evaluated on the closure the reference's
@@ -1151,7 +1151,8 @@ def test_full_size_production_path_vs_oracle_closure(name, n_sampled):
         p, f, D[k] = s.frame(k)
         P[k] = torch.from_numpy(p)
         Fr[k] = torch.from_numpy(f)
-    big = WaterEntropyEngine(s, "interfacial", device=0, chunk_frames=B, table_log2=8)   # 256 slots: must grow
+    # pos_upload = 2: the same through packed uploads (heavy atoms by DMA, light atoms fetched in place)
+    big = WaterEntropyEngine(s, "interfacial", device=0, chunk_frames=B, table_log2=8, pos_upload=pos_upload)   # 256 slots: must grow
     big.submit(P, Fr, D, list(range(n)))
     big.sync()
     assert big.diag()["frames_done"] == n and big.diag()["eig_fallbacks"] == 0
@@ -1167,9 +1168,9 @@ def test_full_size_production_path_vs_oracle_closure(name, n_sampled):
         fsi_o.update(fsi)
         cov_o.merge(cov)
         lab_o.merge(lab)
-    small = WaterEntropyEngine(s, "interfacial", device=0, chunk_frames=1)
+    small = WaterEntropyEngine(s, "interfacial", device=0, chunk_frames=1, pos_upload=pos_upload)
     idx = torch.tensor(sampled)
-    small.submit(P[idx].contiguous(), Fr[idx].contiguous(), D[sampled], sampled)
+    small.submit(P[idx].contiguous().pin_memory(), Fr[idx].contiguous().pin_memory(), D[sampled], sampled)
     small.sync()
     got = small.hb_labels()
     assert gio.plain(got.resid_labelled_shell_counts) == gio.plain(lab_o.resid_labelled_shell_counts)

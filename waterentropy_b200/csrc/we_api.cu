@@ -238,7 +238,7 @@ struct we_ctx {
   // CUDA graphs of the two kernel runs of a batch (before / after the pass-0 event), per ring slot and
   // frame count; host-buffer submissions only (the device pointers of a slot are fixed)
   struct BatchGraph { cudaGraphExec_t exec = nullptr; unsigned long long launches = 0; };
-  std::map<long long, BatchGraph> graphs;
+  std::map<std::pair<long long, const void*>, BatchGraph> graphs;  // (slot / size / mode key, device-input pointer or null)
   bool out_pending[WE_NBUF] = {};
   // results on host
   std::vector<std::vector<int>> frame_records;  // per submitted frame: (atom, nearest) pairs sorted by atom
@@ -889,8 +889,8 @@ static void drop_graphs(we_ctx* c) {
 // in flight every individual launch costs 20-40 us extra (see the upload gating above); a graph is one
 // submission for the whole run.
 struct GraphRegion {
-  we_ctx* c; cudaStream_t st; long long key; bool on; bool capturing = false; unsigned long long l0 = 0;
-  GraphRegion(we_ctx* c_, cudaStream_t st_, long long key_, bool on_) : c(c_), st(st_), key(key_), on(on_) {}
+  we_ctx* c; cudaStream_t st; std::pair<long long, const void*> key; bool on; bool capturing = false; unsigned long long l0 = 0;
+  GraphRegion(we_ctx* c_, cudaStream_t st_, long long key_, const void* ptr_, bool on_) : c(c_), st(st_), key(key_, ptr_), on(on_) {}
   // returns 1: replayed (skip the launches), 0: run the launches (captured if graphs are on), <0: error
   int begin() {
     if (!on) return 0;
@@ -1109,9 +1109,15 @@ static int submit_impl(we_ctx* c, const float* pos, const float* frc, bool on_de
       for (int i = 0; i < 3; ++i) gate = gate && hb.nc[i] >= 8 && hb.sw[i] <= 2;
       gate = gate && (!hb.triclinic || hb.pre_ok);
     }
-    const bool graphs_on = !on_device && c->use_graphs && !c->prof && !c->opt.keep_debug;
-    const long long gkey = ((((long long)buf * 4096 + n) * 2 + (gate ? 1 : 0)) * 2 + (packed ? 1 : 0)) * 2;
-    GraphRegion g1(c, st, gkey, graphs_on), g2(c, st, gkey + 1, graphs_on);
+    auto gkey_of = [](int b, int nn, bool g, bool pk) { return ((((long long)b * 4096 + nn) * 2 + (g ? 1 : 0)) * 2 + (pk ? 1 : 0)) * 2; };
+    // Device-resident inputs: the caller's position pointer is baked into the captured launches, so it is part
+    // of the key (a caller that streams through ever-new device buffers stops capturing at 64 graphs).
+    const void* gptr = on_device ? (const void*)dp : nullptr;
+    bool graphs_on = c->use_graphs && !c->prof && !c->opt.keep_debug;
+    if (on_device && graphs_on && c->graphs.size() >= 64 && !c->graphs.count({gkey_of(buf, n, gate, packed), gptr}))
+      graphs_on = false;
+    const long long gkey = gkey_of(buf, n, gate, packed);
+    GraphRegion g1(c, st, gkey, gptr, graphs_on), g2(c, st, gkey + 1, gptr, graphs_on);
     int replay = g1.begin();
     if (replay < 0) return replay;
     if (!replay) {
@@ -1589,6 +1595,10 @@ extern "C" int we_span_start(we_ctx* c) {
 }
 extern "C" int we_span_stop(we_ctx* c, double* ms) {
   if (!c || !ms || !c->span_open) return fail(WE_ERR_INVALID, "span not started");
+  // the span ends when EVERY stream of the context is done: the covariance kernels run on their own stream
+  if (!c->ev_cov) CK(cudaEventCreateWithFlags(&c->ev_cov, cudaEventDisableTiming));
+  CK(cudaEventRecord(c->ev_cov, c->s_cov));
+  CK(cudaStreamWaitEvent(c->s_comp, c->ev_cov, 0));
   CK(cudaEventRecord(c->span_b, c->s_comp));
   CK(cudaEventSynchronize(c->span_b));
   float f = 0.f;
