@@ -110,7 +110,9 @@ typedef struct we_options {
 /* Tuning knobs read from the environment by we_create (defaults are the measured optimum on B200):
  *   WE_COPY_GATE=1   hold the upload of a batch back until the previous batch's first neighbour pass starts
  *                    (default 0: uploads run back to back as soon as a slot is free)
- *   WE_COV_STREAM=0  zero-copy k_cov on the compute stream (default 1: own low-priority stream)
+ *   WE_COV_STREAM=0  k_cov on the compute stream; 1: own low-priority stream when it reads the forces zero-copy;
+ *                    default 2: own stream always (it runs beside the next batch's cell-list kernels)
+ *   WE_R_FIRST=a,b,c first candidate radius of the three k_rad passes as fractions of the cell radius (default 1)
  *   WE_PACK_THREADS=n  host threads that gather the heavy atoms of packed uploads (default: the cores this
  *                    process may run on, at most 16); WE_PACK_SPIN_US=t lets them spin t microseconds for the
  *                    next batch before they sleep
