@@ -324,6 +324,60 @@ def time_recipe(s, recipe, hP, hF, D, Fps, W, repeats=3):
                      "see); `first_call_seconds` = a call that creates its context"}
 
 
+def time_file_recipe(s, recipe, P, Fr, D, Fps, W, repeats=3):
+    """The same recipe call on a trajectory FILE: the step's frames written as an AMBER NetCDF-3 file (big-endian
+    float32 records, forces in kcal like AMBER writes them), read back through `io.Universe`'s streaming reader
+    into the pinned staging ring.  File in the page cache (just written); `numpy_reader_seconds` is the same call
+    with the pure-NumPy conversion instead of the library's threaded one (`we_convert_be_f32`)."""
+    import tempfile
+
+    from scipy.io import netcdf_file
+
+    from waterentropy_b200.io import Universe
+    from waterentropy_b200.io.amber import NetCDFTrajectory
+    from waterentropy_b200.recipes.bulk_water import get_bulk_water_orient_entropy
+    from waterentropy_b200.recipes.interfacial_solvent import get_interfacial_water_orient_entropy
+
+    path = os.path.join(tempfile.gettempdir(), "we_bench_%d.nc" % os.getpid())
+    try:
+        nc = netcdf_file(path, "w", version=2)
+        for name, size in (("frame", None), ("atom", s.n_atoms), ("spatial", 3), ("cell_spatial", 3), ("cell_angular", 3)):
+            nc.createDimension(name, size)
+        xyz = nc.createVariable("coordinates", "f", ("frame", "atom", "spatial"))
+        frc = nc.createVariable("forces", "f", ("frame", "atom", "spatial"))
+        cl = nc.createVariable("cell_lengths", "d", ("frame", "cell_spatial"))
+        ca = nc.createVariable("cell_angles", "d", ("frame", "cell_angular"))
+        for k in range(Fps):
+            xyz[k], frc[k], cl[k], ca[k] = P[k], Fr[k], D[k][:3], D[k][3:]
+        nc.close()
+        size = os.path.getsize(path)
+        out = {}
+        for native in ("1", "0"):
+            os.environ["WE_NATIVE_READER"] = native
+            u = Universe()
+            u._set_topology(s.names, s.types, s.resnames, s.resids, s.masses, s.charges, s.bonds)
+            u._source = NetCDFTrajectory(path)
+            call = (lambda: get_interfacial_water_orient_entropy(u, 0, Fps, 1)) if recipe == "interfacial" else \
+                   (lambda: get_bulk_water_orient_entropy(u, 0, Fps, 1))
+            call()
+            runs = []
+            for _ in range(repeats):
+                t0 = time.perf_counter()
+                call()
+                runs.append(time.perf_counter() - t0)
+            out[native] = (statistics.median(runs), runs)
+            u._source.close()
+        os.environ.pop("WE_NATIVE_READER", None)
+        sec, runs = out["1"]
+        return {"value": W * Fps / sec, "unit": UNIT, "seconds": sec, "runs_s": [round(t, 4) for t in runs], "frames": Fps,
+                "file_bytes": size, "numpy_reader_seconds": round(out["0"][0], 4),
+                "timed": "whole recipe call on an io.Universe streaming an AMBER NetCDF file (page cache): threaded byte "
+                         "swap + unit conversion into the pinned ring, upload, kernels, read-out, result objects"}
+    finally:
+        if os.path.exists(path):
+            os.remove(path)
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -546,6 +600,11 @@ def run_ours(args, rank, world, local_rank):
     e2e_recipe = None
     if world == 1 and not args.no_recipe:
         e2e_recipe = time_recipe(s, recipe, hP, hF, D, Fps, W)
+        if not args.no_file:
+            try:
+                e2e_recipe["from_file"] = time_file_recipe(s, recipe, P, Fr, D, Fps, W)
+            except Exception as exc:  # pragma: no cover - a full /tmp must not cost the bench line
+                e2e_recipe["from_file"] = {"value": None, "unavailable": str(exc)}
 
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu = None
@@ -606,6 +665,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=2048, help="CPU arm: centres per sampled step (only when complete frames exceed --cpu-budget)")
     ap.add_argument("--cpu-budget", type=float, default=240.0, help="--impl reference: seconds the timed steps may take")
     ap.add_argument("--search-radius", type=float, default=0.0, help="first-pass candidate radius in A (0 = library default); tuning only, results do not depend on it")
+    ap.add_argument("--no-file", action="store_true", help="skip e2e.recipe.from_file (the recipe on a NetCDF file written to the temp dir)")
     ap.add_argument("--no-recipe", action="store_true", help="skip the e2e.recipe measurement")
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")

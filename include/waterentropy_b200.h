@@ -180,6 +180,17 @@ int we_sync(we_ctx *ctx);
 int we_get_diag(we_ctx *ctx, we_diag *out);
 int we_error_location(we_ctx *ctx, int64_t *frame_id, int32_t *atom);
 
+/* ---- trajectory ingestion (host only, no context) -----------------------------------
+ * Big-endian float32 blocks of a trajectory file - the per-frame records of an AMBER NetCDF-3 file, the
+ * XDR position / force blocks of a GROMACS TRR frame - converted to native float32 straight into the (pinned)
+ * frame buffers we_submit takes, with the unit conversion MDAnalysis' readers apply, in float32 like theirs
+ * (NCDFReader: forces *= 4.184; TRRReader: positions *= 10, forces /= 10).  This is the part of
+ * `system.trajectory[index]` (recipes/interfacial_solvent.py:285) that touches every byte; host threads share it.
+ *   src[b], dst[b]: block b (n_each values each);  op: 0 copy, 1 multiply by factor, 2 divide by factor;
+ *   n_threads: 0 = the cores this process may run on (at most 16). */
+int we_convert_be_f32(const void *const *src, float *const *dst, int32_t n_blocks, uint64_t n_each,
+                      int32_t op, float factor, int32_t n_threads);
+
 /* ---- results ------------------------------------------------------------------
  * The read-out calls below wait for every batch submitted so far (they synchronise the context's own
  * streams), so they never return partially accumulated tables; per-frame errors are reported by we_sync. */

@@ -627,3 +627,58 @@ def test_gro_reader_and_template_topology(tmp_path):
         r = Universe(real, real)
         assert np.array_equal(r.atoms.positions, u.atoms.positions) and list(r.atoms.names) == list(u.atoms.names)
         assert np.array_equal(SystemTopology.from_universe(r).bonds, top.bonds)
+
+
+def test_native_frame_converter_is_bit_identical_to_the_numpy_readers(tmp_path, monkeypatch):
+    """`we_convert_be_f32` (threaded byte swap + float32 unit conversion of the NetCDF / TRR readers) against
+    NumPy on every kind of bit pattern, and the NetCDF reader with and without it on a written file."""
+    from scipy.io import netcdf_file
+
+    from waterentropy_b200.io.amber import NetCDFTrajectory
+
+    rng = np.random.default_rng(5)
+    n = 200_003
+    raw = rng.integers(0, 2 ** 32, n, dtype=np.uint32)
+    raw[:4] = [0x7fc00000, 0x7f800000, 0x00000001, 0x80000000]  # NaN, inf, denormal, -0
+    src = raw.astype(">u4").view(">f4")
+    for op, factor in ((0, 1.0), (1, 4.184), (1, 10.0), (2, 10.0)):
+        want = src.astype(np.float32)
+        with np.errstate(all="ignore"):
+            if op == 1:
+                want *= np.float32(factor)
+            elif op == 2:
+                want /= np.float32(factor)
+        for threads in (1, 3):
+            got = np.full(n, 7.0, dtype=np.float32)
+            half = n // 2  # two blocks of different alignment
+            _lib.convert_be_f32([src.ctypes.data, src[half:].ctypes.data], [got.ctypes.data, got[half:].ctypes.data],
+                                half, op, factor, threads)
+            assert np.array_equal(got[:2 * half].view(np.uint32), want[:2 * half].view(np.uint32)), (op, threads)
+            assert got[2 * half:].tolist() == [7.0] * (n - 2 * half)
+    # a NetCDF trajectory: native and NumPy paths of the reader give the same arrays
+    path = str(tmp_path / "t.nc")
+    na, nf = 1234, 5
+    nc = netcdf_file(path, "w", version=2)
+    nc.createDimension("frame", None)
+    nc.createDimension("atom", na)
+    nc.createDimension("spatial", 3)
+    nc.createDimension("cell_spatial", 3)
+    nc.createDimension("cell_angular", 3)
+    xyz = nc.createVariable("coordinates", "f", ("frame", "atom", "spatial"))
+    frc = nc.createVariable("forces", "f", ("frame", "atom", "spatial"))
+    cl = nc.createVariable("cell_lengths", "d", ("frame", "cell_spatial"))
+    ca = nc.createVariable("cell_angles", "d", ("frame", "cell_angular"))
+    P = rng.normal(0, 30, (nf, na, 3)).astype(np.float32)
+    F = rng.normal(0, 200, (nf, na, 3)).astype(np.float32)
+    for k in range(nf):
+        xyz[k], frc[k], cl[k], ca[k] = P[k], F[k], [30.0, 31.0, 32.0], [90.0, 90.0, 90.0]
+    nc.close()
+    outs = []
+    for native in ("1", "0"):
+        monkeypatch.setenv("WE_NATIVE_READER", native)
+        t = NetCDFTrajectory(path)
+        outs.append(t.read([4, 0, 2]))
+        t.close()
+    assert np.array_equal(outs[0][0], P[[4, 0, 2]]) and np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][1], F[[4, 0, 2]] * np.float32(4.184))
+    assert np.array_equal(outs[0][2], outs[1][2])

@@ -56,7 +56,7 @@ EXPORTS = [
     "we_label_entries_device", "we_merge_label_entries", "we_snapshot_cov", "we_wait_cov",
     "we_copy_frame_shells", "we_test_eig3", "we_frames_retired", "we_wait_frames_retired",
     "we_molecule_force_torque", "we_molecule_force_torque_multi", "we_batch_frames", "we_vib_entropy", "we_orient_entropy",
-    "we_copy_frame_records_range",
+    "we_copy_frame_records_range", "we_convert_be_f32",
 ]
 
 WE_ERR_DUPLICATE_COORD = -1
@@ -159,6 +159,8 @@ def load():
         fn.argtypes = [V, V, V, V, V, I]
     L.we_sync.restype = I
     L.we_sync.argtypes = [V]
+    L.we_convert_be_f32.restype = I
+    L.we_convert_be_f32.argtypes = [V, V, I, C.c_uint64, I, C.c_float, I]
     L.we_reset.restype = I
     L.we_reset.argtypes = [V]
     L.we_get_diag.restype = I
@@ -246,3 +248,16 @@ def check(rc: int):
         # maths/trig.py:36-42 raises ValueError in both situations
         raise ValueError(msg)
     raise WaterEntropyError(f"waterentropy_b200 error {rc}: {msg}")
+
+
+def convert_be_f32(src_addrs, dst_addrs, n_each, op=0, factor=1.0, n_threads=0):
+    """Big-endian float32 blocks at `src_addrs` -> native float32 at `dst_addrs` (`n_each` values per block),
+    `op` 0 copy / 1 multiply / 2 divide by `factor` in float32 (we_convert_be_f32: the threaded byte swap +
+    unit conversion of the trajectory readers)."""
+    import numpy as np
+
+    src = np.ascontiguousarray(src_addrs, dtype=np.uint64)
+    dst = np.ascontiguousarray(dst_addrs, dtype=np.uint64)
+    assert src.shape == dst.shape and src.ndim == 1
+    check(load().we_convert_be_f32(src.ctypes.data, dst.ctypes.data, len(src), int(n_each), int(op), float(factor),
+                                   int(n_threads)))

@@ -1608,6 +1608,57 @@ extern "C" int we_span_stop(we_ctx* c, double* ms) {
   return WE_OK;
 }
 
+// Trajectory ingestion: big-endian float32 blocks -> native float32 (+ the readers' unit conversion), threaded.
+// One loop body, compiled twice: for the baseline ISA and for AVX2 (the byte swap then is one vpshufb per eight
+// values); picked once per call with __builtin_cpu_supports.
+#define WE_CONVERT_BODY                                                    \
+  for (uint64_t i = 0; i < n; ++i) {                                       \
+    uint32_t v;                                                            \
+    memcpy(&v, s + 4 * i, 4);                                              \
+    v = __builtin_bswap32(v);                                              \
+    float f;                                                               \
+    memcpy(&f, &v, 4);                                                     \
+    if (op == 1) f = f * factor;                                           \
+    else if (op == 2) f = f / factor;                                      \
+    d[i] = f;                                                              \
+  }
+static void we_convert_base(const unsigned char* s, float* d, uint64_t n, int op, float factor) { WE_CONVERT_BODY }
+__attribute__((target("avx2"))) static void we_convert_avx2(const unsigned char* s, float* d, uint64_t n, int op, float factor) { WE_CONVERT_BODY }
+
+extern "C" int we_convert_be_f32(const void* const* src, float* const* dst, int32_t n_blocks, uint64_t n_each,
+                                 int32_t op, float factor, int32_t n_threads) {
+  if (!src || !dst || n_blocks < 0 || op < 0 || op > 2) return fail(WE_ERR_INVALID, "we_convert_be_f32: bad argument");
+  if (n_blocks == 0 || n_each == 0) return WE_OK;
+  if (n_threads <= 0) {
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    const int avail = (sched_getaffinity(0, sizeof(set), &set) == 0) ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+    n_threads = std::max(1, std::min(16, avail));
+  }
+  const uint64_t slice = 1u << 16;  // values per task
+  const uint64_t per_block = (n_each + slice - 1) / slice;
+  const uint64_t n_tasks = per_block * (uint64_t)n_blocks;
+  n_threads = (int)std::min<uint64_t>((uint64_t)n_threads, n_tasks);
+  std::atomic<uint64_t> next{0};
+  const bool avx2 = __builtin_cpu_supports("avx2");
+  auto work = [&]() {
+    for (;;) {
+      const uint64_t t = next.fetch_add(1);
+      if (t >= n_tasks) break;
+      const uint64_t b = t / per_block, i0 = (t % per_block) * slice, i1 = std::min(n_each, i0 + slice);
+      const unsigned char* s = (const unsigned char*)src[b] + 4 * i0;
+      float* d = dst[b] + i0;
+      if (avx2) we_convert_avx2(s, d, i1 - i0, op, factor);
+      else we_convert_base(s, d, i1 - i0, op, factor);
+    }
+  };
+  std::vector<std::thread> th;
+  for (int i = 1; i < n_threads; ++i) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+  return WE_OK;
+}
+
 extern "C" int we_n_bins(we_ctx* c) { return c ? c->B : 0; }
 extern "C" int we_n_heavy(we_ctx* c) { return c ? c->H : 0; }
 extern "C" int we_n_donors(we_ctx* c) { return c ? c->ND : 0; }

@@ -15,6 +15,8 @@ from __future__ import annotations
 
 import re
 
+import os
+
 import numpy as np
 
 
@@ -116,13 +118,46 @@ class NetCDFTrajectory:
         n = len(idx)
         P = out_pos if out_pos is not None else np.empty((n, self.n_atoms, 3), dtype=np.float32)
         F = out_frc if out_frc is not None else np.empty((n, self.n_atoms, 3), dtype=np.float32)
-        for k, i in enumerate(idx):
-            P[k] = self._xyz[int(i)]  # big-endian file -> native float32
+        if n and not self._convert_native(idx, P, F):
+            for k, i in enumerate(idx):
+                P[k] = self._xyz[int(i)]  # big-endian file -> native float32
+                if self._frc is not None:
+                    F[k] = self._frc[int(i)]
             if self._frc is not None:
-                F[k] = self._frc[int(i)]
-        if self._frc is not None:
-            F[:n] *= np.float32(4.184)  # kcal -> kJ, float32 like MDAnalysis
+                F[:n] *= np.float32(4.184)  # kcal -> kJ, float32 like MDAnalysis
         return P[:n], (F[:n] if self._frc is not None else None), self.dimensions[idx]
+
+    def _convert_native(self, idx, P, F):
+        """The frames' records through `we_convert_be_f32` (host threads: byte swap + the float32 kcal -> kJ
+        factor in one pass, straight into the caller's blocks).  False when the layout is not the plain one
+        (then the NumPy path above does the same arithmetic)."""
+        from .. import _lib
+
+        if os.environ.get("WE_NATIVE_READER", "1") == "0":
+            return False
+        n_each = self.n_atoms * 3
+
+        def addrs(var, out):
+            data = var.data
+            if data.dtype != np.dtype(">f4") or out.dtype != np.float32 or not out.flags.c_contiguous:
+                return None
+            src, dst = [], []
+            for k, i in enumerate(idx):
+                blk = data[int(i)]
+                if not blk.flags.c_contiguous or blk.size != n_each:
+                    return None
+                src.append(blk.ctypes.data)
+                dst.append(out[k].ctypes.data)
+            return src, dst
+
+        jobs = [(addrs(self._xyz, P), 0, 1.0)]
+        if self._frc is not None:
+            jobs.append((addrs(self._frc, F), 1, 4.184))
+        if any(j[0] is None for j in jobs):
+            return False
+        for (src, dst), op, factor in jobs:
+            _lib.convert_be_f32(src, dst, n_each, op, factor)
+        return True
 
     def close(self):
         self._xyz = self._frc = None  # drop the memory-mapped views before closing the file

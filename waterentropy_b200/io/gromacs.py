@@ -57,15 +57,35 @@ class TRRTrajectory:
         n, na = len(idx), self.n_atoms
         P = out_pos if out_pos is not None else np.empty((n, na, 3), dtype=np.float32)
         F = out_frc if out_frc is not None else np.empty((n, na, 3), dtype=np.float32)
-        for k, i in enumerate(idx):
-            xo, fo, dt, _ = self._frames[int(i)]
-            P[k] = np.frombuffer(self._data, dtype=dt, count=na * 3, offset=xo).reshape(na, 3)
+        if n and not self._convert_native(idx, P, F):
+            for k, i in enumerate(idx):
+                xo, fo, dt, _ = self._frames[int(i)]
+                P[k] = np.frombuffer(self._data, dtype=dt, count=na * 3, offset=xo).reshape(na, 3)
+                if self.has_forces:
+                    F[k] = np.frombuffer(self._data, dtype=dt, count=na * 3, offset=fo).reshape(na, 3)
+            P[:n] *= np.float32(10.0)  # nm -> A
             if self.has_forces:
-                F[k] = np.frombuffer(self._data, dtype=dt, count=na * 3, offset=fo).reshape(na, 3)
-        P[:n] *= np.float32(10.0)  # nm -> A
-        if self.has_forces:
-            F[:n] /= np.float32(10.0)  # kJ/mol/nm -> kJ/mol/A
+                F[:n] /= np.float32(10.0)  # kJ/mol/nm -> kJ/mol/A
         return P[:n], (F[:n] if self.has_forces else None), self.dimensions[idx]
+
+    def _convert_native(self, idx, P, F):
+        """Single-precision frames through `we_convert_be_f32` (host threads: XDR byte swap + the float32 unit
+        conversion in one pass, straight into the caller's blocks); False for double-precision files."""
+        from .. import _lib
+
+        if os.environ.get("WE_NATIVE_READER", "1") == "0":
+            return False
+        frames = [self._frames[int(i)] for i in idx]
+        if any(fr[2] != ">f4" for fr in frames) or P.dtype != np.float32 or not P.flags.c_contiguous:
+            return False
+        if self.has_forces and (F.dtype != np.float32 or not F.flags.c_contiguous):
+            return False
+        base = self._data.ctypes.data
+        n_each = self.n_atoms * 3
+        _lib.convert_be_f32([base + fr[0] for fr in frames], [P[k].ctypes.data for k in range(len(frames))], n_each, 1, 10.0)
+        if self.has_forces:
+            _lib.convert_be_f32([base + fr[1] for fr in frames], [F[k].ctypes.data for k in range(len(frames))], n_each, 2, 10.0)
+        return True
 
 
 def read_trr(path: str):
