@@ -394,7 +394,12 @@ def run_ours(args, rank, world, local_rank):
         try:
             cores = sorted(os.sched_getaffinity(0))
             per = max(1, len(cores) // world)
-            mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+            slot = local_rank
+            if os.environ.get("WE_BENCH_AFFINITY") == "reverse":   # probe: does the feed follow the cores?
+                slot = world - 1 - local_rank
+            elif os.environ.get("WE_BENCH_AFFINITY") == "swap":    # probe: halves exchanged
+                slot = (local_rank + world // 2) % world
+            mine = cores[slot * per:(slot + 1) * per] or cores
             os.sched_setaffinity(0, mine)
             affinity = [mine[0], mine[-1]]
         except OSError:
