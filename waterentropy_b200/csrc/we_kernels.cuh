@@ -470,6 +470,7 @@ __device__ __forceinline__ int we_collect(const WeBox& b, const int* __restrict_
       }
     }
     const int len = len0 + len1;
+    WE_ASSERT(len0 >= 0 && len1 >= 0 && beg0 >= 0 && beg1 >= 0);
     int incl = len;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -1006,6 +1007,7 @@ k_rad(WeTopoDev T, const float* __restrict__ pos, const WeBox* __restrict__ boxe
     if (item >= total) break;
     while (S.pref[f + 1] <= item) ++f;  // a warp's claims increase: f never goes back
     const int i = item - S.pref[f];
+    WE_ASSERT(f < n_frames && i >= 0 && i < (work.count ? work.count[f] : work.static_count));
     const int* list = work.list + (size_t)f * work.stride;
     we_rad_one<GATED>(T, pos + (size_t)f * T.n_atoms * 3, boxes[f], cell_start + (size_t)f * (ncap + 1),
                       cell_of + (size_t)f * T.n_heavy, sorted4 + (size_t)f * T.n_heavy, tmp4 + (size_t)f * T.n_heavy,
@@ -1493,6 +1495,7 @@ k_fetch_light(WeTopoDev T, const float* const* __restrict__ src_slot, float* __r
       const int at = nth(t / 3);
       if (at < 0) break;
       const int c = t % 3;
+      WE_ASSERT(at < T.n_atoms && T.heavy_slot[at] < 0);
       dst[3 * (size_t)at + c] = src[3 * (size_t)at + c];
       fetched += (c == 0);
     }
