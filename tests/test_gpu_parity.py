@@ -429,6 +429,92 @@ def test_seeded_systems_vs_oracle(cfg):
     eng.close()
 
 
+@pytest.mark.parametrize("angles", [(75.0, 100.0, 110.0), (109.4712, 109.4712, 109.4712), (100.0, 80.0, 120.0),
+                                    (60.0, 60.0, 60.0), (90.0, 90.0, 120.0)])
+def test_general_triclinic_boxes_vs_oracle(angles):
+    """Cells with negative and mixed off-diagonal components (angles above 90 degrees: truncated octahedra,
+    hexagonal cells), which the synthetic configurations (60 / 60 / 90) never have: the row culling and x
+    trimming of the cell scan, the image shifts of `k_gate` and the triclinic wrap all depend on their signs.
+    A seeded solvated system is re-interpreted in a cell of the same edge lengths with the given angles (the
+    Cartesian coordinates stay; atoms outside the new cell are wrapped by the path itself), and every centre's
+    shell and every donor's acceptor is compared with the oracle, plus the production path's results."""
+    from waterentropy_b200 import synthetic
+    from waterentropy_b200.engine import WaterEntropyEngine
+
+    s = synthetic.make_system(n_waters=3000, n_residues=40, n_chains=2, n_ions=2, triclinic=False, seed=31)
+    P, Fr, D = s.frames(0, 2)
+    D = D.copy()
+    D[:, 3:] = np.asarray(angles, dtype=np.float32)
+    top = wo.OracleTopology(s.masses, s.charges, s.resids, s.resnames, s.types, s.bonds)
+    eng = WaterEntropyEngine(s, "interfacial", device=0, keep_debug=True)
+    eng.submit(P, Fr, D, [0, 1])
+    eng.sync()
+    for f in range(2):
+        fs = wo.FrameState(top, P[f], D[f])
+        sn = eng.debug(f, "shell_n")
+        assert np.array_equal(sn, fs.rad["shell_n"])
+        valid = np.arange(25)[None, :] < sn[:, None]
+        assert np.array_equal(np.where(valid, eng.debug(f, "shell_idx"), -1), fs.rad["shell_idx"])
+        assert np.array_equal(eng.debug(f, "acceptor"), fs.acc)
+    assert eng.diag()["fast_path_mismatches"] == 0
+    eng.close()
+    # the production path (work lists, k_gate, culled scan) on the same frames
+    fsi, cov, lab, _ = wo.interfacial_run(top, P, Fr, D, [0, 1])
+    prod = WaterEntropyEngine(s, "interfacial", device=0)
+    prod.submit(P, Fr, D, [0, 1])
+    prod.sync()
+    got = prod.hb_labels()
+    assert gio.plain(got.resid_labelled_shell_counts) == gio.plain(lab.resid_labelled_shell_counts)
+    assert gio.plain(prod.frame_solvent_indices()) == gio.plain(fsi)
+    _cmp_cov(prod.covariances(), cov, full=_live_oracle_pinned())
+    prod.close()
+
+
+@pytest.mark.parametrize("tag", ["synth_ortho", "synth_tric"])
+def test_unwrapped_coordinates_vs_oracle(tag):
+    """Trajectories are often written unwrapped: whole molecules sit several box lengths outside the cell.  The
+    cell lists bin wrapped coordinates, orthorhombic distances use the raw ones (as the reference does), and the
+    row culling wraps the centre itself - all against the oracle on the same shifted coordinates."""
+    from waterentropy_b200.system import SystemTopology
+
+    inp = gio.load_inputs(tag)
+    top = gio.oracle_topology(inp)
+    st = SystemTopology(inp["masses"], inp["charges"], inp["resids"], list(inp["resnames"]), list(inp["types"]), inp["bonds"])
+    rng = np.random.default_rng(11)
+    P = inp["positions"][:2].copy()
+    D = inp["dimensions"][:2]
+    n_frag = int(st.fragment_id.max()) + 1
+    for f in range(2):
+        lx, ly, lz, al, be, ga = [float(v) for v in D[f]]
+        ca, cb, cg = np.cos(np.radians([al, be, ga]))
+        sg = np.sin(np.radians(ga))
+        a = np.array([lx, 0.0, 0.0])
+        b = np.array([ly * cg, ly * sg, 0.0])
+        cx, cy = lz * cb, lz * (ca - cb * cg) / sg
+        c = np.array([cx, cy, np.sqrt(lz * lz - cx * cx - cy * cy)])
+        k = rng.integers(-3, 4, size=(n_frag, 3))          # whole molecules, up to three cells away
+        shift = (k[:, :1] * a + k[:, 1:2] * b + k[:, 2:] * c).astype(np.float32)
+        P[f] += shift[st.fragment_id]
+    eng = _engine(inp, keep_debug=True)
+    eng.submit(P, inp["forces"][:2], D, [0, 1])
+    eng.sync()
+    for f in range(2):
+        fs = wo.FrameState(top, P[f], D[f])
+        sn = eng.debug(f, "shell_n")
+        assert np.array_equal(sn, fs.rad["shell_n"])
+        valid = np.arange(25)[None, :] < sn[:, None]
+        assert np.array_equal(np.where(valid, eng.debug(f, "shell_idx"), -1), fs.rad["shell_idx"])
+        assert np.array_equal(eng.debug(f, "acceptor"), fs.acc)
+    eng.close()
+    prod = _engine(inp)
+    prod.submit(P, inp["forces"][:2], D, [0, 1])
+    prod.sync()
+    fsi, cov, lab, _ = wo.interfacial_run(top, P, inp["forces"][:2], D, [0, 1])
+    assert gio.plain(prod.frame_solvent_indices()) == gio.plain(fsi)
+    assert gio.plain(prod.hb_labels().resid_labelled_shell_counts) == gio.plain(lab.resid_labelled_shell_counts)
+    prod.close()
+
+
 # ----------------------------------------------------------------- error behaviour, edges
 def test_duplicate_coordinates_raise_value_error():
     # maths/trig.py:25,40-42: a centre whose coordinates equal a candidate's
