@@ -682,3 +682,49 @@ def test_native_frame_converter_is_bit_identical_to_the_numpy_readers(tmp_path, 
     assert np.array_equal(outs[0][0], P[[4, 0, 2]]) and np.array_equal(outs[0][0], outs[1][0])
     assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][1], F[[4, 0, 2]] * np.float32(4.184))
     assert np.array_equal(outs[0][2], outs[1][2])
+
+
+def test_vibrations_over_stacked_bins_equal_the_per_key_path():
+    """`Vibrations.add_data` on a collection decoded from device tables (matrices = views of one array: all bins
+    with array operations) against the per-key path of the reference's class: entropies, frequencies and the
+    in-place SI scaling bit for bit; a collection whose entries were replaced falls back to the per-key path."""
+    from types import SimpleNamespace
+
+    from waterentropy_b200.engine import decode_cov_tables
+    from waterentropy_b200.entropy.convariances import CovarianceCollection
+    from waterentropy_b200.entropy.vibrations import Vibrations
+
+    rng = np.random.default_rng(3)
+    nb = 40
+    top = SimpleNamespace(n_classes=1, resname_table=["ARG", "WAT"], class_resname_ids=[1],
+                          pair_bins=[(0, 100 + k) for k in range(nb)])
+    raw = rng.normal(0, 300, (nb, 2, 3, 3))
+    s = np.einsum("kaij,kalj->kail", raw, raw)
+    s[5, 0, 1, 1] = -3.0   # a negative and a zero diagonal element: the where() branches
+    s[6, 1, 2, 2] = 0.0
+    c = rng.integers(0, 9, nb).astype(np.uint64)
+    c[7] = 0               # an empty bin is skipped
+    dev = decode_cov_tables(top, 0, s.copy(), c)
+    assert len(dev.forces) == int((c > 0).sum()) and ("ARG_107", "WAT") not in dev.forces
+    ref = CovarianceCollection()
+    for b in np.nonzero(c)[0]:
+        ref.set_sums((f"ARG_{100 + b}", "WAT"), s[b, 0], s[b, 1], int(c[b]))
+    va, vb = Vibrations(298), Vibrations(298)
+    va.add_data(dev)
+    vb.add_data(ref)
+    assert list(va.translational_S) == list(vb.translational_S)
+    for key in ref.forces:
+        for x, y in ((va.translational_S[key], vb.translational_S[key]), (va.rotational_S[key], vb.rotational_S[key]),
+                     (va.translational_freq[key], vb.translational_freq[key]),
+                     (va.rotational_freq[key], vb.rotational_freq[key]),
+                     (dev.forces[key], ref.forces[key]), (dev.torques[key], ref.torques[key])):
+            assert np.array_equal(np.asarray(x), np.asarray(y)), key
+        assert dev.counts[key] == ref.counts[key]
+    # replaced entry -> generic path, still the same numbers
+    dev2 = decode_cov_tables(top, 0, s.copy(), c)
+    k0 = next(iter(dev2.forces))
+    dev2.forces[k0] = dev2.forces[k0].copy()
+    vc = Vibrations(298)
+    assert not vc._add_stacked(dev2)
+    vc.add_data(dev2)
+    assert all(np.array_equal(vc.translational_S[k], vb.translational_S[k]) for k in ref.forces)

@@ -188,6 +188,10 @@ struct we_ctx {
   WePackPool* pool = nullptr;
   int pack_threads = 0;
   unsigned long long h2d_bytes = 0, pack_us = 0;
+  struct OrientScratch {  // device scratch of we_orient_entropy (raw cudaMalloc, freed by we_destroy)
+    void *rank = nullptr, *rec = nullptr, *rows = nullptr, *out = nullptr, *keys = nullptr, *ng = nullptr;
+    size_t rank_cap = 0, rec_cap = 0, rows_cap = 0, out_cap = 0, keys_cap = 0, ng_cap = 0;
+  } orient;
   float* d_frc[WE_NBUF] = {};
   WeBox* d_boxes[WE_NBUF] = {};
   long long* d_fids[WE_NBUF] = {};
@@ -609,6 +613,9 @@ extern "C" void we_destroy(we_ctx* c) {
   if (c->s_comp) cudaStreamDestroy(c->s_comp);
   delete c->pool;
   c->pool = nullptr;
+  for (void* q : {c->orient.rank, c->orient.rec, c->orient.rows, c->orient.out, c->orient.keys, c->orient.ng})
+    if (q) cudaFree(q);
+  c->orient = we_ctx::OrientScratch();
   if (c->s_cov) cudaStreamDestroy(c->s_cov);
   if (c->s_aux) cudaStreamDestroy(c->s_aux);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -1429,19 +1436,30 @@ extern "C" int we_orient_entropy(we_ctx* c, const uint16_t* label_rank, int32_t 
   { const int rc = compact_entries(c, n); if (rc) return rc; }
   int n_pad = 1;
   while (n_pad < n) n_pad <<= 1;
-  unsigned short* d_rank = nullptr;
-  WeOrientRec* d_rec = nullptr;
-  WeOrientRow* d_rows = nullptr;
-  double* d_out = nullptr;
-  int *d_keys = nullptr, *d_ng = nullptr;
+  // scratch kept with the context and grown on demand: the recipes call this twice per analysis (per residue
+  // id, per residue name), and six cudaMalloc / cudaFree pairs per call cost more than the kernels
   cudaError_t e = cudaSuccess;
-  auto al = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes ? bytes : 8); };
-  al((void**)&d_rank, 65536 * sizeof(unsigned short));
-  al((void**)&d_rec, (size_t)n_pad * sizeof(WeOrientRec));
-  al((void**)&d_rows, (size_t)n * sizeof(WeOrientRow));
-  al((void**)&d_out, (size_t)max_groups * 8 * sizeof(double));
-  al((void**)&d_keys, (size_t)max_groups * 2 * sizeof(int));
-  al((void**)&d_ng, sizeof(int));
+  auto grow = [&](void** p, size_t* cap, size_t bytes) {
+    if (e != cudaSuccess || (*p && *cap >= bytes)) return;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = bytes + bytes / 2 + 64;
+    e = cudaMalloc(p, *cap);
+    if (e != cudaSuccess) { *p = nullptr; *cap = 0; }
+  };
+  we_ctx::OrientScratch& os = c->orient;
+  grow((void**)&os.rank, &os.rank_cap, 65536 * sizeof(unsigned short));
+  grow((void**)&os.rec, &os.rec_cap, (size_t)n_pad * sizeof(WeOrientRec));
+  grow((void**)&os.rows, &os.rows_cap, (size_t)n * sizeof(WeOrientRow));
+  grow((void**)&os.out, &os.out_cap, (size_t)max_groups * 8 * sizeof(double));
+  grow((void**)&os.keys, &os.keys_cap, (size_t)max_groups * 2 * sizeof(int));
+  grow((void**)&os.ng, &os.ng_cap, sizeof(int));
+  if (e != cudaSuccess) return fail(WE_ERR_CUDA, "we_orient_entropy: scratch allocation failed: %s", cudaGetErrorString(e));
+  unsigned short* d_rank = (unsigned short*)os.rank;
+  WeOrientRec* d_rec = (WeOrientRec*)os.rec;
+  WeOrientRow* d_rows = (WeOrientRow*)os.rows;
+  double* d_out = (double*)os.out;
+  int *d_keys = (int*)os.keys, *d_ng = (int*)os.ng;
   cudaStream_t st = c->s_comp;
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_rank, label_rank, 65536 * sizeof(unsigned short), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemsetAsync(d_ng, 0, sizeof(int), st);
@@ -1462,7 +1480,6 @@ extern "C" int we_orient_entropy(we_ctx* c, const uint16_t* label_rank, int32_t 
     e = cudaMemcpy(out_rows, d_out, (size_t)ng * 8 * sizeof(double), cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(out_keys, d_keys, (size_t)ng * 2 * sizeof(int), cudaMemcpyDeviceToHost);
   }
-  cudaFree(d_rank); cudaFree(d_rec); cudaFree(d_rows); cudaFree(d_out); cudaFree(d_keys); cudaFree(d_ng);
   if (e != cudaSuccess) return fail(WE_ERR_CUDA, "we_orient_entropy failed: %s", cudaGetErrorString(e));
 #ifdef WE_CHECKED
   {

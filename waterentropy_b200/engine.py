@@ -46,15 +46,24 @@ def decode_cov_tables(top, recipe, s, c) -> CovarianceCollection:
     """Dense per-bin sums [B,2,3,3] + counts [B] -> the reference's CovarianceCollection
     (`entropy/convariances.py:10-19`): key (f"{resname}_{resid}", water resname), mean = sum / count."""
     out = CovarianceCollection()
-    for b in np.nonzero(c)[0]:
-        cls = int(b) % top.n_classes
+    idx = np.nonzero(c)[0]
+    # every bin's means in one array (the same float64 division per element as `set_sums`); the dictionaries
+    # hold views of it, so `Vibrations.add_data` can scale and evaluate all bins with array operations
+    means = np.asarray(s, dtype=np.float64)[idx] / np.asarray(c)[idx].astype(np.float64)[:, None, None, None]
+    keys = []
+    for k, b in enumerate(idx.tolist()):
+        cls = b % top.n_classes
         centre_name = top.resname_table[top.class_resname_ids[cls]]
         if recipe == RECIPE_BULK:
             key = (centre_name, centre_name)
         else:
-            rn, rid = top.pair_bins[int(b) // top.n_classes]
+            rn, rid = top.pair_bins[b // top.n_classes]
             key = (f"{top.resname_table[rn]}_{rid}", centre_name)
-        out.set_sums(key, s[b, 0], s[b, 1], int(c[b]))
+        out.forces[key] = means[k, 0]
+        out.torques[key] = means[k, 1]
+        out.counts[key] = int(c[b])
+        keys.append(key)
+    out._stacked = (keys, means)
     return out
 
 

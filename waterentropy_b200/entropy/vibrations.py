@@ -49,6 +49,8 @@ class Vibrations:
         return self._conversion(self.CALORIE_TO_JOULE, self.ANGSTROM_TO_METRE)
 
     def add_data(self, covariances, diagonalise=True):
+        if diagonalise and self._add_stacked(covariances):
+            return
         for key, force_cov in covariances.forces.items():
             torque_cov = covariances.torques[key]
             s_f, lam_f = self.get_data(force_cov, diagonalise)
@@ -57,6 +59,42 @@ class Vibrations:
                                  (self.translational_freq, lam_f), (self.rotational_freq, lam_t)):
                 if key not in store:
                     store[key] = value
+
+    def _add_stacked(self, covariances):
+        """All bins at once when the collection's matrices are views of one array (collections decoded from the
+        device tables, `engine.decode_cov_tables`): the same element-wise arithmetic as the per-key path below -
+        in-place SI scaling of every matrix included - without ~20 us of Python per matrix."""
+        stacked = getattr(covariances, "_stacked", None)
+        if stacked is None:
+            return False
+        keys, M = stacked
+        if len(keys) != len(covariances.forces) or len(keys) != len(covariances.torques):
+            return False
+        for k, key in enumerate(keys):  # still the views we made? (a caller may have replaced or merged entries)
+            f, t = covariances.forces.get(key), covariances.torques.get(key)
+            if f is None or t is None or f.base is not M or t.base is not M or f.shape != (3, 3) or t.shape != (3, 3):
+                return False
+        if len(keys) == 0:
+            return True
+        M *= self.mda_conversion()  # in place, like upstream: every view is scaled
+        eig = M[:, :, (0, 1, 2), (0, 1, 2)]  # [bin, force / torque, 3] diagonals (a copy)
+        lam = np.where(eig >= 0, eig, 0)
+        kT = self.BOLTZMANN * self.temperature
+        a = (self.HBAR * (lam / kT) ** 0.5) / (self.BOLTZMANN * self.temperature)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            b = np.where(a != 0, np.exp(a) - 1, 0.0)
+            c = np.where(a != 0, np.log(1 - np.exp(-a)), 0.0)
+            s = np.where((b != 0) & (c != 0), a / b - c, 0) * self.GAS_CONSTANT
+        for k, key in enumerate(keys):
+            if key not in self.translational_S:
+                self.translational_S[key] = s[k, 0]
+            if key not in self.rotational_S:
+                self.rotational_S[key] = s[k, 1]
+            if key not in self.translational_freq:
+                self.translational_freq[key] = eig[k, 0]
+            if key not in self.rotational_freq:
+                self.rotational_freq[key] = eig[k, 1]
+        return True
 
     def get_data(self, covariance, diagonalise):
         covariance *= self.mda_conversion()  # in place, like upstream
