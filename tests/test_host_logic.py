@@ -728,3 +728,49 @@ def test_vibrations_over_stacked_bins_equal_the_per_key_path():
     assert not vc._add_stacked(dev2)
     vc.add_data(dev2)
     assert all(np.array_equal(vc.translational_S[k], vb.translational_S[k]) for k in ref.forces)
+
+
+@pytest.mark.parametrize("tag", gio.TAGS)
+def test_decode_label_entries_equals_add_counts_entry_by_entry(tag):
+    """`engine.decode_label_entries` (column-wise, what `_entropy_per_step` spends its time in) against the
+    class API fed entry by entry in order of first appearance (`HBLabelCollection.add_counts`): same nested
+    dictionaries, same insertion order at every level (S_orient visits them in that order), N_w of the first
+    insert kept when a key arrives twice."""
+    from waterentropy_b200.analysis.HB_labels import HBLabelCollection
+    from waterentropy_b200.engine import decode_label_entries
+    from waterentropy_b200.system import RECIPE_BULK, RECIPE_INTERFACIAL
+
+    def ordered(d):
+        return [(k, ordered(v)) for k, v in d.items()] if isinstance(d, dict) else d
+
+    inp = gio.load_inputs(tag)
+    ref = gio.load_reference(tag)
+    top = SystemTopology(inp["masses"], inp["charges"], inp["resids"], list(inp["resnames"]), list(inp["types"]), inp["bonds"])
+    rng = np.random.default_rng(9)
+    cases = [(False, step["labels"]) for step in list(ref["per_step"].values())[:2]]
+    cases += [(True, b["labels"]) for b in list(ref["bulk"].values())[:1] if "labels" in b]
+    for bulk, d in cases:
+        entries = _entries_from_golden(top, d, bulk, rng)
+        if len(entries) > 3:   # the same keys again, later, with another N_w (as a second rank would hold them)
+            dup = entries[:3].copy()
+            dup["first_seen_inv"] -= np.uint64(1000)
+            dup["n_w"] += 1
+            entries = np.concatenate([entries, dup])
+        recipe = RECIPE_BULK if bulk else RECIPE_INTERFACIAL
+        want = HBLabelCollection()
+        for e in entries[np.argsort(~entries["first_seen_inv"], kind="stable")]:
+            n = int(e["n_labels"])
+            labels = [top.label_string(int(c)) for c in e["labels"][:n]]
+            don, acc = {}, {}
+            for p in range(n):
+                if e["donates"][p]:
+                    don[labels[p]] = don.get(labels[p], 0) + int(e["donates"][p])
+                if e["accepts"][p]:
+                    acc[labels[p]] = acc.get(labels[p], 0) + int(e["accepts"][p])
+            resname = top.resname_table[int(e["nearest_resname_id"])]
+            want.add_counts(resname if bulk else int(e["nearest_resid"]), resname, labels, int(e["n_w"]),
+                            int(e["shell_count"]), don, acc)
+        got = decode_label_entries(top, recipe, entries)
+        assert ordered(got.resid_labelled_shell_counts) == ordered(want.resid_labelled_shell_counts)
+        assert ordered(got.labelled_shell_counts) == ordered(want.labelled_shell_counts)
+    assert len(decode_label_entries(top, RECIPE_INTERFACIAL, entries[:0]).labelled_shell_counts) == 0

@@ -71,21 +71,46 @@ def decode_label_entries(top, recipe, entries) -> HBLabelCollection:
     """Device label-table entries -> the reference's HBLabelCollection
     (`analysis/HB_labels.py:15-156`).  Label codes become strings, the tuple is sorted the way
     Python sorts strings, and entries are fed in order of first appearance because N_w is frozen
-    by the first insert (`analysis/HB_labels.py:58,71`)."""
+    by the first insert (`analysis/HB_labels.py:58,71`).
+
+    What `HBLabelCollection.add_counts` would do entry by entry, on plain Python lists (the columns of the
+    structured array are converted once): this is most of the reference's unit of work on this path,
+    `_entropy_per_step` - one frame per call, ~1,400 entries on C4 (34 -> 9 ms per call)."""
     out = HBLabelCollection()
-    order = np.argsort(~entries["first_seen_inv"], kind="stable")
-    for e in entries[order]:
-        n = int(e["n_labels"])
-        labels = [top.label_string(int(c)) for c in e["labels"][:n]]
-        don, acc = {}, {}
-        for p in range(n):
-            if e["donates"][p]:
-                don[labels[p]] = don.get(labels[p], 0) + int(e["donates"][p])
-            if e["accepts"][p]:
-                acc[labels[p]] = acc.get(labels[p], 0) + int(e["accepts"][p])
-        resname = top.resname_table[int(e["nearest_resname_id"])]
-        resid = resname if recipe == RECIPE_BULK else int(e["nearest_resid"])
-        out.add_counts(resid, resname, labels, int(e["n_w"]), int(e["shell_count"]), don, acc)
+    if len(entries) == 0:
+        return out
+    e = entries[np.argsort(~entries["first_seen_inv"], kind="stable")]
+    cache = top.__dict__.setdefault("_we_label_strings", {})
+    names = top.resname_table
+    bulk = recipe == RECIPE_BULK
+    by_name, by_resid = out.labelled_shell_counts, out.resid_labelled_shell_counts
+    for n, codes, don, acc, rn, rid, n_w, count in zip(
+            e["n_labels"].tolist(), e["labels"].tolist(), e["donates"].tolist(), e["accepts"].tolist(),
+            e["nearest_resname_id"].tolist(), e["nearest_resid"].tolist(), e["n_w"].tolist(), e["shell_count"].tolist()):
+        labels = []
+        for c in codes[:n]:
+            lab = cache.get(c)
+            if lab is None:
+                lab = cache[c] = top.label_string(c)
+            labels.append(lab)
+        key = tuple(sorted(labels))
+        resname = names[rn]
+        resid = resname if bulk else rid
+        for entry in (by_name[resname][key], by_resid[resid][resname][key]):
+            if "shell_count" in entry:
+                entry["shell_count"] += count
+            else:
+                entry["shell_count"] = count
+                entry["N_w"] = n_w
+            for field, src in (("donates_to", don), ("accepts_from", acc)):
+                dst = None
+                for p in range(n):
+                    v = src[p]
+                    if v:
+                        if dst is None:
+                            dst = entry[field]
+                        lab = labels[p]
+                        dst[lab] = dst.get(lab, 0) + v
     return out
 
 
