@@ -1,3 +1,4 @@
+"""cProfile of the reference's unit of work, `_entropy_per_step` (one frame per call), on C4 (diagnostic)."""
 import os, sys, time, cProfile, pstats
 sys.path.insert(0, "/root/repo")
 import torch
