@@ -478,12 +478,14 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_src = load_peaks()
     achieved = alg_bytes / (k_ms / k_n * 1e-3) / 1e9 if k_n else 0.0
     traffic = None
+    warp_inst = None
     tp = os.path.join(REPO, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
             tj = json.load(open(tp))
             if tj.get("kernel") == top_k and tj.get("config") == args.config and tj.get("frames_per_launch") == chunk:
                 traffic = tj.get("dram_bytes_per_launch")
+                warp_inst = tj.get("warp_instructions_per_launch")
         except Exception:
             pass
     total_k = sum(v[0] for v in merged.values())
@@ -493,6 +495,16 @@ def run_ours(args, rank, world, local_rank):
                 "kernel_ms_per_launch": k_ms / k_n if k_n else None,
                 "kernel_share_of_step": k_ms / total_k if total_k else None,
                 "kernel_ms_per_batch": {k: round(v[0] / n_batches, 4) for k, v in ktimes.items()}}
+    if warp_inst and k_n and k_ms > 0:
+        # the resource that actually binds the kernel: warp-instruction issue slots (4 schedulers per SM at the SM
+        # clock); instructions from the committed ncu capture of the same command, time measured live above
+        props = torch.cuda.get_device_properties(local_rank)
+        sm_hz = 1e3 * float(getattr(props, "clock_rate", 0) or 1965000)  # kHz -> Hz; B200 boost clock as fallback
+        slots = props.multi_processor_count * 4 * sm_hz
+        roofline["issue"] = {"warp_instructions_per_launch": warp_inst, "issue_slots_per_s": slots,
+                             "frac": warp_inst / (slots * (k_ms / k_n) * 1e-3),
+                             "note": "the kernel is bound by instruction issue, not by HBM: share of the issue slots "
+                                     "of the time its launches took"}
     eng.close()
     del dP, dF
 
